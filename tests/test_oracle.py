@@ -1,0 +1,203 @@
+"""CPU tests: the oracle (oracle/fem_oracle.py) against (1) the reference's own golden
+vectors (tests/golden/ref_testdata.npz) and (2) outputs of the real reference on the case
+ladder (tests/golden/<case>.npz, made by tools/gen_golden.py)."""
+import numpy as np
+import pytest
+
+import cases as C
+import golden_util as G
+from oracle import fem_oracle as O
+
+RT = G.ref_testdata()
+
+
+# ---------------------------------------------------------------- reference's own vectors
+def test_ref_multi_index():
+    assert np.array_equal(O.multi_index_matrix(2, 2), RT["multi_index_p2_d2"])
+    assert np.array_equal(O.multi_index_matrix(2, 1), RT["multi_index_p2_d1"])
+
+
+def test_ref_backend_primitives():
+    m = O.Mesh(RT["bk_tri2d_node"], RT["bk_tri2d_cell"])
+    p = int(RT["bk_tri2d_p"])
+    np.testing.assert_allclose(m.cell_measure(), RT["bk_tri2d_simple_measure"], atol=1e-14)
+    np.testing.assert_allclose(m.grad_lambda(), RT["bk_tri2d_triangle_grad_lambda_2d"], atol=1e-14)
+    np.testing.assert_allclose(O.shape_function(RT["bk_tri2d_bcs"], p), RT["bk_tri2d_simple_shape_function"], atol=1e-14)
+    np.testing.assert_allclose(O.grad_shape_function(RT["bk_tri2d_bcs"], p), RT["bk_tri2d_simple_grad_shape_function"], atol=1e-14)
+    np.testing.assert_allclose(m.bc_to_point(RT["bk_tri2d_bcs"]), RT["bk_tri2d_bc_to_points"], atol=1e-14)
+    t = O.Mesh(RT["bk_tet_node"], RT["bk_tet_cell"])
+    np.testing.assert_allclose(t.grad_lambda(), RT["bk_tet_tetrahedron_grad_lambda_3d"], atol=1e-14)
+
+
+def test_ref_element_matrices_p2_q3():
+    # test/fem/test_scalar_diffusion_integrator.py:16-24, test_scalar_mass_integrator.py:16-24
+    node, cell = O.tri_from_box([0, 1, 0, 1], 1, 1)
+    m = O.Mesh(node, cell)
+    np.testing.assert_array_almost_equal(O.diffusion_element(m, 2, q=3, coef=1), RT["diffusion_p2_q3_box1_Ke"])
+    np.testing.assert_array_almost_equal(O.mass_element(m, 2, q=3, coef=1), RT["mass_p2_q3_box1_Ke"])
+
+
+def test_ref_tet_mesh_vectors():
+    # test/mesh/test_tetrahedron_mesh.py:62-162
+    node, cell = O.tet_from_box([0, 1, 0, 1, 0, 1], 3, 2, 1)
+    m = O.Mesh(node, cell)
+    np.testing.assert_allclose(m.cell_measure(), RT["tet_321_cm"], atol=1e-14)
+    np.testing.assert_allclose(m.grad_lambda(), RT["tet_321_glambda"], atol=1e-14)
+    assert np.array_equal(m.cell_to_ipoint(4), RT["tet_321_cell2ipoint_p4"])
+    np.testing.assert_allclose(m.interpolation_points(4), RT["tet_321_ipoints_p4"], atol=1e-14)
+    # thresholded from_box: same node/cell construction, then cells with x,y,z<0.5 barycentre removed
+    bc = node[cell].mean(axis=1)
+    keep = ~((bc[:, 0] < 0.5) & (bc[:, 1] < 0.5) & (bc[:, 2] < 0.5))
+    cell2 = cell[keep]
+    valid = np.zeros(len(node), bool); valid[cell2] = True
+    remap = np.zeros(len(node), np.int32); remap[valid] = np.arange(valid.sum(), dtype=np.int32)
+    m2 = O.Mesh(node[valid], remap[cell2])
+    assert np.array_equal(m2.cell, RT["tet_from_box_321_thr_cell"])
+    assert np.array_equal(m2.edge, RT["tet_from_box_321_thr_edge"])
+    assert np.array_equal(m2.face, RT["tet_from_box_321_thr_face"])
+    np.testing.assert_allclose(m2.node, RT["tet_from_box_321_thr_node"], atol=1e-14)
+    # grad_shape_function p=2 q=3 on from_box(1,1,1)
+    node1, cell1 = O.tet_from_box([0, 1, 0, 1, 0, 1], 1, 1, 1)
+    m1 = O.Mesh(node1, cell1)
+    bcs, _ = O.quadrature(3, 3)
+    np.testing.assert_allclose(O.grad_shape_function(bcs, 2), RT["tet_111_gsf_u_p2_q3"], atol=1e-14)
+    got = np.transpose(O.grad_basis(m1, 2, bcs), (1, 0, 2, 3))      # reference layout is (NQ, NC, ldof, GD)
+    np.testing.assert_allclose(got, RT["tet_111_gsf_x_p2_q3"], atol=1e-13)
+
+
+def test_ref_tri_mesh_vectors():
+    node, cell = O.tri_from_box([0, 1, 0, 1], 2, 2)
+    assert np.array_equal(cell, RT["tri_22_cell"])
+    m = O.Mesh(node, cell)
+    bcs, _ = O.quadrature(2, 3)
+    np.testing.assert_allclose(O.grad_basis(m, 2, bcs), RT["tri_22_gphi_p2_q3"], atol=1e-13)
+    assert np.array_equal(m.cell_to_ipoint(4), RT["tri_22_cip_p4"])
+    np.testing.assert_allclose(m.interpolation_points(4), RT["tri_22_ips_p4"], atol=1e-14)
+    node2, cell2 = O.tri_from_box([-1, 1, -1, 1], 2, 2)
+    np.testing.assert_allclose(O.Mesh(node2, cell2).grad_lambda(), RT["tri_glambda_m11_22"], atol=1e-14)
+
+
+def test_ref_lagrange_space_vectors():
+    node, cell = O.tri_from_box([0, 1, 0, 1], 1, 1)
+    m = O.Mesh(node, cell)
+    assert np.array_equal(m.cell_to_ipoint(2), RT["lfs_box1_p2_cell_to_dof"])
+    assert np.array_equal(O.boundary_dof_flag(m, 2), RT["lfs_box1_p2_is_boundary_dof"])
+    bcs = RT["lfs_box1_p2_bcs"]
+    np.testing.assert_allclose(O.shape_function(bcs, 2)[None], RT["lfs_box1_p2_basis"], atol=1e-14)
+    np.testing.assert_allclose(O.grad_basis(m, 2, bcs), RT["lfs_box1_p2_grad_basis"], atol=1e-13)
+    np.testing.assert_allclose(m.interpolation_points(2), RT["lfs_box1_p2_ipoints"], atol=1e-14)
+
+
+def test_ref_coalesce_and_tocsr():
+    # test/sparse/test_coo_tensor.py:29-48
+    r, c, v = O.coalesce(RT["coo_indices"][0], RT["coo_indices"][1], RT["coo_values"])
+    assert np.array_equal(np.stack([r, c]), RT["coo_expected_indices"])
+    assert np.array_equal(v, RT["coo_expected_values"])
+    # test/sparse/test_coo_tensor.py:377-392
+    D = RT["tocsr_dense"]
+    rr, cc = np.nonzero(D)
+    crow, col, val = O.tocsr(rr, cc, D[rr, cc], D.shape[0])
+    assert np.array_equal(crow, RT["tocsr_crow"]) and np.array_equal(col, RT["tocsr_col"])
+    assert np.array_equal(val, RT["tocsr_values"])
+
+
+@pytest.mark.parametrize("k", [0, 1])
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_ref_bilinear_form_matmul(k, p):
+    # test/fem/test_bilinear_form.py:19-44: matrix-free (element-wise) product == assembled product
+    m = O.Mesh(RT[f"bform_mesh{k}_node"], RT[f"bform_mesh{k}_cell"])
+    Ke = O.diffusion_element(m, p)
+    c2d = m.cell_to_ipoint(p)
+    gdof = m.number_of_global_ipoints(p)
+    x = np.random.default_rng(p).random(gdof)
+    y = np.zeros(gdof)
+    np.add.at(y, c2d.ravel(), np.einsum("cij,cj->ci", Ke, x[c2d]).ravel())
+    crow, col, val = O.assemble([(Ke, c2d)], gdof)
+    assert np.linalg.norm(y - O.csr_matvec(crow, col, val, x)) < 1e-12
+
+
+# ---------------------------------------------------------------- outputs of the reference run
+def build_oracle_case(case, gold):
+    m = O.Mesh(gold["node"], gold["cell"])
+    p = case["p"]
+    c2d = m.cell_to_ipoint(p)
+    sg = m.number_of_global_ipoints(p)
+    tensor = case.get("tensor")
+    if tensor is not None:
+        c2d_use = O.tensor_cell_to_dof(c2d, sg, m.GD, tensor["dof_priority"])
+        gdof = sg * m.GD
+    else:
+        c2d_use, gdof = c2d, sg
+    groups, Kes, k = [], [], 0
+    for grp in case["groups"]:
+        acc = None
+        for kind, spec in grp:
+            q = spec.get("q")
+            if kind == "elasticity":
+                lam, mu = O.lame(spec["E"], spec["nu"])
+                D = O.elastic_matrix(lam, mu, spec["hypo"], spec["E"], spec["nu"])
+                Ke = O.elasticity_element(m, p, D, q=q, dof_priority=tensor["dof_priority"])
+            else:
+                NQ = len(O.quadrature(m.TD, p + 3 if q is None else q)[1])
+                coef = G.case_coef(case, spec, k, gold, m.NC, NQ, m.GD)
+                if kind == "diffusion":
+                    Ke = O.diffusion_element(m, p, q=q, coef=coef, method=spec.get("method"))
+                else:
+                    Ke = O.mass_element(m, p, q=q, coef=coef)
+            Kes.append(Ke)
+            acc = Ke if acc is None else acc + Ke
+            k += 1
+        groups.append((acc, c2d_use))
+    return m, c2d, c2d_use, gdof, groups, Kes
+
+
+@pytest.mark.parametrize("case", C.CASES, ids=[c["name"] for c in C.CASES])
+def test_oracle_matches_reference_run(case):
+    gold = G.load(case["name"])
+    m, c2d, c2d_use, gdof, groups, Kes = build_oracle_case(case, gold)
+    assert np.array_equal(c2d, gold["cell2dof_scalar"])
+    assert np.array_equal(c2d_use, gold["cell2dof"])
+    assert np.array_equal(m.edge, gold["edge"])
+    assert gdof == gold["info"]["gdof"]
+    if case.get("elem"):
+        for k, Ke in enumerate(Kes):
+            assert G.rel_err(Ke, gold[f"Ke_{k}"]) < 1e-13
+    crow, col, val = O.assemble(groups, gdof)
+    assert crow.dtype == np.int64 and col.dtype == gold["col"].dtype
+    assert np.array_equal(crow, gold["crow"]) and np.array_equal(col, gold["col"])
+    assert len(val) == gold["info"]["nnz"]
+    if "values" in gold:
+        assert G.rel_err(val, gold["values"]) < 1e-13
+    else:
+        assert G.rel_err(val[::97], gold["values_sample"]) < 1e-13
+        assert abs(val.sum() - gold["values_sum"][0]) < 1e-10 * gold["values_sum"][1]
+    if case.get("cg"):
+        mv = lambda v: O.csr_matvec(crow, col, val, v)
+        b = mv(np.ones(gdof))
+        # b = A.1 cancels the O(1) diffusion entries: scale the error by max|A|
+        assert np.max(np.abs(b - gold["b"])) < 1e-13 * np.max(np.abs(val))
+        x, info = O.cg(mv, b)
+        assert abs(info["niter"] - gold["info"]["niter"]) <= 1
+        assert np.linalg.norm(x - gold["x"]) / np.linalg.norm(gold["x"]) < 1e-10
+
+
+@pytest.mark.parametrize("case", C.BC_CASES, ids=[c["name"] for c in C.BC_CASES])
+def test_oracle_bc_matches_reference_run(case):
+    gold = G.load(case["name"])
+    m = O.Mesh(gold["node"], gold["cell"])
+    p = case["p"]
+    F = O.source_vector(m, p, C.source_cart)
+    assert G.rel_err(F, gold["F"]) < 1e-13
+    isbd = O.boundary_dof_flag(m, p)
+    assert np.array_equal(isbd, gold["isbd"])
+    ip = m.interpolation_points(p)
+    np.testing.assert_allclose(ip, gold["ipoints"], atol=1e-14)
+    uh = np.zeros(len(F)); uh[isbd] = C.kappa_cart(ip[isbd])
+    A, F2 = O.dirichlet_apply(gold["crow"], gold["col"], gold["values"], F, uh, isbd)
+    assert G.rel_err(F2, gold["F_bc"]) < 1e-13
+    A.eliminate_zeros(); A.sort_indices()
+    assert np.array_equal(A.indptr, gold["Abc_indptr"]) and np.array_equal(A.indices, gold["Abc_indices"])
+    assert G.rel_err(A.data, gold["Abc_data"]) < 1e-13
+    x, info = O.cg(lambda v: A @ v, F2)
+    assert abs(info["niter"] - gold["info"]["niter"]) <= 1
+    assert np.linalg.norm(x - gold["x"]) / np.linalg.norm(gold["x"]) < 1e-10

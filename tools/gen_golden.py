@@ -1,0 +1,225 @@
+"""Generate tests/golden/*.npz by running the REAL reference (numpy backend) on the case
+ladder of tests/cases.py, and at the same time pin the oracle (oracle/fem_oracle.py)
+against it.  Build-container only (needs /root/reference); the fixtures are committed.
+
+    python tools/gen_golden.py            # all cases
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, ROOT)
+import ref_import  # noqa: E402
+ref_import.install()
+
+from fealpy.backend import backend_manager as bm  # noqa: E402
+from fealpy.mesh import TriangleMesh, TetrahedronMesh  # noqa: E402
+from fealpy.functionspace import LagrangeFESpace, TensorFunctionSpace  # noqa: E402
+from fealpy.fem import (BilinearForm, LinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator,  # noqa: E402
+                        LinearElasticityIntegrator, ScalarSourceIntegrator, DirichletBC)
+from fealpy.material.elastic_material import LinearElasticMaterial  # noqa: E402
+from fealpy.solver import cg  # noqa: E402
+from fealpy.decorator import cartesian  # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases as C  # noqa: E402
+from oracle import fem_oracle as O  # noqa: E402
+
+bm.set_backend("numpy")
+GOLD = os.path.join(ROOT, "tests", "golden")
+os.makedirs(GOLD, exist_ok=True)
+
+
+def ref_mesh(case):
+    box = C.box_of(case)
+    if case["mesh"] == "tri":
+        m = TriangleMesh.from_box(box, *case["dims"])
+        cls = TriangleMesh
+    else:
+        m = TetrahedronMesh.from_box(box, *case["dims"])
+        cls = TetrahedronMesh
+    if case.get("jitter") is not None:
+        node = C.perturb(np.asarray(m.node), case["dims"], case["jitter"])
+        m = cls(node, np.asarray(m.cell))
+    return m
+
+
+def rel_err(a, b):
+    scale = np.max(np.abs(b)) if b.size else 1.0
+    return float(np.max(np.abs(a - b)) / scale) if b.size else 0.0
+
+
+def resolve_coef(spec, mesh_o, q, p):
+    """-> (reference-side coef, oracle-side coef, array-to-store or None)"""
+    coef = spec.get("coef")
+    if coef is None or isinstance(coef, (int, float)):
+        return coef, coef, None
+    if coef in C.COEF_FUNCS:
+        f = C.COEF_FUNCS[coef]
+        return cartesian(lambda pts, _f=f: _f(pts)), f, None
+    TD = mesh_o.TD
+    qq = p + 3 if q is None else q
+    NQ = len(O.quadrature(TD, qq)[1])
+    arr = C.coef_array(coef, mesh_o.NC, NQ, mesh_o.GD, seed=hash(coef) % 1000 + mesh_o.NC)
+    return arr, arr, arr
+
+
+def run_case(case):
+    name = case["name"]
+    mesh = ref_mesh(case)
+    p = case["p"]
+    sspace = LagrangeFESpace(mesh, p)
+    mesh_o = O.Mesh(np.asarray(mesh.node), np.asarray(mesh.cell))
+    GD = mesh_o.GD
+    out = dict(node=np.asarray(mesh.node), cell=np.asarray(mesh.cell))
+
+    # ---- numbering
+    c2d_ref = np.asarray(sspace.cell_to_dof())
+    c2d_o = mesh_o.cell_to_ipoint(p)
+    assert np.array_equal(c2d_ref, c2d_o), f"{name}: oracle cell_to_dof differs"
+    assert c2d_ref.dtype == c2d_o.dtype, (c2d_ref.dtype, c2d_o.dtype)
+    assert np.array_equal(np.asarray(mesh.edge), mesh_o.edge), f"{name}: edge differs"
+    sgdof = sspace.number_of_global_dofs()
+    assert sgdof == mesh_o.number_of_global_ipoints(p)
+    out["cell2dof_scalar"] = c2d_ref
+    out["edge"] = np.asarray(mesh.edge)
+
+    space = sspace
+    tensor = case.get("tensor")
+    if tensor is not None:
+        shape = (GD, -1) if tensor["dof_priority"] else (-1, GD)
+        space = TensorFunctionSpace(sspace, shape=shape)
+        c2d_t = np.asarray(space.cell_to_dof())
+        c2d_to = O.tensor_cell_to_dof(c2d_o, sgdof, GD, tensor["dof_priority"])
+        assert np.array_equal(c2d_t, c2d_to), f"{name}: tensor cell_to_dof differs"
+        out["cell2dof"] = c2d_t
+        c2d_use = c2d_to
+    else:
+        out["cell2dof"] = c2d_ref
+        c2d_use = c2d_o
+    gdof = space.number_of_global_dofs()
+
+    bform = BilinearForm(space)
+    groups_o = []
+    k = 0
+    for grp in case["groups"]:
+        ints, Ke_o_sum = [], None
+        for kind, spec in grp:
+            q = spec.get("q")
+            if kind == "elasticity":
+                mat = LinearElasticMaterial("m", elastic_modulus=spec["E"], poisson_ratio=spec["nu"], hypo=spec["hypo"])
+                I = LinearElasticityIntegrator(mat, q=q)
+                lam, mu = O.lame(spec["E"], spec["nu"])
+                D = O.elastic_matrix(lam, mu, spec["hypo"], spec["E"], spec["nu"])
+                assert np.array_equal(D, np.asarray(mat.elastic_matrix())[0, 0]), f"{name}: D differs"
+                Ke_o = O.elasticity_element(mesh_o, p, D, q=q, dof_priority=tensor["dof_priority"])
+            else:
+                cref, corc, carr = resolve_coef(spec, mesh_o, q, p)
+                if carr is not None:
+                    out[f"coef_{k}"] = carr
+                if kind == "diffusion":
+                    I = ScalarDiffusionIntegrator(coef=cref, q=q, method=spec.get("method"))
+                    Ke_o = O.diffusion_element(mesh_o, p, q=q, coef=corc, method=spec.get("method"))
+                else:
+                    I = ScalarMassIntegrator(coef=cref, q=q)
+                    Ke_o = O.mass_element(mesh_o, p, q=q, coef=corc)
+            Ke_ref = np.asarray(I.assembly(space))
+            e = rel_err(Ke_o, Ke_ref)
+            assert e < 1e-13, f"{name}: oracle K_e[{k}] differs rel {e}"
+            if case.get("elem"):
+                out[f"Ke_{k}"] = Ke_ref
+            ints.append(I)
+            Ke_o_sum = Ke_o if Ke_o_sum is None else Ke_o_sum + Ke_o
+            k += 1
+        bform.add_integrator(*ints)
+        groups_o.append((Ke_o_sum, c2d_use))
+
+    A = bform.assembly()
+    crow, col, val = np.asarray(A.crow), np.asarray(A.col), np.asarray(A.values)
+    ocrow, ocol, oval = O.assemble(groups_o, gdof)
+    assert crow.dtype == ocrow.dtype == np.int64 and col.dtype == ocol.dtype, (crow.dtype, col.dtype, ocol.dtype)
+    assert np.array_equal(crow, ocrow) and np.array_equal(col, ocol), f"{name}: oracle CSR pattern differs"
+    e = rel_err(oval, val)
+    assert e < 1e-13, f"{name}: oracle CSR values differ rel {e}"
+    out.update(crow=crow, col=col)
+    if case.get("values_only_checksum"):
+        # large case: keep pattern + a strided sample of values + checksums
+        out["values_sample"] = val[::97].copy()
+        out["values_sum"] = np.array([val.sum(), np.abs(val).sum()])
+    else:
+        out["values"] = val
+    info = dict(gdof=int(gdof), nnz=int(A.nnz))
+
+    if case.get("cg"):
+        b = A @ np.ones(gdof)
+        x, cinfo = cg(A, b, returninfo=True)
+        xo, oinfo = O.cg(lambda v: O.csr_matvec(ocrow, ocol, oval, v), O.csr_matvec(ocrow, ocol, oval, np.ones(gdof)))
+        assert abs(oinfo["niter"] - cinfo["niter"]) <= 1, (name, oinfo, cinfo)
+        ex = np.linalg.norm(xo - x) / np.linalg.norm(x)
+        assert ex < 1e-10, f"{name}: oracle CG solution differs {ex}"
+        out.update(b=b, x=np.asarray(x))
+        info.update(niter=int(cinfo["niter"]), residual=float(cinfo["residual"]))
+    out["info"] = np.array(json.dumps(info))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name:36s} gdof {gdof:7d} nnz {A.nnz:8d} " + (f"cg {info.get('niter')}" if case.get('cg') else ""))
+
+
+def run_bc_case(case):
+    """Poisson with source + Dirichlet data (rows f1/f2): reference LinearForm / DirichletBC / cg."""
+    name = case["name"]
+    mesh = ref_mesh(case)
+    p = case["p"]
+    space = LagrangeFESpace(mesh, p)
+    mesh_o = O.Mesh(np.asarray(mesh.node), np.asarray(mesh.cell))
+    gdof = space.number_of_global_dofs()
+    f = cartesian(lambda pts: C.source_cart(pts))
+    g = cartesian(lambda pts: C.kappa_cart(pts))
+    bform = BilinearForm(space)
+    bform.add_integrator(ScalarDiffusionIntegrator())
+    A = bform.assembly()
+    lform = LinearForm(space)
+    lform.add_integrator(ScalarSourceIntegrator(f))
+    F = np.asarray(lform.assembly())
+    Fo = O.source_vector(mesh_o, p, C.source_cart)
+    assert rel_err(Fo, F) < 1e-13, f"{name}: oracle source vector differs"
+    isbd = np.asarray(space.is_boundary_dof())
+    isbd_o = O.boundary_dof_flag(mesh_o, p)
+    assert np.array_equal(isbd, isbd_o), f"{name}: boundary flags differ"
+    ip = np.asarray(space.interpolation_points())
+    ipo = mesh_o.interpolation_points(p)
+    assert np.max(np.abs(ip - ipo)) < 1e-14, f"{name}: interpolation points differ"
+    A2, F2 = DirichletBC(space, gd=g).apply(A, F)
+    uh = np.zeros(gdof)
+    uh[isbd_o] = C.kappa_cart(ipo[isbd_o])
+    Ao, F2o = O.dirichlet_apply(np.asarray(A.crow), np.asarray(A.col), np.asarray(A.values), Fo, uh, isbd_o)
+    assert rel_err(F2o, np.asarray(F2)) < 1e-13, f"{name}: BC rhs differs"
+    x, cinfo = cg(A2, F2, returninfo=True)
+    A2s = A2.to_scipy().tocsr().copy()          # to_scipy shares buffers with A2
+    A2s.sum_duplicates(); A2s.sort_indices()
+    d = (A2s - Ao)
+    assert (abs(d).max() if d.nnz else 0.0) < 1e-13, f"{name}: BC matrix differs"
+    A2s.eliminate_zeros()
+    out = dict(node=np.asarray(mesh.node), cell=np.asarray(mesh.cell), cell2dof=np.asarray(space.cell_to_dof()),
+               crow=np.asarray(A.crow), col=np.asarray(A.col), values=np.asarray(A.values),
+               F=F, isbd=isbd, ipoints=ip, F_bc=np.asarray(F2),
+               Abc_indptr=A2s.indptr.astype(np.int64), Abc_indices=A2s.indices.astype(np.int32), Abc_data=A2s.data,
+               x=np.asarray(x),
+               info=np.array(json.dumps(dict(gdof=int(gdof), niter=int(cinfo["niter"]), residual=float(cinfo["residual"])))))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name:36s} gdof {gdof:7d} cg {cinfo['niter']}")
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    for case in C.CASES:
+        if not only or case["name"] in only:
+            run_case(case)
+    for case in C.BC_CASES:
+        if not only or case["name"] in only:
+            run_bc_case(case)
+    total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
+    print("golden dir bytes:", total)
