@@ -1,0 +1,479 @@
+// Symbolic + fused numeric assembly: CSR straight from cell2dof, no COO.
+//
+// The CSR pattern of a BilinearForm is a pure function of cell2dof (row = cell2dof[c,i],
+// col = cell2dof[c,j], fem/bilinear_form.py:69-72; kept with explicit zeros by
+// COOTensor.coalesce, sparse/coo_tensor.py:184-213).  So:
+//   symbolic (once per space, cached):  dof -> incident (cell, local index) list in ascending
+//       cell order; per row the sorted set of columns; per (row, cell) the position ("slot")
+//       of each of the cell's dofs inside that row.
+//   numeric (every assembly): one thread owns one CSR row, walks its incident cells in
+//       ascending cell order -- the order the reference's stable sort + np.add.at produces --
+//       recomputes the element-matrix row in registers and accumulates into its private
+//       segment of a shared-memory tile, which the CTA then streams out contiguously.
+// Deterministic by construction: no floating-point atomics, fixed summation order.
+#include "common.cuh"
+#include "sort_scan.cuh"
+#include "assemble.cuh"
+
+namespace fb2 {
+
+static inline unsigned grid_for(int64_t n, int threads = 256) {
+  int64_t b = ceil_div(n, threads);
+  const int64_t cap = (int64_t)kNumSM * 32;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// =====================================================================================
+// symbolic
+// =====================================================================================
+__global__ void __launch_bounds__(256) deg_kernel(const int* __restrict__ c2d, int64_t npair, int* __restrict__ deg) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npair; t += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(deg + c2d[t], 1);
+}
+
+__global__ void __launch_bounds__(256) adj_fill_kernel(const int* __restrict__ c2d, int64_t npair, const int64_t* __restrict__ adj_ptr,
+                                                       int* __restrict__ cursor, int* __restrict__ adj_pair) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npair; t += (int64_t)gridDim.x * blockDim.x) {
+    const int d = c2d[t];
+    const int k = atomicAdd(cursor + d, 1);
+    adj_pair[adj_ptr[d] + k] = (int)t;        // pair id = c*L + i
+  }
+}
+
+// per-dof lists are short: in-place insertion sort restores ascending (cell, local) order
+__global__ void __launch_bounds__(256) adj_sort_kernel(int64_t gdof, const int64_t* __restrict__ adj_ptr, int* __restrict__ adj_pair) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < gdof; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = adj_ptr[r], e = adj_ptr[r + 1];
+    for (int64_t i = b + 1; i < e; ++i) {
+      const int v = adj_pair[i];
+      int64_t j = i - 1;
+      while (j >= b && adj_pair[j] > v) { adj_pair[j + 1] = adj_pair[j]; --j; }
+      adj_pair[j + 1] = v;
+    }
+  }
+}
+
+constexpr int SYM_CAP = 1024;       // max candidate columns (valence*ldof) per row handled in shared memory
+constexpr int SYM_KBITS = 10;
+constexpr int SYM_WARPS = 4;
+
+template <bool FILL, typename SlotT>
+__global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __restrict__ c2d, int L, int64_t gdof,
+                                                                  const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair,
+                                                                  const int64_t* __restrict__ crow, int* __restrict__ rowlen,
+                                                                  int* __restrict__ col, SlotT* __restrict__ slots, int* __restrict__ err) {
+  __shared__ uint64_t buf_all[SYM_WARPS][SYM_CAP];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t* buf = buf_all[wid];
+  const int64_t nwarp = (int64_t)gridDim.x * SYM_WARPS;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int64_t r = (int64_t)blockIdx.x * SYM_WARPS + wid; r < gdof; r += nwarp) {
+    const int64_t a0 = adj_ptr[r];
+    const int deg = (int)(adj_ptr[r + 1] - a0);
+    const int ncand = deg * L;
+    if (ncand > SYM_CAP) {
+      if (lane == 0) atomicExch(err, 1);
+      if (!FILL && lane == 0) rowlen[r] = 0;
+      continue;
+    }
+    int n2 = 32;
+    while (n2 < ncand) n2 <<= 1;
+    for (int k = lane; k < n2; k += 32) {
+      uint64_t key = ~0ull;
+      if (k < ncand) {
+        const int pl = k / L, j = k - pl * L;
+        const int pair = adj_pair[a0 + pl];
+        const int64_t c = pair / L;
+        key = ((uint64_t)(uint32_t)c2d[c * L + j] << SYM_KBITS) | (uint64_t)k;
+      }
+      buf[k] = key;
+    }
+    __syncwarp();
+    for (int size = 2; size <= n2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = lane; t < (n2 >> 1); t += 32) {
+          const int i = 2 * t - (t & (stride - 1));
+          const int j = i + stride;
+          const bool up = (i & size) == 0;
+          const uint64_t x = buf[i], y = buf[j];
+          if ((x > y) == up) { buf[i] = y; buf[j] = x; }
+        }
+        __syncwarp();
+      }
+    }
+    int running = 0;
+    const int64_t cbase = FILL ? crow[r] : 0;
+    for (int k0 = 0; k0 < ncand; k0 += 32) {
+      const int k = k0 + lane;
+      bool head = false;
+      uint64_t key = 0;
+      if (k < ncand) {
+        key = buf[k];
+        head = (k == 0) || ((key >> SYM_KBITS) != (buf[k - 1] >> SYM_KBITS));
+      }
+      const uint32_t hb = __ballot_sync(0xffffffffu, head);
+      if (FILL && k < ncand) {
+        const int rank = running + __popc(hb & lt) + (head ? 1 : 0) - 1;
+        if (head) col[cbase + rank] = (int)(key >> SYM_KBITS);
+        slots[a0 * L + (int64_t)(key & ((1u << SYM_KBITS) - 1u))] = (SlotT)rank;
+      }
+      running += __popc(hb);
+    }
+    if (!FILL && lane == 0) rowlen[r] = running;
+    __syncwarp();
+  }
+}
+
+__global__ void max_kernel(const int* __restrict__ v, int64_t n, int* out) {
+  int m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+size_t sym_workspace_bytes(int64_t NC, int L, int64_t gdof) {
+  return align_up((size_t)gdof * 4) * 2 + scan_workspace_bytes(gdof + 1) + 1024;
+}
+
+int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, int64_t* crow, int64_t* nnz_host,
+              int* max_row_host, void* ws, cudaStream_t s) {
+  const int64_t npair = NC * L;
+  if (npair >= ((int64_t)1 << 31)) return fail(ERR_UNSUPPORTED, "sym_count: NC*ldof=%lld exceeds int32 pair ids", (long long)npair);
+  Carver c(ws);
+  int* deg = c.take<int>(gdof);         // reused as rowlen
+  int* cursor = c.take<int>(gdof);      // cursor[0..1] reused as flags at the end
+  void* scan_ws = c.take<char>(scan_workspace_bytes(gdof + 1));
+  FB2_CUDA(cudaMemsetAsync(deg, 0, (size_t)gdof * 4, s));
+  FB2_CUDA(cudaMemsetAsync(cursor, 0, (size_t)gdof * 4, s));
+  if (npair > 0) deg_kernel<<<grid_for(npair), 256, 0, s>>>(c2d, npair, deg);
+  FB2_TRY(exclusive_scan_i32(deg, adj_ptr, gdof, true, scan_ws, s));
+  if (npair > 0) {
+    adj_fill_kernel<<<grid_for(npair), 256, 0, s>>>(c2d, npair, adj_ptr, cursor, adj_pair);
+    adj_sort_kernel<<<grid_for(gdof), 256, 0, s>>>(gdof, adj_ptr, adj_pair);
+  }
+  FB2_LAUNCH_CHECK();
+  FB2_CUDA(cudaMemsetAsync(cursor, 0, 8, s));
+  int* rowlen = deg;
+  const unsigned nb = (unsigned)std::min<int64_t>(ceil_div(gdof, SYM_WARPS), (int64_t)kNumSM * 16);
+  if (gdof > 0) {
+    sym_rows_kernel<false, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, nullptr, rowlen, nullptr, nullptr, cursor);
+    max_kernel<<<grid_for(gdof), 256, 0, s>>>(rowlen, gdof, cursor + 1);
+  }
+  FB2_LAUNCH_CHECK();
+  FB2_TRY(exclusive_scan_i32(rowlen, crow, gdof, true, scan_ws, s));
+  int flags[2] = {0, 0};
+  FB2_CUDA(cudaMemcpyAsync(flags, cursor, 8, cudaMemcpyDeviceToHost, s));
+  FB2_CUDA(cudaMemcpyAsync(nnz_host, crow + gdof, 8, cudaMemcpyDeviceToHost, s));
+  FB2_CUDA(cudaStreamSynchronize(s));
+  if (flags[0]) return fail(ERR_UNSUPPORTED, "sym_count: a dof touches more than %d candidate columns (valence*ldof)", SYM_CAP);
+  *max_row_host = flags[1];
+  return OK;
+}
+
+int sym_fill(const int* c2d, int64_t NC, int L, int64_t gdof, const int64_t* adj_ptr, const int* adj_pair, const int64_t* crow,
+             int* col, void* slots, int slot_bytes, cudaStream_t s) {
+  if (gdof <= 0) return OK;
+  const unsigned nb = (unsigned)std::min<int64_t>(ceil_div(gdof, SYM_WARPS), (int64_t)kNumSM * 16);
+  if (slot_bytes == 1)
+    sym_rows_kernel<true, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint8_t*)slots, nullptr);
+  else if (slot_bytes == 2)
+    sym_rows_kernel<true, uint16_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint16_t*)slots, nullptr);
+  else
+    return fail(ERR_INVALID, "sym_fill: slot_bytes must be 1 or 2");
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+// =====================================================================================
+// numeric: scalar forms with constant / per-cell coefficients, element rows recomputed
+// =====================================================================================
+template <int TD>
+struct RowGeo {
+  static constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;
+  double cm;
+  double G[NG];
+};
+
+__device__ __forceinline__ void row_geo(const double* __restrict__ node, const int* __restrict__ cell, int64_t c, RowGeo<2>& g) {
+  const int v0 = cell[3 * c], v1 = cell[3 * c + 1], v2 = cell[3 * c + 2];
+  const double2 p0 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v0);
+  const double2 p1 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v1);
+  const double2 p2 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v2);
+  const double e0x = p2.x - p1.x, e0y = p2.y - p1.y;
+  const double e1x = p0.x - p2.x, e1y = p0.y - p2.y;
+  const double e2x = p1.x - p0.x, e2y = p1.y - p0.y;
+  const double nv = e0x * e1y - e0y * e1x, inv = 1.0 / nv;
+  const double D[3][2] = {{-e0y * inv, e0x * inv}, {-e1y * inv, e1x * inv}, {-e2y * inv, e2x * inv}};
+  g.cm = 0.5 * (e2x * e0y - e2y * e0x);
+  int t = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int l = k; l < 3; ++l) g.G[t++] = (D[k][0] * D[l][0] + D[k][1] * D[l][1]) * g.cm;
+}
+
+__device__ __forceinline__ void row_geo(const double* __restrict__ node, const int* __restrict__ cell, int64_t c, RowGeo<3>& g) {
+  const int4 v = *reinterpret_cast<const int4*>(cell + 4 * c);
+  const int vid[4] = {v.x, v.y, v.z, v.w};
+  double P[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double* q = node + 3 * (int64_t)vid[k];
+    P[k][0] = q[0]; P[k][1] = q[1]; P[k][2] = q[2];
+  }
+  double a[3], b[3], cc[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) { a[m] = P[1][m] - P[0][m]; b[m] = P[2][m] - P[1][m]; cc[m] = P[3][m] - P[2][m]; }
+  const double bc0 = b[1] * cc[2] - b[2] * cc[1], bc1 = b[2] * cc[0] - b[0] * cc[2], bc2 = b[0] * cc[1] - b[1] * cc[0];
+  const double det = a[0] * bc0 + a[1] * bc1 + a[2] * bc2;
+  g.cm = det / 6.0;
+  const double inv = 1.0 / det;
+  constexpr int LF[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
+  double D[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = LF[i][0], k = LF[i][1], mm = LF[i][2];
+    double u[3], w[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { u[m] = P[mm][m] - P[j][m]; w[m] = P[k][m] - P[j][m]; }   // v_jm, v_jk
+    D[i][0] = (u[1] * w[2] - u[2] * w[1]) * inv;
+    D[i][1] = (u[2] * w[0] - u[0] * w[2]) * inv;
+    D[i][2] = (u[0] * w[1] - u[1] * w[0]) * inv;
+  }
+  int t = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int l = k; l < 4; ++l) g.G[t++] = (D[k][0] * D[l][0] + D[k][1] * D[l][1] + D[k][2] * D[l][2]) * g.cm;
+}
+
+// first index r in [0, n] with crow[r] >= target (crow has n+1 non-decreasing entries)
+__device__ __forceinline__ int64_t row_lower_bound(const int64_t* __restrict__ crow, int64_t n, int64_t target) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (crow[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// CTA b owns the rows whose first value index lies in [b*tile, (b+1)*tile): equal value
+// volume per CTA whatever the row lengths (vertex rows ~61, edge rows ~24 for P2 tets).
+template <int TD, int L, typename SlotT>
+__global__ void __launch_bounds__(128) assemble_const_kernel(AsmConstArgs a) {
+  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;
+  constexpr int MS_STRIDE = (L * NG) | 1;         // odd stride between local rows i: bank spread
+  constexpr int MM_STRIDE = L | 1;
+  extern __shared__ __align__(16) double sm[];
+  double* sMs = sm;                                            // [L][MS_STRIDE]
+  double* sMm = sMs + (a.has_diff ? L * MS_STRIDE : 0);        // [L][MM_STRIDE]
+  double* acc = sMm + (a.has_mass ? L * MM_STRIDE : 0);        // block tile of CSR values
+  if (a.has_diff)
+    for (int t = threadIdx.x; t < L * L * NG; t += blockDim.x) sMs[(t / (L * NG)) * MS_STRIDE + t % (L * NG)] = a.Ms[t];
+  if (a.has_mass)
+    for (int t = threadIdx.x; t < L * L; t += blockDim.x) sMm[(t / L) * MM_STRIDE + t % L] = a.Mm[t];
+
+  const int64_t lo = (int64_t)blockIdx.x * a.tile;
+  const int64_t r0 = row_lower_bound(a.crow, a.gdof, lo);
+  const int64_t r1 = row_lower_bound(a.crow, a.gdof, lo + a.tile);
+  const int64_t v0 = a.crow[r0];
+  const int nval = (int)(a.crow[r1] - v0);
+  for (int t = threadIdx.x; t < nval; t += blockDim.x) acc[t] = 0.0;
+  __syncthreads();
+
+  const SlotT* __restrict__ slots = static_cast<const SlotT*>(a.slots);
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    double* my = acc + (a.crow[r] - v0);
+    const int64_t q0 = a.adj_ptr[r], q1 = a.adj_ptr[r + 1];
+    for (int64_t q = q0; q < q1; ++q) {
+      const int pair = a.adj_pair[q];
+      const int64_t c = pair / L;
+      const int i = pair - (int)c * L;
+      RowGeo<TD> g;
+      row_geo(a.node, a.cell, c, g);
+      const double kd = a.scal_d * (a.coef_d ? a.coef_d[c] : 1.0);
+      const double km = a.scal_m * (a.coef_m ? a.coef_m[c] : 1.0) * g.cm;
+      const SlotT* sl = slots + q * L;
+      const double* mrow = sMs + i * MS_STRIDE;
+      const double* mm = sMm + i * MM_STRIDE;
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        double v = 0.0;
+        if (a.has_diff) {
+          double s = 0.0;
+#pragma unroll
+          for (int t = 0; t < NG; ++t) s += mrow[j * NG + t] * g.G[t];
+          v = kd * s;
+        }
+        if (a.has_mass) v += km * mm[j];
+        my[sl[j]] += v;
+      }
+    }
+  }
+  __syncthreads();
+  double* out = a.values + v0;
+  for (int t = threadIdx.x; t < nval; t += blockDim.x) out[t] = acc[t];
+}
+
+// =====================================================================================
+// numeric: generic gather of precomputed element-matrix rows (any integrator, tensor spaces)
+//   one thread per output (tensor) row; scalar row r = row / ncomp (interleaved) or row % gdof
+// =====================================================================================
+template <typename SlotT>
+__global__ void __launch_bounds__(128) assemble_from_ke_kernel(AsmKeArgs a) {
+  extern __shared__ __align__(16) double acc[];
+  const int L = a.L, nc = a.ncomp, lt = L * nc;
+  const int64_t nrow = a.gdof * nc;
+  const int64_t lo = (int64_t)blockIdx.x * a.tile;
+  const int64_t R0 = row_lower_bound(a.crow_out, nrow, lo);
+  const int64_t R1 = row_lower_bound(a.crow_out, nrow, lo + a.tile);
+  const int64_t v0 = a.crow_out[R0];
+  const int nval = (int)(a.crow_out[R1] - v0);
+  for (int t = threadIdx.x; t < nval; t += blockDim.x) acc[t] = 0.0;
+  __syncthreads();
+  const SlotT* __restrict__ slots = static_cast<const SlotT*>(a.slots);
+  for (int64_t R = R0 + threadIdx.x; R < R1; R += blockDim.x) {
+    int64_t r;
+    int comp;
+    if (nc == 1) { r = R; comp = 0; }
+    else if (a.dof_priority) { comp = (int)(R / a.gdof); r = R - (int64_t)comp * a.gdof; }
+    else { r = R / nc; comp = (int)(R - r * nc); }
+    const int len = (int)(a.crow_s[r + 1] - a.crow_s[r]);
+    double* my = acc + (a.crow_out[R] - v0);
+    const int64_t q0 = a.adj_ptr[r], q1 = a.adj_ptr[r + 1];
+    for (int64_t q = q0; q < q1; ++q) {
+      const int pair = a.adj_pair[q];
+      const int64_t c = pair / L;
+      const int i = pair - (int)c * L;
+      const int lrow = a.dof_priority ? comp * L + i : i * nc + comp;
+      const double* krow = a.Ke + (c * lt + lrow) * (int64_t)lt;
+      const SlotT* sl = slots + q * L;
+      for (int j = 0; j < L; ++j) {
+        const int s = sl[j];
+        for (int b = 0; b < nc; ++b) {
+          const int lcol = a.dof_priority ? b * L + j : j * nc + b;
+          const int pos = a.dof_priority ? b * len + s : s * nc + b;
+          my[pos] += krow[lcol];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  double* out = a.values + v0;
+  for (int t = threadIdx.x; t < nval; t += blockDim.x) out[t] = acc[t];
+}
+
+__global__ void __launch_bounds__(256) expand_crow_kernel(int64_t gdof, int nc, int prio, const int64_t* __restrict__ crow_s,
+                                                          int64_t* __restrict__ crow_out) {
+  // row lengths of the tensor pattern are nc * len(scalar row); rows are laid out so that
+  // crow_out is available in closed form from crow_s
+  const int64_t nrow = gdof * nc, nnz_s = crow_s[gdof];
+  for (int64_t R = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; R <= nrow; R += (int64_t)gridDim.x * blockDim.x) {
+    if (R == nrow) { crow_out[R] = nnz_s * nc * nc; continue; }
+    if (prio) {
+      const int comp = (int)(R / gdof);
+      const int64_t r = R - (int64_t)comp * gdof;
+      crow_out[R] = (int64_t)comp * nnz_s * nc + crow_s[r] * nc;
+    } else {
+      const int64_t r = R / nc;
+      const int comp = (int)(R - r * nc);
+      const int64_t len = crow_s[r + 1] - crow_s[r];
+      crow_out[R] = crow_s[r] * nc * nc + (int64_t)comp * len * nc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) expand_col_kernel(int64_t gdof, int nc, int prio, const int64_t* __restrict__ crow_s,
+                                                         const int* __restrict__ col_s, const int64_t* __restrict__ crow_out,
+                                                         int* __restrict__ col_out) {
+  const int64_t nrow = gdof * nc;
+  for (int64_t R = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; R < nrow; R += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r;
+    if (prio) r = R % gdof; else r = R / nc;
+    const int64_t b = crow_s[r];
+    const int len = (int)(crow_s[r + 1] - b);
+    int* out = col_out + crow_out[R];
+    for (int s = 0; s < len; ++s) {
+      const int64_t cs = col_s[b + s];
+      for (int q = 0; q < nc; ++q) {
+        if (prio) out[q * len + s] = (int)((int64_t)q * gdof + cs);
+        else out[s * nc + q] = (int)(cs * nc + q);
+      }
+    }
+  }
+}
+
+// ---- host dispatch --------------------------------------------------------------------
+template <int TD, int L>
+static int launch_asm_const(AsmConstArgs a, int slot_bytes, int max_row, cudaStream_t s) {
+  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;
+  const size_t tab = ((a.has_diff ? (size_t)L * ((L * NG) | 1) : 0) + (a.has_mass ? (size_t)L * (L | 1) : 0)) * sizeof(double);
+  if (a.tile <= 0) a.tile = 3072;
+  if (a.threads <= 0) a.threads = 128;
+  if (a.tile < max_row) a.tile = max_row;
+  const size_t smem = tab + (size_t)(a.tile + max_row) * 8;
+  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble_const: row tile does not fit shared memory (max_row=%d)", max_row);
+  const int64_t nb = ceil_div(a.nnz, a.tile);
+  if (nb <= 0) return OK;
+  if (slot_bytes == 1) {
+    auto k = assemble_const_kernel<TD, L, uint8_t>;
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nb, a.threads, smem, s>>>(a);
+  } else {
+    auto k = assemble_const_kernel<TD, L, uint16_t>;
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nb, a.threads, smem, s>>>(a);
+  }
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int assemble_const(int TD, int p, const AsmConstArgs& a, int slot_bytes, int max_row, cudaStream_t s) {
+  if (a.gdof <= 0) return OK;
+  if (slot_bytes != 1 && slot_bytes != 2) return fail(ERR_INVALID, "assemble_const: slot_bytes must be 1 or 2");
+  switch (TD * 10 + p) {
+    case 21: return launch_asm_const<2, 3>(a, slot_bytes, max_row, s);
+    case 22: return launch_asm_const<2, 6>(a, slot_bytes, max_row, s);
+    case 23: return launch_asm_const<2, 10>(a, slot_bytes, max_row, s);
+    case 31: return launch_asm_const<3, 4>(a, slot_bytes, max_row, s);
+    case 32: return launch_asm_const<3, 10>(a, slot_bytes, max_row, s);
+    case 33: return launch_asm_const<3, 20>(a, slot_bytes, max_row, s);
+    default: return fail(ERR_UNSUPPORTED, "assemble_const: unsupported element TD=%d p=%d", TD, p);
+  }
+}
+
+int assemble_from_ke(AsmKeArgs a, int slot_bytes, int max_row, cudaStream_t s) {
+  if (a.gdof <= 0) return OK;
+  const int max_out_row = max_row * a.ncomp;
+  if (a.tile <= 0) a.tile = 3072;
+  if (a.tile < max_out_row) a.tile = max_out_row;
+  const size_t smem = (size_t)(a.tile + max_out_row) * 8;
+  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble_from_ke: row tile does not fit shared memory (max_row=%d)", max_row);
+  const int64_t nb = ceil_div(a.nnz_out, a.tile);
+  if (nb <= 0) return OK;
+  if (slot_bytes == 1) {
+    auto k = assemble_from_ke_kernel<uint8_t>;
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nb, 128, smem, s>>>(a);
+  } else if (slot_bytes == 2) {
+    auto k = assemble_from_ke_kernel<uint16_t>;
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nb, 128, smem, s>>>(a);
+  } else {
+    return fail(ERR_INVALID, "assemble_from_ke: slot_bytes must be 1 or 2");
+  }
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int expand_pattern(int64_t gdof, int nc, int prio, const int64_t* crow_s, const int* col_s, int64_t* crow_out, int* col_out,
+                   cudaStream_t s) {
+  if (gdof <= 0) return OK;
+  expand_crow_kernel<<<grid_for(gdof * nc + 1), 256, 0, s>>>(gdof, nc, prio, crow_s, crow_out);
+  expand_col_kernel<<<grid_for(gdof * nc), 256, 0, s>>>(gdof, nc, prio, crow_s, col_s, crow_out, col_out);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+}  // namespace fb2

@@ -1,0 +1,48 @@
+#pragma once
+#include "common.cuh"
+
+namespace fb2 {
+
+struct AsmConstArgs {
+  const double* node;
+  const int* cell;
+  int64_t gdof, nnz;
+  const int64_t* adj_ptr;     // (gdof+1)
+  const int* adj_pair;        // (NC*L) pair ids c*L+i, ascending per dof
+  const void* slots;          // (NC*L, L) position of the cell's j-th dof inside the row
+  const int64_t* crow;        // (gdof+1)
+  int has_diff, has_mass;
+  const double* Ms;           // [L][L][NG]
+  const double* Mm;           // [L][L]
+  double scal_d, scal_m;
+  const double* coef_d;       // per-cell or null
+  const double* coef_m;
+  double* values;             // (nnz)
+  int tile, threads;          // values per CTA, threads per CTA (<=0: defaults)
+};
+
+struct AsmKeArgs {
+  int64_t gdof;               // scalar dofs
+  int64_t nnz_out;
+  int L, ncomp, dof_priority;
+  const double* Ke;           // (NC, L*ncomp, L*ncomp)
+  const int64_t* adj_ptr;
+  const int* adj_pair;
+  const void* slots;
+  const int64_t* crow_s;      // scalar pattern
+  const int64_t* crow_out;    // tensor pattern (== crow_s when ncomp == 1)
+  double* values;
+  int tile;
+};
+
+size_t sym_workspace_bytes(int64_t NC, int L, int64_t gdof);
+int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, int64_t* crow, int64_t* nnz_host,
+              int* max_row_host, void* ws, cudaStream_t s);
+int sym_fill(const int* c2d, int64_t NC, int L, int64_t gdof, const int64_t* adj_ptr, const int* adj_pair, const int64_t* crow,
+             int* col, void* slots, int slot_bytes, cudaStream_t s);
+int assemble_const(int TD, int p, const AsmConstArgs& a, int slot_bytes, int max_row, cudaStream_t s);
+int assemble_from_ke(AsmKeArgs a, int slot_bytes, int max_row, cudaStream_t s);
+int expand_pattern(int64_t gdof, int nc, int prio, const int64_t* crow_s, const int* col_s, int64_t* crow_out, int* col_out,
+                   cudaStream_t s);
+
+}  // namespace fb2

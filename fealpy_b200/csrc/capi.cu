@@ -1,0 +1,217 @@
+// extern "C" boundary (include/fealpy_b200.h): thin argument marshalling onto the kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/fealpy_b200.h"
+#include "assemble.cuh"
+#include "cg.cuh"
+#include "common.cuh"
+#include "coo_csr.cuh"
+#include "elem.cuh"
+#include "sort_scan.cuh"
+#include "topo.cuh"
+
+namespace fb2 {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+}  // namespace fb2
+
+using namespace fb2;
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* fb2_last_error(void) { return g_last_error.c_str(); }
+int fb2_version(void) { return 100; }
+
+// ---- topology ---------------------------------------------------------------------------
+int fb2_tri_from_box(const double box[4], int nx, int ny, double* node, int32_t* cell, void* stream) {
+  if (nx < 1 || ny < 1) return fail(ERR_INVALID, "tri_from_box: nx, ny must be >= 1");
+  return tri_from_box(box, nx, ny, node, cell, S(stream));
+}
+int fb2_tet_from_box(const double box[6], int nx, int ny, int nz, double* node, int32_t* cell, void* stream) {
+  if (nx < 1 || ny < 1 || nz < 1) return fail(ERR_INVALID, "tet_from_box: nx, ny, nz must be >= 1");
+  return tet_from_box(box, nx, ny, nz, node, cell, S(stream));
+}
+size_t fb2_entity_workspace_bytes(int64_t NC, int per_cell) { return entity_workspace_bytes(NC, per_cell); }
+int fb2_build_entities(const int32_t* cell, int64_t NC, int TD, int kind, int64_t NN, int32_t* cell2ent, int64_t* count_host,
+                       void* ws, void* stream) {
+  if ((TD != 2 && TD != 3) || (kind != 1 && kind != 2) || (kind == 2 && TD != 3))
+    return fail(ERR_INVALID, "build_entities: TD=%d kind=%d not supported", TD, kind);
+  return build_entities(cell, NC, TD, kind, NN, cell2ent, count_host, ws, S(stream));
+}
+int fb2_entities_emit(const int32_t* cell, int64_t NC, int TD, int kind, int32_t* cell2ent, int32_t* ent, void* ws, void* stream) {
+  return entities_emit(cell, NC, TD, kind, cell2ent, ent, ws, S(stream));
+}
+int fb2_cell_to_dof(const int32_t* cell, const int32_t* cell2edge, const int32_t* edge, const int32_t* cell2face, int64_t NC, int TD,
+                    int p, int64_t NN, int64_t NE, int64_t NF, const unsigned char* mi, int ldof, int32_t* c2d, void* stream) {
+  return cell_to_dof(cell, cell2edge, edge, cell2face, NC, TD, p, NN, NE, NF, mi, ldof, c2d, S(stream));
+}
+int fb2_tensor_cell_to_dof(const int32_t* c2d, int64_t NC, int ldof, int GD, int64_t gdof, int prio, int32_t* out, void* stream) {
+  return tensor_cell_to_dof(c2d, NC, ldof, GD, gdof, prio, out, S(stream));
+}
+
+// ---- K1 -----------------------------------------------------------------------------------
+int fb2_elem_scalar_const(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const double* Ms, const double* Mm,
+                          double scal_d, const double* coef_d, double scal_m, const double* coef_m, double* out, void* stream) {
+  if (!Ms && !Mm) return fail(ERR_INVALID, "elem_scalar_const: need a diffusion and/or a mass table");
+  ElemConstArgs a{};
+  a.node = node; a.cell = cell; a.NC = NC;
+  a.has_diff = Ms != nullptr; a.has_mass = Mm != nullptr;
+  a.Ms = Ms; a.Mm = Mm; a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.out = out;
+  return elem_const(TD, p, a, S(stream));
+}
+int fb2_elem_scalar_quad(int TD, int p, int64_t NC, const double* node, const int32_t* cell, int is_mass, int NQ, const double* ws,
+                         const double* table, int coef_kind, const double* coef, double* out, void* stream) {
+  if (coef_kind != 2 && coef_kind != 3) return fail(ERR_INVALID, "elem_scalar_quad: coef_kind must be 2 (NC,NQ) or 3 (NC,NQ,GD,GD)");
+  if (is_mass && coef_kind == 3) return fail(ERR_INVALID, "elem_scalar_quad: matrix coefficients apply to diffusion only");
+  ElemQuadArgs a{};
+  a.node = node; a.cell = cell; a.NC = NC; a.is_mass = is_mass; a.NQ = NQ; a.ws = ws; a.tab = table;
+  a.coef_kind = coef_kind; a.coef = coef; a.out = out;
+  return elem_quad(TD, p, a, S(stream));
+}
+int fb2_elem_elasticity(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const double* M4, double d_diag,
+                        double d_lam, double d_shear, int dof_priority, double* out, void* stream) {
+  ElemElasticityArgs a{};
+  a.node = node; a.cell = cell; a.NC = NC; a.M4 = M4; a.d_diag = d_diag; a.d_lam = d_lam; a.d_shear = d_shear;
+  a.dof_priority = dof_priority; a.out = out;
+  return elem_elasticity(TD, p, a, S(stream));
+}
+
+// ---- K2 -----------------------------------------------------------------------------------
+int fb2_coo_keys_from_c2d(const int32_t* rdof, const int32_t* cdof, int64_t NC, int lr, int lc, int col_bits, uint64_t* keys,
+                          void* stream) {
+  return coo_keys_from_c2d(rdof, cdof, NC, lr, lc, col_bits, keys, S(stream));
+}
+int fb2_coo_keys_from_coo(const void* row, const void* col, int index_bytes, int64_t n, int col_bits, uint64_t* keys, void* stream) {
+  return coo_keys_from_coo(row, col, index_bytes, n, col_bits, keys, S(stream));
+}
+size_t fb2_coo_workspace_bytes(int64_t n) { return coo_symbolic_workspace_bytes(n); }
+int fb2_coo_symbolic(uint64_t* keys, uint32_t* perm, int64_t n, int key_bits, void* ws, int64_t* nnz_host, void* stream) {
+  return coo_symbolic(keys, perm, n, key_bits, ws, nnz_host, S(stream));
+}
+int fb2_coo_fill(const uint64_t* keys, int64_t n, int col_bits, int64_t nrow, void* ws, int64_t* crow, void* col, int col_bytes,
+                 int64_t* seg_start, void* stream) {
+  return coo_fill(keys, n, col_bits, nrow, ws, crow, col, col_bytes, seg_start, S(stream));
+}
+int fb2_coo_reduce(const uint32_t* perm, const int64_t* seg_start, int64_t nnz, const double* vin, double* vout, void* stream) {
+  return coo_reduce(perm, seg_start, nnz, vin, vout, S(stream));
+}
+
+// ---- symbolic + fused numeric ---------------------------------------------------------------
+size_t fb2_sym_workspace_bytes(int64_t NC, int ldof, int64_t gdof) { return sym_workspace_bytes(NC, ldof, gdof); }
+int fb2_sym_count(const int32_t* c2d, int64_t NC, int ldof, int64_t gdof, int64_t* adj_ptr, int32_t* adj_pair, int64_t* crow,
+                  int64_t* nnz_host, int32_t* max_row_host, void* ws, void* stream) {
+  return sym_count(c2d, NC, ldof, gdof, adj_ptr, adj_pair, crow, nnz_host, max_row_host, ws, S(stream));
+}
+int fb2_sym_fill(const int32_t* c2d, int64_t NC, int ldof, int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair,
+                 const int64_t* crow, int32_t* col, void* slots, int slot_bytes, void* stream) {
+  return sym_fill(c2d, NC, ldof, gdof, adj_ptr, adj_pair, crow, col, slots, slot_bytes, S(stream));
+}
+int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,
+                              const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
+                              const int64_t* crow, int32_t max_row, const double* Ms, const double* Mm, double scal_d,
+                              const double* coef_d, double scal_m, const double* coef_m, double* values, void* stream) {
+  if (!Ms && !Mm) return fail(ERR_INVALID, "assemble_scalar_const: need a diffusion and/or a mass table");
+  AsmConstArgs a{};
+  a.node = node; a.cell = cell; a.gdof = gdof;
+  a.adj_ptr = adj_ptr; a.adj_pair = adj_pair; a.slots = slots; a.crow = crow;
+  a.has_diff = Ms != nullptr; a.has_mass = Mm != nullptr; a.Ms = Ms; a.Mm = Mm;
+  a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.values = values;
+  int64_t nnz = 0;
+  FB2_CUDA(cudaMemcpyAsync(&nnz, crow + gdof, 8, cudaMemcpyDeviceToHost, S(stream)));
+  FB2_CUDA(cudaStreamSynchronize(S(stream)));
+  a.nnz = nnz;
+  a.tile = 0; a.threads = 0;
+  return assemble_const(TD, p, a, slot_bytes, max_row, S(stream));
+}
+int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int64_t gdof_scalar, const double* Ke,
+                         const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
+                         const int64_t* crow_scalar, int32_t max_row, const int64_t* crow_out, double* values, void* stream) {
+  AsmKeArgs a{};
+  a.gdof = gdof_scalar; a.L = ldof; a.ncomp = ncomp; a.dof_priority = dof_priority; a.Ke = Ke;
+  a.adj_ptr = adj_ptr; a.adj_pair = adj_pair; a.slots = slots; a.crow_s = crow_scalar;
+  a.crow_out = crow_out ? crow_out : crow_scalar; a.values = values;
+  int64_t nnz = 0;
+  FB2_CUDA(cudaMemcpyAsync(&nnz, a.crow_out + gdof_scalar * ncomp, 8, cudaMemcpyDeviceToHost, S(stream)));
+  FB2_CUDA(cudaStreamSynchronize(S(stream)));
+  a.nnz_out = nnz;
+  a.tile = 0;
+  return assemble_from_ke(a, slot_bytes, max_row, S(stream));
+}
+int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,
+                       int64_t* crow_out, int32_t* col_out, void* stream) {
+  return expand_pattern(gdof_scalar, ncomp, dof_priority, crow_scalar, col_scalar, crow_out, col_out, S(stream));
+}
+
+// ---- K3/K4 ----------------------------------------------------------------------------------
+size_t fb2_partial_workspace_bytes(void) { return partial_workspace_bytes(); }
+int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x, double* y,
+                 void* stream) {
+  return spmv(n, nnz, crow, col, values, x, y, nullptr, 0, nullptr, nullptr, S(stream));
+}
+int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
+                 void* stream) {
+  return spmm(n, crow, col, values, X, Y, nb, S(stream));
+}
+int fb2_dot(int64_t n, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream) {
+  return dot(n, a, b, out_dev, partial_ws, S(stream));
+}
+size_t fb2_cg_workspace_bytes(int64_t n) { return cg_workspace_bytes(n); }
+int fb2_cg(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
+           const double* minv_diag, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_host,
+           double* residual_host, void* stream) {
+  return cg_solve(n, crow, col, values, b, x, minv_diag, atol, rtol, maxit, chunk, ws, niter_host, residual_host, S(stream));
+}
+int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm, double rTr, void* stream) {
+  CgScalars* sc = static_cast<CgScalars*>(scalars);
+  FB2_TRY(cg_init_scalars(sc, atol, rtol, maxit < 0 ? 2147483647 : maxit, S(stream)));
+  FB2_CUDA(cudaMemcpyAsync(&sc->bnorm, &bnorm, 8, cudaMemcpyHostToDevice, S(stream)));
+  FB2_CUDA(cudaMemcpyAsync(&sc->rTr, &rTr, 8, cudaMemcpyHostToDevice, S(stream)));
+  FB2_CUDA(cudaStreamSynchronize(S(stream)));   // bnorm / rTr live on the caller's stack
+  return OK;
+}
+int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
+                    double* Ap, int64_t n_dot, void* scalars, void* partial_ws, void* stream) {
+  // local rows only contribute to p.Ap (n_dot == n: rows are the owned dofs)
+  (void)n_dot;
+  CgScalars* sc = static_cast<CgScalars*>(scalars);
+  return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, &sc->pAp, partial_ws, S(stream));
+}
+int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,
+                     void* partial_ws, int fuse_finalize, void* stream) {
+  return cg_update_xr(n, x, r, p, Ap, minv_diag, static_cast<CgScalars*>(scalars), partial_ws, fuse_finalize, S(stream));
+}
+int fb2_cg_finalize(void* scalars, void* stream) { return cg_finalize(static_cast<CgScalars*>(scalars), S(stream)); }
+int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, void* stream) {
+  return cg_update_p(n, p, r, minv_diag, static_cast<CgScalars*>(scalars), S(stream));
+}
+
+// ---- raw primitives -------------------------------------------------------------------------
+size_t fb2_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n); }
+int fb2_sort_pairs(uint64_t* keys, uint32_t* vals, int identity_payload, int64_t n, int key_bits, void* ws, void* stream) {
+  uint64_t* ko = nullptr;
+  uint32_t* vo = identity_payload ? nullptr : vals;
+  FB2_TRY(radix_sort_pairs(keys, vals, n, key_bits, ws, S(stream), &ko, &vo));
+  if (n > 0 && ko != keys) {
+    FB2_CUDA(cudaMemcpyAsync(keys, ko, (size_t)n * 8, cudaMemcpyDeviceToDevice, S(stream)));
+    FB2_CUDA(cudaMemcpyAsync(vals, vo, (size_t)n * 4, cudaMemcpyDeviceToDevice, S(stream)));
+  }
+  return OK;
+}
+size_t fb2_scan_workspace_bytes(int64_t n) { return scan_workspace_bytes(n); }
+int fb2_exclusive_scan_i32(const int32_t* in, int64_t* out, int64_t n, void* ws, void* stream) {
+  return exclusive_scan_i32(in, out, n, true, ws, S(stream));
+}
+
+}  // extern "C"

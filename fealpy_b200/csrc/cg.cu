@@ -1,0 +1,389 @@
+// K3/K4: CSR SpMV with a fused, deterministic p.Ap reduction and the fused CG vector
+// updates; the whole iteration is three kernels with all scalars resident on the device,
+// captured into a CUDA graph in chunks so that the host only polls a convergence flag.
+//
+// Reference semantics reproduced (solver/cg.py:76-123): zero-rhs early return, stop test on
+// sqrt(r.z) with '<' (atol first, then rtol*|b|, then maxit), x of the stopping iteration is
+// returned, z = M r with M a diagonal (Jacobi) preconditioner or identity.
+// SpMV semantics: sparse/csr_tensor.py:411-452 -> backend csr_spmm (numpy_backend.py:180-199).
+#include "cg.cuh"
+
+#include <climits>
+#include <cmath>
+
+namespace fb2 {
+
+constexpr int CG_THREADS = 256;
+
+// ---- deterministic grid reduction ("last block finishes", fixed summation order) ---------
+template <typename Finish>
+__device__ __forceinline__ void grid_reduce(double v, double* partials, unsigned int* counter, Finish finish) {
+  __shared__ double red[CG_THREADS / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < CG_THREADS / 32; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+    __threadfence();
+    const unsigned int ticket = atomicInc(counter, gridDim.x - 1);   // wraps back to 0 for the next use
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double t = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += CG_THREADS) t += __ldcg(partials + i);
+  t = warp_sum(t);
+  __syncthreads();
+  if (lane == 0) red[wid] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < CG_THREADS / 32; ++w) tot += red[w];
+    finish(tot);
+  }
+}
+
+// ---- SpMV: T lanes per row --------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(CG_THREADS) spmv_kernel(int64_t n, const int64_t* __restrict__ crow, const int32_t* __restrict__ col,
+                                                          const double* __restrict__ val, const double* __restrict__ x,
+                                                          double* __restrict__ y, const double* __restrict__ b, int mode,
+                                                          double* dot_out, double* partials, unsigned int* counter,
+                                                          const CgScalars* sc) {
+  if (sc && sc->done) return;
+  constexpr int RPB = CG_THREADS / T;
+  const int sub = threadIdx.x % T, rib = threadIdx.x / T;
+  double dsum = 0.0;
+  const int64_t ntile = (n + RPB - 1) / RPB;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t r = tile * RPB + rib;
+    double acc = 0.0;
+    if (r < n) {
+      const int64_t s = crow[r], e = crow[r + 1];
+      for (int64_t k = s + sub; k < e; k += T) acc += ld_stream(val + k) * x[ld_stream(col + k)];
+    }
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (r < n && sub == 0) {
+      const double yv = mode ? b[r] - acc : acc;
+      y[r] = yv;
+      if (dot_out) dsum += x[r] * yv;
+    }
+  }
+  if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
+}
+
+template <int T, int NB>
+__global__ void __launch_bounds__(CG_THREADS) spmm_kernel(int64_t n, const int64_t* __restrict__ crow, const int32_t* __restrict__ col,
+                                                          const double* __restrict__ val, const double* __restrict__ X,
+                                                          double* __restrict__ Y, int nb, int b0) {
+  constexpr int RPB = CG_THREADS / T;
+  const int sub = threadIdx.x % T, rib = threadIdx.x / T;
+  const int64_t ntile = (n + RPB - 1) / RPB;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t r = tile * RPB + rib;
+    double acc[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) acc[k] = 0.0;
+    if (r < n) {
+      const int64_t s = crow[r], e = crow[r + 1];
+      for (int64_t k = s + sub; k < e; k += T) {
+        const double v = val[k];
+        const double* xr = X + (int64_t)col[k] * nb + b0;
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+          if (b0 + q < nb) acc[q] += v * xr[q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+#pragma unroll
+      for (int o = T / 2; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (r < n && sub == 0)
+#pragma unroll
+      for (int q = 0; q < NB; ++q)
+        if (b0 + q < nb) Y[r * nb + b0 + q] = acc[q];
+  }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) dot_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                                         double* out, double* partials, unsigned int* counter) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += a[i] * b[i];
+  grid_reduce(acc, partials, counter, [=](double tot) { *out = tot; });
+}
+
+// p = z = M r ; rTr = r.z
+__global__ void __launch_bounds__(CG_THREADS) cg_start_kernel(int64_t n, const double* __restrict__ r, const double* __restrict__ minv,
+                                                              double* __restrict__ p, CgScalars* sc, double* partials) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = r[i], zi = minv ? minv[i] * ri : ri;
+    p[i] = zi;
+    acc += ri * zi;
+  }
+  grid_reduce(acc, partials, &sc->counter[1], [=](double tot) { sc->rTr = tot; });
+}
+
+__device__ __forceinline__ void cg_finalize_dev(CgScalars* sc) {
+  // solver/cg.py:97-121
+  const double rn = sqrt(sc->rTr_new);
+  sc->rnorm = rn;
+  const int it = sc->niter + 1;
+  sc->niter = it;
+  if (rn < sc->atol || rn < sc->rtol * sc->bnorm || it >= sc->maxit) {
+    sc->done = 1;
+  } else {
+    sc->beta = sc->rTr_new / sc->rTr;
+    sc->rTr = sc->rTr_new;
+  }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) cg_update_xr_kernel(int64_t n, double* __restrict__ x, double* __restrict__ r,
+                                                                  const double* __restrict__ p, const double* __restrict__ Ap,
+                                                                  const double* __restrict__ minv, CgScalars* sc, double* partials,
+                                                                  int fuse_finalize) {
+  if (sc->done) return;
+  const double alpha = sc->rTr / sc->pAp;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = x[i] + alpha * p[i];
+    const double ri = r[i] - alpha * Ap[i];
+    r[i] = ri;
+    acc += ri * (minv ? minv[i] * ri : ri);
+  }
+  grid_reduce(acc, partials, &sc->counter[1], [=](double tot) {
+    sc->rTr_new = tot;
+    sc->alpha = alpha;
+    if (fuse_finalize) cg_finalize_dev(sc);
+  });
+}
+
+__global__ void cg_finalize_kernel(CgScalars* sc) {
+  if (sc->done) return;
+  cg_finalize_dev(sc);
+}
+
+__global__ void __launch_bounds__(CG_THREADS) cg_update_p_kernel(int64_t n, double* __restrict__ p, const double* __restrict__ r,
+                                                                 const double* __restrict__ minv, const CgScalars* sc) {
+  if (sc->done) return;
+  const double beta = sc->beta;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = r[i];
+    p[i] = (minv ? minv[i] * ri : ri) + beta * p[i];
+  }
+}
+
+__global__ void cg_init_scalars_kernel(CgScalars* sc, double atol, double rtol, int maxit) {
+  sc->rTr = sc->pAp = sc->rTr_new = sc->rnorm = sc->alpha = sc->beta = 0.0;
+  sc->niter = 0;
+  sc->done = 0;
+  sc->maxit = maxit;
+  sc->atol = atol;
+  sc->rtol = rtol;
+  for (int i = 0; i < 4; ++i) sc->counter[i] = 0;
+}
+
+// ---- host side --------------------------------------------------------------------------
+static inline int vec_grid(int64_t n) {
+  int64_t b = ceil_div(n, CG_THREADS * 4);
+  const int64_t cap = kNumSM * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+static int pick_T(int64_t n, int64_t nnz) {
+  const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
+  if (avg <= 3.0) return 2;
+  if (avg <= 6.0) return 4;
+  if (avg <= 24.0) return 8;
+  if (avg <= 96.0) return 16;
+  return 32;
+}
+
+template <int T>
+static void launch_spmv(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
+                        const double* b, int mode, double* dot_out, double* partials, unsigned int* counter, const CgScalars* sc,
+                        cudaStream_t s) {
+  constexpr int RPB = CG_THREADS / T;
+  int64_t nbk = ceil_div(n, RPB);
+  const int64_t cap = dot_out ? (int64_t)CG_PARTIALS : (int64_t)kNumSM * 64;
+  if (nbk > cap) nbk = cap;
+  if (nbk > kNumSM * 16 && dot_out) nbk = kNumSM * 16;
+  spmv_kernel<T><<<(unsigned)(nbk < 1 ? 1 : nbk), CG_THREADS, 0, s>>>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc);
+}
+
+static int spmv_impl(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
+                     const double* b, int mode, double* dot_out, double* partials, unsigned int* counter, const CgScalars* sc,
+                     cudaStream_t s) {
+  if (n <= 0) return OK;
+  switch (pick_T(n, nnz)) {
+    case 2: launch_spmv<2>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
+    case 4: launch_spmv<4>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
+    case 8: launch_spmv<8>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
+    case 16: launch_spmv<16>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
+    default: launch_spmv<32>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
+  }
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+// workspace layout shared by all entry points: [partials | counters | ... ]
+struct PartialWs {
+  double* partials;
+  unsigned int* counter;
+  explicit PartialWs(void* ws) {
+    partials = static_cast<double*>(ws);
+    counter = reinterpret_cast<unsigned int*>(partials + CG_PARTIALS);
+  }
+  static size_t bytes() { return align_up(CG_PARTIALS * sizeof(double) + 64); }
+};
+
+size_t cg_workspace_bytes(int64_t n) {
+  return PartialWs::bytes() + align_up(sizeof(CgScalars)) + 3 * align_up((size_t)n * sizeof(double)) + 1024;
+}
+
+int spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
+         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s) {
+  if (dot_out && !partial_ws) return fail(ERR_INVALID, "spmv: fused dot needs the (zero-initialised) partial workspace");
+  PartialWs pw(partial_ws);
+  return spmv_impl(n, nnz, crow, col, val, x, y, b, mode, dot_out, partial_ws ? pw.partials : nullptr,
+                   partial_ws ? pw.counter : nullptr, nullptr, s);
+}
+size_t partial_workspace_bytes() { return PartialWs::bytes(); }
+
+int spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* X, double* Y, int nb, cudaStream_t s) {
+  if (n <= 0 || nb <= 0) return OK;
+  int64_t nbk = ceil_div(n, CG_THREADS / 8);
+  if (nbk > (int64_t)kNumSM * 64) nbk = (int64_t)kNumSM * 64;
+  for (int b0 = 0; b0 < nb; b0 += 4) spmm_kernel<8, 4><<<(unsigned)nbk, CG_THREADS, 0, s>>>(n, crow, col, val, X, Y, nb, b0);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int dot(int64_t n, const double* a, const double* b, double* out, void* partial_ws, cudaStream_t s) {
+  PartialWs pw(partial_ws);
+  dot_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, a, b, out, pw.partials, pw.counter);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int cg_init_scalars(CgScalars* sc, double atol, double rtol, int maxit, cudaStream_t s) {
+  cg_init_scalars_kernel<<<1, 1, 0, s>>>(sc, atol, rtol, maxit);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+int cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv, CgScalars* sc,
+                 void* partial_ws, int fuse_finalize, cudaStream_t s) {
+  PartialWs pw(partial_ws);
+  cg_update_xr_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, x, r, p, Ap, minv, sc, pw.partials, fuse_finalize);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+int cg_finalize(CgScalars* sc, cudaStream_t s) {
+  cg_finalize_kernel<<<1, 1, 0, s>>>(sc);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+int cg_update_p(int64_t n, double* p, const double* r, const double* minv, CgScalars* sc, cudaStream_t s) {
+  cg_update_p_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, p, r, minv, sc);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int cg_solve(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* b, double* x,
+             const double* minv, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_out, double* resid_out,
+             cudaStream_t user_stream) {
+  *niter_out = 0;
+  *resid_out = 0.0;
+  if (n <= 0) return OK;
+  // graph capture is illegal on the legacy default stream: borrow a private stream, ordered after it
+  cudaStream_t s = user_stream;
+  if (user_stream == nullptr || user_stream == cudaStreamLegacy || user_stream == cudaStreamPerThread) {
+    static thread_local cudaStream_t priv = nullptr;
+    static thread_local cudaEvent_t ev = nullptr;
+    if (!priv) {
+      FB2_CUDA(cudaStreamCreateWithFlags(&priv, cudaStreamNonBlocking));
+      FB2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    FB2_CUDA(cudaEventRecord(ev, user_stream));
+    FB2_CUDA(cudaStreamWaitEvent(priv, ev, 0));
+    s = priv;
+  }
+  Carver c(ws);
+  char* pws = c.take<char>(PartialWs::bytes());
+  CgScalars* sc = c.take<CgScalars>(1);
+  double* r = c.take<double>(n);
+  double* p = c.take<double>(n);
+  double* Ap = c.take<double>(n);
+  PartialWs pw(pws);
+  int64_t nnz = 0;
+  FB2_CUDA(cudaMemcpyAsync(&nnz, crow + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  FB2_TRY(cg_init_scalars(sc, atol, rtol, maxit < 0 ? INT_MAX : maxit, s));
+  // |b| and the zero-rhs early return (solver/cg.py:79-80)
+  dot_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, b, b, &sc->dot_tmp, pw.partials, &sc->counter[0]);
+  double bb = 0.0;
+  FB2_CUDA(cudaMemcpyAsync(&bb, &sc->dot_tmp, sizeof(double), cudaMemcpyDeviceToHost, s));
+  FB2_CUDA(cudaStreamSynchronize(s));
+  const double bnorm = std::sqrt(bb);
+  if (bnorm < 1e-15) {
+    FB2_CUDA(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), s));
+    return OK;
+  }
+  FB2_CUDA(cudaMemcpyAsync(&sc->bnorm, &bnorm, sizeof(double), cudaMemcpyHostToDevice, s));
+  // r = b - A x0 ; p = z = M r ; rTr = r.z
+  FB2_TRY(spmv_impl(n, nnz, crow, col, val, x, r, b, 1, nullptr, nullptr, nullptr, nullptr, s));
+  cg_start_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, r, minv, p, sc, pw.partials);
+  FB2_LAUNCH_CHECK();
+
+  if (chunk <= 0) {
+    // keep the host poll interval around a few hundred microseconds of GPU work
+    const double bytes_it = 12.0 * (double)nnz + 112.0 * (double)n;
+    const double t_it = bytes_it / 5.0e12 + 8e-6;
+    chunk = (int)(4e-4 / t_it);
+    if (chunk < 2) chunk = 2;
+    if (chunk > 64) chunk = 64;
+  }
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  FB2_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = OK;
+  for (int k = 0; k < chunk && rc == OK; ++k) {
+    rc = spmv_impl(n, nnz, crow, col, val, p, Ap, nullptr, 0, &sc->pAp, pw.partials, &sc->counter[0], sc, s);
+    if (rc == OK) rc = cg_update_xr(n, x, r, p, Ap, minv, sc, pws, 1, s);
+    if (rc == OK) rc = cg_update_p(n, p, r, minv, sc, s);
+  }
+  cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  if (rc != OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  FB2_CUDA(ce);
+  FB2_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  struct { int niter, done; } st = {0, 0};
+  int guard = 0;
+  while (true) {
+    ce = cudaGraphLaunch(exec, s);
+    if (ce != cudaSuccess) break;
+    ce = cudaMemcpyAsync(&st, &sc->niter, sizeof(st), cudaMemcpyDeviceToHost, s);
+    if (ce != cudaSuccess) break;
+    ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) break;
+    if (st.done) break;
+    if (++guard > (1 << 28)) break;
+  }
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  FB2_CUDA(ce);
+  double rn = 0.0;
+  FB2_CUDA(cudaMemcpyAsync(&rn, &sc->rnorm, sizeof(double), cudaMemcpyDeviceToHost, s));
+  FB2_CUDA(cudaStreamSynchronize(s));
+  *niter_out = st.niter;
+  *resid_out = rn;
+  return OK;
+}
+
+}  // namespace fb2

@@ -1,0 +1,39 @@
+#pragma once
+#include "common.cuh"
+
+namespace fb2 {
+
+// device-resident CG scalars (one struct per solve; lives in a caller-provided buffer)
+struct CgScalars {
+  double rTr, pAp, rTr_new, bnorm, rnorm, alpha, beta, dot_tmp;
+  int niter, done, maxit, pad;
+  double atol, rtol;
+  unsigned int counter[4];   // last-block-done tickets for the three reductions
+};
+
+constexpr int CG_PARTIALS = 4096;   // max blocks contributing partial sums per reduction
+
+size_t cg_workspace_bytes(int64_t n);
+
+// y = A x  (mode 0),  y = b - A x (mode 1); optional fused dot  sum_r x[r]*y[r] -> *dot_out (deterministic)
+size_t partial_workspace_bytes();
+int spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
+         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s);
+// SpMM with a row-major (n, nb) dense block: Y = A X
+int spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* X, double* Y, int nb, cudaStream_t s);
+// deterministic dot product
+int dot(int64_t n, const double* a, const double* b, double* out, void* partial_ws, cudaStream_t s);
+
+// full solve: reference recurrence (solver/cg.py:76-123); x holds x0 on entry, the solution on exit
+int cg_solve(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* b, double* x,
+             const double* minv_diag, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_out,
+             double* resid_out, cudaStream_t s);
+
+// building blocks for the distributed (multi-GPU) driver
+int cg_init_scalars(CgScalars* sc, double atol, double rtol, int maxit, cudaStream_t s);
+int cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv, CgScalars* sc,
+                 void* partial_ws, int fuse_finalize, cudaStream_t s);
+int cg_finalize(CgScalars* sc, cudaStream_t s);
+int cg_update_p(int64_t n, double* p, const double* r, const double* minv, CgScalars* sc, cudaStream_t s);
+
+}  // namespace fb2

@@ -1,0 +1,69 @@
+// Shared helpers for the fealpy_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace fb2 {
+
+// status codes returned through the C ABI (0 = ok); see include/fealpy_b200.h
+enum : int { OK = 0, ERR_INVALID = 1, ERR_CUDA = 2, ERR_UNSUPPORTED = 3, ERR_WORKSPACE = 4 };
+
+void set_error(const std::string& msg);   // thread-local last-error string (capi.cu)
+int fail(int code, const char* fmt, ...);
+
+#define FB2_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::fb2::fail(::fb2::ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                  \
+                         cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define FB2_LAUNCH_CHECK() FB2_CUDA(cudaGetLastError())
+
+#define FB2_TRY(expr)                                                                      \
+  do {                                                                                     \
+    int _s = (expr);                                                                       \
+    if (_s != 0) return _s;                                                                \
+  } while (0)
+
+constexpr int kNumSM = 148;  // B200
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// carve typed arrays out of a caller-provided workspace blob
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off += align_up(n * sizeof(T));
+    return r;
+  }
+};
+
+// ---- device helpers -------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming (read-once) loads that do not pollute L1
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+}  // namespace fb2

@@ -1,0 +1,436 @@
+// K1: per-cell element matrices for Lagrange simplex elements, FP64, one thread per cell.
+//
+// Follows the arithmetic of the reference integrators (paths relative to the reference root):
+//   ScalarDiffusionIntegrator.assembly          fem/scalar_diffusion_integrator.py:54-79
+//   ScalarMassIntegrator.assembly               fem/scalar_mass_integrator.py:47-54
+//   LinearElasticityIntegrator.assembly         fem/linear_elasticity_integrator.py:60-181
+//   bilinear_integral (coefficient rules)       functional.py:68-106
+//   cell measure / grad lambda                  backend/numpy_backend.py:413-421,586-598,619-629
+//
+// Design: geometry (vol, Dlambda) lives in registers; the reference-element tables (pre-
+// contracted M tensors for constant coefficients, R / phi / weights for quadrature loops)
+// are staged once per CTA in shared memory and read with warp-uniform (broadcast) LDS;
+// results are staged per warp in shared memory and written back as contiguous segments so
+// that the (NC, l, l) C-order output is stored with full sectors.
+#include "common.cuh"
+#include "elem.cuh"
+
+namespace fb2 {
+
+template <int TD>
+struct Geo {
+  static constexpr int NV = TD + 1;
+  double cm;            // signed measure, det/TD! (never abs'ed, like the reference)
+  double D[NV][TD];     // grad lambda
+};
+
+__device__ __forceinline__ void load_geo(const double* __restrict__ node, const int* __restrict__ cell, int64_t c, Geo<2>& g) {
+  const int v0 = cell[3 * c], v1 = cell[3 * c + 1], v2 = cell[3 * c + 2];
+  const double2 p0 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v0);
+  const double2 p1 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v1);
+  const double2 p2 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v2);
+  const double e0x = p2.x - p1.x, e0y = p2.y - p1.y;
+  const double e1x = p0.x - p2.x, e1y = p0.y - p2.y;
+  const double e2x = p1.x - p0.x, e2y = p1.y - p0.y;
+  const double nv = e0x * e1y - e0y * e1x;
+  const double inv = 1.0 / nv;
+  g.D[0][0] = -e0y * inv; g.D[0][1] = e0x * inv;
+  g.D[1][0] = -e1y * inv; g.D[1][1] = e1x * inv;
+  g.D[2][0] = -e2y * inv; g.D[2][1] = e2x * inv;
+  // simplex_measure: det([p1-p0; p2-p1]) / 2
+  g.cm = 0.5 * (e2x * e0y - e2y * e0x);
+}
+
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__device__ __forceinline__ void load_geo(const double* __restrict__ node, const int* __restrict__ cell, int64_t c, Geo<3>& g) {
+  const int4 v = *reinterpret_cast<const int4*>(cell + 4 * c);
+  const int vid[4] = {v.x, v.y, v.z, v.w};
+  double P[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double* q = node + 3 * (int64_t)vid[k];
+    P[k][0] = q[0]; P[k][1] = q[1]; P[k][2] = q[2];
+  }
+  // volume = det([p1-p0; p2-p1; p3-p2]) / 6
+  double a[3], b[3], cc[3], bc[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) { a[m] = P[1][m] - P[0][m]; b[m] = P[2][m] - P[1][m]; cc[m] = P[3][m] - P[2][m]; }
+  cross3(b, cc, bc);
+  const double det = a[0] * bc[0] + a[1] * bc[1] + a[2] * bc[2];
+  g.cm = det / 6.0;
+  const double inv = 1.0 / det;      // 1 / (6 vol)
+  // Dlambda_i = cross(v_jm, v_jk) / (6 vol), (j,k,m) = localFace[i]
+  constexpr int LF[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = LF[i][0], k = LF[i][1], mm = LF[i][2];
+    double vjk[3], vjm[3], cr[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { vjk[m] = P[k][m] - P[j][m]; vjm[m] = P[mm][m] - P[j][m]; }
+    cross3(vjm, vjk, cr);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) g.D[i][m] = cr[m] * inv;
+  }
+}
+
+// warp-staged store of 32 cells' dense (LL doubles) blocks to out[(c0+lane)*LL + e]
+template <int LL>
+struct WarpStage {
+  static constexpr int S = LL | 1;     // odd stride -> conflict-free 64-bit smem stores
+  static constexpr size_t bytes_per_warp = (size_t)32 * S * sizeof(double);
+};
+
+template <int LL>
+__device__ __forceinline__ void warp_flush(const double* stage, double* __restrict__ out, int64_t c0, int64_t NC) {
+  constexpr int S = WarpStage<LL>::S;
+  const int lane = threadIdx.x & 31;
+  const int64_t ncell = (NC - c0) < 32 ? (NC - c0) : 32;
+  const int64_t tot = ncell * LL;
+  double* dst = out + c0 * LL;
+  for (int64_t idx = lane; idx < tot; idx += 32) {
+    const int cl = (int)(idx / LL), e = (int)(idx - (int64_t)cl * LL);
+    dst[idx] = stage[cl * S + e];
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// constant-coefficient scalar kernel:  K = kd * (Ms : G)  +  km * cm * Mm
+//   Ms[i][j][kl] = sum_q w R[q,i,k] R[q,j,l] (+ k<->l), kl over the upper triangle
+//   G[kl] = cm * Dlam_k . Dlam_l ;  kd / km = scalar * optional per-cell array
+// -------------------------------------------------------------------------------------
+template <int TD, int L, bool STAGED>
+__global__ void __launch_bounds__(128) elem_const_kernel(ElemConstArgs a) {
+  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2, LL = L * L;
+  extern __shared__ __align__(16) double sm[];
+  double* sMs = sm;                               // [LL][NG] (only if diffusion)
+  double* sMm = sMs + (a.has_diff ? LL * NG : 0); // [LL]
+  double* sStage = sMm + (a.has_mass ? LL : 0);
+  if (a.has_diff) for (int i = threadIdx.x; i < LL * NG; i += blockDim.x) sMs[i] = a.Ms[i];
+  if (a.has_mass) for (int i = threadIdx.x; i < LL; i += blockDim.x) sMm[i] = a.Mm[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t c0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wid) * 32;
+  if (c0 >= a.NC) return;
+  const int64_t c = c0 + lane;
+  const bool ok = c < a.NC;
+  double* stage = STAGED ? sStage + (size_t)wid * 32 * WarpStage<LL>::S : nullptr;
+
+  double G[NG], kd = 0.0, km = 0.0;
+  if (ok) {
+    Geo<TD> g;
+    load_geo(a.node, a.cell, c, g);
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int l = k; l < NV; ++l) {
+        double d = 0.0;
+#pragma unroll
+        for (int m = 0; m < TD; ++m) d += g.D[k][m] * g.D[l][m];
+        G[t++] = d * g.cm;
+      }
+    kd = a.scal_d * (a.coef_d ? a.coef_d[c] : 1.0);
+    km = a.scal_m * (a.coef_m ? a.coef_m[c] : 1.0) * g.cm;
+  }
+  if (ok) {
+#pragma unroll 1
+    for (int i = 0; i < L; ++i) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        double v = 0.0;
+        if (a.has_diff) {
+          const double* m = sMs + (i * L + j) * NG;
+          double s = 0.0;
+#pragma unroll
+          for (int t = 0; t < NG; ++t) s += m[t] * G[t];
+          v = kd * s;
+        }
+        if (a.has_mass) v += km * sMm[i * L + j];
+        if (STAGED) stage[lane * WarpStage<LL>::S + i * L + j] = v;
+        else a.out[c * LL + i * L + j] = v;
+      }
+    }
+  }
+  if (STAGED) {
+    __syncwarp();
+    warp_flush<LL>(stage, a.out, c0, a.NC);
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// quadrature-loop scalar kernel (variable coefficients):
+//   diffusion: K[i][j] = cm * sum_q w_q * gphi_i^T C_q gphi_j,  gphi = R[q] Dlam
+//              C_q = kappa[c,q] * I  (coef_kind 2)  or full matrix (NC,NQ,GD,GD) (coef_kind 3)
+//   mass:      K[i][j] = cm * sum_q w_q kappa[c,q] phi_i phi_j
+// rows are processed in passes of RB rows so that the accumulators stay in registers.
+// -------------------------------------------------------------------------------------
+template <int TD, int L, int RB, int R0, bool STAGED>
+__device__ __forceinline__ void quad_pass(const ElemQuadArgs& a, const Geo<TD>& g, const double* sW, const double* sT,
+                                          const double* coefc, double* stage, int64_t c) {
+  constexpr int NV = TD + 1, LL = L * L;
+  constexpr int NR = (R0 + RB <= L) ? RB : (L - R0);     // rows in this pass
+  const int NQ = a.NQ, lane = threadIdx.x & 31;
+  double acc[NR][L];
+#pragma unroll
+  for (int i = 0; i < NR; ++i)
+#pragma unroll
+    for (int j = 0; j < L; ++j) acc[i][j] = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < NQ; ++q) {
+    const double w = sW[q];
+    if (a.is_mass) {
+      const double wk = w * coefc[q];
+      const double* ph = sT + q * L;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const double pi = wk * ph[R0 + i];
+#pragma unroll
+        for (int j = 0; j < L; ++j) acc[i][j] += pi * ph[j];
+      }
+    } else {
+      double gp[L][TD];                       // physical gradients of all basis functions at q
+      const double* R = sT + q * L * NV;
+#pragma unroll
+      for (int j = 0; j < L; ++j)
+#pragma unroll
+        for (int m = 0; m < TD; ++m) {
+          double s = 0.0;
+#pragma unroll
+          for (int b = 0; b < NV; ++b) s += R[j * NV + b] * g.D[b][m];
+          gp[j][m] = s;
+        }
+      if (a.coef_kind == 3) {                 // full matrix coefficient: gphi_i^T C gphi_j
+        double C[TD][TD];
+#pragma unroll
+        for (int d = 0; d < TD; ++d)
+#pragma unroll
+          for (int n = 0; n < TD; ++n) C[d][n] = w * coefc[(q * TD + d) * TD + n];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          double tv[TD];
+#pragma unroll
+          for (int n = 0; n < TD; ++n) {
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < TD; ++d) s += gp[R0 + i][d] * C[d][n];
+            tv[n] = s;
+          }
+#pragma unroll
+          for (int j = 0; j < L; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int n = 0; n < TD; ++n) s += tv[n] * gp[j][n];
+            acc[i][j] += s;
+          }
+        }
+      } else {
+        const double wk = w * coefc[q];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          double tv[TD];
+#pragma unroll
+          for (int n = 0; n < TD; ++n) tv[n] = wk * gp[R0 + i][n];
+#pragma unroll
+          for (int j = 0; j < L; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int n = 0; n < TD; ++n) s += tv[n] * gp[j][n];
+            acc[i][j] += s;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NR; ++i)
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const double v = acc[i][j] * g.cm;
+      if (STAGED) stage[lane * WarpStage<LL>::S + (R0 + i) * L + j] = v;
+      else a.out[c * LL + (R0 + i) * L + j] = v;
+    }
+  if constexpr (R0 + RB < L) quad_pass<TD, L, RB, R0 + RB, STAGED>(a, g, sW, sT, coefc, stage, c);
+}
+
+template <int TD, int L, int RB, bool STAGED>
+__global__ void __launch_bounds__(128) elem_quad_kernel(ElemQuadArgs a) {
+  constexpr int NV = TD + 1, LL = L * L;
+  extern __shared__ __align__(16) double sm[];
+  const int NQ = a.NQ;
+  double* sW = sm;                                     // [NQ]
+  double* sT = sW + NQ;                                // diffusion: R[NQ][L][NV]; mass: phi[NQ][L]
+  const int tab = a.is_mass ? NQ * L : NQ * L * NV;
+  double* sStage = sT + tab;
+  for (int i = threadIdx.x; i < NQ; i += blockDim.x) sW[i] = a.ws[i];
+  for (int i = threadIdx.x; i < tab; i += blockDim.x) sT[i] = a.tab[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t c0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wid) * 32;
+  if (c0 >= a.NC) return;
+  const int64_t c = c0 + lane;
+  double* stage = STAGED ? sStage + (size_t)wid * 32 * WarpStage<LL>::S : nullptr;
+  if (c < a.NC) {
+    Geo<TD> g;
+    load_geo(a.node, a.cell, c, g);
+    const double* coefc = a.coef + c * (int64_t)NQ * (a.coef_kind == 3 ? TD * TD : 1);
+    quad_pass<TD, L, RB, 0, STAGED>(a, g, sW, sT, coefc, stage, c);
+  }
+  if (STAGED) {
+    __syncwarp();
+    warp_flush<LL>(stage, a.out, c0, a.NC);
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// linear elasticity (constant isotropic material), simplex cells:
+//   A_ab[i][j] = cm * sum_{kl} M4[i][j][k][l] Dlam[k][a] Dlam[l][b]
+//   KK(i a, j a) = d_diag * A_aa + d_shear * sum_{b != a} A_bb
+//   KK(i a, j b) = d_lam * A_ab + d_shear * A_ba                       (a != b)
+//   layout: interleaved row = GD*i + a (dof_priority False) or blocked row = a*L + i (True)
+// -------------------------------------------------------------------------------------
+template <int TD, int L>
+__global__ void __launch_bounds__(128) elem_elasticity_kernel(ElemElasticityArgs a) {
+  constexpr int NV = TD + 1, LD = L * TD;
+  extern __shared__ __align__(16) double sm[];
+  for (int i = threadIdx.x; i < L * L * NV * NV; i += blockDim.x) sm[i] = a.M4[i];
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.NC) return;
+  Geo<TD> g;
+  load_geo(a.node, a.cell, c, g);
+  double* out = a.out + c * (int64_t)LD * LD;
+#pragma unroll 1
+  for (int i = 0; i < L; ++i) {
+#pragma unroll 1
+    for (int j = 0; j < L; ++j) {
+      const double* m = sm + (i * L + j) * NV * NV;
+      double A[TD][TD];
+#pragma unroll
+      for (int x = 0; x < TD; ++x)
+#pragma unroll
+        for (int y = 0; y < TD; ++y) A[x][y] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int l = 0; l < NV; ++l) {
+          const double mv = m[k * NV + l];
+#pragma unroll
+          for (int x = 0; x < TD; ++x)
+#pragma unroll
+            for (int y = 0; y < TD; ++y) A[x][y] += mv * (g.D[k][x] * g.D[l][y]);
+        }
+#pragma unroll
+      for (int x = 0; x < TD; ++x)
+#pragma unroll
+        for (int y = 0; y < TD; ++y) {
+          double v;
+          if (x == y) {
+            double oth = 0.0;
+#pragma unroll
+            for (int z = 0; z < TD; ++z) if (z != x) oth += A[z][z];
+            v = a.d_diag * A[x][x] + a.d_shear * oth;
+          } else {
+            v = a.d_lam * A[x][y] + a.d_shear * A[y][x];
+          }
+          v *= g.cm;
+          const int row = a.dof_priority ? x * L + i : i * TD + x;
+          const int col = a.dof_priority ? y * L + j : j * TD + y;
+          out[row * LD + col] = v;
+        }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// host-side dispatch
+// -------------------------------------------------------------------------------------
+static int ldof_of(int TD, int p) { return TD == 2 ? (p + 1) * (p + 2) / 2 : (p + 1) * (p + 2) * (p + 3) / 6; }
+
+template <int TD, int L>
+static int launch_const(const ElemConstArgs& a, cudaStream_t s) {
+  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2, LL = L * L;
+  size_t tab = ((a.has_diff ? LL * NG : 0) + (a.has_mass ? LL : 0)) * sizeof(double);
+  constexpr bool STAGED = WarpStage<LL>::bytes_per_warp <= 26 * 1024;
+  const int warps = 4;
+  size_t smem = tab + (STAGED ? warps * WarpStage<LL>::bytes_per_warp : 0);
+  auto kern = elem_const_kernel<TD, L, STAGED>;
+  FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t nb = ceil_div(a.NC, 32 * warps);
+  kern<<<(unsigned)nb, 32 * warps, smem, s>>>(a);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+template <int TD, int L>
+static int launch_quad(const ElemQuadArgs& a, cudaStream_t s) {
+  constexpr int NV = TD + 1, LL = L * L;
+  constexpr int RB = L <= 6 ? L : (L <= 10 ? 5 : 2);
+  size_t tab = ((size_t)a.NQ + (size_t)a.NQ * L * (a.is_mass ? 1 : NV)) * sizeof(double);
+  constexpr bool STAGED = WarpStage<LL>::bytes_per_warp <= 26 * 1024;
+  const int warps = 4;
+  size_t smem = tab + (STAGED ? warps * WarpStage<LL>::bytes_per_warp : 0);
+  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "elem_quad: quadrature table too large for shared memory (NQ=%d)", a.NQ);
+  auto kern = elem_quad_kernel<TD, L, RB, STAGED>;
+  FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t nb = ceil_div(a.NC, 32 * warps);
+  kern<<<(unsigned)nb, 32 * warps, smem, s>>>(a);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+template <int TD, int L>
+static int launch_elast(const ElemElasticityArgs& a, cudaStream_t s) {
+  constexpr int NV = TD + 1;
+  size_t smem = (size_t)L * L * NV * NV * sizeof(double);
+  auto kern = elem_elasticity_kernel<TD, L>;
+  FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)ceil_div(a.NC, 128), 128, smem, s>>>(a);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+#define FB2_DISPATCH_TD_P(FN, TDv, Pv, ...)                                          \
+  do {                                                                               \
+    const int _key = (TDv) * 10 + (Pv);                                              \
+    switch (_key) {                                                                  \
+      case 21: return FN<2, 3>(__VA_ARGS__);                                         \
+      case 22: return FN<2, 6>(__VA_ARGS__);                                         \
+      case 23: return FN<2, 10>(__VA_ARGS__);                                        \
+      case 31: return FN<3, 4>(__VA_ARGS__);                                         \
+      case 32: return FN<3, 10>(__VA_ARGS__);                                        \
+      case 33: return FN<3, 20>(__VA_ARGS__);                                        \
+      default:                                                                       \
+        return fail(ERR_UNSUPPORTED, "unsupported element TD=%d p=%d (simplex p=1..3)", (TDv), (Pv)); \
+    }                                                                                \
+  } while (0)
+
+int elem_const(int TD, int p, const ElemConstArgs& a, cudaStream_t s) {
+  if (a.NC <= 0) return OK;
+  (void)ldof_of;
+  FB2_DISPATCH_TD_P(launch_const, TD, p, a, s);
+}
+int elem_quad(int TD, int p, const ElemQuadArgs& a, cudaStream_t s) {
+  if (a.NC <= 0) return OK;
+  FB2_DISPATCH_TD_P(launch_quad, TD, p, a, s);
+}
+int elem_elasticity(int TD, int p, const ElemElasticityArgs& a, cudaStream_t s) {
+  if (a.NC <= 0) return OK;
+  const int key = TD * 10 + p;
+  switch (key) {
+    case 21: return launch_elast<2, 3>(a, s);
+    case 22: return launch_elast<2, 6>(a, s);
+    case 23: return launch_elast<2, 10>(a, s);
+    case 31: return launch_elast<3, 4>(a, s);
+    case 32: return launch_elast<3, 10>(a, s);
+    default: return fail(ERR_UNSUPPORTED, "elasticity: unsupported element TD=%d p=%d", TD, p);
+  }
+}
+
+}  // namespace fb2

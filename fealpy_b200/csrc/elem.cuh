@@ -1,0 +1,47 @@
+// argument blocks of the element-matrix kernels (elem.cu)
+#pragma once
+#include "common.cuh"
+
+namespace fb2 {
+
+struct ElemConstArgs {
+  const double* node;    // (NN, GD)
+  const int* cell;       // (NC, TD+1)
+  int64_t NC;
+  int has_diff, has_mass;
+  const double* Ms;      // [L][L][NG]  pre-contracted diffusion tensor (device)
+  const double* Mm;      // [L][L]      reference mass matrix (device)
+  double scal_d, scal_m; // scalar factors
+  const double* coef_d;  // optional per-cell factor (NC,) or null
+  const double* coef_m;
+  double* out;           // (NC, L, L)
+};
+
+struct ElemQuadArgs {
+  const double* node;
+  const int* cell;
+  int64_t NC;
+  int is_mass;           // 0: diffusion, 1: mass
+  int NQ;
+  const double* ws;      // [NQ]
+  const double* tab;     // diffusion: R[NQ][L][TD+1]; mass: phi[NQ][L]
+  int coef_kind;         // 2: (NC,NQ) scalar field, 3: (NC,NQ,GD,GD) matrix field (diffusion only)
+  const double* coef;
+  double* out;
+};
+
+struct ElemElasticityArgs {
+  const double* node;
+  const int* cell;
+  int64_t NC;
+  const double* M4;      // [L][L][NV][NV] = sum_q w R[q,i,k] R[q,j,l]
+  double d_diag, d_lam, d_shear;
+  int dof_priority;
+  double* out;           // (NC, GD*L, GD*L)
+};
+
+int elem_const(int TD, int p, const ElemConstArgs& a, cudaStream_t s);
+int elem_quad(int TD, int p, const ElemQuadArgs& a, cudaStream_t s);
+int elem_elasticity(int TD, int p, const ElemElasticityArgs& a, cudaStream_t s);
+
+}  // namespace fb2

@@ -1,0 +1,337 @@
+"""BilinearForm: global assembly of cell integrators into a CSRTensor on the GPU.
+
+Drop-in for the reference call surface (fem/form.py:39-188, fem/bilinear_form.py:11-158):
+    BilinearForm(space).add_integrator(I, ...).assembly(format='csr') -> CSRTensor
+Integrators added in ONE add_integrator call form a group (their element matrices are
+summed, fem/integrator.py:295-378); separate calls are separate groups whose COO blocks the
+reference concatenates and sums in coalesce().  Three device paths produce the same matrix:
+
+  'fused'  symbolic pattern (cached per space) + row-owner numeric kernel that recomputes the
+           element rows in registers (constant / per-cell coefficients, scalar spaces)
+  'gather' symbolic pattern + K1 element matrices + row-owner gather (any integrator,
+           variable coefficients, tensor spaces)
+  'coo'    K1 + the literal COO -> stable (row, col) sort -> ordered segmented reduce (K2)
+
+`assembly_path='auto'` picks fused, else gather.  The pattern (explicit zeros included) is
+identical for all three and bit-identical to the reference's coalesce().tocsr().
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Sequence
+
+import torch
+
+from .. import _lib
+from ..sparse import COOTensor, CSRTensor
+from .integrators import Integrator
+
+
+class GroupIntegrator(Integrator):
+    """sum of the member element matrices, in list order (fem/integrator.py:295-378)"""
+
+    def __init__(self, *ints, region=None):
+        super().__init__()
+        if len(ints) == 0:
+            raise ValueError("No integrators provided.")
+        self.ints = []
+        for it in ints:
+            if isinstance(it, GroupIntegrator):
+                self.ints.extend(it.ints)
+            elif hasattr(it, "assembly"):
+                self.ints.append(it)
+            else:
+                raise TypeError(f"Unsupported type {it.__class__.__name__} found in the inputs.")
+        self.set_region(region)
+
+    def __iter__(self):
+        return iter(self.ints)
+
+    def __len__(self):
+        return len(self.ints)
+
+    def __iadd__(self, other):
+        if isinstance(other, GroupIntegrator):
+            self.ints.extend(other.ints)
+        else:
+            self.ints.append(other)
+        return self
+
+    def to_global_dof(self, space, indices=None):
+        return self.ints[0].to_global_dof(space)
+
+    def assembly(self, space, indices=None):
+        ct = self.ints[0].assembly(space)
+        for it in self.ints[1:]:
+            ct = ct + it.assembly(space)
+        return ct
+
+
+def _bits(n: int) -> int:
+    b = 1
+    while (1 << b) < n:
+        b += 1
+    return b
+
+
+def symbolic_pattern(space):
+    """cached per scalar space: adjacency, CSR pattern and slot map (csrc/assemble.cu)"""
+    cache = getattr(space, "_b200_symbolic", None)
+    if cache is not None:
+        return cache
+    lib = _lib.load()
+    c2d = space.cell_to_dof().contiguous()
+    NC, L = c2d.shape
+    gdof = space.number_of_global_dofs()
+    dev = c2d.device
+    adj_ptr = torch.empty(gdof + 1, dtype=torch.int64, device=dev)
+    adj_pair = torch.empty(NC * L, dtype=torch.int32, device=dev)
+    crow = torch.empty(gdof + 1, dtype=torch.int64, device=dev)
+    ws = _lib.workspace(lib.fb2_sym_workspace_bytes(NC, L, gdof), dev)
+    nnz, max_row = C.c_int64(0), C.c_int32(0)
+    _lib.call("fb2_sym_count", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow),
+              C.byref(nnz), C.byref(max_row), _lib.ptr(ws), _lib.stream())
+    slot_bytes = 1 if max_row.value <= 255 else 2
+    col = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+    slots = torch.empty(NC * L * L, dtype=torch.uint8 if slot_bytes == 1 else torch.int16, device=dev)
+    _lib.call("fb2_sym_fill", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow), _lib.ptr(col),
+              _lib.ptr(slots), slot_bytes, _lib.stream())
+    cache = dict(adj_ptr=adj_ptr, adj_pair=adj_pair, crow=crow, col=col, slots=slots, slot_bytes=slot_bytes,
+                 max_row=max_row.value, nnz=nnz.value, NC=NC, L=L, gdof=gdof)
+    space._b200_symbolic = cache
+    return cache
+
+
+def tensor_pattern(space):
+    """pattern of a TensorFunctionSpace = scalar pattern (x) dense ncomp x ncomp blocks"""
+    cache = getattr(space, "_b200_pattern", None)
+    if cache is not None:
+        return cache
+    sym = symbolic_pattern(space.scalar_space)
+    nc = space.dof_numel
+    dev = sym["crow"].device
+    crow = torch.empty(sym["gdof"] * nc + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(sym["nnz"] * nc * nc, dtype=torch.int32, device=dev)
+    _lib.call("fb2_expand_pattern", sym["gdof"], nc, int(space.dof_priority), _lib.ptr(sym["crow"]), _lib.ptr(sym["col"]),
+              _lib.ptr(crow), _lib.ptr(col), _lib.stream())
+    cache = dict(crow=crow, col=col)
+    space._b200_pattern = cache
+    return cache
+
+
+class BilinearForm:
+    def __init__(self, space, batch_size: int = 0, *, assembly_path: str = "auto"):
+        if isinstance(space, (tuple, list)):
+            if len(space) != 1:
+                raise NotImplementedError("two-space (rectangular) forms are not on the accelerated path")
+            space = space[0]
+        if batch_size:
+            raise NotImplementedError("batched forms (batch_size > 0) are not on the accelerated path")
+        self.space = space
+        self._spaces = (space,)
+        self.batch_size = 0
+        self.integrators = {}
+        self.splitters = {}
+        self._cursor = 0
+        self._M = None
+        self._transposed = False
+        if assembly_path not in ("auto", "fused", "gather", "coo"):
+            raise ValueError(f"unknown assembly_path {assembly_path!r}")
+        self.assembly_path = assembly_path
+        self.last_path = None
+
+    # ---- bookkeeping (fem/form.py:92-144) ----------------------------------------------------
+    @property
+    def shape(self):
+        g = self.space.number_of_global_dofs()
+        return (g, g)
+
+    sparse_shape = shape
+
+    def add_integrator(self, *I, region=None, splitter=None, group=None):
+        if len(I) == 0:
+            return self
+        if len(I) == 1 and isinstance(I[0], Sequence):
+            I = tuple(I[0])
+        if region is not None:
+            raise NotImplementedError("region / sub-domain integration is not on the accelerated path")
+        I = I[0] if len(I) == 1 else GroupIntegrator(*I)
+        # `splitter` chunks the element loop to bound the reference's memory; the GPU path never
+        # materialises gphi, so it is accepted and ignored.
+        return self._add_integrator_impl(I, group, splitter)
+
+    def __lshift__(self, other):
+        if hasattr(other, "assembly"):
+            return self._add_integrator_impl(other, None)
+        return NotImplemented
+
+    def _add_integrator_impl(self, I, group=None, splitter=None):
+        group = f"_group_{self._cursor}" if group is None else group
+        self._cursor += 1
+        if group in self.integrators:
+            cur = self.integrators[group]
+            if not isinstance(cur, GroupIntegrator):
+                cur = GroupIntegrator(cur)
+            cur += I
+            self.integrators[group] = cur
+        else:
+            self.integrators[group] = I
+        self.splitters[group] = splitter
+        self._M = None
+        return self
+
+    def _flat_integrators(self):
+        out = []
+        for it in self.integrators.values():
+            out.extend(it.ints if isinstance(it, GroupIntegrator) else [it])
+        return out
+
+    def assembly_local_iterative(self):
+        for it in self.integrators.values():
+            etg = it.to_global_dof(self.space)
+            yield it.assembly(self.space), (etg,)
+
+    # ---- assembly ------------------------------------------------------------------------------
+    def _is_tensor_space(self):
+        return hasattr(self.space, "scalar_space")
+
+    def _plan_fused(self):
+        """merge constant / per-cell scalar integrators into (<=1 diffusion, <=1 mass) kernels"""
+        if self._is_tensor_space():
+            return None
+        merged = {}
+        for it in self._flat_integrators():
+            desc = getattr(it, "describe", None)
+            if desc is None:
+                return None
+            d = desc(self.space)
+            if d["coef_kind"] not in ("scalar", "cell"):
+                return None
+            m = merged.setdefault(d["kind"], dict(q=d["q"], tabs=d["tabs"], scal=0.0, arr=None))
+            if m["q"] != d["q"]:
+                return None
+            if d["coef_kind"] == "scalar":
+                if m["arr"] is None:
+                    m["scal"] += d["coef"]
+                else:
+                    m["arr"] = m["arr"] + d["coef"]
+            else:
+                m["arr"] = d["coef"] + (m["scal"] if m["arr"] is None else m["arr"])
+                m["scal"] = 0.0
+        return merged
+
+    def _assemble_fused(self, plan):
+        space, mesh = self.space, self.space.mesh
+        sym = symbolic_pattern(space)
+        values = torch.empty(sym["nnz"], dtype=torch.float64, device=mesh.device)
+        dm, mm = plan.get("diffusion"), plan.get("mass")
+
+        def parts(m):
+            if m is None:
+                return 0.0, None
+            return (1.0, m["arr"].contiguous()) if m["arr"] is not None else (m["scal"], None)
+        sd, ad = parts(dm)
+        sm_, am = parts(mm)
+        _lib.call("fb2_assemble_scalar_const", mesh.TD, space.p, sym["NC"], sym["gdof"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
+                  _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]), _lib.ptr(sym["slots"]), sym["slot_bytes"],
+                  _lib.ptr(sym["crow"]), sym["max_row"],
+                  _lib.ptr(dm["tabs"]["Ms"]) if dm else None, _lib.ptr(mm["tabs"]["Mm"]) if mm else None,
+                  sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(values), _lib.stream())
+        return sym["crow"], sym["col"], values
+
+    def _summed_ke(self):
+        ke = None
+        for it in self.integrators.values():
+            k = it.assembly(self.space)
+            if not isinstance(k, torch.Tensor) or k.ndim != 3:
+                raise ValueError("Output of operator integrators should be 3D, "
+                                 f"but got shape {tuple(getattr(k, 'shape', ()))}.")
+            ke = k if ke is None else ke.add_(k)
+        return ke.contiguous()
+
+    def _assemble_gather(self):
+        space = self.space
+        ke = self._summed_ke()
+        if self._is_tensor_space():
+            sspace, nc, prio = space.scalar_space, space.dof_numel, int(space.dof_priority)
+            sym = symbolic_pattern(sspace)
+            pat = tensor_pattern(space)
+            crow, col = pat["crow"], pat["col"]
+        else:
+            sym = symbolic_pattern(space)
+            nc, prio = 1, 0
+            crow, col = sym["crow"], sym["col"]
+        if ke.shape != (sym["NC"], sym["L"] * nc, sym["L"] * nc):
+            raise ValueError(f"entity_to_global.shape[0] != local_tensor.shape[0] or wrong local shape {tuple(ke.shape)}")
+        values = torch.empty(col.shape[0], dtype=torch.float64, device=ke.device)
+        _lib.call("fb2_assemble_from_ke", sym["NC"], sym["L"], nc, prio, sym["gdof"], _lib.ptr(ke), _lib.ptr(sym["adj_ptr"]),
+                  _lib.ptr(sym["adj_pair"]), _lib.ptr(sym["slots"]), sym["slot_bytes"], _lib.ptr(sym["crow"]), sym["max_row"],
+                  _lib.ptr(crow), _lib.ptr(values), _lib.stream())
+        return crow, col, values
+
+    def _assemble_coo(self):
+        """the literal reference pipeline on the device: COO of every group -> sort -> reduce"""
+        lib = _lib.load()
+        space = self.space
+        gdof = space.number_of_global_dofs()
+        blocks = [(it.assembly(space), it.to_global_dof(space).contiguous()) for it in self.integrators.values()]
+        dev = blocks[0][0].device
+        n = sum(k.numel() for k, _ in blocks)
+        cbits = _bits(max(gdof, 2))
+        keys = torch.empty(n, dtype=torch.int64, device=dev)
+        vals = torch.empty(n, dtype=torch.float64, device=dev)
+        off = 0
+        for k, c2d in blocks:
+            NC, lr, lc = k.shape
+            if c2d.shape != (NC, lr) or lr != lc:
+                raise ValueError("entity_to_global.shape[0] != local_tensor.shape[0]")
+            m = k.numel()
+            _lib.call("fb2_coo_keys_from_c2d", _lib.ptr(c2d), _lib.ptr(c2d), NC, lr, lc, cbits,
+                      C.c_void_p(keys.data_ptr() + 8 * off), _lib.stream())
+            vals[off:off + m] = k.reshape(-1)
+            off += m
+        perm = torch.empty(n, dtype=torch.int32, device=dev)
+        ws = _lib.workspace(lib.fb2_coo_workspace_bytes(n), dev)
+        nnz = C.c_int64(0)
+        _lib.call("fb2_coo_symbolic", _lib.ptr(keys), _lib.ptr(perm), n, 2 * cbits, _lib.ptr(ws), C.byref(nnz), _lib.stream())
+        nnz = nnz.value
+        crow = torch.empty(gdof + 1, dtype=torch.int64, device=dev)
+        col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        seg = torch.empty(nnz + 1, dtype=torch.int64, device=dev)
+        _lib.call("fb2_coo_fill", _lib.ptr(keys), n, cbits, gdof, _lib.ptr(ws), _lib.ptr(crow), _lib.ptr(col), 4, _lib.ptr(seg),
+                  _lib.stream())
+        values = torch.empty(nnz, dtype=torch.float64, device=dev)
+        _lib.call("fb2_coo_reduce", _lib.ptr(perm), _lib.ptr(seg), nnz, _lib.ptr(vals), _lib.ptr(values), _lib.stream())
+        return crow, col, values
+
+    def assembly(self, *, format="csr"):
+        """fem/bilinear_form.py:83-105"""
+        if format not in ("csr", "coo"):
+            raise ValueError(f"Unsupported format {format}.")
+        if not self.integrators:
+            raise ValueError("no integrators added")
+        path = self.assembly_path
+        plan = None
+        if path in ("auto", "fused"):
+            plan = self._plan_fused()
+            if plan is None and path == "fused":
+                raise NotImplementedError("the fused path needs constant / per-cell scalar coefficients on a scalar space")
+        if plan is not None:
+            crow, col, values = self._assemble_fused(plan)
+            self.last_path = "fused"
+        elif path == "coo":
+            crow, col, values = self._assemble_coo()
+            self.last_path = "coo"
+        else:
+            crow, col, values = self._assemble_gather()
+            self.last_path = "gather"
+        M = CSRTensor(crow, col, values, self.shape)
+        if self._transposed:
+            raise NotImplementedError("transposed forms are not on the accelerated path")
+        self._M = M if format == "csr" else M.tocoo()
+        return self._M
+
+    def __matmul__(self, u):
+        if self._M is None:
+            self.assembly()
+        return self._M @ u

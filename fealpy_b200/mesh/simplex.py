@@ -1,0 +1,216 @@
+"""Simplex meshes living on the GPU: TriangleMesh / TetrahedronMesh.
+
+Mirrors the part of the reference mesh API the assembly path consumes
+(fealpy/mesh/triangle_mesh.py, tetrahedron_mesh.py, mesh_data_structure.py, mesh_base.py):
+node/cell storage, `from_box`, the edge/face topology `construct()` builds, and the global
+interpolation-point (DOF) numbering `cell_to_ipoint(p)`.  All integer work runs in the CUDA
+library (csrc/topo.cu); torch tensors are only containers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..basis import multi_index_matrix, number_of_local_dofs
+from ..quadrature import simplex_quadrature
+
+
+class SimplexMesh:
+    TD = None
+
+    def __init__(self, node: torch.Tensor, cell: torch.Tensor):
+        if not (isinstance(node, torch.Tensor) and isinstance(cell, torch.Tensor)):
+            raise TypeError("node and cell must be torch tensors (PyTorch tensors are the only device containers)")
+        if node.device.type != "cuda" or cell.device != node.device:
+            raise RuntimeError("fealpy_b200 meshes live on a CUDA device; there is no CPU path")
+        if node.dtype != torch.float64:
+            raise TypeError("node must be float64")
+        if cell.dtype != torch.int32:
+            if cell.dtype == torch.int64:
+                cell = cell.to(torch.int32)
+            else:
+                raise TypeError("cell must be int32 (or int64, converted)")
+        if cell.ndim != 2 or cell.shape[1] != self.TD + 1 or node.ndim != 2 or node.shape[1] != self.TD:
+            raise ValueError(f"expected node (NN,{self.TD}) and cell (NC,{self.TD + 1})")
+        self.node = node.contiguous()
+        self.cell = cell.contiguous()
+        self.itype = torch.int32
+        self.ftype = torch.float64
+        self.device = node.device
+        self._edge = None
+        self._cell2edge = None
+        self._face = None
+        self._cell2face = None
+        self._c2ip = {}
+        self.meshdata = {}
+
+    # ---- sizes -----------------------------------------------------------------------
+    def top_dimension(self): return self.TD
+    def geo_dimension(self): return self.node.shape[1]
+    def number_of_nodes(self): return self.node.shape[0]
+    def number_of_cells(self): return self.cell.shape[0]
+    def number_of_edges(self): return self.edge.shape[0]
+    def number_of_faces(self): return self.face.shape[0]
+
+    def entity(self, etype):
+        if etype in ("node", 0): return self.node
+        if etype in ("cell", self.TD): return self.cell
+        if etype in ("edge", 1): return self.edge
+        if etype in ("face", self.TD - 1): return self.face
+        raise ValueError(f"unknown entity type {etype}")
+
+    # ---- topology (MeshDS.construct, mesh/mesh_data_structure.py:428-464) ----------------
+    def _build_entities(self, kind):
+        lib = _lib.load()
+        NC, NN = self.number_of_cells(), self.number_of_nodes()
+        per_cell = {(2, 1): 3, (3, 1): 6, (3, 2): 4}[(self.TD, kind)]
+        nve = 2 if kind == 1 else 3
+        ws = _lib.workspace(lib.fb2_entity_workspace_bytes(NC, per_cell), self.device)
+        c2e = torch.empty((NC, per_cell), dtype=torch.int32, device=self.device)
+        cnt = C.c_int64(0)
+        _lib.call("fb2_build_entities", _lib.ptr(self.cell), NC, self.TD, kind, NN, _lib.ptr(c2e), C.byref(cnt),
+                  _lib.ptr(ws), _lib.stream())
+        ent = torch.empty((cnt.value, nve), dtype=torch.int32, device=self.device)
+        _lib.call("fb2_entities_emit", _lib.ptr(self.cell), NC, self.TD, kind, _lib.ptr(c2e), _lib.ptr(ent), _lib.ptr(ws),
+                  _lib.stream())
+        return ent, c2e
+
+    @property
+    def edge(self):
+        if self._edge is None:
+            self._edge, self._cell2edge = self._build_entities(1)
+        return self._edge
+
+    @property
+    def cell2edge(self):
+        self.edge
+        return self._cell2edge
+
+    @property
+    def face(self):
+        if self.TD == 2:
+            return self.edge
+        if self._face is None:
+            self._face, self._cell2face = self._build_entities(2)
+        return self._face
+
+    @property
+    def cell2face(self):
+        if self.TD == 2:
+            return self.cell2edge
+        self.face
+        return self._cell2face
+
+    def cell_to_edge(self): return self.cell2edge
+    def cell_to_face(self): return self.cell2face
+
+    # ---- interpolation points / dof numbering -----------------------------------------------
+    def multi_index_matrix(self, p, TD=None):
+        return multi_index_matrix(p, self.TD if TD is None else TD)
+
+    def number_of_local_ipoints(self, p, iptype="cell"):
+        if iptype in ("cell", self.TD):
+            return number_of_local_dofs(self.TD, p)
+        if iptype in ("face", self.TD - 1) and self.TD == 3:
+            return (p + 1) * (p + 2) // 2
+        return p + 1
+
+    def number_of_global_ipoints(self, p):
+        NN, NC = self.number_of_nodes(), self.number_of_cells()
+        if p == 1:
+            return NN
+        n = NN + (p - 1) * self.number_of_edges()
+        if self.TD == 2:
+            return n + (p - 1) * (p - 2) // 2 * NC
+        if p >= 3:
+            n += (p - 1) * (p - 2) // 2 * self.number_of_faces() + (p - 1) * (p - 2) * (p - 3) // 6 * NC
+        return n
+
+    def cell_to_ipoint(self, p, index=None):
+        """(NC, ldof) int32 global dof ids (mesh/triangle_mesh.py:218-270, tetrahedron_mesh.py:388-441)."""
+        if p not in self._c2ip:
+            if p == 1:
+                self._c2ip[p] = self.cell
+            else:
+                if p > 3:
+                    raise NotImplementedError("fealpy_b200 supports Lagrange degree p = 1..3")
+                NC, L = self.number_of_cells(), number_of_local_dofs(self.TD, p)
+                need_face = self.TD == 3 and p >= 3
+                c2f = self.cell2face if need_face else None
+                NF = self.number_of_faces() if need_face else 0
+                mi = np.ascontiguousarray(self.multi_index_matrix(p).astype(np.uint8))
+                out = torch.empty((NC, L), dtype=torch.int32, device=self.device)
+                _lib.call("fb2_cell_to_dof", _lib.ptr(self.cell), _lib.ptr(self.cell2edge), _lib.ptr(self.edge), _lib.ptr(c2f),
+                          NC, self.TD, p, self.number_of_nodes(), self.number_of_edges(), NF,
+                          mi.ctypes.data_as(C.c_void_p), L, _lib.ptr(out), _lib.stream())
+                self._c2ip[p] = out
+        c2d = self._c2ip[p]
+        return c2d if index is None else c2d[index]
+
+    def quadrature_formula(self, q, etype="cell"):
+        if etype not in ("cell", self.TD):
+            raise NotImplementedError("only cell quadrature is on the accelerated path")
+        return simplex_quadrature(self.TD, q)
+
+    def bc_to_point(self, bcs, index=None):
+        """physical points of barycentric points, (NC, NQ, GD) (mesh_base.py bc_to_point)."""
+        cell = self.cell if index is None else self.cell[index]
+        b = torch.as_tensor(bcs, dtype=torch.float64, device=self.device)
+        return torch.einsum("cjk,qj->cqk", self.node[cell.long()], b)
+
+    def interpolation_points(self, p):
+        """(gdof, GD) coordinates of the global interpolation points."""
+        gdof = self.number_of_global_ipoints(p)
+        mi = torch.as_tensor(self.multi_index_matrix(p) / p, dtype=torch.float64, device=self.device)
+        pts = torch.einsum("cjk,ij->cik", self.node[self.cell.long()], mi)
+        ip = torch.zeros((gdof, self.geo_dimension()), dtype=torch.float64, device=self.device)
+        ip[self.cell_to_ipoint(p).long().reshape(-1)] = pts.reshape(-1, self.geo_dimension())
+        ip[: self.number_of_nodes()] = self.node
+        return ip
+
+    def boundary_face_flag(self):
+        cnt = torch.bincount(self.cell2face.reshape(-1).long(), minlength=self.number_of_faces())
+        return cnt == 1
+
+
+class TriangleMesh(SimplexMesh):
+    TD = 2
+
+    @classmethod
+    def from_box(cls, box=(0, 1, 0, 1), nx=10, ny=10, *, threshold=None, itype=None, ftype=None, device="cuda"):
+        """mesh/triangle_mesh.py:1386-1435"""
+        if threshold is not None:
+            raise NotImplementedError("from_box(threshold=...) is not on the accelerated path")
+        _lib.require_cuda()
+        device = torch.device(device if device is not None else "cuda")
+        NN, NC = (nx + 1) * (ny + 1), 2 * nx * ny
+        node = torch.empty((NN, 2), dtype=torch.float64, device=device)
+        cell = torch.empty((NC, 3), dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            b = (C.c_double * 4)(*[float(v) for v in box])
+            _lib.call("fb2_tri_from_box", b, nx, ny, _lib.ptr(node), _lib.ptr(cell), _lib.stream())
+        return cls(node, cell)
+
+
+class TetrahedronMesh(SimplexMesh):
+    TD = 3
+
+    @classmethod
+    def from_box(cls, box=(0, 1, 0, 1, 0, 1), nx=10, ny=10, nz=10, threshold=None, device="cuda"):
+        """mesh/tetrahedron_mesh.py:1016-1086"""
+        if threshold is not None:
+            raise NotImplementedError("from_box(threshold=...) is not on the accelerated path")
+        _lib.require_cuda()
+        device = torch.device(device if device is not None else "cuda")
+        NN, NC = (nx + 1) * (ny + 1) * (nz + 1), 6 * nx * ny * nz
+        node = torch.empty((NN, 3), dtype=torch.float64, device=device)
+        cell = torch.empty((NC, 4), dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            b = (C.c_double * 6)(*[float(v) for v in box])
+            _lib.call("fb2_tet_from_box", b, nx, ny, nz, _lib.ptr(node), _lib.ptr(cell), _lib.stream())
+        m = cls(node, cell)
+        m.box = list(box)
+        return m

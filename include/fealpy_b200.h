@@ -1,0 +1,142 @@
+/* fealpy_b200 -- C ABI of the B200-native (sm_100a) Lagrange-FEM assembly + CG hot path.
+ *
+ * This is the drop-in boundary for FEALPy's path
+ *     BilinearForm(space).add_integrator(...).assembly() -> CSRTensor -> fealpy.solver.cg
+ * Every entry point takes plain device pointers (from tensor.data_ptr()), sizes and a
+ * cudaStream_t passed as void*; no torch types.  All functions return 0 on success or a
+ * non-zero FB2_ERR_* code; fb2_last_error() returns the message of the calling thread's last
+ * failure.  Paths cited below are relative to the reference tree (FEALPy 3.4.0).
+ *
+ * Memory protocol: outputs and workspaces are caller-allocated (the Python shim allocates
+ * torch tensors).  Where an output size is data dependent (nnz, number of edges) the call is
+ * split in a "symbolic/count" step that returns the size through a host pointer (it
+ * synchronises the stream) and a "fill" step.
+ */
+#ifndef FEALPY_B200_H
+#define FEALPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { FB2_OK = 0, FB2_ERR_INVALID = 1, FB2_ERR_CUDA = 2, FB2_ERR_UNSUPPORTED = 3, FB2_ERR_WORKSPACE = 4 };
+
+const char* fb2_last_error(void);
+int fb2_version(void);
+
+/* ---- mesh generation + topology -> DOF numbering --------------------------------------
+ * replaces TriangleMesh.from_box (mesh/triangle_mesh.py:1386-1435), TetrahedronMesh.from_box
+ * (mesh/tetrahedron_mesh.py:1016-1086), MeshDS.construct (mesh/mesh_data_structure.py:428-464),
+ * cell_to_ipoint (mesh/triangle_mesh.py:218-270, mesh/tetrahedron_mesh.py:388-441) and
+ * to_tensor_dof (functionspace/utils.py:83-95). */
+int fb2_tri_from_box(const double box[4], int nx, int ny, double* node, int32_t* cell, void* stream);
+int fb2_tet_from_box(const double box[6], int nx, int ny, int nz, double* node, int32_t* cell, void* stream);
+size_t fb2_entity_workspace_bytes(int64_t NC, int per_cell);
+/* kind: 1 = edges, 2 = faces (tets).  Step 1 fills cell2ent (NC x per_cell) and *count. */
+int fb2_build_entities(const int32_t* cell, int64_t NC, int TD, int kind, int64_t NN, int32_t* cell2ent, int64_t* count_host,
+                       void* ws, void* stream);
+/* Step 2 (same ws): ent (count x nve) = first-occurrence vertex tuples. */
+int fb2_entities_emit(const int32_t* cell, int64_t NC, int TD, int kind, int32_t* cell2ent, int32_t* ent, void* ws, void* stream);
+int fb2_cell_to_dof(const int32_t* cell, const int32_t* cell2edge, const int32_t* edge, const int32_t* cell2face, int64_t NC, int TD,
+                    int p, int64_t NN, int64_t NE, int64_t NF, const unsigned char* multi_index_host, int ldof, int32_t* cell2dof,
+                    void* stream);
+int fb2_tensor_cell_to_dof(const int32_t* cell2dof, int64_t NC, int ldof, int GD, int64_t gdof, int dof_priority, int32_t* out,
+                           void* stream);
+
+/* ---- K1: element matrices ---------------------------------------------------------------
+ * replaces ScalarDiffusionIntegrator.assembly / ScalarMassIntegrator.assembly /
+ * LinearElasticityIntegrator.assembly (fem/scalar_diffusion_integrator.py:54-79,
+ * fem/scalar_mass_integrator.py:47-54, fem/linear_elasticity_integrator.py:60-181) and
+ * bilinear_integral (functional.py:68-106).  out is (NC, l, l) C-order float64.
+ *
+ * constant / per-cell coefficients:  out = sd*cd[c] * (Ms : G_c) + sm*cm[c] * vol_c * Mm
+ *   Ms (l,l,NG) device table, NG = (TD+1)(TD+2)/2;  Mm (l,l) device table; either may be NULL. */
+int fb2_elem_scalar_const(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const double* Ms, const double* Mm,
+                          double scal_d, const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* out,
+                          void* stream);
+/* quadrature loop: is_mass 0 -> table = R (NQ,l,TD+1), 1 -> table = phi (NQ,l);
+ * coef_kind 2 -> coef (NC,NQ), 3 -> coef (NC,NQ,GD,GD) (diffusion only). */
+int fb2_elem_scalar_quad(int TD, int p, int64_t NC, const double* node, const int32_t* cell, int is_mass, int NQ, const double* ws,
+                         const double* table, int coef_kind, const double* coef, double* out, void* stream);
+/* isotropic linear elasticity; M4 (l,l,TD+1,TD+1) device table; out (NC, GD*l, GD*l). */
+int fb2_elem_elasticity(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const double* M4, double d_diag,
+                        double d_lam, double d_shear, int dof_priority, double* out, void* stream);
+
+/* ---- K2: deterministic COO -> CSR ---------------------------------------------------------
+ * replaces BilinearForm._scalar_assembly index build (fem/bilinear_form.py:46-75),
+ * COOTensor.coalesce (sparse/coo_tensor.py:184-213) and COOTensor.tocsr (:137-157). */
+int fb2_coo_keys_from_c2d(const int32_t* row_dof, const int32_t* col_dof, int64_t NC, int lr, int lc, int col_bits, uint64_t* keys,
+                          void* stream);
+int fb2_coo_keys_from_coo(const void* row, const void* col, int index_bytes, int64_t n, int col_bits, uint64_t* keys, void* stream);
+size_t fb2_coo_workspace_bytes(int64_t n);
+/* sorts keys in place (perm = original positions), returns the number of distinct keys */
+int fb2_coo_symbolic(uint64_t* keys, uint32_t* perm, int64_t n, int key_bits, void* ws, int64_t* nnz_host, void* stream);
+/* crow (nrow+1, int64), col (nnz, int32 or int64 by col_bytes), seg_start (nnz+1, int64) */
+int fb2_coo_fill(const uint64_t* keys, int64_t n, int col_bits, int64_t nrow, void* ws, int64_t* crow, void* col, int col_bytes,
+                 int64_t* seg_start, void* stream);
+/* values_out[s] = sum (left to right, original COO order) of values_in[perm[k]], k in segment s */
+int fb2_coo_reduce(const uint32_t* perm, const int64_t* seg_start, int64_t nnz, const double* values_in, double* values_out,
+                   void* stream);
+
+/* ---- symbolic + fused numeric assembly (pattern cached per space) -------------------------
+ * Same result as K1 + K2, without materialising the COO: the CSR pattern is a pure function
+ * of cell2dof (fem/bilinear_form.py:69-72), so it is built once (symbolic) and every row then
+ * sums its incident cells in ascending cell order (numeric). */
+size_t fb2_sym_workspace_bytes(int64_t NC, int ldof, int64_t gdof);
+/* step 1: dof -> (cell, local index) adjacency, row lengths; returns nnz and max row length */
+int fb2_sym_count(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, int64_t* adj_ptr, int32_t* adj_pair, int64_t* crow,
+                  int64_t* nnz_host, int32_t* max_row_host, void* ws, void* stream);
+/* step 2: col (nnz) and slot map (NC*ldof pairs x ldof, uint8 when max_row<=255 else uint16) */
+int fb2_sym_fill(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair,
+                 const int64_t* crow, int32_t* col, void* slots, int slot_bytes, void* stream);
+/* numeric, constant / per-cell coefficient scalar forms (diffusion and/or mass fused) */
+int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,
+                              const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
+                              const int64_t* crow, int32_t max_row, const double* Ms, const double* Mm, double scal_d,
+                              const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* values, void* stream);
+/* numeric, generic: gathers rows of a precomputed element-matrix block Ke (NC, lt, lt);
+ * ncomp > 1 = tensor space over the scalar pattern (interleaved or dof-priority layout) */
+int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int64_t gdof_scalar, const double* Ke,
+                         const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
+                         const int64_t* crow_scalar, int32_t max_row, const int64_t* crow_out, double* values, void* stream);
+/* expands the scalar pattern to the tensor-space pattern */
+int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,
+                       int64_t* crow_out, int32_t* col_out, void* stream);
+
+/* ---- K3/K4: SpMV + CG ----------------------------------------------------------------------
+ * replaces CSRTensor.matmul -> bm.csr_spmm (sparse/csr_tensor.py:411-452,
+ * backend/numpy_backend.py:180-199) and fealpy.solver.cg (solver/cg.py:14-123). */
+size_t fb2_partial_workspace_bytes(void);           /* zero-initialise once */
+int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
+                 double* y, void* stream);
+int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
+                 void* stream);
+int fb2_dot(int64_t n, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream);
+size_t fb2_cg_workspace_bytes(int64_t n);
+/* x: x0 on entry, solution on exit.  minv_diag: NULL or the diagonal of M (z = M r).
+ * maxit < 0 means "no limit" (reference maxit=None).  chunk <= 0: automatic. */
+int fb2_cg(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
+           const double* minv_diag, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_host,
+           double* residual_host, void* stream);
+/* building blocks of the distributed driver (device-resident scalars in `scalars`, 256 bytes) */
+int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm, double rTr, void* stream);
+int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
+                    double* Ap, int64_t n_dot, void* scalars, void* partial_ws, void* stream);
+int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,
+                     void* partial_ws, int fuse_finalize, void* stream);
+int fb2_cg_finalize(void* scalars, void* stream);
+int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, void* stream);
+
+/* ---- raw primitives (exported for tests) ---------------------------------------------------*/
+size_t fb2_sort_workspace_bytes(int64_t n);
+int fb2_sort_pairs(uint64_t* keys, uint32_t* vals, int identity_payload, int64_t n, int key_bits, void* ws, void* stream);
+size_t fb2_scan_workspace_bytes(int64_t n);
+int fb2_exclusive_scan_i32(const int32_t* in, int64_t* out, int64_t n, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEALPY_B200_H */

@@ -1,0 +1,239 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against golden outputs of the real
+reference (tests/golden/*.npz) and against the oracle on seeded inputs.  Run with -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+IDS = [c["name"] for c in C.CASES]
+
+
+@pytest.fixture(scope="module")
+def U():
+    import gpu_util
+    return gpu_util
+
+
+@pytest.mark.parametrize("case", [c for c in C.CASES if c.get("jitter") is None], ids=lambda c: c["name"])
+def test_from_box_bit_exact(case, U):
+    gold = G.load(case["name"])
+    mesh = U.make_mesh(case, gold, from_box=True)
+    assert np.array_equal(mesh.node.cpu().numpy(), gold["node"]), "node coordinates must match numpy.linspace bits"
+    assert np.array_equal(mesh.cell.cpu().numpy(), gold["cell"])
+    assert mesh.cell.dtype == torch.int32 and mesh.node.dtype == torch.float64
+
+
+@pytest.mark.parametrize("case", C.CASES, ids=IDS)
+def test_numbering_bit_exact(case, U):
+    gold = G.load(case["name"])
+    mesh = U.make_mesh(case, gold)
+    sspace, space = U.make_space(case, mesh)
+    assert np.array_equal(mesh.edge.cpu().numpy(), gold["edge"])
+    assert np.array_equal(sspace.cell_to_dof().cpu().numpy(), gold["cell2dof_scalar"])
+    assert np.array_equal(space.cell_to_dof().cpu().numpy(), gold["cell2dof"])
+    assert space.number_of_global_dofs() == gold["info"]["gdof"]
+
+
+@pytest.mark.parametrize("case", [c for c in C.CASES if c.get("elem")], ids=lambda c: c["name"])
+def test_element_matrices(case, U):
+    gold = G.load(case["name"])
+    mesh, space, bform, groups = U.make_form(case, gold)
+    k = 0
+    for ints in groups:
+        for it in ints:
+            Ke = it.assembly(space).cpu().numpy()
+            ref = gold[f"Ke_{k}"]
+            assert Ke.shape == ref.shape
+            assert np.max(np.abs(Ke - ref)) <= 1e-12 * np.max(np.abs(ref)), f"K_e[{k}] of {case['name']}"
+            k += 1
+
+
+@pytest.mark.parametrize("path", ["auto", "gather", "coo"])
+@pytest.mark.parametrize("case", C.CASES, ids=IDS)
+def test_assembly_csr(case, path, U):
+    gold = G.load(case["name"])
+    mesh, space, bform, _ = U.make_form(case, gold, path=path)
+    A = bform.assembly()
+    assert A.shape == (gold["info"]["gdof"],) * 2 and A.nnz == gold["info"]["nnz"]
+    U.assert_csr_matches(A, gold)
+    # second call (warm pattern cache) gives the same bits as the first
+    B = bform.assembly()
+    assert torch.equal(A.values, B.values) and torch.equal(A.col, B.col) and torch.equal(A.crow, B.crow)
+
+
+@pytest.mark.parametrize("case", [c for c in C.CASES if c.get("cg")], ids=lambda c: c["name"])
+def test_spmv_and_cg(case, U):
+    from fealpy_b200.solver import cg
+    gold = G.load(case["name"])
+    mesh, space, bform, _ = U.make_form(case, gold)
+    A = bform.assembly()
+    n = A.shape[0]
+    ones = torch.ones(n, dtype=torch.float64, device="cuda")
+    b = A @ ones
+    scale = np.max(np.abs(A.values.cpu().numpy()))
+    assert np.max(np.abs(b.cpu().numpy() - gold["b"])) <= 1e-12 * scale
+    bref = U.t64(gold["b"])
+    x, info = cg(A, bref, returninfo=True)
+    xr = gold["x"]
+    assert np.linalg.norm(x.cpu().numpy() - xr) / np.linalg.norm(xr) <= 1e-10
+    assert abs(info["niter"] - gold["info"]["niter"]) <= 1
+    assert info["residual"] < max(1e-12, 1e-8 * np.linalg.norm(gold["b"]))
+    # inputs untouched, x0 honoured, maxit honoured
+    assert torch.equal(bref, U.t64(gold["b"]))
+    x1, info1 = cg(A, bref, x0=x, returninfo=True)
+    assert info1["niter"] <= 2
+    x2, info2 = cg(A, bref, maxit=3, returninfo=True)
+    assert info2["niter"] == 3
+    xz = cg(A, torch.zeros_like(bref))
+    assert float(xz.abs().max()) == 0.0
+
+
+def test_jacobi_preconditioned_cg_matches_oracle(U):
+    from oracle import fem_oracle as O
+    from fealpy_b200.solver import cg
+    case = C.by_name("tet_p2_4_diffmass_jit")
+    gold = G.load(case["name"])
+    mesh, space, bform, _ = U.make_form(case, gold)
+    A = bform.assembly()
+    d = A.diags()
+    x, info = cg(A, U.t64(gold["b"]), M=1.0 / d, returninfo=True)
+    crow, col, val = gold["crow"], gold["col"], gold["values"]
+    diag = O.csr_matvec(crow, col, val, np.ones(len(crow) - 1)) * 0
+    rows = np.repeat(np.arange(len(crow) - 1), np.diff(crow))
+    diag = np.zeros(len(crow) - 1); np.add.at(diag, rows[rows == col], val[rows == col])
+    xo, oinfo = O.cg(lambda v: O.csr_matvec(crow, col, val, v), gold["b"], Minv=lambda r: r / diag)
+    assert abs(info["niter"] - oinfo["niter"]) <= 1
+    assert np.linalg.norm(x.cpu().numpy() - xo) / np.linalg.norm(xo) <= 1e-10
+
+
+def test_sort_and_scan_primitives(U):
+    import ctypes as Ct
+    from fealpy_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n, bits in [(1, 8), (37, 5), (4096, 13), (100003, 40), (1 << 20, 50)]:
+        keys_np = rng.integers(0, 1 << bits, size=n, dtype=np.uint64)
+        keys = torch.as_tensor(keys_np.view(np.int64), device="cuda")
+        vals = torch.empty(n, dtype=torch.int32, device="cuda")
+        ws = _lib.workspace(lib.fb2_sort_workspace_bytes(n), "cuda")
+        _lib.call("fb2_sort_pairs", _lib.ptr(keys), _lib.ptr(vals), 1, n, bits, _lib.ptr(ws), _lib.stream())
+        order = np.argsort(keys_np, kind="stable")
+        assert np.array_equal(keys.cpu().numpy().view(np.uint64), keys_np[order])
+        assert np.array_equal(vals.cpu().numpy().view(np.uint32), order.astype(np.uint32)), "sort must be stable"
+    for n in [1, 255, 4096, 4097, 1000003]:
+        a = rng.integers(0, 7, size=n, dtype=np.int32)
+        out = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+        ws = _lib.workspace(lib.fb2_scan_workspace_bytes(n), "cuda")
+        _lib.call("fb2_exclusive_scan_i32", _lib.ptr(U.t64(a)), _lib.ptr(out), n, _lib.ptr(ws), _lib.stream())
+        assert np.array_equal(out.cpu().numpy(), np.concatenate([[0], np.cumsum(a, dtype=np.int64)]))
+
+
+def test_reference_sparse_vectors(U):
+    # test/sparse/test_coo_tensor.py:29-48 and :377-392 of the reference
+    from fealpy_b200.sparse import COOTensor
+    RT = G.ref_testdata()
+    coo = COOTensor(U.t64(RT["coo_indices"]), U.t64(RT["coo_values"]), (3, 3), is_coalesced=False)
+    c = coo.coalesce()
+    assert c.is_coalesced
+    assert np.array_equal(c.indices.cpu().numpy(), RT["coo_expected_indices"])
+    assert np.array_equal(c.values.cpu().numpy(), RT["coo_expected_values"])
+    D = RT["tocsr_dense"]
+    rr, cc = np.nonzero(D)
+    A = COOTensor(U.t64(np.stack([rr, cc])), U.t64(D[rr, cc]), D.shape, is_coalesced=True).tocsr()
+    assert np.array_equal(A.crow.cpu().numpy(), RT["tocsr_crow"])
+    assert np.array_equal(A.col.cpu().numpy(), RT["tocsr_col"])
+    assert np.array_equal(A.values.cpu().numpy(), RT["tocsr_values"])
+    assert np.array_equal(A.toarray().cpu().numpy(), D)
+
+
+def test_reference_element_vectors(U):
+    # test/fem/test_scalar_diffusion_integrator.py:16-24, test_scalar_mass_integrator.py:16-24
+    from fealpy_b200.mesh import TriangleMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import ScalarDiffusionIntegrator, ScalarMassIntegrator
+    RT = G.ref_testdata()
+    mesh = TriangleMesh.from_box([0, 1, 0, 1], 1, 1)
+    space = LagrangeFESpace(mesh, 2)
+    np.testing.assert_array_almost_equal(ScalarDiffusionIntegrator(1, 3).assembly(space).cpu().numpy(), RT["diffusion_p2_q3_box1_Ke"])
+    np.testing.assert_array_almost_equal(ScalarMassIntegrator(1, 3).assembly(space).cpu().numpy(), RT["mass_p2_q3_box1_Ke"])
+    assert np.array_equal(space.cell_to_dof().cpu().numpy(), RT["lfs_box1_p2_cell_to_dof"])
+    assert np.array_equal(space.is_boundary_dof().cpu().numpy(), RT["lfs_box1_p2_is_boundary_dof"])
+
+
+@pytest.mark.parametrize("k", [0, 1])
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_reference_bilinear_form_matmul(k, p, U):
+    # test/fem/test_bilinear_form.py:19-44: element-wise product == assembled product
+    from fealpy_b200.mesh import TriangleMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator
+    RT = G.ref_testdata()
+    mesh = TriangleMesh(U.t64(RT[f"bform_mesh{k}_node"]), U.t64(RT[f"bform_mesh{k}_cell"].astype(np.int32)))
+    space = LagrangeFESpace(mesh, p)
+    gdof = space.number_of_global_dofs()
+    x = torch.rand(gdof, dtype=torch.float64, device="cuda")
+    I = ScalarDiffusionIntegrator()
+    Ke, c2d = I.assembly(space), space.cell_to_dof().long()
+    y = torch.zeros(gdof, dtype=torch.float64, device="cuda")
+    y.index_add_(0, c2d.reshape(-1), torch.einsum("cij,cj->ci", Ke, x[c2d]).reshape(-1))
+    bform = BilinearForm(space).add_integrator(I)
+    z = bform.assembly() @ x
+    assert float((y - z).norm()) < 1e-12
+
+
+@pytest.mark.parametrize("mesh_kind,p,n", [("tri", 1, 96), ("tri", 3, 40), ("tet", 1, 20), ("tet", 2, 14), ("tet", 3, 6)])
+def test_paths_agree_and_properties_at_size(mesh_kind, p, n, U):
+    """sizes beyond the golden ladder: the three device paths must give the same pattern
+    bit-for-bit and values to 1e-12; diffusion rows sum to 0, the mass matrix sums to |domain|,
+    both symmetric (size-independent properties)."""
+    from fealpy_b200.mesh import TriangleMesh, TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    mesh = TriangleMesh.from_box([0, 1, 0, 1], n, n) if mesh_kind == "tri" else TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], n, n, n)
+    space = LagrangeFESpace(mesh, p)
+    mats = {}
+    for path in ("auto", "gather", "coo"):
+        bf = BilinearForm(space, assembly_path=path)
+        bf.add_integrator(ScalarDiffusionIntegrator())
+        bf.add_integrator(ScalarMassIntegrator())
+        mats[path] = bf.assembly()
+    A = mats["auto"]
+    scale = float(A.values.abs().max())
+    for path in ("gather", "coo"):
+        B = mats[path]
+        assert torch.equal(A.crow, B.crow) and torch.equal(A.col, B.col), path
+        assert float((A.values - B.values).abs().max()) <= 1e-12 * scale, path
+    one = torch.ones(A.shape[0], dtype=torch.float64, device="cuda")
+    K = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).assembly()
+    Mm = BilinearForm(space).add_integrator(ScalarMassIntegrator()).assembly()
+    assert float((K @ one).abs().max()) <= 1e-11 * float(K.values.abs().max())
+    assert abs(float((Mm @ one).sum()) - 1.0) <= 1e-12
+    S = A.to_scipy()
+    assert abs(S - S.T).max() <= 1e-12 * scale
+    assert S.has_sorted_indices, "columns must be ascending within every row"
+
+
+def test_unsupported_features_raise(U):
+    from fealpy_b200.mesh import TriangleMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator
+    from fealpy_b200.solver import cg
+    mesh = TriangleMesh.from_box([0, 1, 0, 1], 2, 2)
+    with pytest.raises(NotImplementedError):
+        LagrangeFESpace(mesh, 4)
+    space = LagrangeFESpace(mesh, 1)
+    with pytest.raises(NotImplementedError):
+        BilinearForm(space, batch_size=2)
+    with pytest.raises(NotImplementedError):
+        ScalarDiffusionIntegrator(method="isopara")
+    with pytest.raises(ValueError):
+        BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).assembly(format="dense")
+    A = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).assembly()
+    with pytest.raises(ValueError):
+        cg(A, torch.zeros(3, dtype=torch.float64, device="cuda"))
+    with pytest.raises(TypeError):
+        cg(A.to_scipy(), torch.zeros(A.shape[0], dtype=torch.float64, device="cuda"))
