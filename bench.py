@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: P2 tetrahedral Poisson (diffusion + mass) global assembly to CSR
+plus CG, on synthetic `TetrahedronMesh.from_box` meshes (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the CPU arm (oracle port of the reference)
+
+One "step" = one assembly() of the form (pattern cached per space = "warm") followed by a
+fixed number of CG iterations on A x = A 1.  `value` = assembled nnz/s with all inputs resident
+in HBM; `cg.iters_per_s` is reported beside it; `e2e` repeats the step through the public API
+with HOST (pinned) inputs: H2D of node/cell/cell2dof and of b, D2H of the CSR values and of x,
+all inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "assembled_nnz_per_s"
+UNIT = "nnz/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=128, help="cells per box edge (per GPU)")
+    ap.add_argument("--p", type=int, default=2)
+    ap.add_argument("--cg-iters", type=int, default=100)
+    ap.add_argument("--cpu-n", type=int, default=20, help="box edge of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_problem(n, p):
+    from oracle import fem_oracle as O
+    node, cell = O.tet_from_box([0, 1, 0, 1, 0, 1], n, n, n)
+    mesh = O.Mesh(node, cell)
+    c2d = mesh.cell_to_ipoint(p)
+    return O, mesh, c2d, mesh.number_of_global_ipoints(p)
+
+
+def cpu_step(O, mesh, c2d, gdof, p, cg_iters):
+    t0 = time.perf_counter()
+    groups = [(O.diffusion_element(mesh, p), c2d), (O.mass_element(mesh, p), c2d)]
+    crow, col, val = O.assemble(groups, gdof)
+    t1 = time.perf_counter()
+    b = O.csr_matvec(crow, col, val, __import__("numpy").ones(gdof))
+    t2 = time.perf_counter()
+    x, info = O.cg(lambda v: O.csr_matvec(crow, col, val, v), b, atol=0.0, rtol=0.0, maxit=cg_iters)
+    t3 = time.perf_counter()
+    return len(val), t1 - t0, info["niter"], t3 - t2
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O, mesh, c2d, gdof = cpu_problem(args.cpu_n, args.p)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(O, mesh, c2d, gdof, args.p, 5)
+    t_asm = t_cg = 0.0
+    nnz = its = 0
+    for _ in range(args.steps):
+        nz, ta, it, tc = cpu_step(O, mesh, c2d, gdof, args.p, args.cg_iters)
+        nnz += nz; t_asm += ta; its += it; t_cg += tc
+    val = nnz / t_asm
+    sample = f"tet P{args.p} from_box n={args.cpu_n} ({mesh.NC} cells, gdof {gdof}), diffusion+mass q={args.p + 3}, numpy oracle port"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * (t_asm + t_cg) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"tet P{args.p} Poisson diffusion+mass assembly + CG, from_box n=128 per GPU (CPU arm: bounded sample)"},
+        "cg": {"iters_per_s": its / t_cg, "iters_per_step": args.cg_iters},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "cg_iters_per_s": its / t_cg},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from fealpy_b200.mesh import TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    from fealpy_b200.fem.bilinear_form import symbolic_pattern
+    from fealpy_b200.solver import cg
+
+    n, p = args.n, args.p
+    stream = torch.cuda.Stream(device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        # ---- setup (not timed as part of the step; reported as cold costs) --------------------
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        # weak scaling: every rank owns an n^3 box (independent sub-domain)
+        mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], n, n, n, device=dev)
+        space = LagrangeFESpace(mesh, p)
+        c2d = space.cell_to_dof()
+        e1.record()
+        sym = symbolic_pattern(space)
+        e2.record()
+        bform = BilinearForm(space)
+        bform.add_integrator(ScalarDiffusionIntegrator())
+        bform.add_integrator(ScalarMassIntegrator())
+        A = bform.assembly()
+        e3.record()
+        torch.cuda.synchronize(dev)
+        t_mesh, t_sym, t_first = e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)
+        nnz, gdof, NC, NN = A.nnz, A.shape[0], mesh.number_of_cells(), mesh.number_of_nodes()
+        L = c2d.shape[1]
+        ones = torch.ones(gdof, dtype=torch.float64, device=dev)
+        b = A @ ones
+
+        def step():
+            s0, s1, s2 = ev(), ev(), ev()
+            s0.record()
+            A_ = bform.assembly()
+            s1.record()
+            x, info = cg(A_, b, atol=0.0, rtol=0.0, maxit=args.cg_iters, returninfo=True)
+            s2.record()
+            return s0, s1, s2, info["niter"], x
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        t_wall0 = time.perf_counter()
+        recs = [step() for _ in range(args.steps)]
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop() if rank == 0 else {}
+        t_asm = sum(r[0].elapsed_time(r[1]) for r in recs) * 1e-3
+        t_cg = sum(r[1].elapsed_time(r[2]) for r in recs) * 1e-3
+        iters = sum(r[3] for r in recs)
+        xerr = float((recs[-1][4] - 1.0).abs().max())
+
+        # ---- e2e: host (pinned) inputs, copies inside the timed region ------------------------------
+        e2e = None
+        if not args.no_e2e:
+            h_node, h_cell, h_c2d = (t.cpu().pin_memory() for t in (mesh.node, mesh.cell, c2d))
+            h_b = b.cpu().pin_memory()
+            h_vals = torch.empty(nnz, dtype=torch.float64).pin_memory()
+            h_x = torch.empty(gdof, dtype=torch.float64).pin_memory()
+
+            def e2e_step():
+                s0, s1, s2 = ev(), ev(), ev()
+                s0.record()
+                mesh.node.copy_(h_node, non_blocking=True)
+                mesh.cell.copy_(h_cell, non_blocking=True)
+                c2d.copy_(h_c2d, non_blocking=True)
+                A_ = bform.assembly()
+                h_vals.copy_(A_.values, non_blocking=True)
+                s1.record()
+                b.copy_(h_b, non_blocking=True)
+                x, info = cg(A_, b, atol=0.0, rtol=0.0, maxit=args.cg_iters, returninfo=True)
+                h_x.copy_(x, non_blocking=True)
+                s2.record()
+                return s0, s1, s2, info["niter"]
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            er = [e2e_step() for _ in range(max(2, min(args.steps, 5)))]
+            barrier()
+            ta = sum(r[0].elapsed_time(r[1]) for r in er) * 1e-3
+            tc = sum(r[1].elapsed_time(r[2]) for r in er) * 1e-3
+            e2e = {"value": nnz * len(er) / ta, "unit": UNIT,
+                   "h2d_bytes_per_step": int(h_node.nbytes + h_cell.nbytes + h_c2d.nbytes + h_b.nbytes),
+                   "d2h_bytes_per_step": int(h_vals.nbytes + h_x.nbytes),
+                   "cg_iters_per_s": sum(r[3] for r in er) / tc,
+                   "note": "assembly: H2D node+cell+cell2dof -> assembly() -> D2H values; CG: H2D b -> cg -> D2H x"}
+
+    # ---- reduce over ranks (max time) ----------------------------------------------------------------
+    times = torch.tensor([t_asm, t_cg, t_wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        if e2e is not None:
+            ev_ = torch.tensor([nnz * 1.0 / e2e["value"], 1.0 / e2e["cg_iters_per_s"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(ev_, op=dist.ReduceOp.MAX)
+            e2e["value"] = world * nnz / float(ev_[0])
+            e2e["cg_iters_per_s"] = 1.0 / float(ev_[1])
+    t_asm, t_cg, t_wall = (float(v) for v in times)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # algorithmic bytes, per launch == per step for both kernels
+        b_asm = 4 * NC * 4 + 4 * NC * L + 8 * 3 * NN + 12 * nnz + 8 * (gdof + 1)
+        b_it = 12 * nnz + 8 * (gdof + 1) + 104 * gdof
+        asm_gbs = b_asm * args.steps / t_asm / 1e9
+        cg_gbs = b_it * iters / t_cg / 1e9
+        line = {
+            "metric": METRIC, "value": world * nnz * args.steps / t_asm, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * (t_asm + t_cg) / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"tet P{p} Poisson: ScalarDiffusionIntegrator + ScalarMassIntegrator (q={p + 3}) assembly to CSR "
+                                   f"+ {args.cg_iters} CG iterations, TetrahedronMesh.from_box n={n} per GPU",
+                       "NC": NC, "gdof": gdof, "nnz": nnz, "l2_policy": "inputs larger than L2 (multi-GB arrays per step)",
+                       "assembly_path": bform.last_path, "pattern": "warm (symbolic cached per space)",
+                       "parallelism": f"{world} independent sub-domains" if world > 1 else "single GPU"},
+            "cg": {"iters_per_s": iters / t_cg, "iters_per_step": args.cg_iters, "ms_per_iter": 1e3 * t_cg / iters,
+                   "x_err_vs_exact": xerr},
+            "assembly_ms": 1e3 * t_asm / args.steps,
+            "cold": {"mesh_topology_ms": t_mesh, "symbolic_ms": t_sym, "first_assembly_ms": t_first,
+                     "nnz_per_s_incl_symbolic": nnz / ((t_sym + t_first) * 1e-3)},
+            "roofline": {"bound": "hbm", "kernel": "spmv_kernel (CG iteration = spmv+dot, update_xr, update_p)",
+                         "achieved": cg_gbs, "peak": peak, "unit": "GB/s", "frac": cg_gbs / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_iter": b_it},
+            "roofline_assembly": {"bound": "hbm", "kernel": "assemble_const_kernel", "achieved": asm_gbs, "peak": peak,
+                                  "unit": "GB/s", "frac": asm_gbs / peak, "traffic": None, "algorithmic_bytes": b_asm},
+            "e2e": e2e, "gpu_launches": args.steps * (1 + 3 * args.cg_iters + 4),
+            "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            O, om, oc2d, ogdof = cpu_problem(args.cpu_n, p)
+            nz, ta, it, tc = cpu_step(O, om, oc2d, ogdof, p, min(args.cg_iters, 50))
+            line["cpu_baseline"] = {"value": nz / ta, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"tet P{p} from_box n={args.cpu_n} ({om.NC} cells, nnz {nz}), numpy oracle port of the "
+                                              f"reference path, {ta:.1f}s assembly",
+                                    "cg_iters_per_s": it / tc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

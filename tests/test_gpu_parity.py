@@ -237,3 +237,56 @@ def test_unsupported_features_raise(U):
         cg(A, torch.zeros(3, dtype=torch.float64, device="cuda"))
     with pytest.raises(TypeError):
         cg(A.to_scipy(), torch.zeros(A.shape[0], dtype=torch.float64, device="cuda"))
+
+
+def test_fused_vs_sorted_coo_at_64(U):
+    """config-2 family at n=64 (1.57M cells, 61M nnz, 315M COO entries through the radix sort):
+    the fused row-owner path and the literal COO sort path give the same CSR."""
+    from fealpy_b200.mesh import TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], 64, 64, 64)
+    space = LagrangeFESpace(mesh, 2)
+    out = {}
+    for path in ("auto", "coo"):
+        bf = BilinearForm(space, assembly_path=path)
+        bf.add_integrator(ScalarDiffusionIntegrator())
+        bf.add_integrator(ScalarMassIntegrator())
+        out[path] = bf.assembly()
+    A, B = out["auto"], out["coo"]
+    assert A.nnz == 60_865_793 == B.nnz and A.shape[0] == 2_146_689       # closed forms of SURVEY.md section 8
+    assert torch.equal(A.crow, B.crow) and torch.equal(A.col, B.col)
+    assert float((A.values - B.values).abs().max()) <= 1e-12 * float(A.values.abs().max())
+
+
+def test_config2_full_size_properties(U):
+    """BASELINE config 2 (tet P2, 128^3): sizes, pattern invariants, K 1 = 0, 1^T M 1 = 1, CG recovers x = 1."""
+    from fealpy_b200.mesh import TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    from fealpy_b200.solver import cg
+    mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], 128, 128, 128)
+    space = LagrangeFESpace(mesh, 2)
+    assert mesh.number_of_cells() == 12_582_912 and space.number_of_global_dofs() == 16_974_593
+    K = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).assembly()
+    assert K.nnz == 484_609_025
+    one = torch.ones(K.shape[0], dtype=torch.float64, device="cuda")
+    assert float((K @ one).abs().max()) <= 1e-10 * float(K.values.abs().max())
+    crow, col = K.crow, K.col
+    assert int(crow[0]) == 0 and int(crow[-1]) == K.nnz and bool((crow[1:] > crow[:-1]).all())
+    inner = torch.ones(K.nnz, dtype=torch.bool, device="cuda")
+    inner[crow[1:-1]] = False                                   # first entry of every row but row 0
+    assert bool((col[1:] > col[:-1])[inner[1:]].all()), "columns strictly ascending within rows"
+    del inner
+    vK = K.values.clone()
+    del K
+    Mm = BilinearForm(space).add_integrator(ScalarMassIntegrator()).assembly()
+    assert abs(float((Mm @ one).sum()) - 1.0) <= 1e-11
+    bf = BilinearForm(space)
+    bf.add_integrator(ScalarDiffusionIntegrator())
+    bf.add_integrator(ScalarMassIntegrator())
+    A = bf.assembly()
+    assert float((A.values - (vK + Mm.values)).abs().max()) <= 1e-12 * float(A.values.abs().max())   # linearity
+    b = A @ one
+    x, info = cg(A, b, returninfo=True)
+    assert info["niter"] < 2000 and float((x - 1.0).abs().max()) < 1e-6
