@@ -156,9 +156,26 @@ int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const i
 
 // ---- K3/K4 ----------------------------------------------------------------------------------
 size_t fb2_partial_workspace_bytes(void) { return partial_workspace_bytes(); }
+int fb2_spmv_plan_blocks(int64_t nnz, int tile) { return spmv_plan_blocks(nnz, tile); }
+int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t nnz, int32_t* max_row_host,
+                        void* stream) {
+  const int nblk = spmv_plan_blocks(nnz, tile);
+  int* dmax = blk_row + nblk + 1;        // the caller allocates nblk + 2 entries; the last one is scratch
+  FB2_TRY(spmv_plan_build(n, crow, tile, nblk, blk_row, dmax, S(stream)));
+  FB2_CUDA(cudaMemcpyAsync(max_row_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+  FB2_CUDA(cudaStreamSynchronize(S(stream)));
+  return OK;
+}
+static SpmvPlan make_plan(const int32_t* blk_row, int64_t nnz, int tile, int max_row) {
+  SpmvPlan pl{};
+  pl.blk_row = blk_row; pl.tile = tile; pl.max_row = max_row;
+  pl.nblk = blk_row ? spmv_plan_blocks(nnz, tile) : 0;
+  return pl;
+}
 int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x, double* y,
-                 void* stream) {
-  return spmv(n, nnz, crow, col, values, x, y, nullptr, 0, nullptr, nullptr, S(stream));
+                 const int32_t* blk_row, int tile, int32_t max_row, void* stream) {
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
+  return spmv(n, nnz, crow, col, values, x, y, nullptr, 0, nullptr, nullptr, S(stream), blk_row ? &pl : nullptr);
 }
 int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
                  void* stream) {
@@ -167,11 +184,11 @@ int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const doubl
 int fb2_dot(int64_t n, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream) {
   return dot(n, a, b, out_dev, partial_ws, S(stream));
 }
-size_t fb2_cg_workspace_bytes(int64_t n) { return cg_workspace_bytes(n); }
-int fb2_cg(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
+size_t fb2_cg_workspace_bytes(int64_t n, int64_t nnz) { return cg_workspace_bytes(n, nnz); }
+int fb2_cg(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
            const double* minv_diag, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_host,
            double* residual_host, void* stream) {
-  return cg_solve(n, crow, col, values, b, x, minv_diag, atol, rtol, maxit, chunk, ws, niter_host, residual_host, S(stream));
+  return cg_solve(n, nnz, crow, col, values, b, x, minv_diag, atol, rtol, maxit, chunk, ws, niter_host, residual_host, S(stream));
 }
 int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm, double rTr, void* stream) {
   CgScalars* sc = static_cast<CgScalars*>(scalars);
@@ -182,11 +199,10 @@ int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm
   return OK;
 }
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, int64_t n_dot, void* scalars, void* partial_ws, void* stream) {
-  // local rows only contribute to p.Ap (n_dot == n: rows are the owned dofs)
-  (void)n_dot;
+                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars, void* partial_ws, void* stream) {
   CgScalars* sc = static_cast<CgScalars*>(scalars);
-  return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, &sc->pAp, partial_ws, S(stream));
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
+  return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, &sc->pAp, partial_ws, S(stream), blk_row ? &pl : nullptr);
 }
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,
                      void* partial_ws, int fuse_finalize, void* stream) {

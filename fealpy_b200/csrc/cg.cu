@@ -113,6 +113,87 @@ __global__ void __launch_bounds__(CG_THREADS) spmm_kernel(int64_t n, const int64
   }
 }
 
+// ---- SpMV, "row-aligned nnz tiles": CTA b owns the rows whose first entry index lies in
+// [b*tile, (b+1)*tile).  Phase 1 streams the tile's (val, col) with perfectly coalesced, deeply
+// unrolled loads (memory-level parallelism independent of the row lengths), gathers x and
+// parks the products in shared memory; phase 2 reduces each row with G lanes.  Row sums and
+// the fused p.Ap partials are formed in a fixed order -> bitwise reproducible.
+constexpr int ST_UNROLL = 4;
+
+template <int G>
+__global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, const int64_t* __restrict__ crow,
+                                                                 const int32_t* __restrict__ col, const double* __restrict__ val,
+                                                                 const double* __restrict__ x, double* __restrict__ y,
+                                                                 const double* __restrict__ b, int mode,
+                                                                 const int32_t* __restrict__ blk_row, int nblk, double* dot_out,
+                                                                 double* partials, unsigned int* counter, const CgScalars* sc) {
+  if (sc && sc->done) return;
+  extern __shared__ __align__(16) double prod[];
+  const int tid = threadIdx.x;
+  const int g = tid % G, grp = tid / G;
+  constexpr int NGRP = CG_THREADS / G;
+  double dsum = 0.0;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int r0 = blk_row[blk], r1 = blk_row[blk + 1];
+    if (r0 == r1) continue;
+    const int64_t v0 = crow[r0];
+    const int nval = (int)(crow[r1] - v0);
+    const double* __restrict__ vp = val + v0;
+    const int32_t* __restrict__ cp = col + v0;
+    int k = tid;
+    for (; k + (ST_UNROLL - 1) * CG_THREADS < nval; k += ST_UNROLL * CG_THREADS) {
+      double vv[ST_UNROLL];
+      int cc[ST_UNROLL];
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u) { vv[u] = ld_stream(vp + k + u * CG_THREADS); cc[u] = ld_stream(cp + k + u * CG_THREADS); }
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * CG_THREADS] = vv[u] * x[cc[u]];
+    }
+    for (; k < nval; k += CG_THREADS) prod[k] = ld_stream(vp + k) * x[ld_stream(cp + k)];
+    __syncthreads();
+    for (int base = r0; base < r1; base += NGRP) {
+      const int r = base + grp;
+      double acc = 0.0;
+      if (r < r1) {
+        const int s = (int)(crow[r] - v0), e = (int)(crow[r + 1] - v0);
+        for (int q = s + g; q < e; q += G) acc += prod[q];
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (r < r1 && g == 0) {
+        const double yv = mode ? b[r] - acc : acc;
+        y[r] = yv;
+        if (dot_out) dsum += x[r] * yv;
+      }
+    }
+    __syncthreads();
+  }
+  if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
+}
+
+__global__ void __launch_bounds__(256) partition_rows_kernel(const int64_t* __restrict__ crow, int64_t n, int tile, int nblk,
+                                                             int32_t* __restrict__ blk_row) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nblk) return;
+  if (b == nblk) { blk_row[b] = (int32_t)n; return; }
+  const int64_t target = (int64_t)b * tile;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (crow[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  blk_row[b] = (int32_t)lo;
+}
+
+__global__ void __launch_bounds__(256) max_row_kernel(const int64_t* __restrict__ crow, int64_t n, int* out) {
+  int m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, (int)(crow[i + 1] - crow[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 __global__ void __launch_bounds__(CG_THREADS) dot_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
                                                          double* out, double* partials, unsigned int* counter) {
   double acc = 0.0;
@@ -219,10 +300,48 @@ static void launch_spmv(int64_t n, const int64_t* crow, const int32_t* col, cons
   spmv_kernel<T><<<(unsigned)(nbk < 1 ? 1 : nbk), CG_THREADS, 0, s>>>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc);
 }
 
+int spmv_plan_blocks(int64_t nnz, int tile) { return (int)ceil_div(nnz > 0 ? nnz : 1, tile); }
+
+// blk_row (nblk+1 int32) and the longest row; *max_row_dev is a device int (zeroed here)
+int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t* blk_row, int* max_row_dev, cudaStream_t s) {
+  if (n >= ((int64_t)1 << 31)) return fail(ERR_UNSUPPORTED, "spmv_plan: more than 2^31 rows");
+  FB2_CUDA(cudaMemsetAsync(max_row_dev, 0, sizeof(int), s));
+  partition_rows_kernel<<<(unsigned)ceil_div(nblk + 1, 256), 256, 0, s>>>(crow, n, tile, nblk, blk_row);
+  if (n > 0) max_row_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSM * 8), 256, 0, s>>>(crow, n, max_row_dev);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x,
+                              double* y, const double* b, int mode, const SpmvPlan& plan, double* dot_out, double* partials,
+                              unsigned int* counter, const CgScalars* sc, cudaStream_t s) {
+  const size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
+  const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
+  const int per_sm = (int)std::min<size_t>(8, (200 * 1024) / (smem + 1024));
+  int grid = std::min(plan.nblk, kNumSM * std::max(per_sm, 1));
+  if (grid > CG_PARTIALS) grid = CG_PARTIALS;
+  if (grid < 1) grid = 1;
+#define FB2_ST(GV)                                                                                             \
+  do {                                                                                                         \
+    auto kern = spmv_stream_kernel<GV>;                                                                        \
+    if (smem > 48 * 1024) FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, CG_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc); \
+  } while (0)
+  if (avg <= 6.0) FB2_ST(2);
+  else if (avg <= 12.0) FB2_ST(4);
+  else if (avg <= 48.0) FB2_ST(8);
+  else FB2_ST(16);
+#undef FB2_ST
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
 static int spmv_impl(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
                      const double* b, int mode, double* dot_out, double* partials, unsigned int* counter, const CgScalars* sc,
-                     cudaStream_t s) {
+                     cudaStream_t s, const SpmvPlan* plan = nullptr) {
   if (n <= 0) return OK;
+  if (plan && plan->blk_row && (size_t)(plan->tile + plan->max_row) * 8 <= 200 * 1024)
+    return spmv_stream_launch(n, nnz, crow, col, val, x, y, b, mode, *plan, dot_out, partials, counter, sc, s);
   switch (pick_T(n, nnz)) {
     case 2: launch_spmv<2>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
     case 4: launch_spmv<4>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
@@ -245,16 +364,19 @@ struct PartialWs {
   static size_t bytes() { return align_up(CG_PARTIALS * sizeof(double) + 64); }
 };
 
-size_t cg_workspace_bytes(int64_t n) {
-  return PartialWs::bytes() + align_up(sizeof(CgScalars)) + 3 * align_up((size_t)n * sizeof(double)) + 1024;
+constexpr int CG_TILE = 2048;
+
+size_t cg_workspace_bytes(int64_t n, int64_t nnz) {
+  return PartialWs::bytes() + align_up(sizeof(CgScalars)) + 3 * align_up((size_t)n * sizeof(double)) +
+         align_up((size_t)(spmv_plan_blocks(nnz, CG_TILE) + 2) * sizeof(int32_t)) + 1024;
 }
 
 int spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
-         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s) {
+         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s, const SpmvPlan* plan) {
   if (dot_out && !partial_ws) return fail(ERR_INVALID, "spmv: fused dot needs the (zero-initialised) partial workspace");
   PartialWs pw(partial_ws);
   return spmv_impl(n, nnz, crow, col, val, x, y, b, mode, dot_out, partial_ws ? pw.partials : nullptr,
-                   partial_ws ? pw.counter : nullptr, nullptr, s);
+                   partial_ws ? pw.counter : nullptr, nullptr, s, plan);
 }
 size_t partial_workspace_bytes() { return PartialWs::bytes(); }
 
@@ -297,7 +419,7 @@ int cg_update_p(int64_t n, double* p, const double* r, const double* minv, CgSca
   return OK;
 }
 
-int cg_solve(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* b, double* x,
+int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* b, double* x,
              const double* minv, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_out, double* resid_out,
              cudaStream_t user_stream) {
   *niter_out = 0;
@@ -323,9 +445,14 @@ int cg_solve(int64_t n, const int64_t* crow, const int32_t* col, const double* v
   double* p = c.take<double>(n);
   double* Ap = c.take<double>(n);
   PartialWs pw(pws);
-  int64_t nnz = 0;
-  FB2_CUDA(cudaMemcpyAsync(&nnz, crow + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  SpmvPlan plan{};
+  plan.tile = CG_TILE;
+  plan.nblk = spmv_plan_blocks(nnz, CG_TILE);
+  int32_t* blk_row = c.take<int32_t>(plan.nblk + 2);
+  plan.blk_row = blk_row;
   FB2_TRY(cg_init_scalars(sc, atol, rtol, maxit < 0 ? INT_MAX : maxit, s));
+  FB2_TRY(spmv_plan_build(n, crow, CG_TILE, plan.nblk, blk_row, &sc->pad, s));
+  FB2_CUDA(cudaMemcpyAsync(&plan.max_row, &sc->pad, sizeof(int), cudaMemcpyDeviceToHost, s));
   // |b| and the zero-rhs early return (solver/cg.py:79-80)
   dot_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, b, b, &sc->dot_tmp, pw.partials, &sc->counter[0]);
   double bb = 0.0;
@@ -338,7 +465,7 @@ int cg_solve(int64_t n, const int64_t* crow, const int32_t* col, const double* v
   }
   FB2_CUDA(cudaMemcpyAsync(&sc->bnorm, &bnorm, sizeof(double), cudaMemcpyHostToDevice, s));
   // r = b - A x0 ; p = z = M r ; rTr = r.z
-  FB2_TRY(spmv_impl(n, nnz, crow, col, val, x, r, b, 1, nullptr, nullptr, nullptr, nullptr, s));
+  FB2_TRY(spmv_impl(n, nnz, crow, col, val, x, r, b, 1, nullptr, nullptr, nullptr, nullptr, s, &plan));
   cg_start_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, r, minv, p, sc, pw.partials);
   FB2_LAUNCH_CHECK();
 
@@ -355,7 +482,7 @@ int cg_solve(int64_t n, const int64_t* crow, const int32_t* col, const double* v
   FB2_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = OK;
   for (int k = 0; k < chunk && rc == OK; ++k) {
-    rc = spmv_impl(n, nnz, crow, col, val, p, Ap, nullptr, 0, &sc->pAp, pw.partials, &sc->counter[0], sc, s);
+    rc = spmv_impl(n, nnz, crow, col, val, p, Ap, nullptr, 0, &sc->pAp, pw.partials, &sc->counter[0], sc, s, &plan);
     if (rc == OK) rc = cg_update_xr(n, x, r, p, Ap, minv, sc, pws, 1, s);
     if (rc == OK) rc = cg_update_p(n, p, r, minv, sc, s);
   }

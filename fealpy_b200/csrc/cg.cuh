@@ -11,21 +11,29 @@ struct CgScalars {
   unsigned int counter[4];   // last-block-done tickets for the three reductions
 };
 
-constexpr int CG_PARTIALS = 4096;   // max blocks contributing partial sums per reduction
+constexpr int CG_PARTIALS = 4096;
 
-size_t cg_workspace_bytes(int64_t n);
+// row-aligned nnz tiling of a CSR matrix (built once per matrix, see spmv_plan_build)
+struct SpmvPlan {
+  const int32_t* blk_row = nullptr;   // (nblk+1) first row of every tile
+  int nblk = 0, tile = 0, max_row = 0;
+};   // max blocks contributing partial sums per reduction
+
+size_t cg_workspace_bytes(int64_t n, int64_t nnz);
+int spmv_plan_blocks(int64_t nnz, int tile);
+int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t* blk_row, int* max_row_dev, cudaStream_t s);
 
 // y = A x  (mode 0),  y = b - A x (mode 1); optional fused dot  sum_r x[r]*y[r] -> *dot_out (deterministic)
 size_t partial_workspace_bytes();
 int spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
-         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s);
+         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s, const SpmvPlan* plan = nullptr);
 // SpMM with a row-major (n, nb) dense block: Y = A X
 int spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* X, double* Y, int nb, cudaStream_t s);
 // deterministic dot product
 int dot(int64_t n, const double* a, const double* b, double* out, void* partial_ws, cudaStream_t s);
 
 // full solve: reference recurrence (solver/cg.py:76-123); x holds x0 on entry, the solution on exit
-int cg_solve(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* b, double* x,
+int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* b, double* x,
              const double* minv_diag, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_out,
              double* resid_out, cudaStream_t s);
 

@@ -48,9 +48,9 @@ def cg(A, b, x0=None, M=None, *, batch_first=False, atol=1e-12, rtol=1e-8, maxit
     x = torch.zeros_like(b) if x0 is None else x0.clone().contiguous()   # inputs are never mutated
     bb = b.contiguous()
     minv = _minv_diag(M, n, b.device)
-    ws = _lib.workspace(lib.fb2_cg_workspace_bytes(n), b.device)
+    ws = _lib.workspace(lib.fb2_cg_workspace_bytes(n, A.nnz), b.device)
     niter, resid = C.c_int(0), C.c_double(0.0)
-    _lib.call("fb2_cg", n, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(bb), _lib.ptr(x), _lib.ptr(minv),
+    _lib.call("fb2_cg", n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(bb), _lib.ptr(x), _lib.ptr(minv),
               float(atol), float(rtol), -1 if maxit is None else int(maxit), 0, _lib.ptr(ws), C.byref(niter), C.byref(resid),
               _lib.stream())
     info = {"residual": resid.value, "niter": niter.value}

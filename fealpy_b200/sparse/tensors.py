@@ -72,8 +72,9 @@ class CSRTensor:
             x = other.contiguous()
             if x.ndim == 1:
                 y = torch.empty(n, dtype=torch.float64, device=x.device)
+                blk_row, tile, max_row = self.spmv_plan()
                 _lib.call("fb2_csr_spmv", n, self.nnz, _lib.ptr(self._crow), _lib.ptr(self._col), _lib.ptr(self._values),
-                          _lib.ptr(x), _lib.ptr(y), _lib.stream())
+                          _lib.ptr(x), _lib.ptr(y), _lib.ptr(blk_row), tile, max_row, _lib.stream())
                 return y
             if x.ndim == 2:
                 y = torch.empty((n, x.shape[1]), dtype=torch.float64, device=x.device)
@@ -84,6 +85,21 @@ class CSRTensor:
         raise TypeError(f"unsupported operand for @: {type(other).__name__}")
 
     __matmul__ = matmul
+
+    SPMV_TILE = 2048
+
+    def spmv_plan(self):
+        """row-aligned nnz tiling used by the streaming SpMV kernel; built once per pattern"""
+        if getattr(self, "_plan", None) is None:
+            lib = _lib.load()
+            n = self._spshape[0]
+            nblk = lib.fb2_spmv_plan_blocks(self.nnz, self.SPMV_TILE)
+            blk_row = torch.empty(nblk + 2, dtype=torch.int32, device=self.device)
+            mr = C.c_int32(0)
+            _lib.call("fb2_spmv_plan_build", n, _lib.ptr(self._crow), self.SPMV_TILE, _lib.ptr(blk_row), self.nnz, C.byref(mr),
+                      _lib.stream())
+            self._plan = (blk_row, self.SPMV_TILE, mr.value)
+        return self._plan
 
     # --- conversions ----------------------------------------------------------------------
     def row_indices(self):

@@ -110,21 +110,27 @@ int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const i
  * replaces CSRTensor.matmul -> bm.csr_spmm (sparse/csr_tensor.py:411-452,
  * backend/numpy_backend.py:180-199) and fealpy.solver.cg (solver/cg.py:14-123). */
 size_t fb2_partial_workspace_bytes(void);           /* zero-initialise once */
+/* SpMV plan (built once per matrix): row-aligned tiles of `tile` stored values.
+ * blk_row has fb2_spmv_plan_blocks(nnz, tile) + 1 int32 entries; *max_row_host = longest row. */
+int fb2_spmv_plan_blocks(int64_t nnz, int tile);
+int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t nnz, int32_t* max_row_host,
+                        void* stream);
+/* y = A x.  blk_row may be NULL (row-per-lane-group kernel); with a plan the streaming kernel runs. */
 int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                 double* y, void* stream);
+                 double* y, const int32_t* blk_row, int tile, int32_t max_row, void* stream);
 int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
                  void* stream);
 int fb2_dot(int64_t n, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream);
-size_t fb2_cg_workspace_bytes(int64_t n);
+size_t fb2_cg_workspace_bytes(int64_t n, int64_t nnz);
 /* x: x0 on entry, solution on exit.  minv_diag: NULL or the diagonal of M (z = M r).
  * maxit < 0 means "no limit" (reference maxit=None).  chunk <= 0: automatic. */
-int fb2_cg(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
+int fb2_cg(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
            const double* minv_diag, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_host,
            double* residual_host, void* stream);
 /* building blocks of the distributed driver (device-resident scalars in `scalars`, 256 bytes) */
 int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm, double rTr, void* stream);
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, int64_t n_dot, void* scalars, void* partial_ws, void* stream);
+                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars, void* partial_ws, void* stream);
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,
                      void* partial_ws, int fuse_finalize, void* stream);
 int fb2_cg_finalize(void* scalars, void* stream);

@@ -37,7 +37,7 @@ def test_size_queries_run_without_gpu():
     lib = _lib.load()
     assert lib.fb2_sort_workspace_bytes(1000) > 12000
     assert lib.fb2_coo_workspace_bytes(1000) > lib.fb2_sort_workspace_bytes(1000)
-    assert lib.fb2_cg_workspace_bytes(1000) >= 3 * 8000
+    assert lib.fb2_cg_workspace_bytes(1000, 9000) >= 3 * 8000 and lib.fb2_spmv_plan_blocks(9000, 2048) == 5
     assert lib.fb2_partial_workspace_bytes() >= 4096 * 8
     assert lib.fb2_entity_workspace_bytes(100, 6) > 0 and lib.fb2_sym_workspace_bytes(100, 10, 500) > 0
 
