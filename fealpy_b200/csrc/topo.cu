@@ -278,4 +278,107 @@ int tensor_cell_to_dof(const int* c2d, int64_t NC, int L, int GD, int64_t gdof, 
   return OK;
 }
 
+// =====================================================================================
+// x-slabs of TetrahedronMesh.from_box with the GLOBAL numbering in closed form (SURVEY.md
+// appendix D): node id = i*(ny+1)(nz+1) + j*(nz+1) + k; every edge leaves its smaller node in
+// one of 7 non-negative directions, ordered by node-id offset; edge id = number of edges
+// leaving smaller nodes + rank of the direction among the ones that exist at that node.
+// Used by the multi-GPU row partition: a rank generates only its slab of cube layers
+// [cl0, cl1) and numbers DOFs in a "window" of the global numbering:
+//   nodes of planes [cl0, cl1]             -> [0, nwin_nodes)
+//   edges whose smaller node lies there    -> nwin_nodes + (global edge id - first such id)
+// =====================================================================================
+struct BoxDims { int nx, ny, nz; };
+
+// number of edges leaving all nodes that precede node (i,j,k) in id order
+__host__ __device__ inline int64_t box_edges_before(BoxDims d, int i, int j, int k) {
+  const int64_t Sb = 2 * (int64_t)d.ny + 1, Sc = 2 * (int64_t)d.nz + 1;
+  const int64_t plane_full = 2 * Sb * Sc - (int64_t)(d.ny + 1) * (d.nz + 1);   // a plane with i < nx
+  int64_t cnt = (int64_t)i * plane_full;           // all planes before i have i' < nx
+  const int64_t a1 = (i < d.nx) ? 2 : 1;
+  cnt += (int64_t)j * (a1 * 2 * Sc - (d.nz + 1));   // rows j' < j (<= ny - 1 < ny): (1+b) = 2
+  const int64_t b1 = (j < d.ny) ? 2 : 1;
+  cnt += (int64_t)k * (a1 * b1 * 2 - 1);            // k' < k (< nz): (1+c) = 2
+  return cnt;
+}
+
+// rank of direction (di,dj,dk) among the directions that exist at node (i,j,k)
+__host__ __device__ inline int box_dir_rank(BoxDims d, int i, int j, int k, int di, int dj, int dk) {
+  const bool a = i < d.nx, b = j < d.ny, c = k < d.nz;
+  // directions in id-offset order: 001 010 011 100 101 110 111
+  const bool ex[7] = {c, b, b && c, a, a && c, a && b, a && b && c};
+  const int idx = di * 4 + dj * 2 + dk - 1;
+  int r = 0;
+  for (int q = 0; q < idx; ++q) r += ex[q] ? 1 : 0;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) tet_slab_kernel(double x0, double x1, double y0, double y1, double z0, double z1, BoxDims d,
+                                                       int cl0, int cl1, int p, int64_t win_edge0, double* __restrict__ node,
+                                                       int* __restrict__ cell, int* __restrict__ c2d) {
+  const int64_t nyz = (int64_t)(d.ny + 1) * (d.nz + 1);
+  const int nplanes = cl1 - cl0 + 1;
+  const int64_t NNw = (int64_t)nplanes * nyz, NB = (int64_t)(cl1 - cl0) * d.ny * d.nz;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < NNw; t += (int64_t)gridDim.x * blockDim.x) {
+    const int il = (int)(t / nyz);
+    const int rem = (int)(t - (int64_t)il * nyz);
+    const int j = rem / (d.nz + 1), k = rem % (d.nz + 1);
+    node[3 * t] = linspace_at(x0, x1, d.nx, cl0 + il);
+    node[3 * t + 1] = linspace_at(y0, y1, d.ny, j);
+    node[3 * t + 2] = linspace_at(z0, z1, d.nz, k);
+  }
+  constexpr int K[6][4] = {{0, 1, 2, 6}, {0, 5, 1, 6}, {0, 4, 5, 6}, {0, 7, 4, 6}, {0, 3, 7, 6}, {0, 2, 3, 6}};
+  constexpr int CO[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+  constexpr int LE[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+  constexpr int P2POS[6] = {1, 2, 3, 5, 6, 8};           // local dof of edge (a,b) in the P2 ordering
+  constexpr int P2V[4] = {0, 4, 7, 9};
+  const int L = p == 1 ? 4 : 10;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < NB * 6; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t cube = t / 6;
+    const int q = (int)(t - cube * 6);
+    const int il = (int)(cube / ((int64_t)d.ny * d.nz));
+    const int rem = (int)(cube - (int64_t)il * d.ny * d.nz);
+    const int j = rem / d.nz, k = rem % d.nz;
+    int vi[4], vj[4], vk[4];
+    int64_t vloc[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int cidx = K[q][v];
+      vi[v] = il + CO[cidx][0]; vj[v] = j + CO[cidx][1]; vk[v] = k + CO[cidx][2];
+      vloc[v] = (int64_t)vi[v] * nyz + (int64_t)vj[v] * (d.nz + 1) + vk[v];      // window-local node id
+      cell[4 * t + v] = (int)vloc[v];
+    }
+    if (p == 1) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) c2d[L * t + v] = (int)vloc[v];
+    } else {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) c2d[L * t + P2V[v]] = (int)vloc[v];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {
+        int a = LE[e][0], b = LE[e][1];
+        if (vloc[a] > vloc[b]) { const int s = a; a = b; b = s; }
+        const int gi = cl0 + vi[a];                                              // global plane of the smaller node
+        const int64_t eid = box_edges_before(d, gi, vj[a], vk[a]) +
+                            box_dir_rank(d, gi, vj[a], vk[a], vi[b] - vi[a], vj[b] - vj[a], vk[b] - vk[a]);
+        c2d[L * t + P2POS[e]] = (int)(NNw + (eid - win_edge0));
+      }
+    }
+  }
+}
+
+int64_t box_edges_before_host(int nx, int ny, int nz, int i, int j, int k) { return box_edges_before(BoxDims{nx, ny, nz}, i, j, k); }
+
+int tet_box_slab(const double* box, int nx, int ny, int nz, int cl0, int cl1, int p, double* node, int* cell, int* c2d,
+                 cudaStream_t s) {
+  if (p != 1 && p != 2) return fail(ERR_UNSUPPORTED, "tet_box_slab: closed-form numbering is available for p = 1, 2");
+  if (cl0 < 0 || cl1 > nx || cl0 >= cl1) return fail(ERR_INVALID, "tet_box_slab: bad cube-layer range [%d, %d)", cl0, cl1);
+  const BoxDims d{nx, ny, nz};
+  const int64_t e0 = box_edges_before(d, cl0, 0, 0);
+  const int64_t nwork = (int64_t)(cl1 - cl0) * ny * nz * 6;
+  tet_slab_kernel<<<grid_for(nwork), 256, 0, s>>>(box[0], box[1], box[2], box[3], box[4], box[5], d, cl0, cl1, p, e0, node, cell, c2d);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
 }  // namespace fb2
