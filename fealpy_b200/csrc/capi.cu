@@ -198,15 +198,35 @@ int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm
   FB2_CUDA(cudaStreamSynchronize(S(stream)));   // bnorm / rTr live on the caller's stack
   return OK;
 }
+static OwnRange make_own(const int64_t* own) {
+  OwnRange o{};
+  if (own) { o.lo0 = own[0]; o.hi0 = own[1]; o.lo1 = own[2]; o.hi1 = own[3]; }
+  return o;
+}
+int fb2_cg_residual(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
+                    const double* b, double* r, const int32_t* blk_row, int tile, int32_t max_row, void* stream) {
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
+  return spmv(n, nnz, crow, col, values, x, r, b, 1, nullptr, nullptr, S(stream), blk_row ? &pl : nullptr);
+}
+int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p, void* scalars, void* partial_ws,
+                 const int64_t own[4], void* stream) {
+  return cg_start(n, r, minv_diag, p, static_cast<CgScalars*>(scalars), partial_ws, make_own(own), S(stream));
+}
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars, void* partial_ws, void* stream) {
+                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars, void* partial_ws,
+                    const int64_t own[4], void* stream) {
   CgScalars* sc = static_cast<CgScalars*>(scalars);
   const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
-  return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, &sc->pAp, partial_ws, S(stream), blk_row ? &pl : nullptr);
+  return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, &sc->pAp, partial_ws, S(stream), blk_row ? &pl : nullptr, make_own(own), sc);
 }
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,
-                     void* partial_ws, int fuse_finalize, void* stream) {
-  return cg_update_xr(n, x, r, p, Ap, minv_diag, static_cast<CgScalars*>(scalars), partial_ws, fuse_finalize, S(stream));
+                     void* partial_ws, int fuse_finalize, const int64_t own[4], void* stream) {
+  return cg_update_xr(n, x, r, p, Ap, minv_diag, static_cast<CgScalars*>(scalars), partial_ws, fuse_finalize, S(stream), make_own(own));
+}
+int64_t fb2_box_edges_before(int nx, int ny, int nz, int i, int j, int k) { return box_edges_before_host(nx, ny, nz, i, j, k); }
+int fb2_tet_box_slab(const double box[6], int nx, int ny, int nz, int cube_layer_lo, int cube_layer_hi, int p, double* node,
+                     int32_t* cell, int32_t* cell2dof, void* stream) {
+  return tet_box_slab(box, nx, ny, nz, cube_layer_lo, cube_layer_hi, p, node, cell, cell2dof, S(stream));
 }
 int fb2_cg_finalize(void* scalars, void* stream) { return cg_finalize(static_cast<CgScalars*>(scalars), S(stream)); }
 int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, void* stream) {

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_kernel(int64_t n, const int64
                                                           const double* __restrict__ val, const double* __restrict__ x,
                                                           double* __restrict__ y, const double* __restrict__ b, int mode,
                                                           double* dot_out, double* partials, unsigned int* counter,
-                                                          const CgScalars* sc) {
+                                                          const CgScalars* sc, OwnRange own) {
   if (sc && sc->done) return;
   constexpr int RPB = CG_THREADS / T;
   const int sub = threadIdx.x % T, rib = threadIdx.x / T;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_kernel(int64_t n, const int64
     if (r < n && sub == 0) {
       const double yv = mode ? b[r] - acc : acc;
       y[r] = yv;
-      if (dot_out) dsum += x[r] * yv;
+      if (dot_out && own.has(r)) dsum += x[r] * yv;
     }
   }
   if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
                                                                  const double* __restrict__ x, double* __restrict__ y,
                                                                  const double* __restrict__ b, int mode,
                                                                  const int32_t* __restrict__ blk_row, int nblk, double* dot_out,
-                                                                 double* partials, unsigned int* counter, const CgScalars* sc) {
+                                                                 double* partials, unsigned int* counter, const CgScalars* sc,
+                                                                 OwnRange own) {
   if (sc && sc->done) return;
   extern __shared__ __align__(16) double prod[];
   const int tid = threadIdx.x;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
       if (r < r1 && g == 0) {
         const double yv = mode ? b[r] - acc : acc;
         y[r] = yv;
-        if (dot_out) dsum += x[r] * yv;
+        if (dot_out && own.has(r)) dsum += x[r] * yv;
       }
     }
     __syncthreads();
@@ -203,12 +204,12 @@ __global__ void __launch_bounds__(CG_THREADS) dot_kernel(int64_t n, const double
 
 // p = z = M r ; rTr = r.z
 __global__ void __launch_bounds__(CG_THREADS) cg_start_kernel(int64_t n, const double* __restrict__ r, const double* __restrict__ minv,
-                                                              double* __restrict__ p, CgScalars* sc, double* partials) {
+                                                              double* __restrict__ p, CgScalars* sc, double* partials, OwnRange own) {
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double ri = r[i], zi = minv ? minv[i] * ri : ri;
     p[i] = zi;
-    acc += ri * zi;
+    if (own.has(i)) acc += ri * zi;
   }
   grid_reduce(acc, partials, &sc->counter[1], [=](double tot) { sc->rTr = tot; });
 }
@@ -230,7 +231,7 @@ __device__ __forceinline__ void cg_finalize_dev(CgScalars* sc) {
 __global__ void __launch_bounds__(CG_THREADS) cg_update_xr_kernel(int64_t n, double* __restrict__ x, double* __restrict__ r,
                                                                   const double* __restrict__ p, const double* __restrict__ Ap,
                                                                   const double* __restrict__ minv, CgScalars* sc, double* partials,
-                                                                  int fuse_finalize) {
+                                                                  int fuse_finalize, OwnRange own) {
   if (sc->done) return;
   const double alpha = sc->rTr / sc->pAp;
   double acc = 0.0;
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(CG_THREADS) cg_update_xr_kernel(int64_t n, dou
     x[i] = x[i] + alpha * p[i];
     const double ri = r[i] - alpha * Ap[i];
     r[i] = ri;
-    acc += ri * (minv ? minv[i] * ri : ri);
+    if (own.has(i)) acc += ri * (minv ? minv[i] * ri : ri);
   }
   grid_reduce(acc, partials, &sc->counter[1], [=](double tot) {
     sc->rTr_new = tot;
@@ -291,13 +292,13 @@ static int pick_T(int64_t n, int64_t nnz) {
 template <int T>
 static void launch_spmv(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
                         const double* b, int mode, double* dot_out, double* partials, unsigned int* counter, const CgScalars* sc,
-                        cudaStream_t s) {
+                        cudaStream_t s, OwnRange own) {
   constexpr int RPB = CG_THREADS / T;
   int64_t nbk = ceil_div(n, RPB);
   const int64_t cap = dot_out ? (int64_t)CG_PARTIALS : (int64_t)kNumSM * 64;
   if (nbk > cap) nbk = cap;
   if (nbk > kNumSM * 16 && dot_out) nbk = kNumSM * 16;
-  spmv_kernel<T><<<(unsigned)(nbk < 1 ? 1 : nbk), CG_THREADS, 0, s>>>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc);
+  spmv_kernel<T><<<(unsigned)(nbk < 1 ? 1 : nbk), CG_THREADS, 0, s>>>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, own);
 }
 
 int spmv_plan_blocks(int64_t nnz, int tile) { return (int)ceil_div(nnz > 0 ? nnz : 1, tile); }
@@ -314,7 +315,7 @@ int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t*
 
 static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x,
                               double* y, const double* b, int mode, const SpmvPlan& plan, double* dot_out, double* partials,
-                              unsigned int* counter, const CgScalars* sc, cudaStream_t s) {
+                              unsigned int* counter, const CgScalars* sc, cudaStream_t s, OwnRange own) {
   const size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
   const int per_sm = (int)std::min<size_t>(8, (200 * 1024) / (smem + 1024));
@@ -325,7 +326,7 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
   do {                                                                                                         \
     auto kern = spmv_stream_kernel<GV>;                                                                        \
     if (smem > 48 * 1024) FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, CG_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc); \
+    kern<<<grid, CG_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own); \
   } while (0)
   if (avg <= 6.0) FB2_ST(2);
   else if (avg <= 12.0) FB2_ST(4);
@@ -338,16 +339,17 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
 
 static int spmv_impl(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
                      const double* b, int mode, double* dot_out, double* partials, unsigned int* counter, const CgScalars* sc,
-                     cudaStream_t s, const SpmvPlan* plan = nullptr) {
+                     cudaStream_t s, const SpmvPlan* plan = nullptr, OwnRange own = OwnRange{}) {
   if (n <= 0) return OK;
+  if (own.hi0 == 0 && own.hi1 == 0) own.hi0 = n;      // default: every row contributes to the dot
   if (plan && plan->blk_row && (size_t)(plan->tile + plan->max_row) * 8 <= 200 * 1024)
-    return spmv_stream_launch(n, nnz, crow, col, val, x, y, b, mode, *plan, dot_out, partials, counter, sc, s);
+    return spmv_stream_launch(n, nnz, crow, col, val, x, y, b, mode, *plan, dot_out, partials, counter, sc, s, own);
   switch (pick_T(n, nnz)) {
-    case 2: launch_spmv<2>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
-    case 4: launch_spmv<4>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
-    case 8: launch_spmv<8>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
-    case 16: launch_spmv<16>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
-    default: launch_spmv<32>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s); break;
+    case 2: launch_spmv<2>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s, own); break;
+    case 4: launch_spmv<4>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s, own); break;
+    case 8: launch_spmv<8>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s, own); break;
+    case 16: launch_spmv<16>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s, own); break;
+    default: launch_spmv<32>(n, crow, col, val, x, y, b, mode, dot_out, partials, counter, sc, s, own); break;
   }
   FB2_LAUNCH_CHECK();
   return OK;
@@ -372,11 +374,12 @@ size_t cg_workspace_bytes(int64_t n, int64_t nnz) {
 }
 
 int spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
-         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s, const SpmvPlan* plan) {
+         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s, const SpmvPlan* plan, OwnRange own,
+         const CgScalars* sc) {
   if (dot_out && !partial_ws) return fail(ERR_INVALID, "spmv: fused dot needs the (zero-initialised) partial workspace");
   PartialWs pw(partial_ws);
   return spmv_impl(n, nnz, crow, col, val, x, y, b, mode, dot_out, partial_ws ? pw.partials : nullptr,
-                   partial_ws ? pw.counter : nullptr, nullptr, s, plan);
+                   partial_ws ? pw.counter : nullptr, sc, s, plan, own);
 }
 size_t partial_workspace_bytes() { return PartialWs::bytes(); }
 
@@ -401,10 +404,19 @@ int cg_init_scalars(CgScalars* sc, double atol, double rtol, int maxit, cudaStre
   FB2_LAUNCH_CHECK();
   return OK;
 }
-int cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv, CgScalars* sc,
-                 void* partial_ws, int fuse_finalize, cudaStream_t s) {
+int cg_start(int64_t n, const double* r, const double* minv, double* p, CgScalars* sc, void* partial_ws, OwnRange own,
+             cudaStream_t s) {
   PartialWs pw(partial_ws);
-  cg_update_xr_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, x, r, p, Ap, minv, sc, pw.partials, fuse_finalize);
+  if (own.hi0 == 0 && own.hi1 == 0) own.hi0 = n;
+  cg_start_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, r, minv, p, sc, pw.partials, own);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+int cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv, CgScalars* sc,
+                 void* partial_ws, int fuse_finalize, cudaStream_t s, OwnRange own) {
+  PartialWs pw(partial_ws);
+  if (own.hi0 == 0 && own.hi1 == 0) own.hi0 = n;
+  cg_update_xr_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, x, r, p, Ap, minv, sc, pw.partials, fuse_finalize, own);
   FB2_LAUNCH_CHECK();
   return OK;
 }
@@ -466,7 +478,7 @@ int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, co
   FB2_CUDA(cudaMemcpyAsync(&sc->bnorm, &bnorm, sizeof(double), cudaMemcpyHostToDevice, s));
   // r = b - A x0 ; p = z = M r ; rTr = r.z
   FB2_TRY(spmv_impl(n, nnz, crow, col, val, x, r, b, 1, nullptr, nullptr, nullptr, nullptr, s, &plan));
-  cg_start_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, r, minv, p, sc, pw.partials);
+  cg_start_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, r, minv, p, sc, pw.partials, OwnRange{0, n, 0, 0});
   FB2_LAUNCH_CHECK();
 
   if (chunk <= 0) {
@@ -483,7 +495,7 @@ int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, co
   int rc = OK;
   for (int k = 0; k < chunk && rc == OK; ++k) {
     rc = spmv_impl(n, nnz, crow, col, val, p, Ap, nullptr, 0, &sc->pAp, pw.partials, &sc->counter[0], sc, s, &plan);
-    if (rc == OK) rc = cg_update_xr(n, x, r, p, Ap, minv, sc, pws, 1, s);
+    if (rc == OK) rc = cg_update_xr(n, x, r, p, Ap, minv, sc, pws, 1, s, OwnRange{0, n, 0, 0});
     if (rc == OK) rc = cg_update_p(n, p, r, minv, sc, s);
   }
   cudaError_t ce = cudaStreamEndCapture(s, &graph);

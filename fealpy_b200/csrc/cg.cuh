@@ -13,6 +13,12 @@ struct CgScalars {
 
 constexpr int CG_PARTIALS = 4096;
 
+// rows that contribute to dot products (the owned rows of a rank): [lo0,hi0) U [lo1,hi1)
+struct OwnRange {
+  int64_t lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+  __host__ __device__ bool has(int64_t r) const { return (r >= lo0 && r < hi0) || (r >= lo1 && r < hi1); }
+};
+
 // row-aligned nnz tiling of a CSR matrix (built once per matrix, see spmv_plan_build)
 struct SpmvPlan {
   const int32_t* blk_row = nullptr;   // (nblk+1) first row of every tile
@@ -26,7 +32,8 @@ int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t*
 // y = A x  (mode 0),  y = b - A x (mode 1); optional fused dot  sum_r x[r]*y[r] -> *dot_out (deterministic)
 size_t partial_workspace_bytes();
 int spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
-         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s, const SpmvPlan* plan = nullptr);
+         const double* b, int mode, double* dot_out, void* partial_ws, cudaStream_t s, const SpmvPlan* plan = nullptr,
+         OwnRange own = OwnRange{}, const CgScalars* sc = nullptr);
 // SpMM with a row-major (n, nb) dense block: Y = A X
 int spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* val, const double* X, double* Y, int nb, cudaStream_t s);
 // deterministic dot product
@@ -39,8 +46,9 @@ int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, co
 
 // building blocks for the distributed (multi-GPU) driver
 int cg_init_scalars(CgScalars* sc, double atol, double rtol, int maxit, cudaStream_t s);
+int cg_start(int64_t n, const double* r, const double* minv, double* p, CgScalars* sc, void* partial_ws, OwnRange own, cudaStream_t s);
 int cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv, CgScalars* sc,
-                 void* partial_ws, int fuse_finalize, cudaStream_t s);
+                 void* partial_ws, int fuse_finalize, cudaStream_t s, OwnRange own = OwnRange{});
 int cg_finalize(CgScalars* sc, cudaStream_t s);
 int cg_update_p(int64_t n, double* p, const double* r, const double* minv, CgScalars* sc, cudaStream_t s);
 

@@ -45,6 +45,14 @@ int fb2_cell_to_dof(const int32_t* cell, const int32_t* cell2edge, const int32_t
                     void* stream);
 int fb2_tensor_cell_to_dof(const int32_t* cell2dof, int64_t NC, int ldof, int GD, int64_t gdof, int dof_priority, int32_t* out,
                            void* stream);
+/* x-slab of TetrahedronMesh.from_box for the multi-GPU row partition: cube layers
+ * [cube_layer_lo, cube_layer_hi), node planes [lo, hi]; node coordinates and cell2dof follow the
+ * GLOBAL from_box numbering in closed form (no sort), expressed in the slab's window:
+ * nodes -> [0, NNw), edges whose smaller node lies in the window -> NNw + (global edge id -
+ * fb2_box_edges_before(nx,ny,nz,lo,0,0)).  p = 1 or 2. */
+int64_t fb2_box_edges_before(int nx, int ny, int nz, int i, int j, int k);
+int fb2_tet_box_slab(const double box[6], int nx, int ny, int nz, int cube_layer_lo, int cube_layer_hi, int p, double* node,
+                     int32_t* cell, int32_t* cell2dof, void* stream);
 
 /* ---- K1: element matrices ---------------------------------------------------------------
  * replaces ScalarDiffusionIntegrator.assembly / ScalarMassIntegrator.assembly /
@@ -129,10 +137,17 @@ int fb2_cg(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, cons
            double* residual_host, void* stream);
 /* building blocks of the distributed driver (device-resident scalars in `scalars`, 256 bytes) */
 int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm, double rTr, void* stream);
+/* own[4] = {lo0, hi0, lo1, hi1}: rows (owned dofs of this rank) that contribute to the dot
+ * products; NULL = all rows.  The caller all-reduces scalars[1] (p.Ap) / scalars[2] (r.z). */
+int fb2_cg_residual(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
+                    const double* b, double* r, const int32_t* blk_row, int tile, int32_t max_row, void* stream);
+int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p, void* scalars, void* partial_ws,
+                 const int64_t own[4], void* stream);
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars, void* partial_ws, void* stream);
+                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars, void* partial_ws,
+                    const int64_t own[4], void* stream);
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,
-                     void* partial_ws, int fuse_finalize, void* stream);
+                     void* partial_ws, int fuse_finalize, const int64_t own[4], void* stream);
 int fb2_cg_finalize(void* scalars, void* stream);
 int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, void* stream);
 
