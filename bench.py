@@ -252,7 +252,7 @@ def run_ours(args):
         if not args.no_e2e:
             h_node, h_cell, h_c2d = (t.cpu().pin_memory() for t in (mesh.node, mesh.cell, c2d))
             h_b = b.cpu().pin_memory()
-            h_vals = torch.empty(nnz, dtype=torch.float64).pin_memory()
+            h_vals = torch.empty(A.nnz, dtype=torch.float64).pin_memory()
             h_x = torch.empty(gdof, dtype=torch.float64).pin_memory()
 
             def e2e_step():

@@ -61,7 +61,8 @@ template <bool FILL, typename SlotT>
 __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __restrict__ c2d, int L, int64_t gdof,
                                                                   const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair,
                                                                   const int64_t* __restrict__ crow, int* __restrict__ rowlen,
-                                                                  int* __restrict__ col, SlotT* __restrict__ slots, int* __restrict__ err) {
+                                                                  int* __restrict__ col, SlotT* __restrict__ slots, int slot_stride,
+                                                                  int* __restrict__ err) {
   __shared__ uint64_t buf_all[SYM_WARPS][SYM_CAP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint64_t* buf = buf_all[wid];
@@ -115,7 +116,9 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
       if (FILL && k < ncand) {
         const int rank = running + __popc(hb & lt) + (head ? 1 : 0) - 1;
         if (head) col[cbase + rank] = (int)(key >> SYM_KBITS);
-        slots[a0 * L + (int64_t)(key & ((1u << SYM_KBITS) - 1u))] = (SlotT)rank;
+        const int kk = (int)(key & ((1u << SYM_KBITS) - 1u));      // candidate index = pair_local * L + j
+        const int pl = kk / L;
+        slots[(a0 + pl) * slot_stride + (kk - pl * L)] = (SlotT)rank;
       }
       running += __popc(hb);
     }
@@ -130,6 +133,12 @@ __global__ void max_kernel(const int* __restrict__ v, int64_t n, int* out) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// elements per slot record: records are padded to 4-byte multiples (see SlotRec)
+int slot_stride(int L, int slot_bytes) {
+  const int per_word = 4 / slot_bytes;
+  return (L + per_word - 1) / per_word * per_word;
 }
 
 size_t sym_workspace_bytes(int64_t NC, int L, int64_t gdof) {
@@ -157,7 +166,7 @@ int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr,
   int* rowlen = deg;
   const unsigned nb = (unsigned)std::min<int64_t>(ceil_div(gdof, SYM_WARPS), (int64_t)kNumSM * 16);
   if (gdof > 0) {
-    sym_rows_kernel<false, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, nullptr, rowlen, nullptr, nullptr, cursor);
+    sym_rows_kernel<false, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, nullptr, rowlen, nullptr, nullptr, 0, cursor);
     max_kernel<<<grid_for(gdof), 256, 0, s>>>(rowlen, gdof, cursor + 1);
   }
   FB2_LAUNCH_CHECK();
@@ -175,10 +184,11 @@ int sym_fill(const int* c2d, int64_t NC, int L, int64_t gdof, const int64_t* adj
              int* col, void* slots, int slot_bytes, cudaStream_t s) {
   if (gdof <= 0) return OK;
   const unsigned nb = (unsigned)std::min<int64_t>(ceil_div(gdof, SYM_WARPS), (int64_t)kNumSM * 16);
+  const int stride = slot_stride(L, slot_bytes);
   if (slot_bytes == 1)
-    sym_rows_kernel<true, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint8_t*)slots, nullptr);
+    sym_rows_kernel<true, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint8_t*)slots, stride, nullptr);
   else if (slot_bytes == 2)
-    sym_rows_kernel<true, uint16_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint16_t*)slots, nullptr);
+    sym_rows_kernel<true, uint16_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint16_t*)slots, stride, nullptr);
   else
     return fail(ERR_INVALID, "sym_fill: slot_bytes must be 1 or 2");
   FB2_LAUNCH_CHECK();
@@ -188,46 +198,59 @@ int sym_fill(const int* c2d, int64_t NC, int L, int64_t gdof, const int64_t* adj
 // =====================================================================================
 // numeric: scalar forms with constant / per-cell coefficients, element rows recomputed
 // =====================================================================================
+// ---- geometry from preloaded vertex coordinates ------------------------------------------
 template <int TD>
-struct RowGeo {
-  static constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;
-  double cm;
-  double G[NG];
+struct CellX {                       // vertex ids + coordinates of one cell (software-pipelined loads)
+  int v[TD + 1];
+  double x[TD + 1][TD];
 };
 
-__device__ __forceinline__ void row_geo(const double* __restrict__ node, const int* __restrict__ cell, int64_t c, RowGeo<2>& g) {
-  const int v0 = cell[3 * c], v1 = cell[3 * c + 1], v2 = cell[3 * c + 2];
-  const double2 p0 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v0);
-  const double2 p1 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v1);
-  const double2 p2 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v2);
-  const double e0x = p2.x - p1.x, e0y = p2.y - p1.y;
-  const double e1x = p0.x - p2.x, e1y = p0.y - p2.y;
-  const double e2x = p1.x - p0.x, e2y = p1.y - p0.y;
+template <int TD>
+__device__ __forceinline__ void load_verts(const int* __restrict__ cell, int64_t c, int (&v)[TD + 1]) {
+  if constexpr (TD == 3) {
+    const int4 t = *reinterpret_cast<const int4*>(cell + 4 * c);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = cell[3 * c]; v[1] = cell[3 * c + 1]; v[2] = cell[3 * c + 2];
+  }
+}
+
+template <int TD>
+__device__ __forceinline__ void load_coords(const double* __restrict__ node, const int (&v)[TD + 1], double (&x)[TD + 1][TD]) {
+#pragma unroll
+  for (int k = 0; k <= TD; ++k) {
+    if constexpr (TD == 2) {
+      const double2 p = *reinterpret_cast<const double2*>(node + 2 * (int64_t)v[k]);
+      x[k][0] = p.x; x[k][1] = p.y;
+    } else {
+      const double* q = node + 3 * (int64_t)v[k];
+      x[k][0] = q[0]; x[k][1] = q[1]; x[k][2] = q[2];
+    }
+  }
+}
+
+// G[kl] = vol * grad(lambda_k).grad(lambda_l) (upper triangle), cm = signed measure
+__device__ __forceinline__ void geo_from_coords(const double (&P)[3][2], double& cm, double (&G)[6]) {
+  const double e0x = P[2][0] - P[1][0], e0y = P[2][1] - P[1][1];
+  const double e1x = P[0][0] - P[2][0], e1y = P[0][1] - P[2][1];
+  const double e2x = P[1][0] - P[0][0], e2y = P[1][1] - P[0][1];
   const double nv = e0x * e1y - e0y * e1x, inv = 1.0 / nv;
   const double D[3][2] = {{-e0y * inv, e0x * inv}, {-e1y * inv, e1x * inv}, {-e2y * inv, e2x * inv}};
-  g.cm = 0.5 * (e2x * e0y - e2y * e0x);
+  cm = 0.5 * (e2x * e0y - e2y * e0x);
   int t = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
-    for (int l = k; l < 3; ++l) g.G[t++] = (D[k][0] * D[l][0] + D[k][1] * D[l][1]) * g.cm;
+    for (int l = k; l < 3; ++l) G[t++] = (D[k][0] * D[l][0] + D[k][1] * D[l][1]) * cm;
 }
 
-__device__ __forceinline__ void row_geo(const double* __restrict__ node, const int* __restrict__ cell, int64_t c, RowGeo<3>& g) {
-  const int4 v = *reinterpret_cast<const int4*>(cell + 4 * c);
-  const int vid[4] = {v.x, v.y, v.z, v.w};
-  double P[4][3];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double* q = node + 3 * (int64_t)vid[k];
-    P[k][0] = q[0]; P[k][1] = q[1]; P[k][2] = q[2];
-  }
+__device__ __forceinline__ void geo_from_coords(const double (&P)[4][3], double& cm, double (&G)[10]) {
   double a[3], b[3], cc[3];
 #pragma unroll
   for (int m = 0; m < 3; ++m) { a[m] = P[1][m] - P[0][m]; b[m] = P[2][m] - P[1][m]; cc[m] = P[3][m] - P[2][m]; }
   const double bc0 = b[1] * cc[2] - b[2] * cc[1], bc1 = b[2] * cc[0] - b[0] * cc[2], bc2 = b[0] * cc[1] - b[1] * cc[0];
   const double det = a[0] * bc0 + a[1] * bc1 + a[2] * bc2;
-  g.cm = det / 6.0;
+  cm = det / 6.0;
   const double inv = 1.0 / det;
   constexpr int LF[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
   double D[4][3];
@@ -245,75 +268,112 @@ __device__ __forceinline__ void row_geo(const double* __restrict__ node, const i
 #pragma unroll
   for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int l = k; l < 4; ++l) g.G[t++] = (D[k][0] * D[l][0] + D[k][1] * D[l][1] + D[k][2] * D[l][2]) * g.cm;
+    for (int l = k; l < 4; ++l) G[t++] = (D[k][0] * D[l][0] + D[k][1] * D[l][1] + D[k][2] * D[l][2]) * cm;
 }
 
-// first index r in [0, n] with crow[r] >= target (crow has n+1 non-decreasing entries)
-__device__ __forceinline__ int64_t row_lower_bound(const int64_t* __restrict__ crow, int64_t n, int64_t target) {
-  int64_t lo = 0, hi = n;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (crow[mid] < target) lo = mid + 1; else hi = mid;
+// slot records are padded to 4-byte multiples so that one pair's slots are a few 32-bit loads
+template <typename SlotT, int L>
+struct SlotRec {
+  static constexpr int PER_WORD = 4 / (int)sizeof(SlotT);
+  static constexpr int WORDS = (L + PER_WORD - 1) / PER_WORD;
+  static constexpr int STRIDE = WORDS * PER_WORD;            // elements per record
+  __device__ static __forceinline__ int get(const uint32_t (&w)[WORDS], int j) {
+    if constexpr (sizeof(SlotT) == 1) return (w[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+    else return (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
   }
-  return lo;
-}
+};
 
-// CTA b owns the rows whose first value index lies in [b*tile, (b+1)*tile): equal value
-// volume per CTA whatever the row lengths (vertex rows ~61, edge rows ~24 for P2 tets).
+// CTA b owns the rows [blk_row[b], blk_row[b+1]) (equal value volume per CTA whatever the row
+// lengths).  Inside, every warp owns 32 consecutive rows at a time and is fully autonomous:
+// private accumulator segment, no CTA barrier after start-up, its own contiguous write-back.
+// The dependent chain adjacency -> cell vertices -> node coordinates is software-pipelined
+// three deep so that the global-load latency of pair q+1..q+3 hides behind the FP64 work of pair q.
 template <int TD, int L, typename SlotT>
 __global__ void __launch_bounds__(128) assemble_const_kernel(AsmConstArgs a) {
   constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;
   constexpr int MS_STRIDE = (L * NG) | 1;         // odd stride between local rows i: bank spread
   constexpr int MM_STRIDE = L | 1;
+  using SR = SlotRec<SlotT, L>;
   extern __shared__ __align__(16) double sm[];
   double* sMs = sm;                                            // [L][MS_STRIDE]
   double* sMm = sMs + (a.has_diff ? L * MS_STRIDE : 0);        // [L][MM_STRIDE]
-  double* acc = sMm + (a.has_mass ? L * MM_STRIDE : 0);        // block tile of CSR values
+  double* acc = sMm + (a.has_mass ? L * MM_STRIDE : 0);        // CTA tile of CSR values
   if (a.has_diff)
     for (int t = threadIdx.x; t < L * L * NG; t += blockDim.x) sMs[(t / (L * NG)) * MS_STRIDE + t % (L * NG)] = a.Ms[t];
   if (a.has_mass)
     for (int t = threadIdx.x; t < L * L; t += blockDim.x) sMm[(t / L) * MM_STRIDE + t % L] = a.Mm[t];
 
-  const int64_t lo = (int64_t)blockIdx.x * a.tile;
-  const int64_t r0 = row_lower_bound(a.crow, a.gdof, lo);
-  const int64_t r1 = row_lower_bound(a.crow, a.gdof, lo + a.tile);
+  const int64_t r0 = a.blk_row[blockIdx.x], r1 = a.blk_row[blockIdx.x + 1];
   const int64_t v0 = a.crow[r0];
   const int nval = (int)(a.crow[r1] - v0);
   for (int t = threadIdx.x; t < nval; t += blockDim.x) acc[t] = 0.0;
   __syncthreads();
 
-  const SlotT* __restrict__ slots = static_cast<const SlotT*>(a.slots);
-  for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-    double* my = acc + (a.crow[r] - v0);
-    const int64_t q0 = a.adj_ptr[r], q1 = a.adj_ptr[r + 1];
-    for (int64_t q = q0; q < q1; ++q) {
-      const int pair = a.adj_pair[q];
-      const int64_t c = pair / L;
-      const int i = pair - (int)c * L;
-      RowGeo<TD> g;
-      row_geo(a.node, a.cell, c, g);
-      const double kd = a.scal_d * (a.coef_d ? a.coef_d[c] : 1.0);
-      const double km = a.scal_m * (a.coef_m ? a.coef_m[c] : 1.0) * g.cm;
-      const SlotT* sl = slots + q * L;
-      const double* mrow = sMs + i * MS_STRIDE;
-      const double* mm = sMm + i * MM_STRIDE;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t* __restrict__ slot_words = static_cast<const uint32_t*>(a.slots);
+  for (int64_t rb = r0 + 32 * wid; rb < r1; rb += blockDim.x) {
+    const int64_t r = rb + lane;
+    const bool act = r < r1;
+    const int64_t q0 = act ? a.adj_ptr[r] : 0, q1 = act ? a.adj_ptr[r + 1] : 0;
+    double* my = acc + (act ? (a.crow[r] - v0) : 0);
+    if (q0 < q1) {
+      const int64_t qlast = q1 - 1;
+      auto clampq = [&](int64_t q) { return q < qlast ? q : qlast; };
+      // prologue of the 3-deep pipeline
+      int pair0 = a.adj_pair[q0], pair1 = a.adj_pair[clampq(q0 + 1)], pair2 = a.adj_pair[clampq(q0 + 2)];
+      int v_cur[NV], v_nxt[NV];
+      load_verts<TD>(a.cell, pair0 / L, v_cur);
+      load_verts<TD>(a.cell, pair1 / L, v_nxt);
+      double x_cur[NV][TD];
+      load_coords<TD>(a.node, v_cur, x_cur);
+      for (int64_t q = q0; q < q1; ++q) {
+        // ---- issue the loads of the following pairs
+        double x_nxt[NV][TD];
+        load_coords<TD>(a.node, v_nxt, x_nxt);
+        int v_nn[NV];
+        load_verts<TD>(a.cell, pair2 / L, v_nn);
+        const int pair3 = a.adj_pair[clampq(q + 3)];
+        uint32_t sw[SR::WORDS];
 #pragma unroll
-      for (int j = 0; j < L; ++j) {
-        double v = 0.0;
-        if (a.has_diff) {
-          double s = 0.0;
+        for (int w = 0; w < SR::WORDS; ++w) sw[w] = slot_words[q * SR::WORDS + w];
+        // ---- FP64 work of the current pair
+        const int64_t c = pair0 / L;
+        const int i = pair0 - (int)c * L;
+        double cm, G[NG];
+        geo_from_coords(x_cur, cm, G);
+        const double kd = a.scal_d * (a.coef_d ? a.coef_d[c] : 1.0);
+        const double km = a.scal_m * (a.coef_m ? a.coef_m[c] : 1.0) * cm;
+        const double* mrow = sMs + i * MS_STRIDE;
+        const double* mm = sMm + i * MM_STRIDE;
 #pragma unroll
-          for (int t = 0; t < NG; ++t) s += mrow[j * NG + t] * g.G[t];
-          v = kd * s;
+        for (int j = 0; j < L; ++j) {
+          double v = 0.0;
+          if (a.has_diff) {
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < NG; ++t) s += mrow[j * NG + t] * G[t];
+            v = kd * s;
+          }
+          if (a.has_mass) v += km * mm[j];
+          my[SR::get(sw, j)] += v;
         }
-        if (a.has_mass) v += km * mm[j];
-        my[sl[j]] += v;
+        // ---- rotate the pipeline
+        pair0 = pair1; pair1 = pair2; pair2 = pair3;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          v_nxt[k] = v_nn[k];
+#pragma unroll
+          for (int m = 0; m < TD; ++m) x_cur[k][m] = x_nxt[k][m];
+        }
       }
     }
+    __syncwarp();
+    // the warp's 32 rows are a contiguous value range: stream it out
+    const int64_t rend = (rb + 32 < r1) ? rb + 32 : r1;
+    const int s0 = (int)(a.crow[rb] - v0), s1 = (int)(a.crow[rend] - v0);
+    double* out = a.values + v0;
+    for (int t = s0 + lane; t < s1; t += 32) out[t] = acc[t];
   }
-  __syncthreads();
-  double* out = a.values + v0;
-  for (int t = threadIdx.x; t < nval; t += blockDim.x) out[t] = acc[t];
 }
 
 // =====================================================================================
@@ -324,10 +384,7 @@ template <typename SlotT>
 __global__ void __launch_bounds__(128) assemble_from_ke_kernel(AsmKeArgs a) {
   extern __shared__ __align__(16) double acc[];
   const int L = a.L, nc = a.ncomp, lt = L * nc;
-  const int64_t nrow = a.gdof * nc;
-  const int64_t lo = (int64_t)blockIdx.x * a.tile;
-  const int64_t R0 = row_lower_bound(a.crow_out, nrow, lo);
-  const int64_t R1 = row_lower_bound(a.crow_out, nrow, lo + a.tile);
+  const int64_t R0 = a.blk_row[blockIdx.x], R1 = a.blk_row[blockIdx.x + 1];
   const int64_t v0 = a.crow_out[R0];
   const int nval = (int)(a.crow_out[R1] - v0);
   for (int t = threadIdx.x; t < nval; t += blockDim.x) acc[t] = 0.0;
@@ -348,7 +405,7 @@ __global__ void __launch_bounds__(128) assemble_from_ke_kernel(AsmKeArgs a) {
       const int i = pair - (int)c * L;
       const int lrow = a.dof_priority ? comp * L + i : i * nc + comp;
       const double* krow = a.Ke + (c * lt + lrow) * (int64_t)lt;
-      const SlotT* sl = slots + q * L;
+      const SlotT* sl = slots + q * a.slot_stride;
       for (int j = 0; j < L; ++j) {
         const int s = sl[j];
         for (int b = 0; b < nc; ++b) {
@@ -409,12 +466,10 @@ template <int TD, int L>
 static int launch_asm_const(AsmConstArgs a, int slot_bytes, int max_row, cudaStream_t s) {
   constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;
   const size_t tab = ((a.has_diff ? (size_t)L * ((L * NG) | 1) : 0) + (a.has_mass ? (size_t)L * (L | 1) : 0)) * sizeof(double);
-  if (a.tile <= 0) a.tile = 3072;
   if (a.threads <= 0) a.threads = 128;
-  if (a.tile < max_row) a.tile = max_row;
   const size_t smem = tab + (size_t)(a.tile + max_row) * 8;
   if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble_const: row tile does not fit shared memory (max_row=%d)", max_row);
-  const int64_t nb = ceil_div(a.nnz, a.tile);
+  const int64_t nb = a.nblk;
   if (nb <= 0) return OK;
   if (slot_bytes == 1) {
     auto k = assemble_const_kernel<TD, L, uint8_t>;
@@ -446,11 +501,10 @@ int assemble_const(int TD, int p, const AsmConstArgs& a, int slot_bytes, int max
 int assemble_from_ke(AsmKeArgs a, int slot_bytes, int max_row, cudaStream_t s) {
   if (a.gdof <= 0) return OK;
   const int max_out_row = max_row * a.ncomp;
-  if (a.tile <= 0) a.tile = 3072;
-  if (a.tile < max_out_row) a.tile = max_out_row;
   const size_t smem = (size_t)(a.tile + max_out_row) * 8;
   if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble_from_ke: row tile does not fit shared memory (max_row=%d)", max_row);
-  const int64_t nb = ceil_div(a.nnz_out, a.tile);
+  a.slot_stride = slot_stride(a.L, slot_bytes);
+  const int64_t nb = a.nblk;
   if (nb <= 0) return OK;
   if (slot_bytes == 1) {
     auto k = assemble_from_ke_kernel<uint8_t>;

@@ -18,7 +18,8 @@ struct AsmConstArgs {
   const double* coef_d;       // per-cell or null
   const double* coef_m;
   double* values;             // (nnz)
-  int tile, threads;          // values per CTA, threads per CTA (<=0: defaults)
+  const int32_t* blk_row;     // (nblk+1) first row of every CTA tile (fb2_spmv_plan_build on crow)
+  int nblk, tile, threads;    // tile = values per CTA the partition was built with
 };
 
 struct AsmKeArgs {
@@ -32,9 +33,11 @@ struct AsmKeArgs {
   const int64_t* crow_s;      // scalar pattern
   const int64_t* crow_out;    // tensor pattern (== crow_s when ncomp == 1)
   double* values;
-  int tile;
+  const int32_t* blk_row;     // (nblk+1) tiling of the OUTPUT rows (crow_out)
+  int nblk, tile, slot_stride;
 };
 
+int slot_stride(int L, int slot_bytes);
 size_t sym_workspace_bytes(int64_t NC, int L, int64_t gdof);
 int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, int64_t* crow, int64_t* nnz_host,
               int* max_row_host, void* ws, cudaStream_t s);

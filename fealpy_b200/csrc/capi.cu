@@ -110,6 +110,7 @@ int fb2_coo_reduce(const uint32_t* perm, const int64_t* seg_start, int64_t nnz, 
 
 // ---- symbolic + fused numeric ---------------------------------------------------------------
 size_t fb2_sym_workspace_bytes(int64_t NC, int ldof, int64_t gdof) { return sym_workspace_bytes(NC, ldof, gdof); }
+int fb2_slot_stride(int ldof, int slot_bytes) { return slot_stride(ldof, slot_bytes); }
 int fb2_sym_count(const int32_t* c2d, int64_t NC, int ldof, int64_t gdof, int64_t* adj_ptr, int32_t* adj_pair, int64_t* crow,
                   int64_t* nnz_host, int32_t* max_row_host, void* ws, void* stream) {
   return sym_count(c2d, NC, ldof, gdof, adj_ptr, adj_pair, crow, nnz_host, max_row_host, ws, S(stream));
@@ -120,7 +121,8 @@ int fb2_sym_fill(const int32_t* c2d, int64_t NC, int ldof, int64_t gdof, const i
 }
 int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,
                               const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
-                              const int64_t* crow, int32_t max_row, const double* Ms, const double* Mm, double scal_d,
+                              const int64_t* crow, int32_t max_row, const int32_t* blk_row, int nblk, int tile,
+                              const double* Ms, const double* Mm, double scal_d,
                               const double* coef_d, double scal_m, const double* coef_m, double* values, void* stream) {
   if (!Ms && !Mm) return fail(ERR_INVALID, "assemble_scalar_const: need a diffusion and/or a mass table");
   AsmConstArgs a{};
@@ -128,25 +130,20 @@ int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const dou
   a.adj_ptr = adj_ptr; a.adj_pair = adj_pair; a.slots = slots; a.crow = crow;
   a.has_diff = Ms != nullptr; a.has_mass = Mm != nullptr; a.Ms = Ms; a.Mm = Mm;
   a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.values = values;
-  int64_t nnz = 0;
-  FB2_CUDA(cudaMemcpyAsync(&nnz, crow + gdof, 8, cudaMemcpyDeviceToHost, S(stream)));
-  FB2_CUDA(cudaStreamSynchronize(S(stream)));
-  a.nnz = nnz;
-  a.tile = 0; a.threads = 0;
+  a.nnz = 0;
+  a.blk_row = blk_row; a.nblk = nblk; a.tile = tile; a.threads = 0;
   return assemble_const(TD, p, a, slot_bytes, max_row, S(stream));
 }
 int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int64_t gdof_scalar, const double* Ke,
                          const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
-                         const int64_t* crow_scalar, int32_t max_row, const int64_t* crow_out, double* values, void* stream) {
+                         const int64_t* crow_scalar, int32_t max_row, const int64_t* crow_out, const int32_t* blk_row, int nblk,
+                         int tile, double* values, void* stream) {
   AsmKeArgs a{};
   a.gdof = gdof_scalar; a.L = ldof; a.ncomp = ncomp; a.dof_priority = dof_priority; a.Ke = Ke;
   a.adj_ptr = adj_ptr; a.adj_pair = adj_pair; a.slots = slots; a.crow_s = crow_scalar;
   a.crow_out = crow_out ? crow_out : crow_scalar; a.values = values;
-  int64_t nnz = 0;
-  FB2_CUDA(cudaMemcpyAsync(&nnz, a.crow_out + gdof_scalar * ncomp, 8, cudaMemcpyDeviceToHost, S(stream)));
-  FB2_CUDA(cudaStreamSynchronize(S(stream)));
-  a.nnz_out = nnz;
-  a.tile = 0;
+  a.nnz_out = 0;
+  a.blk_row = blk_row; a.nblk = nblk; a.tile = tile;
   return assemble_from_ke(a, slot_bytes, max_row, S(stream));
 }
 int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,

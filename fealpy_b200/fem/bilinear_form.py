@@ -93,13 +93,28 @@ def symbolic_pattern(space):
               C.byref(nnz), C.byref(max_row), _lib.ptr(ws), _lib.stream())
     slot_bytes = 1 if max_row.value <= 255 else 2
     col = torch.empty(nnz.value, dtype=torch.int32, device=dev)
-    slots = torch.empty(NC * L * L, dtype=torch.uint8 if slot_bytes == 1 else torch.int16, device=dev)
+    stride = lib.fb2_slot_stride(L, slot_bytes)
+    slots = torch.zeros(NC * L * stride, dtype=torch.uint8 if slot_bytes == 1 else torch.int16, device=dev)
     _lib.call("fb2_sym_fill", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow), _lib.ptr(col),
               _lib.ptr(slots), slot_bytes, _lib.stream())
+    blk_row, nblk = row_tiling(crow, gdof, nnz.value, ASM_TILE)
     cache = dict(adj_ptr=adj_ptr, adj_pair=adj_pair, crow=crow, col=col, slots=slots, slot_bytes=slot_bytes,
-                 max_row=max_row.value, nnz=nnz.value, NC=NC, L=L, gdof=gdof)
+                 max_row=max_row.value, nnz=nnz.value, NC=NC, L=L, gdof=gdof, blk_row=blk_row, nblk=nblk, tile=ASM_TILE)
     space._b200_symbolic = cache
     return cache
+
+
+ASM_TILE = 3072      # CSR values per CTA of the numeric assembly kernels
+
+
+def row_tiling(crow, nrow, nnz, tile):
+    """first row of every `tile`-value CTA tile (csrc/cg.cu partition_rows_kernel)"""
+    lib = _lib.load()
+    nblk = lib.fb2_spmv_plan_blocks(nnz, tile)
+    blk_row = torch.empty(nblk + 2, dtype=torch.int32, device=crow.device)
+    mr = C.c_int32(0)
+    _lib.call("fb2_spmv_plan_build", nrow, _lib.ptr(crow), tile, _lib.ptr(blk_row), nnz, C.byref(mr), _lib.stream())
+    return blk_row, nblk
 
 
 def tensor_pattern(space):
@@ -114,7 +129,8 @@ def tensor_pattern(space):
     col = torch.empty(sym["nnz"] * nc * nc, dtype=torch.int32, device=dev)
     _lib.call("fb2_expand_pattern", sym["gdof"], nc, int(space.dof_priority), _lib.ptr(sym["crow"]), _lib.ptr(sym["col"]),
               _lib.ptr(crow), _lib.ptr(col), _lib.stream())
-    cache = dict(crow=crow, col=col)
+    blk_row, nblk = row_tiling(crow, sym["gdof"] * nc, sym["nnz"] * nc * nc, ASM_TILE)
+    cache = dict(crow=crow, col=col, blk_row=blk_row, nblk=nblk, tile=ASM_TILE)
     space._b200_pattern = cache
     return cache
 
@@ -234,7 +250,7 @@ class BilinearForm:
         sm_, am = parts(mm)
         _lib.call("fb2_assemble_scalar_const", mesh.TD, space.p, sym["NC"], sym["gdof"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
                   _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]), _lib.ptr(sym["slots"]), sym["slot_bytes"],
-                  _lib.ptr(sym["crow"]), sym["max_row"],
+                  _lib.ptr(sym["crow"]), sym["max_row"], _lib.ptr(sym["blk_row"]), sym["nblk"], sym["tile"],
                   _lib.ptr(dm["tabs"]["Ms"]) if dm else None, _lib.ptr(mm["tabs"]["Mm"]) if mm else None,
                   sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(values), _lib.stream())
         return sym["crow"], sym["col"], values
@@ -256,17 +272,17 @@ class BilinearForm:
             sspace, nc, prio = space.scalar_space, space.dof_numel, int(space.dof_priority)
             sym = symbolic_pattern(sspace)
             pat = tensor_pattern(space)
-            crow, col = pat["crow"], pat["col"]
+            crow, col, tiling = pat["crow"], pat["col"], pat
         else:
             sym = symbolic_pattern(space)
             nc, prio = 1, 0
-            crow, col = sym["crow"], sym["col"]
+            crow, col, tiling = sym["crow"], sym["col"], sym
         if ke.shape != (sym["NC"], sym["L"] * nc, sym["L"] * nc):
             raise ValueError(f"entity_to_global.shape[0] != local_tensor.shape[0] or wrong local shape {tuple(ke.shape)}")
         values = torch.empty(col.shape[0], dtype=torch.float64, device=ke.device)
         _lib.call("fb2_assemble_from_ke", sym["NC"], sym["L"], nc, prio, sym["gdof"], _lib.ptr(ke), _lib.ptr(sym["adj_ptr"]),
                   _lib.ptr(sym["adj_pair"]), _lib.ptr(sym["slots"]), sym["slot_bytes"], _lib.ptr(sym["crow"]), sym["max_row"],
-                  _lib.ptr(crow), _lib.ptr(values), _lib.stream())
+                  _lib.ptr(crow), _lib.ptr(tiling["blk_row"]), tiling["nblk"], tiling["tile"], _lib.ptr(values), _lib.stream())
         return crow, col, values
 
     def _assemble_coo(self):

@@ -97,19 +97,24 @@ size_t fb2_sym_workspace_bytes(int64_t NC, int ldof, int64_t gdof);
 /* step 1: dof -> (cell, local index) adjacency, row lengths; returns nnz and max row length */
 int fb2_sym_count(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, int64_t* adj_ptr, int32_t* adj_pair, int64_t* crow,
                   int64_t* nnz_host, int32_t* max_row_host, void* ws, void* stream);
-/* step 2: col (nnz) and slot map (NC*ldof pairs x ldof, uint8 when max_row<=255 else uint16) */
+/* step 2: col (nnz) and slot map: NC*ldof records of fb2_slot_stride(ldof, slot_bytes) elements
+ * (uint8 when max_row<=255 else uint16; records padded to 4-byte multiples) */
+int fb2_slot_stride(int ldof, int slot_bytes);
 int fb2_sym_fill(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair,
                  const int64_t* crow, int32_t* col, void* slots, int slot_bytes, void* stream);
-/* numeric, constant / per-cell coefficient scalar forms (diffusion and/or mass fused) */
+/* numeric, constant / per-cell coefficient scalar forms (diffusion and/or mass fused).
+ * blk_row/nblk/tile: row tiling of crow from fb2_spmv_plan_build (one CTA per tile). */
 int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,
                               const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
-                              const int64_t* crow, int32_t max_row, const double* Ms, const double* Mm, double scal_d,
+                              const int64_t* crow, int32_t max_row, const int32_t* blk_row, int nblk, int tile,
+                              const double* Ms, const double* Mm, double scal_d,
                               const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* values, void* stream);
 /* numeric, generic: gathers rows of a precomputed element-matrix block Ke (NC, lt, lt);
  * ncomp > 1 = tensor space over the scalar pattern (interleaved or dof-priority layout) */
 int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int64_t gdof_scalar, const double* Ke,
                          const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
-                         const int64_t* crow_scalar, int32_t max_row, const int64_t* crow_out, double* values, void* stream);
+                         const int64_t* crow_scalar, int32_t max_row, const int64_t* crow_out, const int32_t* blk_row, int nblk,
+                         int tile, double* values, void* stream);
 /* expands the scalar pattern to the tensor-space pattern */
 int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,
                        int64_t* crow_out, int32_t* col_out, void* stream);
