@@ -67,6 +67,12 @@ SIGNATURES = {
     "fb2_tet_box_slab": (_i32, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "fb2_cg_finalize": (_i32, [_p, _p]),
     "fb2_cg_update_p": (_i32, [_i64, _p, _p, _p, _p, _p]),
+    "fb2_elem_source": (_i32, [_i32, _i64, _i32, _i32, _p, _p, _p, _i32, _f64, _p, _p, _p]),
+    "fb2_gather_vector": (_i32, [_i64, _p, _p, _p, _p, _p]),
+    "fb2_bc_workspace_bytes": (_sz, [_i64]),
+    "fb2_bc_matrix_count": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p]),
+    "fb2_bc_matrix_fill": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fb2_bc_vector": (_i32, [_i64, _p, _p, _p, _p]),
     "fb2_sort_workspace_bytes": (_sz, [_i64]),
     "fb2_sort_pairs": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p]),
     "fb2_scan_workspace_bytes": (_sz, [_i64]),

@@ -1,0 +1,165 @@
+// "Next" rows of the path: the right-hand side and the Dirichlet step
+// that sit between assembly() and cg() in every real caller.
+//   LinearForm.assembly + ScalarSourceIntegrator   fem/linear_form.py:36-86, fem/scalar_source_integrator.py:13-57,
+//                                                  functional.py linear_integral
+//   DirichletBC.apply / apply_matrix / apply_vector fem/dirichlet_bc.py:101-235
+#include "common.cuh"
+#include "sort_scan.cuh"
+#include "bc_source.cuh"
+
+namespace fb2 {
+
+static inline unsigned grid_for(int64_t n, int threads = 256) {
+  int64_t b = ceil_div(n, threads);
+  const int64_t cap = (int64_t)kNumSM * 32;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <int TD>
+__device__ __forceinline__ double cell_measure(const double* __restrict__ node, const int* __restrict__ cell, int64_t c);
+
+template <>
+__device__ __forceinline__ double cell_measure<2>(const double* __restrict__ node, const int* __restrict__ cell, int64_t c) {
+  const double2 p0 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)cell[3 * c]);
+  const double2 p1 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)cell[3 * c + 1]);
+  const double2 p2 = *reinterpret_cast<const double2*>(node + 2 * (int64_t)cell[3 * c + 2]);
+  return 0.5 * ((p1.x - p0.x) * (p2.y - p1.y) - (p1.y - p0.y) * (p2.x - p1.x));
+}
+
+template <>
+__device__ __forceinline__ double cell_measure<3>(const double* __restrict__ node, const int* __restrict__ cell, int64_t c) {
+  const int4 v = *reinterpret_cast<const int4*>(cell + 4 * c);
+  const double* q0 = node + 3 * (int64_t)v.x;
+  const double* q1 = node + 3 * (int64_t)v.y;
+  const double* q2 = node + 3 * (int64_t)v.z;
+  const double* q3 = node + 3 * (int64_t)v.w;
+  double a[3], b[3], cc[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) { a[m] = q1[m] - q0[m]; b[m] = q2[m] - q1[m]; cc[m] = q3[m] - q2[m]; }
+  const double det = a[0] * (b[1] * cc[2] - b[2] * cc[1]) + a[1] * (b[2] * cc[0] - b[0] * cc[2]) + a[2] * (b[0] * cc[1] - b[1] * cc[0]);
+  return det / 6.0;
+}
+
+// F_e[c][i] = vol_c * sum_q w_q phi_i(q) f_cq ;  f: scalar (kind 0), per cell (1), per quadrature point (2)
+template <int TD>
+__global__ void __launch_bounds__(256) elem_source_kernel(const double* __restrict__ node, const int* __restrict__ cell, int64_t NC, int L,
+                                                          int NQ, const double* __restrict__ phiw /*[NQ][L] = w_q phi_i(q)*/,
+                                                          int kind, double scal, const double* __restrict__ f, double* __restrict__ out) {
+  extern __shared__ double sp[];
+  for (int t = threadIdx.x; t < NQ * L; t += blockDim.x) sp[t] = phiw[t];
+  __syncthreads();
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < NC; c += (int64_t)gridDim.x * blockDim.x) {
+    const double cm = cell_measure<TD>(node, cell, c);
+    for (int i = 0; i < L; ++i) {
+      double s = 0.0;
+      if (kind == 2) {
+        for (int q = 0; q < NQ; ++q) s += sp[q * L + i] * f[c * NQ + q];
+      } else {
+        for (int q = 0; q < NQ; ++q) s += sp[q * L + i];
+        s *= (kind == 1) ? f[c] : 1.0;
+      }
+      out[c * L + i] = cm * scal * s;
+    }
+  }
+}
+
+// F[d] = sum over the (cell, i) pairs of dof d, ascending (the order of the reference's index_add)
+__global__ void __launch_bounds__(256) gather_vector_kernel(int64_t gdof, const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair,
+                                                            const double* __restrict__ fe, double* __restrict__ F) {
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < gdof; d += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int64_t q = adj_ptr[d]; q < adj_ptr[d + 1]; ++q) s += fe[adj_pair[q]];
+    F[d] = s;
+  }
+}
+
+int elem_source(int TD, int64_t NC, int L, int NQ, const double* node, const int* cell, const double* phiw, int kind, double scal,
+                const double* f, double* out, cudaStream_t s) {
+  if (NC <= 0) return OK;
+  const size_t smem = (size_t)NQ * L * sizeof(double);
+  if (smem > 48 * 1024) return fail(ERR_UNSUPPORTED, "elem_source: quadrature table too large");
+  if (TD == 2) elem_source_kernel<2><<<grid_for(NC), 256, smem, s>>>(node, cell, NC, L, NQ, phiw, kind, scal, f, out);
+  else if (TD == 3) elem_source_kernel<3><<<grid_for(NC), 256, smem, s>>>(node, cell, NC, L, NQ, phiw, kind, scal, f, out);
+  else return fail(ERR_UNSUPPORTED, "elem_source: TD=%d", TD);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int gather_vector(int64_t gdof, const int64_t* adj_ptr, const int* adj_pair, const double* fe, double* F, cudaStream_t s) {
+  if (gdof <= 0) return OK;
+  gather_vector_kernel<<<grid_for(gdof), 256, 0, s>>>(gdof, adj_ptr, adj_pair, fe, F);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+// ---- Dirichlet ---------------------------------------------------------------------------
+// matrix: rows/columns of boundary dofs removed, unit diagonal on boundary rows (canonical
+// sorted CSR; the reference reaches the same matrix through _mul + spdiags, dirichlet_bc.py:133-229)
+__global__ void __launch_bounds__(256) bc_count_kernel(int64_t n, const int64_t* __restrict__ crow, const int* __restrict__ col,
+                                                       const uint8_t* __restrict__ isbd, int* __restrict__ cnt) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    int c = 1;
+    if (!isbd[r]) {
+      c = 0;
+      for (int64_t k = crow[r]; k < crow[r + 1]; ++k) c += isbd[col[k]] ? 0 : 1;
+    }
+    cnt[r] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256) bc_fill_kernel(int64_t n, const int64_t* __restrict__ crow, const int* __restrict__ col,
+                                                      const double* __restrict__ val, const uint8_t* __restrict__ isbd,
+                                                      const int64_t* __restrict__ crow_new, int* __restrict__ col_new,
+                                                      double* __restrict__ val_new) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t o = crow_new[r];
+    if (isbd[r]) {
+      col_new[o] = (int)r;
+      val_new[o] = 1.0;
+    } else {
+      for (int64_t k = crow[r]; k < crow[r + 1]; ++k) {
+        const int c = col[k];
+        if (!isbd[c]) { col_new[o] = c; val_new[o] = val[k]; ++o; }
+      }
+    }
+  }
+}
+
+// f <- isbd ? uh : f   (f already holds f - A uh)
+__global__ void __launch_bounds__(256) bc_vector_kernel(int64_t n, const uint8_t* __restrict__ isbd, const double* __restrict__ uh,
+                                                        double* __restrict__ f) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+    if (isbd[r]) f[r] = uh[r];
+}
+
+size_t bc_workspace_bytes(int64_t n) { return align_up((size_t)n * 4) + scan_workspace_bytes(n) + 1024; }
+
+int bc_matrix_count(int64_t n, const int64_t* crow, const int* col, const uint8_t* isbd, int64_t* crow_new, int64_t* nnz_host, void* ws,
+                    cudaStream_t s) {
+  Carver c(ws);
+  int* cnt = c.take<int>(n);
+  void* scan_ws = c.take<char>(scan_workspace_bytes(n));
+  if (n > 0) bc_count_kernel<<<grid_for(n), 256, 0, s>>>(n, crow, col, isbd, cnt);
+  FB2_LAUNCH_CHECK();
+  FB2_TRY(exclusive_scan_i32(cnt, crow_new, n, true, scan_ws, s));
+  FB2_CUDA(cudaMemcpyAsync(nnz_host, crow_new + n, 8, cudaMemcpyDeviceToHost, s));
+  FB2_CUDA(cudaStreamSynchronize(s));
+  return OK;
+}
+
+int bc_matrix_fill(int64_t n, const int64_t* crow, const int* col, const double* val, const uint8_t* isbd, const int64_t* crow_new,
+                   int* col_new, double* val_new, cudaStream_t s) {
+  if (n <= 0) return OK;
+  bc_fill_kernel<<<grid_for(n), 256, 0, s>>>(n, crow, col, val, isbd, crow_new, col_new, val_new);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int bc_vector(int64_t n, const uint8_t* isbd, const double* uh, double* f, cudaStream_t s) {
+  if (n <= 0) return OK;
+  bc_vector_kernel<<<grid_for(n), 256, 0, s>>>(n, isbd, uh, f);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+}  // namespace fb2

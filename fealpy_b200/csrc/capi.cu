@@ -5,6 +5,7 @@
 
 #include "../../include/fealpy_b200.h"
 #include "assemble.cuh"
+#include "bc_source.cuh"
 #include "cg.cuh"
 #include "common.cuh"
 #include "coo_csr.cuh"
@@ -228,6 +229,28 @@ int fb2_tet_box_slab(const double box[6], int nx, int ny, int nz, int cube_layer
 int fb2_cg_finalize(void* scalars, void* stream) { return cg_finalize(static_cast<CgScalars*>(scalars), S(stream)); }
 int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, void* stream) {
   return cg_update_p(n, p, r, minv_diag, static_cast<CgScalars*>(scalars), S(stream));
+}
+
+// ---- next rows: source vector, Dirichlet -----------------------------------------------------
+int fb2_elem_source(int TD, int64_t NC, int ldof, int NQ, const double* node, const int32_t* cell, const double* phiw, int kind,
+                    double scal, const double* f, double* out, void* stream) {
+  if (kind < 0 || kind > 2) return fail(ERR_INVALID, "elem_source: kind must be 0 (scalar), 1 (NC,) or 2 (NC,NQ)");
+  return elem_source(TD, NC, ldof, NQ, node, cell, phiw, kind, scal, f, out, S(stream));
+}
+int fb2_gather_vector(int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair, const double* fe, double* F, void* stream) {
+  return gather_vector(gdof, adj_ptr, adj_pair, fe, F, S(stream));
+}
+size_t fb2_bc_workspace_bytes(int64_t n) { return bc_workspace_bytes(n); }
+int fb2_bc_matrix_count(int64_t n, const int64_t* crow, const int32_t* col, const uint8_t* isbd, int64_t* crow_new,
+                        int64_t* nnz_host, void* ws, void* stream) {
+  return bc_matrix_count(n, crow, col, isbd, crow_new, nnz_host, ws, S(stream));
+}
+int fb2_bc_matrix_fill(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const uint8_t* isbd,
+                       const int64_t* crow_new, int32_t* col_new, double* values_new, void* stream) {
+  return bc_matrix_fill(n, crow, col, values, isbd, crow_new, col_new, values_new, S(stream));
+}
+int fb2_bc_vector(int64_t n, const uint8_t* isbd, const double* uh, double* f, void* stream) {
+  return bc_vector(n, isbd, uh, f, S(stream));
 }
 
 // ---- raw primitives -------------------------------------------------------------------------

@@ -156,6 +156,23 @@ int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const dou
 int fb2_cg_finalize(void* scalars, void* stream);
 int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, void* stream);
 
+/* ---- next rows: right-hand side and Dirichlet step ------------------------
+ * replaces ScalarSourceIntegrator.assembly + LinearForm.assembly (fem/scalar_source_integrator.py:13-57,
+ * fem/linear_form.py:36-86) and DirichletBC.apply (fem/dirichlet_bc.py:101-235). */
+/* F_e (NC,l) = vol_c * scal * sum_q phiw[q][i] f_cq; kind 0: f = 1, 1: f (NC,), 2: f (NC,NQ) */
+int fb2_elem_source(int TD, int64_t NC, int ldof, int NQ, const double* node, const int32_t* cell, const double* phiw, int kind,
+                    double scal, const double* f, double* out, void* stream);
+/* F[d] = sum of F_e over the (cell, i) pairs of dof d in ascending order (adjacency of fb2_sym_count) */
+int fb2_gather_vector(int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair, const double* fe, double* F, void* stream);
+size_t fb2_bc_workspace_bytes(int64_t n);
+/* canonical CSR of the constrained matrix: boundary rows/columns removed, unit diagonal on boundary rows */
+int fb2_bc_matrix_count(int64_t n, const int64_t* crow, const int32_t* col, const uint8_t* isbd, int64_t* crow_new,
+                        int64_t* nnz_host, void* ws, void* stream);
+int fb2_bc_matrix_fill(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const uint8_t* isbd,
+                       const int64_t* crow_new, int32_t* col_new, double* values_new, void* stream);
+/* f[r] = uh[r] on boundary dofs (f must already hold f - A uh, e.g. from fb2_cg_residual) */
+int fb2_bc_vector(int64_t n, const uint8_t* isbd, const double* uh, double* f, void* stream);
+
 /* ---- raw primitives (exported for tests) ---------------------------------------------------*/
 size_t fb2_sort_workspace_bytes(int64_t n);
 int fb2_sort_pairs(uint64_t* keys, uint32_t* vals, int identity_payload, int64_t n, int key_bits, void* ws, void* stream);
