@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(CG_THREADS) spmm_kernel(int64_t n, const int64
 // unrolled loads (memory-level parallelism independent of the row lengths), gathers x and
 // parks the products in shared memory; phase 2 reduces each row with G lanes.  Row sums and
 // the fused p.Ap partials are formed in a fixed order -> bitwise reproducible.
-constexpr int ST_UNROLL = 4;
+constexpr int ST_UNROLL = 8;
+constexpr int ST_ROWCAP = 1024;      // row pointers of a tile staged in shared memory (else read from global)
 
 template <int G>
 __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, const int64_t* __restrict__ crow,
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
                                                                  double* partials, unsigned int* counter, const CgScalars* sc,
                                                                  OwnRange own) {
   if (sc && sc->done) return;
-  extern __shared__ __align__(16) double prod[];
+  extern __shared__ __align__(16) double prod[];               // [tile + max_row] products, then [ST_ROWCAP+1] row offsets
+  __shared__ int rowoff[ST_ROWCAP + 1];
   const int tid = threadIdx.x;
   const int g = tid % G, grp = tid / G;
   constexpr int NGRP = CG_THREADS / G;
@@ -137,31 +139,58 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     const int r0 = blk_row[blk], r1 = blk_row[blk + 1];
     if (r0 == r1) continue;
+    const int nrow = r1 - r0;
+    const bool staged = nrow <= ST_ROWCAP;
     const int64_t v0 = crow[r0];
     const int nval = (int)(crow[r1] - v0);
     const double* __restrict__ vp = val + v0;
     const int32_t* __restrict__ cp = col + v0;
+    // row offsets of the tile (coalesced) -- issued before the value stream so both are in flight
+    if (staged)
+      for (int t = tid; t <= nrow; t += CG_THREADS) rowoff[t] = (int)(crow[r0 + t] - v0);
     int k = tid;
     for (; k + (ST_UNROLL - 1) * CG_THREADS < nval; k += ST_UNROLL * CG_THREADS) {
       double vv[ST_UNROLL];
       int cc[ST_UNROLL];
 #pragma unroll
       for (int u = 0; u < ST_UNROLL; ++u) { vv[u] = ld_stream(vp + k + u * CG_THREADS); cc[u] = ld_stream(cp + k + u * CG_THREADS); }
+      double xx[ST_UNROLL];
 #pragma unroll
-      for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * CG_THREADS] = vv[u] * x[cc[u]];
+      for (int u = 0; u < ST_UNROLL; ++u) xx[u] = x[cc[u]];
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * CG_THREADS] = vv[u] * xx[u];
     }
-    for (; k < nval; k += CG_THREADS) prod[k] = ld_stream(vp + k) * x[ld_stream(cp + k)];
+    {
+      // tail: predicated, still all loads first
+      double vv[ST_UNROLL];
+      int cc[ST_UNROLL];
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u) {
+        const int kk = k + u * CG_THREADS;
+        const bool ok = kk < nval;
+        vv[u] = ok ? ld_stream(vp + kk) : 0.0;
+        cc[u] = ok ? ld_stream(cp + kk) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u) {
+        const int kk = k + u * CG_THREADS;
+        if (kk < nval) prod[kk] = vv[u] * x[cc[u]];
+      }
+    }
     __syncthreads();
-    for (int base = r0; base < r1; base += NGRP) {
-      const int r = base + grp;
+    for (int base = 0; base < nrow; base += NGRP) {
+      const int rl = base + grp;
       double acc = 0.0;
-      if (r < r1) {
-        const int s = (int)(crow[r] - v0), e = (int)(crow[r + 1] - v0);
+      if (rl < nrow) {
+        int s, e;
+        if (staged) { s = rowoff[rl]; e = rowoff[rl + 1]; }
+        else { s = (int)(crow[r0 + rl] - v0); e = (int)(crow[r0 + rl + 1] - v0); }
         for (int q = s + g; q < e; q += G) acc += prod[q];
       }
 #pragma unroll
       for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (r < r1 && g == 0) {
+      if (rl < nrow && g == 0) {
+        const int64_t r = r0 + rl;
         const double yv = mode ? b[r] - acc : acc;
         y[r] = yv;
         if (dot_out && own.has(r)) dsum += x[r] * yv;

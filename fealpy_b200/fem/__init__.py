@@ -1,5 +1,6 @@
 from .integrators import Integrator, ScalarDiffusionIntegrator, ScalarMassIntegrator, LinearElasticityIntegrator
 from .bilinear_form import BilinearForm, GroupIntegrator
+from .linear_form import LinearForm, ScalarSourceIntegrator, DirichletBC
 
 __all__ = ["Integrator", "ScalarDiffusionIntegrator", "ScalarMassIntegrator", "LinearElasticityIntegrator",
-           "BilinearForm", "GroupIntegrator"]
+           "BilinearForm", "GroupIntegrator", "LinearForm", "ScalarSourceIntegrator", "DirichletBC"]

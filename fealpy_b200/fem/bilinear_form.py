@@ -23,6 +23,7 @@ from collections.abc import Sequence
 import torch
 
 from .. import _lib
+from ..basis import host_tables
 from ..sparse import COOTensor, CSRTensor
 from .integrators import Integrator
 
@@ -104,7 +105,8 @@ def symbolic_pattern(space):
     return cache
 
 
-ASM_TILE = 3072      # CSR values per CTA of the numeric assembly kernels
+import os as _os
+ASM_TILE = int(_os.environ.get("FB2_ASM_TILE", "3072"))      # CSR values per CTA of the numeric assembly kernels
 
 
 def row_tiling(crow, nrow, nnz, tile):
@@ -248,10 +250,19 @@ class BilinearForm:
             return (1.0, m["arr"].contiguous()) if m["arr"] is not None else (m["scal"], None)
         sd, ad = parts(dm)
         sm_, am = parts(mm)
+        NV = mesh.TD + 1
+        geom = torch.empty((sym["NC"], NV * (NV + 1) // 2 + 1), dtype=torch.float64, device=mesh.device)
+
+        def hostp(m, key):
+            if m is None:
+                return None
+            h = host_tables(mesh.TD, space.p, m["q"])[key]
+            return h.ctypes.data_as(C.c_void_p)
         _lib.call("fb2_assemble_scalar_const", mesh.TD, space.p, sym["NC"], sym["gdof"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
                   _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]), _lib.ptr(sym["slots"]), sym["slot_bytes"],
                   _lib.ptr(sym["crow"]), sym["max_row"], _lib.ptr(sym["blk_row"]), sym["nblk"], sym["tile"],
                   _lib.ptr(dm["tabs"]["Ms"]) if dm else None, _lib.ptr(mm["tabs"]["Mm"]) if mm else None,
+                  hostp(dm, "Ms"), hostp(mm, "Mm"), _lib.ptr(geom),
                   sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(values), _lib.stream())
         return sym["crow"], sym["col"], values
 

@@ -352,3 +352,107 @@ def test_distributed_driver_single_rank_matches_cg(U):
     assert i1["niter"] == i2["niter"]
     assert float((x1 - x2).abs().max()) <= 1e-13
     G = U  # keep fixture used
+
+
+@pytest.mark.parametrize("case", C.BC_CASES, ids=lambda c: c["name"])
+def test_poisson_source_dirichlet_cg(case, U):
+    """rows f1/f2: LinearForm + ScalarSourceIntegrator, DirichletBC.apply, then cg -- against the
+    reference run (golden) of the same Poisson problem"""
+    from fealpy_b200.fem import BilinearForm, LinearForm, ScalarDiffusionIntegrator, ScalarSourceIntegrator, DirichletBC
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.solver import cg
+    gold = G.load(case["name"])
+    mesh = U.make_mesh(case, gold)
+    space = LagrangeFESpace(mesh, case["p"])
+    A = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).assembly()
+    U.assert_csr_matches(A, gold)
+    F = LinearForm(space).add_integrator(ScalarSourceIntegrator(U.torch_coef_func(C.source_cart))).assembly()
+    assert np.max(np.abs(F.cpu().numpy() - gold["F"])) <= 1e-13 * np.max(np.abs(gold["F"]))
+    assert np.array_equal(space.is_boundary_dof().cpu().numpy(), gold["isbd"])
+    np.testing.assert_allclose(space.interpolation_points().cpu().numpy(), gold["ipoints"], atol=1e-14)
+    bc = DirichletBC(space, gd=U.torch_coef_func(C.kappa_cart))
+    A2, F2 = bc.apply(A, F)
+    assert np.max(np.abs(F2.cpu().numpy() - gold["F_bc"])) <= 1e-12 * np.max(np.abs(gold["F_bc"]))
+    S = A2.to_scipy()
+    assert S.has_sorted_indices
+    S.eliminate_zeros()
+    assert np.array_equal(S.indptr, gold["Abc_indptr"]) and np.array_equal(S.indices, gold["Abc_indices"])
+    assert np.max(np.abs(S.data - gold["Abc_data"])) <= 1e-12 * np.max(np.abs(gold["Abc_data"]))
+    x, info = cg(A2, F2, returninfo=True)
+    assert np.linalg.norm(x.cpu().numpy() - gold["x"]) / np.linalg.norm(gold["x"]) <= 1e-10
+    assert abs(info["niter"] - gold["info"]["niter"]) <= 1
+    # inputs untouched
+    U.assert_csr_matches(A, gold)
+
+
+def test_config1_tri_p1_1024_full_size(U):
+    """BASELINE config 1: tri P1 1024^2, diffusion q=3 (+ mass for CG): closed-form sizes, K 1 = 0, CG."""
+    from fealpy_b200.mesh import TriangleMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    from fealpy_b200.solver import cg
+    mesh = TriangleMesh.from_box([0, 1, 0, 1], 1024, 1024)
+    space = LagrangeFESpace(mesh, 1)
+    K = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator(q=3)).assembly()
+    assert (mesh.number_of_cells(), K.shape[0], K.nnz) == (2_097_152, 1_050_625, 7_346_177)
+    one = torch.ones(K.shape[0], dtype=torch.float64, device="cuda")
+    assert float((K @ one).abs().max()) <= 1e-11 * float(K.values.abs().max())
+    bf = BilinearForm(space)
+    bf.add_integrator(ScalarDiffusionIntegrator(q=3))
+    bf.add_integrator(ScalarMassIntegrator(q=3))
+    A = bf.assembly()
+    x, info = cg(A, A @ one, returninfo=True)
+    assert info["niter"] < 10000 and float((x - 1.0).abs().max()) < 1e-5
+
+
+def test_config3_tri_p3_varcoef_full_size(U):
+    """BASELINE config 3: tri P3 1024^2 with a variable coefficient (quadrature-loop kernel + gather path):
+    a coefficient callable returning a constant must reproduce the constant-coefficient (fused) matrix."""
+    from fealpy_b200.mesh import TriangleMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator
+    from fealpy_b200.decorator import cartesian
+    mesh = TriangleMesh.from_box([0, 1, 0, 1], 1024, 1024)
+    space = LagrangeFESpace(mesh, 3)
+
+    @cartesian
+    def kappa(p):
+        return 1.0 + 0.5 * torch.sin(2 * torch.pi * p[..., 0]) * torch.cos(2 * torch.pi * p[..., 1])
+
+    bf = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator(coef=kappa, q=6))
+    A = bf.assembly()
+    assert bf.last_path == "gather"
+    assert (A.shape[0], A.nnz) == (9_443_329, 160_462_849)
+    one = torch.ones(A.shape[0], dtype=torch.float64, device="cuda")
+    assert float((A @ one).abs().max()) <= 1e-10 * float(A.values.abs().max())
+    S = A.to_scipy()
+    assert abs(S - S.T).max() <= 1e-12 * float(A.values.abs().max())
+
+    @cartesian
+    def two(p):
+        return torch.full(p.shape[:-1], 2.0, dtype=torch.float64, device=p.device)
+    B = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator(coef=two, q=6)).assembly()
+    Cc = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator(coef=2.0, q=6)).assembly()
+    assert torch.equal(B.col, Cc.col) and float((B.values - Cc.values).abs().max()) <= 1e-12 * float(Cc.values.abs().max())
+
+
+def test_config4_tet_p1_elasticity_full_size(U):
+    """BASELINE config 4: tet P1 x3 elasticity 128^3 (interleaved dofs): sizes, rigid translations in the
+    kernel (K t = 0), symmetry sample."""
+    from fealpy_b200.mesh import TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace, TensorFunctionSpace
+    from fealpy_b200.fem import BilinearForm, LinearElasticityIntegrator
+    from fealpy_b200.material import LinearElasticMaterial
+    mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], 128, 128, 128)
+    space = TensorFunctionSpace(LagrangeFESpace(mesh, 1), shape=(-1, 3))
+    mat = LinearElasticMaterial("m", elastic_modulus=1.0, poisson_ratio=0.3, hypo="3D")
+    A = BilinearForm(space).add_integrator(LinearElasticityIntegrator(mat, q=4)).assembly()
+    assert (A.shape[0], A.nnz) == (6_440_067, 286_222_473)
+    scale = float(A.values.abs().max())
+    for comp in range(3):
+        t = torch.zeros(A.shape[0], dtype=torch.float64, device="cuda")
+        t[comp::3] = 1.0
+        assert float((A @ t).abs().max()) <= 1e-10 * scale
+    x = torch.rand(A.shape[0], dtype=torch.float64, device="cuda")
+    y = torch.rand(A.shape[0], dtype=torch.float64, device="cuda")
+    assert abs(float(y @ (A @ x)) - float(x @ (A @ y))) <= 1e-9 * abs(float(y @ (A @ x)))
