@@ -298,7 +298,7 @@ struct SlotRec {
 // The dependent chain adjacency -> cell vertices -> node coordinates is software-pipelined
 // three deep so that the global-load latency of pair q+1..q+3 hides behind the FP64 work of pair q.
 #ifndef FB2_ASM_MINBLOCKS
-#define FB2_ASM_MINBLOCKS 4
+#define FB2_ASM_MINBLOCKS 3
 #endif
 template <int TD, int L, typename SlotT>
 __global__ void __launch_bounds__(128, FB2_ASM_MINBLOCKS) assemble_const_kernel(AsmConstArgs a) {

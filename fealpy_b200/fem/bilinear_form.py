@@ -106,7 +106,7 @@ def symbolic_pattern(space):
 
 
 import os as _os
-ASM_TILE = int(_os.environ.get("FB2_ASM_TILE", "3072"))      # CSR values per CTA of the numeric assembly kernels
+ASM_TILE = int(_os.environ.get("FB2_ASM_TILE", "4096"))      # CSR values per CTA of the numeric assembly kernels
 
 
 def row_tiling(crow, nrow, nnz, tile):
@@ -251,7 +251,9 @@ class BilinearForm:
         sd, ad = parts(dm)
         sm_, am = parts(mm)
         NV = mesh.TD + 1
-        geom = torch.empty((sym["NC"], NV * (NV + 1) // 2 + 1), dtype=torch.float64, device=mesh.device)
+        geom = None
+        if _os.environ.get("FB2_ASM_KERNEL", "v2") == "v3":     # per-cell geometry precompute variant (slower so far)
+            geom = torch.empty((sym["NC"], NV * (NV + 1) // 2 + 1), dtype=torch.float64, device=mesh.device)
 
         def hostp(m, key):
             if m is None:
