@@ -729,3 +729,273 @@ int expand_pattern(int64_t gdof, int nc, int prio, const int64_t* crow_s, const 
 }
 
 }  // namespace fb2
+
+// =====================================================================================
+// v4: scheduled batches.  The symbolic phase turns every tile (a run of rows holding at most
+// `tile` values, owned by ONE warp) into a list of 32-entry batches such that
+//   * all entries of a batch share the local index i      -> the table row T[i] is warp-uniform,
+//   * all entries of a batch belong to different rows      -> conflict-free accumulation,
+//   * per row, entries appear in (i, cell) order           -> fixed, reproducible summation order.
+// The numeric kernel is then a flat loop over batches with every lane busy: lane = one
+// (row, cell) pair; geometry comes precomputed per cell (H), the element row is 11 FMAs per
+// column against broadcast table reads, the result is added into the warp's private tile.
+// =====================================================================================
+namespace fb2 {
+
+constexpr int A4_ROWCHUNK = 128;     // rows scheduled together (conflict mask width)
+
+struct A4Entry { int cell; int q; unsigned short base; };
+
+// one thread per tile; COUNT pass returns the number of batches, FILL pass writes them
+template <bool FILL>
+__global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int32_t* __restrict__ blk_row, const int64_t* __restrict__ crow,
+                                                            const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair, int L,
+                                                            int* __restrict__ nbatch_of_tile, const int64_t* __restrict__ batch_ptr,
+                                                            unsigned char* __restrict__ batch_i, int* __restrict__ ent_cell,
+                                                            unsigned short* __restrict__ ent_base, uint32_t* __restrict__ ent_slots,
+                                                            const uint32_t* __restrict__ slot_words, int slot_nwords) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntile) return;
+  const int64_t r0 = blk_row[t], r1 = blk_row[t + 1];
+  const int64_t v0 = crow[r0];
+  int64_t nb = 0;                                  // batches emitted so far (tile-local)
+  const int64_t b0 = FILL ? batch_ptr[t] : 0;
+  int64_t cursor[A4_ROWCHUNK];
+  for (int64_t c0 = r0; c0 < r1; c0 += A4_ROWCHUNK) {
+    const int nr = (int)((r1 - c0) < A4_ROWCHUNK ? (r1 - c0) : A4_ROWCHUNK);
+    for (int k = 0; k < nr; ++k) cursor[k] = adj_ptr[c0 + k];
+    for (int i = 0; i < L; ++i) {
+      int fill = 0;                                // entries in the open batch
+      uint32_t mask[A4_ROWCHUNK / 32] = {0, 0, 0, 0};
+      bool any = true;
+      while (any) {
+        any = false;
+        for (int k = 0; k < nr; ++k) {
+          const int64_t q = cursor[k];
+          if (q >= adj_ptr[c0 + k + 1]) continue;
+          const int pair = adj_pair[q];
+          if (pair % L != i) continue;
+          any = true;
+          if (fill == 32 || (mask[k >> 5] >> (k & 31)) & 1u) {       // full, or this row is already in the batch
+            if (FILL) for (int z = fill; z < 32; ++z) ent_cell[(b0 + nb) * 32 + z] = -1;
+            ++nb; fill = 0;
+            mask[0] = mask[1] = mask[2] = mask[3] = 0;
+          }
+          if (FILL) {
+            const int64_t e = (b0 + nb) * 32 + fill;
+            if (fill == 0) batch_i[b0 + nb] = (unsigned char)i;
+            ent_cell[e] = pair / L;
+            ent_base[e] = (unsigned short)(crow[c0 + k] - v0);
+            for (int w = 0; w < slot_nwords; ++w) ent_slots[e * slot_nwords + w] = slot_words[q * slot_nwords + w];
+          }
+          mask[k >> 5] |= 1u << (k & 31);
+          ++fill;
+          cursor[k] = q + 1;
+        }
+      }
+      if (fill > 0) {                              // close the batch at the end of the i-group
+        if (FILL) for (int z = fill; z < 32; ++z) ent_cell[(b0 + nb) * 32 + z] = -1;
+        ++nb;
+      }
+    }
+  }
+  if (!FILL) nbatch_of_tile[t] = (int)nb;
+}
+
+template <int TD, int L, typename SlotT, int I>
+__device__ __forceinline__ void a4_row(const double* __restrict__ sT, const double (&h)[(TD + 1) * (TD + 2) / 2 + 1],
+                                       const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
+  constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1, ROW = ((NH + 1) / 2) * 2;
+  using SR = SlotRec<SlotT, L>;
+  constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
+#pragma unroll
+  for (int j0 = 0; j0 < L; j0 += JC) {
+    double val[JC];
+#pragma unroll
+    for (int jj = 0; jj < JC; ++jj) {
+      const double2* __restrict__ row = reinterpret_cast<const double2*>(sT + ((I * L) + j0 + jj) * ROW);
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < ROW / 2; ++t) {
+        const double2 m = row[t];
+        s0 += m.x * h[2 * t];
+        if (2 * t + 1 < NH) s1 += m.y * h[2 * t + 1];
+      }
+      val[jj] = s0 + s1;
+    }
+    double old[JC];
+#pragma unroll
+    for (int jj = 0; jj < JC; ++jj) old[jj] = my[SR::get(sw, j0 + jj)];
+#pragma unroll
+    for (int jj = 0; jj < JC; ++jj) my[SR::get(sw, j0 + jj)] = old[jj] + val[jj];
+  }
+}
+
+template <int TD, int L, typename SlotT, int I>
+__device__ __forceinline__ void a4_dispatch(int i, const double* __restrict__ sT, const double (&h)[(TD + 1) * (TD + 2) / 2 + 1],
+                                            const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
+  if (i == I) a4_row<TD, L, SlotT, I>(sT, h, sw, my);
+  else if constexpr (I + 1 < L) a4_dispatch<TD, L, SlotT, I + 1>(i, sT, h, sw, my);
+}
+
+#ifndef FB2_ASM4_WARPS
+#define FB2_ASM4_WARPS 8
+#endif
+#ifndef FB2_ASM4_MINBLOCKS
+#define FB2_ASM4_MINBLOCKS 2
+#endif
+
+// H rows are padded to HS doubles (multiple of 2) so that they are read with 128-bit loads
+template <int TD, int L, typename SlotT>
+__global__ void __launch_bounds__(FB2_ASM4_WARPS * 32, FB2_ASM4_MINBLOCKS) assemble_const_v4_kernel(const __grid_constant__ Asm4Args a) {
+  constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1, ROW = ((NH + 1) / 2) * 2, HS = ROW;
+  using SR = SlotRec<SlotT, L>;
+  extern __shared__ __align__(16) double sm4[];
+  double* sT = sm4;                                             // [L][L][ROW]
+  for (int t = threadIdx.x; t < L * L * ROW; t += blockDim.x) {
+    const int ij = t / ROW, k = t - ij * ROW;
+    double v = 0.0;
+    if (k < NG) v = a.Ms ? a.Ms[ij * NG + k] : 0.0;
+    else if (k == NG) v = a.Mm ? a.Mm[ij] : 0.0;
+    sT[t] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tile = blockIdx.x * FB2_ASM4_WARPS + wid;
+  if (tile >= a.ntile) return;
+  double* acc = sT + L * L * ROW + (size_t)wid * a.acc_stride;  // this warp's private tile
+  const int64_t r0 = a.blk_row[tile], r1 = a.blk_row[tile + 1];
+  const int64_t v0 = a.crow[r0];
+  const int nval = (int)(a.crow[r1] - v0);
+  for (int t = lane; t < nval; t += 32) acc[t] = 0.0;
+  __syncwarp();
+  const int64_t b0 = a.batch_ptr[tile], b1 = a.batch_ptr[tile + 1];
+  // software pipeline: entry + geometry of batch b+1 are in flight while batch b is computed
+  int cell_n = -1, base_n = 0, i_n = 0;
+  uint32_t sw_n[SR::WORDS];
+  double h_n[HS];
+  auto fetch = [&](int64_t b) {
+    const int64_t e = b * 32 + lane;
+    cell_n = a.ent_cell[e];
+    base_n = a.ent_base[e];
+    i_n = a.batch_i[b];
+#pragma unroll
+    for (int w = 0; w < SR::WORDS; ++w) sw_n[w] = a.ent_slots[e * SR::WORDS + w];
+    const double2* hp = reinterpret_cast<const double2*>(a.H + (int64_t)(cell_n < 0 ? 0 : cell_n) * HS);
+#pragma unroll
+    for (int t = 0; t < HS / 2; ++t) { const double2 v = hp[t]; h_n[2 * t] = v.x; h_n[2 * t + 1] = v.y; }
+  };
+  if (b0 < b1) fetch(b0);
+  for (int64_t b = b0; b < b1; ++b) {
+    const int cell = cell_n, base = base_n, i = i_n;
+    uint32_t sw[SR::WORDS];
+    double h[NH];
+#pragma unroll
+    for (int w = 0; w < SR::WORDS; ++w) sw[w] = sw_n[w];
+#pragma unroll
+    for (int t = 0; t < NH; ++t) h[t] = h_n[t];
+    if (b + 1 < b1) fetch(b + 1);
+    if (cell >= 0) a4_dispatch<TD, L, SlotT, 0>(i, sT, h, sw, acc + base);
+    __syncwarp();
+  }
+  double* out = a.values + v0;
+  for (int t = lane; t < nval; t += 32) out[t] = acc[t];
+}
+
+// H rows padded to a multiple of 2 doubles
+template <int TD>
+__global__ void __launch_bounds__(256) cell_geometry4_kernel(const double* __restrict__ node, const int* __restrict__ cell, int64_t NC,
+                                                             double scal_d, const double* __restrict__ coef_d, double scal_m,
+                                                             const double* __restrict__ coef_m, double* __restrict__ H) {
+  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2, NH = NG + 1, HS = ((NH + 1) / 2) * 2;
+  __shared__ double stage[256 * HS];
+  const int64_t c0 = (int64_t)blockIdx.x * 256;
+  const int64_t c = c0 + threadIdx.x;
+  if (c < NC) {
+    int v[NV];
+    double x[NV][TD], cm, G[NG];
+    load_verts<TD>(cell, c, v);
+    load_coords<TD>(node, v, x);
+    geo_from_coords(x, cm, G);
+    const double kd = scal_d * (coef_d ? coef_d[c] : 1.0);
+    const double km = scal_m * (coef_m ? coef_m[c] : 1.0) * cm;
+    double* h = stage + threadIdx.x * HS;
+#pragma unroll
+    for (int t = 0; t < NG; ++t) h[t] = kd * G[t];
+    h[NG] = km;
+    if (HS > NH) h[NH] = 0.0;
+  }
+  __syncthreads();
+  const int64_t ncell = (NC - c0) < 256 ? (NC - c0) : 256;
+  double* dst = H + c0 * HS;
+  for (int64_t t = threadIdx.x; t < ncell * HS; t += 256) dst[t] = stage[t];       // contiguous, fully coalesced
+}
+
+size_t asm4_workspace_bytes(int ntile) { return align_up((size_t)(ntile + 1) * 4) + scan_workspace_bytes(ntile + 1) + 1024; }
+
+int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
+                    int64_t* batch_ptr, int64_t* nbatch_host, void* ws, cudaStream_t s) {
+  Carver c(ws);
+  int* cnt = c.take<int>(ntile + 1);
+  void* scan_ws = c.take<char>(scan_workspace_bytes(ntile + 1));
+  if (ntile > 0)
+    asm4_schedule_kernel<false><<<(unsigned)ceil_div(ntile, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, cnt, nullptr,
+                                                                               nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+  FB2_LAUNCH_CHECK();
+  FB2_TRY(exclusive_scan_i32(cnt, batch_ptr, ntile, true, scan_ws, s));
+  FB2_CUDA(cudaMemcpyAsync(nbatch_host, batch_ptr + ntile, 8, cudaMemcpyDeviceToHost, s));
+  FB2_CUDA(cudaStreamSynchronize(s));
+  return OK;
+}
+
+int asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
+                   const int64_t* batch_ptr, unsigned char* batch_i, int* ent_cell, unsigned short* ent_base, uint32_t* ent_slots,
+                   const void* slots, int slot_bytes, cudaStream_t s) {
+  if (ntile <= 0) return OK;
+  const int nwords = slot_stride(L, slot_bytes) * slot_bytes / 4;
+  asm4_schedule_kernel<true><<<(unsigned)ceil_div(ntile, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, nullptr, batch_ptr,
+                                                                            batch_i, ent_cell, ent_base, ent_slots,
+                                                                            static_cast<const uint32_t*>(slots), nwords);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+template <int TD, int L>
+static int launch_asm4(Asm4Args a, int slot_bytes, cudaStream_t s) {
+  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2, ROW = ((NG + 2) / 2) * 2;
+  cell_geometry4_kernel<TD><<<(unsigned)ceil_div(a.NC, 256), 256, 0, s>>>(a.node, a.cell, a.NC, a.Ms ? a.scal_d : 0.0, a.coef_d,
+                                                                         a.Mm ? a.scal_m : 0.0, a.coef_m, a.Hbuf);
+  a.H = a.Hbuf;
+  a.acc_stride = (a.tile + a.max_row + 1) & ~1;
+  const size_t smem = ((size_t)L * L * ROW + (size_t)FB2_ASM4_WARPS * a.acc_stride) * 8;
+  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble v4: tiles do not fit shared memory (tile=%d max_row=%d)", a.tile, a.max_row);
+  if (a.tile + a.max_row > 65535) return fail(ERR_UNSUPPORTED, "assemble v4: tile offsets exceed 16 bits");
+  const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
+  if (grid == 0) return OK;
+  if (slot_bytes == 1) {
+    auto k = assemble_const_v4_kernel<TD, L, uint8_t>;
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a);
+  } else {
+    auto k = assemble_const_v4_kernel<TD, L, uint16_t>;
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a);
+  }
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int assemble_v4(int TD, int p, const Asm4Args& a, int slot_bytes, cudaStream_t s) {
+  if (slot_bytes != 1 && slot_bytes != 2) return fail(ERR_INVALID, "assemble v4: slot_bytes must be 1 or 2");
+  switch (TD * 10 + p) {
+    case 21: return launch_asm4<2, 3>(a, slot_bytes, s);
+    case 22: return launch_asm4<2, 6>(a, slot_bytes, s);
+    case 23: return launch_asm4<2, 10>(a, slot_bytes, s);
+    case 31: return launch_asm4<3, 4>(a, slot_bytes, s);
+    case 32: return launch_asm4<3, 10>(a, slot_bytes, s);
+    case 33: return launch_asm4<3, 20>(a, slot_bytes, s);
+    default: return fail(ERR_UNSUPPORTED, "assemble v4: unsupported element TD=%d p=%d", TD, p);
+  }
+}
+
+}  // namespace fb2

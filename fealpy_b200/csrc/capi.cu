@@ -149,6 +149,29 @@ int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int6
   a.blk_row = blk_row; a.nblk = nblk; a.tile = tile;
   return assemble_from_ke(a, slot_bytes, max_row, S(stream));
 }
+size_t fb2_asm4_workspace_bytes(int ntile) { return asm4_workspace_bytes(ntile); }
+int fb2_asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
+                        int ldof, int64_t* batch_ptr, int64_t* nbatch_host, void* ws, void* stream) {
+  return asm4_plan_count(ntile, blk_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, nbatch_host, ws, S(stream));
+}
+int fb2_asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
+                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, int32_t* ent_cell, uint16_t* ent_base,
+                       uint32_t* ent_slots, const void* slots, int slot_bytes, void* stream) {
+  return asm4_plan_fill(ntile, blk_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, batch_i, ent_cell, ent_base, ent_slots, slots,
+                        slot_bytes, S(stream));
+}
+int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
+                                 const int32_t* blk_row, int ntile, int tile, int32_t max_row, const int64_t* batch_ptr,
+                                 const uint8_t* batch_i, const int32_t* ent_cell, const uint16_t* ent_base, const uint32_t* ent_slots,
+                                 int slot_bytes, const double* Ms, const double* Mm, double scal_d, const double* coef_d,
+                                 double scal_m, const double* coef_m, double* geom_ws, double* values, void* stream) {
+  if (!Ms && !Mm) return fail(ERR_INVALID, "assemble_scalar_const_v4: need a diffusion and/or a mass table");
+  Asm4Args a{};
+  a.node = node; a.cell = cell; a.NC = NC; a.crow = crow; a.blk_row = blk_row; a.ntile = ntile; a.tile = tile; a.max_row = max_row;
+  a.batch_ptr = batch_ptr; a.batch_i = batch_i; a.ent_cell = ent_cell; a.ent_base = ent_base; a.ent_slots = ent_slots;
+  a.Ms = Ms; a.Mm = Mm; a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.Hbuf = geom_ws; a.values = values;
+  return assemble_v4(TD, p, a, slot_bytes, S(stream));
+}
 int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,
                        int64_t* crow_out, int32_t* col_out, void* stream) {
   return expand_pattern(gdof_scalar, ncomp, dof_priority, crow_scalar, col_scalar, crow_out, col_out, S(stream));

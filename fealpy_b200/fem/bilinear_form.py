@@ -119,6 +119,36 @@ def row_tiling(crow, nrow, nnz, tile):
     return blk_row, nblk
 
 
+ASM4_TILE = int(_os.environ.get("FB2_ASM4_TILE", "1536"))     # values per WARP tile of the v4 kernel
+
+
+def asm4_plan(space):
+    """batch schedule of the v4 numeric kernel (cached per space; csrc/assemble.cu asm4_schedule_kernel)"""
+    sym = symbolic_pattern(space)
+    if "asm4" in sym:
+        return sym["asm4"]
+    lib = _lib.load()
+    dev = sym["crow"].device
+    blk_row, ntile = row_tiling(sym["crow"], sym["gdof"], sym["nnz"], ASM4_TILE)
+    ws = _lib.workspace(lib.fb2_asm4_workspace_bytes(ntile), dev)
+    batch_ptr = torch.empty(ntile + 1, dtype=torch.int64, device=dev)
+    nb = C.c_int64(0)
+    _lib.call("fb2_asm4_plan_count", ntile, _lib.ptr(blk_row), _lib.ptr(sym["crow"]), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
+              sym["L"], _lib.ptr(batch_ptr), C.byref(nb), _lib.ptr(ws), _lib.stream())
+    nb = nb.value
+    nwords = lib.fb2_slot_stride(sym["L"], sym["slot_bytes"]) * sym["slot_bytes"] // 4
+    batch_i = torch.empty(nb, dtype=torch.uint8, device=dev)
+    ent_cell = torch.empty(nb * 32, dtype=torch.int32, device=dev)
+    ent_base = torch.zeros(nb * 32, dtype=torch.int16, device=dev)
+    ent_slots = torch.zeros(nb * 32 * nwords, dtype=torch.int32, device=dev)
+    _lib.call("fb2_asm4_plan_fill", ntile, _lib.ptr(blk_row), _lib.ptr(sym["crow"]), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
+              sym["L"], _lib.ptr(batch_ptr), _lib.ptr(batch_i), _lib.ptr(ent_cell), _lib.ptr(ent_base), _lib.ptr(ent_slots),
+              _lib.ptr(sym["slots"]), sym["slot_bytes"], _lib.stream())
+    sym["asm4"] = dict(blk_row=blk_row, ntile=ntile, tile=ASM4_TILE, batch_ptr=batch_ptr, batch_i=batch_i, ent_cell=ent_cell,
+                       ent_base=ent_base, ent_slots=ent_slots, nbatch=nb)
+    return sym["asm4"]
+
+
 def tensor_pattern(space):
     """pattern of a TensorFunctionSpace = scalar pattern (x) dense ncomp x ncomp blocks"""
     cache = getattr(space, "_b200_pattern", None)
@@ -251,9 +281,20 @@ class BilinearForm:
         sd, ad = parts(dm)
         sm_, am = parts(mm)
         NV = mesh.TD + 1
+        kernel = _os.environ.get("FB2_ASM_KERNEL", "v4")
+        NH = NV * (NV + 1) // 2 + 1
+        if kernel == "v4":
+            pl = asm4_plan(space)
+            geom = torch.empty((sym["NC"], (NH + 1) // 2 * 2), dtype=torch.float64, device=mesh.device)
+            _lib.call("fb2_assemble_scalar_const_v4", mesh.TD, space.p, sym["NC"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
+                      _lib.ptr(sym["crow"]), _lib.ptr(pl["blk_row"]), pl["ntile"], pl["tile"], sym["max_row"], _lib.ptr(pl["batch_ptr"]),
+                      _lib.ptr(pl["batch_i"]), _lib.ptr(pl["ent_cell"]), _lib.ptr(pl["ent_base"]), _lib.ptr(pl["ent_slots"]),
+                      sym["slot_bytes"], _lib.ptr(dm["tabs"]["Ms"]) if dm else None, _lib.ptr(mm["tabs"]["Mm"]) if mm else None,
+                      sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(geom), _lib.ptr(values), _lib.stream())
+            return sym["crow"], sym["col"], values
         geom = None
-        if _os.environ.get("FB2_ASM_KERNEL", "v2") == "v3":     # per-cell geometry precompute variant (slower so far)
-            geom = torch.empty((sym["NC"], NV * (NV + 1) // 2 + 1), dtype=torch.float64, device=mesh.device)
+        if kernel == "v3":     # per-cell geometry precompute with lane = row (kept for comparison)
+            geom = torch.empty((sym["NC"], NH), dtype=torch.float64, device=mesh.device)
 
         def hostp(m, key):
             if m is None:
