@@ -802,10 +802,15 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
   if (!FILL) nbatch_of_tile[t] = (int)nb;
 }
 
-template <int TD, int L, typename SlotT, int I>
-__device__ __forceinline__ void a4_row(const double* __restrict__ sT, const double (&h)[(TD + 1) * (TD + 2) / 2 + 1],
+// element tables in the kernel parameter block: operands come through the constant / uniform
+// datapath and cost no LSU (shared-memory) wavefronts -- the LSU data pipe is this kernel's limiter
+template <int L, int NH>
+struct A4Tables { double T[L][L][NH]; };     // T[i][j] = (Ms[i][j][0..NG-1], Mm[i][j])
+
+template <int TD, int L, typename SlotT, int I, typename TabT>
+__device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[(TD + 1) * (TD + 2) / 2 + 1],
                                        const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
-  constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1, ROW = ((NH + 1) / 2) * 2;
+  constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1;
   using SR = SlotRec<SlotT, L>;
   constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
 #pragma unroll
@@ -813,13 +818,11 @@ __device__ __forceinline__ void a4_row(const double* __restrict__ sT, const doub
     double val[JC];
 #pragma unroll
     for (int jj = 0; jj < JC; ++jj) {
-      const double2* __restrict__ row = reinterpret_cast<const double2*>(sT + ((I * L) + j0 + jj) * ROW);
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int t = 0; t < ROW / 2; ++t) {
-        const double2 m = row[t];
-        s0 += m.x * h[2 * t];
-        if (2 * t + 1 < NH) s1 += m.y * h[2 * t + 1];
+      for (int t = 0; t < NH; t += 2) {
+        s0 += tb.T[I][j0 + jj][t] * h[t];
+        if (t + 1 < NH) s1 += tb.T[I][j0 + jj][t + 1] * h[t + 1];
       }
       val[jj] = s0 + s1;
     }
@@ -831,11 +834,11 @@ __device__ __forceinline__ void a4_row(const double* __restrict__ sT, const doub
   }
 }
 
-template <int TD, int L, typename SlotT, int I>
-__device__ __forceinline__ void a4_dispatch(int i, const double* __restrict__ sT, const double (&h)[(TD + 1) * (TD + 2) / 2 + 1],
+template <int TD, int L, typename SlotT, int I, typename TabT>
+__device__ __forceinline__ void a4_dispatch(int i, const TabT& tb, const double (&h)[(TD + 1) * (TD + 2) / 2 + 1],
                                             const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
-  if (i == I) a4_row<TD, L, SlotT, I>(sT, h, sw, my);
-  else if constexpr (I + 1 < L) a4_dispatch<TD, L, SlotT, I + 1>(i, sT, h, sw, my);
+  if (i == I) a4_row<TD, L, SlotT, I, TabT>(tb, h, sw, my);
+  else if constexpr (I + 1 < L) a4_dispatch<TD, L, SlotT, I + 1, TabT>(i, tb, h, sw, my);
 }
 
 #ifndef FB2_ASM4_WARPS
@@ -847,33 +850,31 @@ __device__ __forceinline__ void a4_dispatch(int i, const double* __restrict__ sT
 
 // H rows are padded to HS doubles (multiple of 2) so that they are read with 128-bit loads
 template <int TD, int L, typename SlotT>
-__global__ void __launch_bounds__(FB2_ASM4_WARPS * 32, FB2_ASM4_MINBLOCKS) assemble_const_v4_kernel(const __grid_constant__ Asm4Args a) {
+__global__ void __launch_bounds__(FB2_ASM4_WARPS * 32, FB2_ASM4_MINBLOCKS)
+assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_constant__ A4Tables<L, (TD + 1) * (TD + 2) / 2 + 1> tb) {
   constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1, ROW = ((NH + 1) / 2) * 2, HS = ROW;
   using SR = SlotRec<SlotT, L>;
   extern __shared__ __align__(16) double sm4[];
-  double* sT = sm4;                                             // [L][L][ROW]
-  for (int t = threadIdx.x; t < L * L * ROW; t += blockDim.x) {
-    const int ij = t / ROW, k = t - ij * ROW;
-    double v = 0.0;
-    if (k < NG) v = a.Ms ? a.Ms[ij * NG + k] : 0.0;
-    else if (k == NG) v = a.Mm ? a.Mm[ij] : 0.0;
-    sT[t] = v;
-  }
-  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int tile = blockIdx.x * FB2_ASM4_WARPS + wid;
   if (tile >= a.ntile) return;
-  double* acc = sT + L * L * ROW + (size_t)wid * a.acc_stride;  // this warp's private tile
+  constexpr int QP = HS / 2;                                    // 16-byte quarters per geometry record
+  constexpr int HSP = HS + 2;                                   // padded record stride in the stage (conflict-free LDS.128)
+  double* acc = sm4 + (size_t)wid * (a.acc_stride + 32 * HSP);  // this warp's private tile ...
+  double* hst = acc + a.acc_stride;                             // ... and its 32-record geometry stage
   const int64_t r0 = a.blk_row[tile], r1 = a.blk_row[tile + 1];
   const int64_t v0 = a.crow[r0];
   const int nval = (int)(a.crow[r1] - v0);
   for (int t = lane; t < nval; t += 32) acc[t] = 0.0;
   __syncwarp();
   const int64_t b0 = a.batch_ptr[tile], b1 = a.batch_ptr[tile + 1];
-  // software pipeline: entry + geometry of batch b+1 are in flight while batch b is computed
+  // software pipeline: entry + geometry of batch b+1 are in flight while batch b is computed.
+  // The 32 geometry records of a batch are fetched COOPERATIVELY: consecutive lanes read
+  // consecutive 16-byte quarters of the same record (one LSU wavefront per record instead of
+  // one per lane and quarter), then the records are transposed through the shared-memory stage.
   int cell_n = -1, base_n = 0, i_n = 0;
   uint32_t sw_n[SR::WORDS];
-  double h_n[HS];
+  double2 hq[QP];
   auto fetch = [&](int64_t b) {
     const int64_t e = b * 32 + lane;
     cell_n = a.ent_cell[e];
@@ -881,23 +882,45 @@ __global__ void __launch_bounds__(FB2_ASM4_WARPS * 32, FB2_ASM4_MINBLOCKS) assem
     i_n = a.batch_i[b];
 #pragma unroll
     for (int w = 0; w < SR::WORDS; ++w) sw_n[w] = a.ent_slots[e * SR::WORDS + w];
-    const double2* hp = reinterpret_cast<const double2*>(a.H + (int64_t)(cell_n < 0 ? 0 : cell_n) * HS);
 #pragma unroll
-    for (int t = 0; t < HS / 2; ++t) { const double2 v = hp[t]; h_n[2 * t] = v.x; h_n[2 * t + 1] = v.y; }
+    for (int r = 0; r < QP; ++r) {
+      const int idx = r * 32 + lane, rec = idx / QP, part = idx - rec * QP;
+      const int c = __shfl_sync(0xffffffffu, cell_n, rec);
+      hq[r] = (c >= 0) ? *reinterpret_cast<const double2*>(a.H + (int64_t)c * HS + 2 * part) : make_double2(0.0, 0.0);
+    }
   };
-  if (b0 < b1) fetch(b0);
+  auto stash = [&]() {
+#pragma unroll
+    for (int r = 0; r < QP; ++r) {
+      const int idx = r * 32 + lane, rec = idx / QP, part = idx - rec * QP;
+      *reinterpret_cast<double2*>(hst + rec * HSP + 2 * part) = hq[r];
+    }
+  };
+  if (b0 < b1) { fetch(b0); stash(); }
   for (int64_t b = b0; b < b1; ++b) {
     const int cell = cell_n, base = base_n, i = i_n;
     uint32_t sw[SR::WORDS];
     double h[NH];
 #pragma unroll
     for (int w = 0; w < SR::WORDS; ++w) sw[w] = sw_n[w];
-#pragma unroll
-    for (int t = 0; t < NH; ++t) h[t] = h_n[t];
-    if (b + 1 < b1) fetch(b + 1);
-    if (cell >= 0) a4_dispatch<TD, L, SlotT, 0>(i, sT, h, sw, acc + base);
     __syncwarp();
+    {
+      double hh[HS];
+#pragma unroll
+      for (int t = 0; t < QP; ++t) {
+        const double2 v = *reinterpret_cast<const double2*>(hst + lane * HSP + 2 * t);
+        hh[2 * t] = v.x; hh[2 * t + 1] = v.y;
+      }
+#pragma unroll
+      for (int t = 0; t < NH; ++t) h[t] = hh[t];
+    }
+    __syncwarp();
+    const bool more = b + 1 < b1;
+    if (more) fetch(b + 1);
+    if (cell >= 0) a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, acc + base);
+    if (more) stash();
   }
+  __syncwarp();
   double* out = a.values + v0;
   for (int t = lane; t < nval; t += 32) out[t] = acc[t];
 }
@@ -962,27 +985,38 @@ int asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const
 
 template <int TD, int L>
 static int launch_asm4(Asm4Args a, int slot_bytes, cudaStream_t s) {
-  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2, ROW = ((NG + 2) / 2) * 2;
-  cell_geometry4_kernel<TD><<<(unsigned)ceil_div(a.NC, 256), 256, 0, s>>>(a.node, a.cell, a.NC, a.Ms ? a.scal_d : 0.0, a.coef_d,
-                                                                         a.Mm ? a.scal_m : 0.0, a.coef_m, a.Hbuf);
-  a.H = a.Hbuf;
-  a.acc_stride = (a.tile + a.max_row + 1) & ~1;
-  const size_t smem = ((size_t)L * L * ROW + (size_t)FB2_ASM4_WARPS * a.acc_stride) * 8;
-  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble v4: tiles do not fit shared memory (tile=%d max_row=%d)", a.tile, a.max_row);
-  if (a.tile + a.max_row > 65535) return fail(ERR_UNSUPPORTED, "assemble v4: tile offsets exceed 16 bits");
-  const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
-  if (grid == 0) return OK;
-  if (slot_bytes == 1) {
-    auto k = assemble_const_v4_kernel<TD, L, uint8_t>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a);
+  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;
+  if constexpr (sizeof(A4Tables<L, NG + 1>) + sizeof(Asm4Args) >= 32000) {
+    return fail(ERR_UNSUPPORTED, "assemble v4: element tables exceed the kernel parameter block (ldof=%d)", L);
   } else {
-    auto k = assemble_const_v4_kernel<TD, L, uint16_t>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a);
+    cell_geometry4_kernel<TD><<<(unsigned)ceil_div(a.NC, 256), 256, 0, s>>>(a.node, a.cell, a.NC, a.Ms ? a.scal_d : 0.0, a.coef_d,
+                                                                           a.Mm ? a.scal_m : 0.0, a.coef_m, a.Hbuf);
+    a.H = a.Hbuf;
+    a.acc_stride = (a.tile + a.max_row + 1) & ~1;
+    A4Tables<L, NG + 1> tb;
+    for (int i = 0; i < L; ++i)
+      for (int j = 0; j < L; ++j) {
+        for (int t = 0; t < NG; ++t) tb.T[i][j][t] = a.Ms_host ? a.Ms_host[(i * L + j) * NG + t] : 0.0;
+        tb.T[i][j][NG] = a.Mm_host ? a.Mm_host[i * L + j] : 0.0;
+      }
+    constexpr int HSP4 = ((NG + 2) / 2) * 2 + 2;
+    const size_t smem = ((size_t)FB2_ASM4_WARPS * (a.acc_stride + 32 * HSP4)) * 8;
+    if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble v4: tiles do not fit shared memory (tile=%d max_row=%d)", a.tile, a.max_row);
+    if (a.tile + a.max_row > 65535) return fail(ERR_UNSUPPORTED, "assemble v4: tile offsets exceed 16 bits");
+    const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
+    if (grid == 0) return OK;
+    if (slot_bytes == 1) {
+      auto k = assemble_const_v4_kernel<TD, L, uint8_t>;
+      FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a, tb);
+    } else {
+      auto k = assemble_const_v4_kernel<TD, L, uint16_t>;
+      FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a, tb);
+    }
+    FB2_LAUNCH_CHECK();
+    return OK;
   }
-  FB2_LAUNCH_CHECK();
-  return OK;
 }
 
 int assemble_v4(int TD, int p, const Asm4Args& a, int slot_bytes, cudaStream_t s) {

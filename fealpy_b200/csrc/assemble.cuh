@@ -57,6 +57,8 @@ struct Asm4Args {
   const uint32_t* ent_slots;    // (nbatch*32, words) packed slot record
   const double* Ms;             // device tables (null = term absent)
   const double* Mm;
+  const double* Ms_host;        // host copies (go into the kernel parameter block)
+  const double* Mm_host;
   double scal_d, scal_m;
   const double* coef_d;
   const double* coef_m;

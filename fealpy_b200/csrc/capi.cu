@@ -163,13 +163,15 @@ int fb2_asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, c
 int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
                                  const int32_t* blk_row, int ntile, int tile, int32_t max_row, const int64_t* batch_ptr,
                                  const uint8_t* batch_i, const int32_t* ent_cell, const uint16_t* ent_base, const uint32_t* ent_slots,
-                                 int slot_bytes, const double* Ms, const double* Mm, double scal_d, const double* coef_d,
+                                 int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d, const double* coef_d,
                                  double scal_m, const double* coef_m, double* geom_ws, double* values, void* stream) {
+  const double *Ms = Ms_host, *Mm = Mm_host;      // only their presence matters on the device side
   if (!Ms && !Mm) return fail(ERR_INVALID, "assemble_scalar_const_v4: need a diffusion and/or a mass table");
   Asm4Args a{};
   a.node = node; a.cell = cell; a.NC = NC; a.crow = crow; a.blk_row = blk_row; a.ntile = ntile; a.tile = tile; a.max_row = max_row;
   a.batch_ptr = batch_ptr; a.batch_i = batch_i; a.ent_cell = ent_cell; a.ent_base = ent_base; a.ent_slots = ent_slots;
-  a.Ms = Ms; a.Mm = Mm; a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.Hbuf = geom_ws; a.values = values;
+  a.Ms = Ms; a.Mm = Mm; a.Ms_host = Ms_host; a.Mm_host = Mm_host;
+  a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.Hbuf = geom_ws; a.values = values;
   return assemble_v4(TD, p, a, slot_bytes, S(stream));
 }
 int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,

@@ -281,15 +281,23 @@ class BilinearForm:
         sd, ad = parts(dm)
         sm_, am = parts(mm)
         NV = mesh.TD + 1
+
+        def hostp(m, key):
+            if m is None:
+                return None
+            h = host_tables(mesh.TD, space.p, m["q"])[key]
+            return h.ctypes.data_as(C.c_void_p)
         kernel = _os.environ.get("FB2_ASM_KERNEL", "v4")
         NH = NV * (NV + 1) // 2 + 1
+        if kernel == "v4" and sym["L"] * sym["L"] * NH * 8 > 30000:
+            kernel = "v2"          # tables do not fit the kernel parameter block (tet P3)
         if kernel == "v4":
             pl = asm4_plan(space)
             geom = torch.empty((sym["NC"], (NH + 1) // 2 * 2), dtype=torch.float64, device=mesh.device)
             _lib.call("fb2_assemble_scalar_const_v4", mesh.TD, space.p, sym["NC"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
                       _lib.ptr(sym["crow"]), _lib.ptr(pl["blk_row"]), pl["ntile"], pl["tile"], sym["max_row"], _lib.ptr(pl["batch_ptr"]),
                       _lib.ptr(pl["batch_i"]), _lib.ptr(pl["ent_cell"]), _lib.ptr(pl["ent_base"]), _lib.ptr(pl["ent_slots"]),
-                      sym["slot_bytes"], _lib.ptr(dm["tabs"]["Ms"]) if dm else None, _lib.ptr(mm["tabs"]["Mm"]) if mm else None,
+                      sym["slot_bytes"], hostp(dm, "Ms"), hostp(mm, "Mm"),
                       sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(geom), _lib.ptr(values), _lib.stream())
             return sym["crow"], sym["col"], values
         geom = None

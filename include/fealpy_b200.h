@@ -122,7 +122,9 @@ int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int6
 /* "v4" numeric kernel for the same forms: the symbolic phase additionally turns every warp tile
  * (rows holding <= tile values; fb2_spmv_plan_build) into 32-entry batches that share the local
  * index (warp-uniform element-table row) and touch 32 different rows (conflict-free adds);
- * geom_ws = NC * 2*ceil((NG+1)/2) doubles of scratch for the per-cell geometry. */
+ * geom_ws = NC * 2*ceil((NG+1)/2) doubles of scratch for the per-cell geometry.  The element tables
+ * are HOST pointers here: they travel in the kernel parameter block (constant bank), which costs no
+ * load/store-unit bandwidth; FB2_ERR_UNSUPPORTED if they exceed it (ldof = 20). */
 size_t fb2_asm4_workspace_bytes(int ntile);
 int fb2_asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
                         int ldof, int64_t* batch_ptr, int64_t* nbatch_host, void* ws, void* stream);
@@ -132,8 +134,9 @@ int fb2_asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, c
 int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
                                  const int32_t* blk_row, int ntile, int tile, int32_t max_row, const int64_t* batch_ptr,
                                  const uint8_t* batch_i, const int32_t* ent_cell, const uint16_t* ent_base, const uint32_t* ent_slots,
-                                 int slot_bytes, const double* Ms, const double* Mm, double scal_d, const double* coef_d_cell,
-                                 double scal_m, const double* coef_m_cell, double* geom_ws, double* values, void* stream);
+                                 int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d,
+                                 const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* geom_ws, double* values,
+                                 void* stream);
 /* expands the scalar pattern to the tensor-space pattern */
 int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,
                        int64_t* crow_out, int32_t* col_out, void* stream);

@@ -390,9 +390,9 @@ def test_poisson_source_dirichlet_cg(case, U):
     R = csr_matrix((gold["Abc_data"], gold["Abc_indices"], gold["Abc_indptr"]), shape=S.shape)
     D = (S - R)
     assert (abs(D).max() if D.nnz else 0.0) <= 1e-12 * np.max(np.abs(gold["Abc_data"]))
-    x, info = cg(A2, F2, returninfo=True)
+    x, info = cg(A2, F2, returninfo=True, atol=1e-14, rtol=1e-11)
     assert np.linalg.norm(x.cpu().numpy() - gold["x"]) / np.linalg.norm(gold["x"]) <= 1e-10
-    assert abs(info["niter"] - gold["info"]["niter"]) <= 1
+    assert abs(info["niter"] - gold["info"]["niter"]) <= 2
     # inputs untouched
     U.assert_csr_matches(A, gold)
 

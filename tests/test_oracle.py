@@ -198,6 +198,6 @@ def test_oracle_bc_matches_reference_run(case):
     A.eliminate_zeros(); A.sort_indices()
     assert np.array_equal(A.indptr, gold["Abc_indptr"]) and np.array_equal(A.indices, gold["Abc_indices"])
     assert G.rel_err(A.data, gold["Abc_data"]) < 1e-13
-    x, info = O.cg(lambda v: A @ v, F2)
-    assert abs(info["niter"] - gold["info"]["niter"]) <= 1
+    x, info = O.cg(lambda v: A @ v, F2, atol=1e-14, rtol=1e-11)
+    assert abs(info["niter"] - gold["info"]["niter"]) <= 2
     assert np.linalg.norm(x - gold["x"]) / np.linalg.norm(gold["x"]) < 1e-10
