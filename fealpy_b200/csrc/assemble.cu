@@ -842,7 +842,7 @@ __device__ __forceinline__ void a4_dispatch(int i, const TabT& tb, const double 
 }
 
 #ifndef FB2_ASM4_WARPS
-#define FB2_ASM4_WARPS 8
+#define FB2_ASM4_WARPS 4
 #endif
 #ifndef FB2_ASM4_MINBLOCKS
 #define FB2_ASM4_MINBLOCKS 2
