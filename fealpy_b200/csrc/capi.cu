@@ -182,24 +182,24 @@ int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const i
 // ---- K3/K4 ----------------------------------------------------------------------------------
 size_t fb2_partial_workspace_bytes(void) { return partial_workspace_bytes(); }
 int fb2_spmv_plan_blocks(int64_t nnz, int tile) { return spmv_plan_blocks(nnz, tile); }
-int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t nnz, int32_t* max_row_host,
-                        void* stream) {
+int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t* blk_v0, int64_t nnz,
+                        int32_t* max_row_host, void* stream) {
   const int nblk = spmv_plan_blocks(nnz, tile);
   int* dmax = blk_row + nblk + 1;        // the caller allocates nblk + 2 entries; the last one is scratch
-  FB2_TRY(spmv_plan_build(n, crow, tile, nblk, blk_row, dmax, S(stream)));
+  FB2_TRY(spmv_plan_build(n, crow, tile, nblk, blk_row, dmax, S(stream), blk_v0));
   FB2_CUDA(cudaMemcpyAsync(max_row_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
   FB2_CUDA(cudaStreamSynchronize(S(stream)));
   return OK;
 }
-static SpmvPlan make_plan(const int32_t* blk_row, int64_t nnz, int tile, int max_row) {
+static SpmvPlan make_plan(const int32_t* blk_row, int64_t nnz, int tile, int max_row, const int64_t* blk_v0 = nullptr) {
   SpmvPlan pl{};
-  pl.blk_row = blk_row; pl.tile = tile; pl.max_row = max_row;
+  pl.blk_row = blk_row; pl.blk_v0 = blk_v0; pl.tile = tile; pl.max_row = max_row;
   pl.nblk = blk_row ? spmv_plan_blocks(nnz, tile) : 0;
   return pl;
 }
 int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x, double* y,
-                 const int32_t* blk_row, int tile, int32_t max_row, void* stream) {
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
+                 const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row, void* stream) {
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, blk_v0);
   return spmv(n, nnz, crow, col, values, x, y, nullptr, 0, nullptr, nullptr, S(stream), blk_row ? &pl : nullptr);
 }
 int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
@@ -229,8 +229,9 @@ static OwnRange make_own(const int64_t* own) {
   return o;
 }
 int fb2_cg_residual(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                    const double* b, double* r, const int32_t* blk_row, int tile, int32_t max_row, void* stream) {
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
+                    const double* b, double* r, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row,
+                    void* stream) {
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, blk_v0);
   return spmv(n, nnz, crow, col, values, x, r, b, 1, nullptr, nullptr, S(stream), blk_row ? &pl : nullptr);
 }
 int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p, void* scalars, void* partial_ws,
@@ -238,10 +239,10 @@ int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p,
   return cg_start(n, r, minv_diag, p, static_cast<CgScalars*>(scalars), partial_ws, make_own(own), S(stream));
 }
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars, void* partial_ws,
-                    const int64_t own[4], void* stream) {
+                    double* Ap, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row, void* scalars,
+                    void* partial_ws, const int64_t own[4], void* stream) {
   CgScalars* sc = static_cast<CgScalars*>(scalars);
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, blk_v0);
   return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, &sc->pAp, partial_ws, S(stream), blk_row ? &pl : nullptr, make_own(own), sc);
 }
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,

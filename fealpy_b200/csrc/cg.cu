@@ -118,8 +118,7 @@ __global__ void __launch_bounds__(CG_THREADS) spmm_kernel(int64_t n, const int64
 // unrolled loads (memory-level parallelism independent of the row lengths), gathers x and
 // parks the products in shared memory; phase 2 reduces each row with G lanes.  Row sums and
 // the fused p.Ap partials are formed in a fixed order -> bitwise reproducible.
-constexpr int ST_UNROLL = 8;
-constexpr int ST_ROWCAP = 1024;      // row pointers of a tile staged in shared memory (else read from global)
+constexpr int ST_UNROLL = 4;
 
 template <int G>
 __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, const int64_t* __restrict__ crow,
@@ -130,8 +129,7 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
                                                                  double* partials, unsigned int* counter, const CgScalars* sc,
                                                                  OwnRange own) {
   if (sc && sc->done) return;
-  extern __shared__ __align__(16) double prod[];               // [tile + max_row] products, then [ST_ROWCAP+1] row offsets
-  __shared__ int rowoff[ST_ROWCAP + 1];
+  extern __shared__ __align__(16) double prod[];
   const int tid = threadIdx.x;
   const int g = tid % G, grp = tid / G;
   constexpr int NGRP = CG_THREADS / G;
@@ -139,58 +137,31 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     const int r0 = blk_row[blk], r1 = blk_row[blk + 1];
     if (r0 == r1) continue;
-    const int nrow = r1 - r0;
-    const bool staged = nrow <= ST_ROWCAP;
     const int64_t v0 = crow[r0];
     const int nval = (int)(crow[r1] - v0);
     const double* __restrict__ vp = val + v0;
     const int32_t* __restrict__ cp = col + v0;
-    // row offsets of the tile (coalesced) -- issued before the value stream so both are in flight
-    if (staged)
-      for (int t = tid; t <= nrow; t += CG_THREADS) rowoff[t] = (int)(crow[r0 + t] - v0);
     int k = tid;
     for (; k + (ST_UNROLL - 1) * CG_THREADS < nval; k += ST_UNROLL * CG_THREADS) {
       double vv[ST_UNROLL];
       int cc[ST_UNROLL];
 #pragma unroll
       for (int u = 0; u < ST_UNROLL; ++u) { vv[u] = ld_stream(vp + k + u * CG_THREADS); cc[u] = ld_stream(cp + k + u * CG_THREADS); }
-      double xx[ST_UNROLL];
 #pragma unroll
-      for (int u = 0; u < ST_UNROLL; ++u) xx[u] = x[cc[u]];
-#pragma unroll
-      for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * CG_THREADS] = vv[u] * xx[u];
+      for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * CG_THREADS] = vv[u] * x[cc[u]];
     }
-    {
-      // tail: predicated, still all loads first
-      double vv[ST_UNROLL];
-      int cc[ST_UNROLL];
-#pragma unroll
-      for (int u = 0; u < ST_UNROLL; ++u) {
-        const int kk = k + u * CG_THREADS;
-        const bool ok = kk < nval;
-        vv[u] = ok ? ld_stream(vp + kk) : 0.0;
-        cc[u] = ok ? ld_stream(cp + kk) : 0;
-      }
-#pragma unroll
-      for (int u = 0; u < ST_UNROLL; ++u) {
-        const int kk = k + u * CG_THREADS;
-        if (kk < nval) prod[kk] = vv[u] * x[cc[u]];
-      }
-    }
+    for (; k < nval; k += CG_THREADS) prod[k] = ld_stream(vp + k) * x[ld_stream(cp + k)];
     __syncthreads();
-    for (int base = 0; base < nrow; base += NGRP) {
-      const int rl = base + grp;
+    for (int base = r0; base < r1; base += NGRP) {
+      const int r = base + grp;
       double acc = 0.0;
-      if (rl < nrow) {
-        int s, e;
-        if (staged) { s = rowoff[rl]; e = rowoff[rl + 1]; }
-        else { s = (int)(crow[r0 + rl] - v0); e = (int)(crow[r0 + rl + 1] - v0); }
+      if (r < r1) {
+        const int s = (int)(crow[r] - v0), e = (int)(crow[r + 1] - v0);
         for (int q = s + g; q < e; q += G) acc += prod[q];
       }
 #pragma unroll
       for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (rl < nrow && g == 0) {
-        const int64_t r = r0 + rl;
+      if (r < r1 && g == 0) {
         const double yv = mode ? b[r] - acc : acc;
         y[r] = yv;
         if (dot_out && own.has(r)) dsum += x[r] * yv;
@@ -201,11 +172,134 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
   if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
 }
 
+// ---- SpMV, software-pipelined over tiles: while tile t is reduced out of shared memory, the
+// (val, col) stream of tile t+2 and the x gathers of tile t+1 are already in flight in registers,
+// so every DRAM / L2 round trip is issued a full tile ahead of its use.
+constexpr int SP_U = 9;                  // values per thread and tile: tile + max_row <= SP_U * 256
+constexpr int SP_ROWCAP = 768;           // rows of a tile staged in shared memory
+constexpr int SP_RU = SP_ROWCAP / CG_THREADS + 1;
+
+struct SpTile { int r0, r1, nval; int64_t v0; };
+
+template <int G>
+__global__ void __launch_bounds__(CG_THREADS, 2) spmv_pipe_kernel(int64_t n, const int64_t* __restrict__ crow,
+                                                                  const int32_t* __restrict__ col, const double* __restrict__ val,
+                                                                  const double* __restrict__ x, double* __restrict__ y,
+                                                                  const double* __restrict__ b, int mode,
+                                                                  const int32_t* __restrict__ blk_row,
+                                                                  const int64_t* __restrict__ blk_v0, int nblk, double* dot_out,
+                                                                  double* partials, unsigned int* counter, const CgScalars* sc,
+                                                                  OwnRange own) {
+  if (sc && sc->done) return;
+  __shared__ __align__(16) double prod[SP_U * CG_THREADS];
+  __shared__ int rowoff[SP_ROWCAP + 1];
+  const int tid = threadIdx.x;
+  const int g = tid % G, grp = tid / G;
+  constexpr int NGRP = CG_THREADS / G;
+  double dsum = 0.0;
+
+  auto tile_of = [&](int blk) {          // four independent (uniform) loads: no dependent chain
+    SpTile t;
+    t.r0 = blk_row[blk]; t.r1 = blk_row[blk + 1];
+    t.v0 = blk_v0[blk];
+    t.nval = (int)(blk_v0[blk + 1] - t.v0);
+    return t;
+  };
+  double vv1[SP_U], xx1[SP_U], vv2[SP_U];
+  int cc1[SP_U], cc2[SP_U], ro1[SP_RU], ro2[SP_RU];
+  auto load_raw = [&](const SpTile& t, double (&vv)[SP_U], int (&cc)[SP_U], int (&ro)[SP_RU]) {
+#pragma unroll
+    for (int u = 0; u < SP_U; ++u) {
+      const int k = tid + u * CG_THREADS;
+      const bool ok = k < t.nval;
+      vv[u] = ok ? ld_stream(val + t.v0 + k) : 0.0;
+      cc[u] = ok ? ld_stream(col + t.v0 + k) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < SP_RU; ++u) {
+      const int k = tid + u * CG_THREADS;
+      ro[u] = (k <= t.r1 - t.r0 && k <= SP_ROWCAP) ? (int)(crow[t.r0 + k] - t.v0) : 0;
+    }
+  };
+  auto gather = [&](const SpTile& t, const int (&cc)[SP_U], double (&xx)[SP_U]) {
+#pragma unroll
+    for (int u = 0; u < SP_U; ++u) xx[u] = (tid + u * CG_THREADS < t.nval) ? x[cc[u]] : 0.0;
+  };
+  auto store_prod = [&](const SpTile& t, const double (&vv)[SP_U], const double (&xx)[SP_U], const int (&ro)[SP_RU]) {
+#pragma unroll
+    for (int u = 0; u < SP_U; ++u) {
+      const int k = tid + u * CG_THREADS;
+      if (k < t.nval) prod[k] = vv[u] * xx[u];
+    }
+#pragma unroll
+    for (int u = 0; u < SP_RU; ++u) {
+      const int k = tid + u * CG_THREADS;
+      if (k <= t.r1 - t.r0 && k <= SP_ROWCAP) rowoff[k] = ro[u];
+    }
+  };
+
+  int blk = blockIdx.x;
+  if (blk >= nblk) { if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; }); return; }
+  const int gs = (int)gridDim.x;
+  SpTile t0 = tile_of(blk), t1{}, t2{}, t3{};
+  // prologue: tile t0 into shared memory, raw stream of t1 in flight, metadata of t2 in flight
+  load_raw(t0, vv1, cc1, ro1);
+  gather(t0, cc1, xx1);
+  store_prod(t0, vv1, xx1, ro1);
+  const bool has1 = blk + gs < nblk;
+  if (has1) { t1 = tile_of(blk + gs); load_raw(t1, vv1, cc1, ro1); }
+  if (blk + 2 * gs < nblk) t2 = tile_of(blk + 2 * gs);
+  __syncthreads();
+  bool have_next = has1;
+  while (true) {
+    const bool has2 = have_next && blk + 2 * gs < nblk;
+    if (have_next) gather(t1, cc1, xx1);                         // cc1 arrived during the previous iteration
+    if (has2) load_raw(t2, vv2, cc2, ro2);                       // t2's metadata arrived during the previous iteration
+    if (blk + 3 * gs < nblk) t3 = tile_of(blk + 3 * gs);
+    // ---- reduce tile t0 out of shared memory
+    const int nrow = t0.r1 - t0.r0;
+    const bool staged = nrow <= SP_ROWCAP;
+    for (int base = 0; base < nrow; base += NGRP) {
+      const int rl = base + grp;
+      double acc = 0.0;
+      if (rl < nrow) {
+        int s, e;
+        if (staged) { s = rowoff[rl]; e = rowoff[rl + 1]; }
+        else { s = (int)(crow[t0.r0 + rl] - t0.v0); e = (int)(crow[t0.r0 + rl + 1] - t0.v0); }
+        for (int q = s + g; q < e; q += G) acc += prod[q];
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (rl < nrow && g == 0) {
+        const int64_t r = t0.r0 + rl;
+        const double yv = mode ? b[r] - acc : acc;
+        y[r] = yv;
+        if (dot_out && own.has(r)) dsum += x[r] * yv;
+      }
+    }
+    if (!have_next) break;
+    __syncthreads();
+    store_prod(t1, vv1, xx1, ro1);
+    __syncthreads();
+    // rotate
+    t0 = t1; blk += gs;
+    have_next = has2;
+    if (has2) {
+      t1 = t2; t2 = t3;
+#pragma unroll
+      for (int u = 0; u < SP_U; ++u) { vv1[u] = vv2[u]; cc1[u] = cc2[u]; }
+#pragma unroll
+      for (int u = 0; u < SP_RU; ++u) ro1[u] = ro2[u];
+    }
+  }
+  if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
+}
+
 __global__ void __launch_bounds__(256) partition_rows_kernel(const int64_t* __restrict__ crow, int64_t n, int tile, int nblk,
-                                                             int32_t* __restrict__ blk_row) {
+                                                             int32_t* __restrict__ blk_row, int64_t* __restrict__ blk_v0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nblk) return;
-  if (b == nblk) { blk_row[b] = (int32_t)n; return; }
+  if (b == nblk) { blk_row[b] = (int32_t)n; if (blk_v0) blk_v0[b] = crow[n]; return; }
   const int64_t target = (int64_t)b * tile;
   int64_t lo = 0, hi = n;
   while (lo < hi) {
@@ -213,6 +307,7 @@ __global__ void __launch_bounds__(256) partition_rows_kernel(const int64_t* __re
     if (crow[mid] < target) lo = mid + 1; else hi = mid;
   }
   blk_row[b] = (int32_t)lo;
+  if (blk_v0) blk_v0[b] = crow[lo];
 }
 
 __global__ void __launch_bounds__(256) max_row_kernel(const int64_t* __restrict__ crow, int64_t n, int* out) {
@@ -333,10 +428,11 @@ static void launch_spmv(int64_t n, const int64_t* crow, const int32_t* col, cons
 int spmv_plan_blocks(int64_t nnz, int tile) { return (int)ceil_div(nnz > 0 ? nnz : 1, tile); }
 
 // blk_row (nblk+1 int32) and the longest row; *max_row_dev is a device int (zeroed here)
-int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t* blk_row, int* max_row_dev, cudaStream_t s) {
+int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t* blk_row, int* max_row_dev, cudaStream_t s,
+                    int64_t* blk_v0) {
   if (n >= ((int64_t)1 << 31)) return fail(ERR_UNSUPPORTED, "spmv_plan: more than 2^31 rows");
   FB2_CUDA(cudaMemsetAsync(max_row_dev, 0, sizeof(int), s));
-  partition_rows_kernel<<<(unsigned)ceil_div(nblk + 1, 256), 256, 0, s>>>(crow, n, tile, nblk, blk_row);
+  partition_rows_kernel<<<(unsigned)ceil_div(nblk + 1, 256), 256, 0, s>>>(crow, n, tile, nblk, blk_row, blk_v0);
   if (n > 0) max_row_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSM * 8), 256, 0, s>>>(crow, n, max_row_dev);
   FB2_LAUNCH_CHECK();
   return OK;
@@ -347,6 +443,21 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
                               unsigned int* counter, const CgScalars* sc, cudaStream_t s, OwnRange own) {
   const size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
+#ifndef FB2_SPMV_NOPIPE
+  if (plan.blk_v0 && plan.tile + plan.max_row <= SP_U * CG_THREADS) {
+    int gridp = std::min(plan.nblk, kNumSM * 2);
+    if (gridp > CG_PARTIALS) gridp = CG_PARTIALS;
+    if (gridp < 1) gridp = 1;
+#define FB2_SP(GV) spmv_pipe_kernel<GV><<<gridp, CG_THREADS, 0, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.blk_v0, plan.nblk, dot_out, partials, counter, sc, own)
+    if (avg <= 6.0) FB2_SP(2);
+    else if (avg <= 12.0) FB2_SP(4);
+    else if (avg <= 48.0) FB2_SP(8);
+    else FB2_SP(16);
+#undef FB2_SP
+    FB2_LAUNCH_CHECK();
+    return OK;
+  }
+#endif
   const int per_sm = (int)std::min<size_t>(8, (200 * 1024) / (smem + 1024));
   int grid = std::min(plan.nblk, kNumSM * std::max(per_sm, 1));
   if (grid > CG_PARTIALS) grid = CG_PARTIALS;
@@ -399,7 +510,8 @@ constexpr int CG_TILE = 2048;
 
 size_t cg_workspace_bytes(int64_t n, int64_t nnz) {
   return PartialWs::bytes() + align_up(sizeof(CgScalars)) + 3 * align_up((size_t)n * sizeof(double)) +
-         align_up((size_t)(spmv_plan_blocks(nnz, CG_TILE) + 2) * sizeof(int32_t)) + 1024;
+         align_up((size_t)(spmv_plan_blocks(nnz, CG_TILE) + 2) * sizeof(int32_t)) +
+         align_up((size_t)(spmv_plan_blocks(nnz, CG_TILE) + 2) * sizeof(int64_t)) + 1024;
 }
 
 int spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x, double* y,
@@ -490,9 +602,11 @@ int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, co
   plan.tile = CG_TILE;
   plan.nblk = spmv_plan_blocks(nnz, CG_TILE);
   int32_t* blk_row = c.take<int32_t>(plan.nblk + 2);
+  int64_t* blk_v0 = c.take<int64_t>(plan.nblk + 2);
   plan.blk_row = blk_row;
+  plan.blk_v0 = blk_v0;
   FB2_TRY(cg_init_scalars(sc, atol, rtol, maxit < 0 ? INT_MAX : maxit, s));
-  FB2_TRY(spmv_plan_build(n, crow, CG_TILE, plan.nblk, blk_row, &sc->pad, s));
+  FB2_TRY(spmv_plan_build(n, crow, CG_TILE, plan.nblk, blk_row, &sc->pad, s, blk_v0));
   FB2_CUDA(cudaMemcpyAsync(&plan.max_row, &sc->pad, sizeof(int), cudaMemcpyDeviceToHost, s));
   // |b| and the zero-rhs early return (solver/cg.py:79-80)
   dot_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, b, b, &sc->dot_tmp, pw.partials, &sc->counter[0]);

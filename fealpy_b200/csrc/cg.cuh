@@ -22,12 +22,14 @@ struct OwnRange {
 // row-aligned nnz tiling of a CSR matrix (built once per matrix, see spmv_plan_build)
 struct SpmvPlan {
   const int32_t* blk_row = nullptr;   // (nblk+1) first row of every tile
+  const int64_t* blk_v0 = nullptr;    // (nblk+1) first value index of every tile (pipelined kernel) or null
   int nblk = 0, tile = 0, max_row = 0;
 };   // max blocks contributing partial sums per reduction
 
 size_t cg_workspace_bytes(int64_t n, int64_t nnz);
 int spmv_plan_blocks(int64_t nnz, int tile);
-int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t* blk_row, int* max_row_dev, cudaStream_t s);
+int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t* blk_row, int* max_row_dev, cudaStream_t s,
+                    int64_t* blk_v0 = nullptr);
 
 // y = A x  (mode 0),  y = b - A x (mode 1); optional fused dot  sum_r x[r]*y[r] -> *dot_out (deterministic)
 size_t partial_workspace_bytes();

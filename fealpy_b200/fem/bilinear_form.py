@@ -115,7 +115,7 @@ def row_tiling(crow, nrow, nnz, tile):
     nblk = lib.fb2_spmv_plan_blocks(nnz, tile)
     blk_row = torch.empty(nblk + 2, dtype=torch.int32, device=crow.device)
     mr = C.c_int32(0)
-    _lib.call("fb2_spmv_plan_build", nrow, _lib.ptr(crow), tile, _lib.ptr(blk_row), nnz, C.byref(mr), _lib.stream())
+    _lib.call("fb2_spmv_plan_build", nrow, _lib.ptr(crow), tile, _lib.ptr(blk_row), None, nnz, C.byref(mr), _lib.stream())
     return blk_row, nblk
 
 

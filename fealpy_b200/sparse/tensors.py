@@ -72,9 +72,9 @@ class CSRTensor:
             x = other.contiguous()
             if x.ndim == 1:
                 y = torch.empty(n, dtype=torch.float64, device=x.device)
-                blk_row, tile, max_row = self.spmv_plan()
+                blk_row, blk_v0, tile, max_row = self.spmv_plan()
                 _lib.call("fb2_csr_spmv", n, self.nnz, _lib.ptr(self._crow), _lib.ptr(self._col), _lib.ptr(self._values),
-                          _lib.ptr(x), _lib.ptr(y), _lib.ptr(blk_row), tile, max_row, _lib.stream())
+                          _lib.ptr(x), _lib.ptr(y), _lib.ptr(blk_row), _lib.ptr(blk_v0), tile, max_row, _lib.stream())
                 return y
             if x.ndim == 2:
                 y = torch.empty((n, x.shape[1]), dtype=torch.float64, device=x.device)
@@ -95,10 +95,11 @@ class CSRTensor:
             n = self._spshape[0]
             nblk = lib.fb2_spmv_plan_blocks(self.nnz, self.SPMV_TILE)
             blk_row = torch.empty(nblk + 2, dtype=torch.int32, device=self.device)
+            blk_v0 = torch.empty(nblk + 2, dtype=torch.int64, device=self.device)
             mr = C.c_int32(0)
-            _lib.call("fb2_spmv_plan_build", n, _lib.ptr(self._crow), self.SPMV_TILE, _lib.ptr(blk_row), self.nnz, C.byref(mr),
-                      _lib.stream())
-            self._plan = (blk_row, self.SPMV_TILE, mr.value)
+            _lib.call("fb2_spmv_plan_build", n, _lib.ptr(self._crow), self.SPMV_TILE, _lib.ptr(blk_row), _lib.ptr(blk_v0), self.nnz,
+                      C.byref(mr), _lib.stream())
+            self._plan = (blk_row, blk_v0, self.SPMV_TILE, mr.value)
         return self._plan
 
     # --- conversions ----------------------------------------------------------------------

@@ -148,11 +148,11 @@ size_t fb2_partial_workspace_bytes(void);           /* zero-initialise once */
 /* SpMV plan (built once per matrix): row-aligned tiles of `tile` stored values.
  * blk_row has fb2_spmv_plan_blocks(nnz, tile) + 1 int32 entries; *max_row_host = longest row. */
 int fb2_spmv_plan_blocks(int64_t nnz, int tile);
-int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t nnz, int32_t* max_row_host,
-                        void* stream);
+int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t* blk_v0, int64_t nnz,
+                        int32_t* max_row_host, void* stream);      /* blk_v0 (blocks+1 int64, may be NULL): first value index per tile */
 /* y = A x.  blk_row may be NULL (row-per-lane-group kernel); with a plan the streaming kernel runs. */
 int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                 double* y, const int32_t* blk_row, int tile, int32_t max_row, void* stream);
+                 double* y, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row, void* stream);
 int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
                  void* stream);
 int fb2_dot(int64_t n, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream);
@@ -167,12 +167,13 @@ int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm
 /* own[4] = {lo0, hi0, lo1, hi1}: rows (owned dofs of this rank) that contribute to the dot
  * products; NULL = all rows.  The caller all-reduces scalars[1] (p.Ap) / scalars[2] (r.z). */
 int fb2_cg_residual(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                    const double* b, double* r, const int32_t* blk_row, int tile, int32_t max_row, void* stream);
+                    const double* b, double* r, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row,
+                    void* stream);
 int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p, void* scalars, void* partial_ws,
                  const int64_t own[4], void* stream);
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars, void* partial_ws,
-                    const int64_t own[4], void* stream);
+                    double* Ap, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row, void* scalars,
+                    void* partial_ws, const int64_t own[4], void* stream);
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,
                      void* partial_ws, int fuse_finalize, const int64_t own[4], void* stream);
 int fb2_cg_finalize(void* scalars, void* stream);
