@@ -9,6 +9,7 @@
 #include "cg.cuh"
 
 #include <climits>
+#include <cstdlib>
 #include <cmath>
 
 namespace fb2 {
@@ -295,6 +296,104 @@ __global__ void __launch_bounds__(CG_THREADS, 2) spmv_pipe_kernel(int64_t n, con
   if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
 }
 
+// ---- SpMV with an asynchronous shared-memory ring: the (val, col) stream of the next tiles is
+// copied global->shared with cp.async (LDGSTS: no registers, no warps blocked) while the current
+// tile gathers x and is reduced.  Keeps full occupancy AND several tiles of DRAM traffic in flight.
+#ifndef FB2_SA_STAGES
+#define FB2_SA_STAGES 3
+#endif
+constexpr int SA_STAGES = FB2_SA_STAGES;
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+template <int G>
+__global__ void __launch_bounds__(CG_THREADS) spmv_async_kernel(int64_t n, const int64_t* __restrict__ crow,
+                                                                const int32_t* __restrict__ col, const double* __restrict__ val,
+                                                                const double* __restrict__ x, double* __restrict__ y,
+                                                                const double* __restrict__ b, int mode,
+                                                                const int32_t* __restrict__ blk_row,
+                                                                const int64_t* __restrict__ blk_v0, int nblk, int cap, double* dot_out,
+                                                                double* partials, unsigned int* counter, const CgScalars* sc,
+                                                                OwnRange own) {
+  if (sc && sc->done) return;
+  extern __shared__ __align__(16) unsigned char sa_raw[];
+  // per stage: cap doubles (values, overwritten in place by the products) + cap ints (columns)
+  auto sval = [&](int st) { return reinterpret_cast<double*>(sa_raw + (size_t)st * cap * 12); };
+  auto scol = [&](int st) { return reinterpret_cast<int*>(sa_raw + (size_t)st * cap * 12 + (size_t)cap * 8); };
+  const int tid = threadIdx.x;
+  const int g = tid % G, grp = tid / G;
+  constexpr int NGRP = CG_THREADS / G;
+  const int gs = (int)gridDim.x;
+  double dsum = 0.0;
+  auto issue = [&](int blk, int st) {
+    if (blk < nblk) {
+      const int64_t v0 = blk_v0[blk];
+      const int nval = (int)(blk_v0[blk + 1] - v0);
+      double* dv = sval(st);
+      int* dc = scol(st);
+      for (int k = tid; k < nval; k += CG_THREADS) { cp_async8(dv + k, val + v0 + k); cp_async4(dc + k, col + v0 + k); }
+    }
+    cp_async_commit();            // always commit so that group counting stays uniform
+  };
+  int blk = blockIdx.x;
+#pragma unroll
+  for (int s = 0; s < SA_STAGES - 1; ++s) issue(blk + s * gs, s);
+  int st = 0;
+  for (; blk < nblk; blk += gs) {
+    issue(blk + (SA_STAGES - 1) * gs, (st + SA_STAGES - 1) % SA_STAGES);
+    cp_async_wait<SA_STAGES - 1>();
+    __syncthreads();
+    const int r0 = blk_row[blk], r1 = blk_row[blk + 1];
+    const int64_t v0 = blk_v0[blk];
+    const int nval = (int)(blk_v0[blk + 1] - v0);
+    double* pv = sval(st);
+    const int* pc = scol(st);
+    {
+      int k = tid;
+      for (; k + 3 * CG_THREADS < nval; k += 4 * CG_THREADS) {
+        double xx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xx[u] = x[pc[k + u * CG_THREADS]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pv[k + u * CG_THREADS] *= xx[u];
+      }
+      for (; k < nval; k += CG_THREADS) pv[k] *= x[pc[k]];
+    }
+    __syncthreads();
+    const int nrow = r1 - r0;
+    for (int base = 0; base < nrow; base += NGRP) {
+      const int rl = base + grp;
+      double acc = 0.0;
+      if (rl < nrow) {
+        const int s = (int)(crow[r0 + rl] - v0), e = (int)(crow[r0 + rl + 1] - v0);
+        for (int q = s + g; q < e; q += G) acc += pv[q];
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (rl < nrow && g == 0) {
+        const int64_t r = (int64_t)r0 + rl;
+        const double yv = mode ? b[r] - acc : acc;
+        y[r] = yv;
+        if (dot_out && own.has(r)) dsum += x[r] * yv;
+      }
+    }
+    __syncthreads();              // the stage is recycled by the issue() of the next iteration
+    st = (st + 1) % SA_STAGES;
+  }
+  cp_async_wait<0>();
+  if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
+}
+
 __global__ void __launch_bounds__(256) partition_rows_kernel(const int64_t* __restrict__ crow, int64_t n, int tile, int nblk,
                                                              int32_t* __restrict__ blk_row, int64_t* __restrict__ blk_v0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -443,7 +542,33 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
                               unsigned int* counter, const CgScalars* sc, cudaStream_t s, OwnRange own) {
   const size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
-#ifndef FB2_SPMV_NOPIPE
+#ifndef FB2_SPMV_NOASYNC
+  if (plan.blk_v0) {
+    const int cap = (plan.tile + plan.max_row + 3) & ~3;
+    const size_t smem_a = (size_t)SA_STAGES * cap * 12;
+    if (smem_a <= 200 * 1024) {
+      const int per_sm_a = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem_a + 1024)));
+      int grida = std::min(plan.nblk, kNumSM * per_sm_a);
+      if (grida > CG_PARTIALS) grida = CG_PARTIALS;
+      if (grida < 1) grida = 1;
+#define FB2_SA(GV)                                                                                                   \
+  do {                                                                                                               \
+    auto kern = spmv_async_kernel<GV>;                                                                               \
+    if (smem_a > 48 * 1024) FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)); \
+    kern<<<grida, CG_THREADS, smem_a, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.blk_v0, plan.nblk, cap, dot_out,   \
+                                           partials, counter, sc, own);                                              \
+  } while (0)
+      if (avg <= 6.0) FB2_SA(2);
+      else if (avg <= 12.0) FB2_SA(4);
+      else if (avg <= 48.0) FB2_SA(8);
+      else FB2_SA(16);
+#undef FB2_SA
+      FB2_LAUNCH_CHECK();
+      return OK;
+    }
+  }
+#endif
+#ifdef FB2_SPMV_REGPIPE      // register-pipelined variant: measured slower (2.59 vs 1.93 ms/iteration), kept for reference
   if (plan.blk_v0 && plan.tile + plan.max_row <= SP_U * CG_THREADS) {
     int gridp = std::min(plan.nblk, kNumSM * 2);
     if (gridp > CG_PARTIALS) gridp = CG_PARTIALS;
@@ -506,7 +631,12 @@ struct PartialWs {
   static size_t bytes() { return align_up(CG_PARTIALS * sizeof(double) + 64); }
 };
 
-constexpr int CG_TILE = 2048;
+// values per SpMV tile inside fb2_cg (FB2_SPMV_TILE overrides, for tuning)
+static int cg_tile() {
+  static int t = [] { const char* e = getenv("FB2_SPMV_TILE"); const int v = e ? atoi(e) : 0; return v >= 256 ? v : 1024; }();
+  return t;
+}
+#define CG_TILE cg_tile()
 
 size_t cg_workspace_bytes(int64_t n, int64_t nnz) {
   return PartialWs::bytes() + align_up(sizeof(CgScalars)) + 3 * align_up((size_t)n * sizeof(double)) +
