@@ -812,7 +812,11 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[(TD + 1
                                        const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
   constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1;
   using SR = SlotRec<SlotT, L>;
+#ifdef FB2_A4_JC
+  constexpr int JC = (L % FB2_A4_JC == 0) ? FB2_A4_JC : 1;
+#else
   constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
+#endif
 #pragma unroll
   for (int j0 = 0; j0 < L; j0 += JC) {
     double val[JC];
@@ -831,6 +835,9 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[(TD + 1
     for (int jj = 0; jj < JC; ++jj) old[jj] = my[SR::get(sw, j0 + jj)];
 #pragma unroll
     for (int jj = 0; jj < JC; ++jj) my[SR::get(sw, j0 + jj)] = old[jj] + val[jj];
+#ifdef FB2_A4_CHUNKFENCE
+    __syncwarp();                 // keeps the live range of one chunk from overlapping the next
+#endif
   }
 }
 

@@ -176,9 +176,9 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
 // ---- SpMV, software-pipelined over tiles: while tile t is reduced out of shared memory, the
 // (val, col) stream of tile t+2 and the x gathers of tile t+1 are already in flight in registers,
 // so every DRAM / L2 round trip is issued a full tile ahead of its use.
-constexpr int SP_U = 9;                  // values per thread and tile: tile + max_row <= SP_U * 256
-constexpr int SP_ROWCAP = 768;           // rows of a tile staged in shared memory
-constexpr int SP_RU = SP_ROWCAP / CG_THREADS + 1;
+[[maybe_unused]] constexpr int SP_U = 9;                  // values per thread and tile: tile + max_row <= SP_U * 256
+[[maybe_unused]] constexpr int SP_ROWCAP = 768;           // rows of a tile staged in shared memory
+[[maybe_unused]] constexpr int SP_RU = SP_ROWCAP / CG_THREADS + 1;
 
 struct SpTile { int r0, r1, nval; int64_t v0; };
 
@@ -542,7 +542,7 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
                               unsigned int* counter, const CgScalars* sc, cudaStream_t s, OwnRange own) {
   const size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
-#ifndef FB2_SPMV_NOASYNC
+#ifdef FB2_SPMV_ASYNC        // cp.async ring variant: measured slower (2.9-4.4 vs 1.92 ms/iteration), kept for reference
   if (plan.blk_v0) {
     const int cap = (plan.tile + plan.max_row + 3) & ~3;
     const size_t smem_a = (size_t)SA_STAGES * cap * 12;
@@ -633,7 +633,7 @@ struct PartialWs {
 
 // values per SpMV tile inside fb2_cg (FB2_SPMV_TILE overrides, for tuning)
 static int cg_tile() {
-  static int t = [] { const char* e = getenv("FB2_SPMV_TILE"); const int v = e ? atoi(e) : 0; return v >= 256 ? v : 1024; }();
+  static int t = [] { const char* e = getenv("FB2_SPMV_TILE"); const int v = e ? atoi(e) : 0; return v >= 256 ? v : 2048; }();
   return t;
 }
 #define CG_TILE cg_tile()
