@@ -812,11 +812,10 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[(TD + 1
                                        const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
   constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1;
   using SR = SlotRec<SlotT, L>;
-#ifdef FB2_A4_JC
-  constexpr int JC = (L % FB2_A4_JC == 0) ? FB2_A4_JC : 1;
-#else
-  constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
+#ifndef FB2_A4_JC
+#define FB2_A4_JC 2
 #endif
+  constexpr int JC = (L % FB2_A4_JC == 0) ? FB2_A4_JC : 1;
 #pragma unroll
   for (int j0 = 0; j0 < L; j0 += JC) {
     double val[JC];
@@ -835,9 +834,7 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[(TD + 1
     for (int jj = 0; jj < JC; ++jj) old[jj] = my[SR::get(sw, j0 + jj)];
 #pragma unroll
     for (int jj = 0; jj < JC; ++jj) my[SR::get(sw, j0 + jj)] = old[jj] + val[jj];
-#ifdef FB2_A4_CHUNKFENCE
-    __syncwarp();                 // keeps the live range of one chunk from overlapping the next
-#endif
+    __syncwarp();      // all 32 lanes get here (padding lanes add zeros to a dummy slot): bounds the live range of a chunk
   }
 }
 
@@ -924,7 +921,9 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
     __syncwarp();
     const bool more = b + 1 < b1;
     if (more) fetch(b + 1);
-    if (cell >= 0) a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, acc + base);
+    // padding lanes (cell < 0) carry h = 0 and slot words 0: they add zeros to a private dummy slot, so the
+    // whole warp stays converged through the batch (the chunk barriers in a4_row need that)
+    a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, (cell >= 0) ? acc + base : acc + (a.tile + a.max_row - 1));
     if (more) stash();
   }
   __syncwarp();

@@ -259,6 +259,18 @@ int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_di
   return cg_update_p(n, p, r, minv_diag, static_cast<CgScalars*>(scalars), S(stream));
 }
 
+int fb2_bcg_dots(int64_t n, int nb, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream) {
+  return bcg_dots(n, nb, a, b, out_dev, partial_ws, S(stream));
+}
+int fb2_bcg_update_xr(int64_t n, int nb, double* x, double* r, const double* p, const double* Ap, const double* rTr, const double* pAp,
+                      void* stream) {
+  return bcg_update_xr(n, nb, x, r, p, Ap, rTr, pAp, S(stream));
+}
+int fb2_bcg_update_p(int64_t n, int nb, double* p, const double* r, const double* minv_diag, const double* rTr_new, const double* rTr,
+                     void* stream) {
+  return bcg_update_p(n, nb, p, r, minv_diag, rTr_new, rTr, S(stream));
+}
+
 // ---- next rows: source vector, Dirichlet -----------------------------------------------------
 int fb2_elem_source(int TD, int64_t NC, int ldof, int NQ, const double* node, const int32_t* cell, const double* phiw, int kind,
                     double scal, const double* f, double* out, void* stream) {

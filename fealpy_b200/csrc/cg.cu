@@ -799,3 +799,95 @@ int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, co
 }
 
 }  // namespace fb2
+
+// =====================================================================================
+// batched right-hand sides (b of shape (n, B), row-major): per-column alpha / beta, joint stopping
+// test on sqrt(sum_k r_k.z_k)  (solver/cg.py:88-121).  Building blocks driven from the host.
+// =====================================================================================
+namespace fb2 {
+
+constexpr int BCG_MAXB = 32;
+
+// out[k] = sum_i a[i,k]*b[i,k]  (deterministic: per-CTA partials, last CTA sums in order)
+__global__ void __launch_bounds__(CG_THREADS) bcg_dots_kernel(int64_t n, int B, const double* __restrict__ a, const double* __restrict__ b,
+                                                              double* __restrict__ out, double* __restrict__ partials,
+                                                              unsigned int* counter) {
+  __shared__ double red[CG_THREADS / 32][BCG_MAXB];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = 0; k < B; ++k) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += a[i * B + k] * b[i * B + k];
+    acc = warp_sum(acc);
+    if (lane == 0) red[wid][k] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < B) {
+    double t = 0.0;
+    for (int w = 0; w < CG_THREADS / 32; ++w) t += red[w][threadIdx.x];
+    partials[(int64_t)blockIdx.x * B + threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicInc(counter, gridDim.x - 1);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < B) {
+    double t = 0.0;
+    for (int g = 0; g < (int)gridDim.x; ++g) t += __ldcg(partials + (int64_t)g * B + threadIdx.x);
+    out[threadIdx.x] = t;
+  }
+}
+
+// x += alpha_k p ; r -= alpha_k Ap   with alpha_k = rTr[k] / pAp[k]
+__global__ void __launch_bounds__(CG_THREADS) bcg_update_xr_kernel(int64_t n, int B, double* __restrict__ x, double* __restrict__ r,
+                                                                   const double* __restrict__ p, const double* __restrict__ Ap,
+                                                                   const double* __restrict__ rTr, const double* __restrict__ pAp) {
+  const int64_t tot = n * B;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t % B);
+    const double alpha = rTr[k] / pAp[k];
+    x[t] += alpha * p[t];
+    r[t] -= alpha * Ap[t];
+  }
+}
+
+// p = z + beta_k p  with beta_k = rTr_new[k] / rTr[k],  z = minv .* r (or r)
+__global__ void __launch_bounds__(CG_THREADS) bcg_update_p_kernel(int64_t n, int B, double* __restrict__ p, const double* __restrict__ r,
+                                                                  const double* __restrict__ minv, const double* __restrict__ rTr_new,
+                                                                  const double* __restrict__ rTr) {
+  const int64_t tot = n * B;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t % B);
+    const double z = minv ? minv[t / B] * r[t] : r[t];
+    p[t] = z + (rTr_new[k] / rTr[k]) * p[t];
+  }
+}
+
+int bcg_dots(int64_t n, int B, const double* a, const double* b, double* out, void* partial_ws, cudaStream_t s) {
+  if (B < 1 || B > BCG_MAXB) return fail(ERR_UNSUPPORTED, "batched cg: 1 <= batch <= %d", BCG_MAXB);
+  PartialWs pw(partial_ws);
+  int grid = vec_grid(n);
+  if ((int64_t)grid * B > CG_PARTIALS) grid = CG_PARTIALS / B;
+  bcg_dots_kernel<<<grid, CG_THREADS, 0, s>>>(n, B, a, b, out, pw.partials, pw.counter);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+int bcg_update_xr(int64_t n, int B, double* x, double* r, const double* p, const double* Ap, const double* rTr, const double* pAp,
+                  cudaStream_t s) {
+  bcg_update_xr_kernel<<<vec_grid(n * B), CG_THREADS, 0, s>>>(n, B, x, r, p, Ap, rTr, pAp);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+int bcg_update_p(int64_t n, int B, double* p, const double* r, const double* minv, const double* rTr_new, const double* rTr,
+                 cudaStream_t s) {
+  bcg_update_p_kernel<<<vec_grid(n * B), CG_THREADS, 0, s>>>(n, B, p, r, minv, rTr_new, rTr);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+}  // namespace fb2

@@ -54,4 +54,10 @@ int cg_update_xr(int64_t n, double* x, double* r, const double* p, const double*
 int cg_finalize(CgScalars* sc, cudaStream_t s);
 int cg_update_p(int64_t n, double* p, const double* r, const double* minv, CgScalars* sc, cudaStream_t s);
 
+// batched right-hand sides (row-major (n, B))
+int bcg_dots(int64_t n, int B, const double* a, const double* b, double* out, void* partial_ws, cudaStream_t s);
+int bcg_update_xr(int64_t n, int B, double* x, double* r, const double* p, const double* Ap, const double* rTr, const double* pAp,
+                  cudaStream_t s);
+int bcg_update_p(int64_t n, int B, double* p, const double* r, const double* minv, const double* rTr_new, const double* rTr,
+                 cudaStream_t s);
 }  // namespace fb2

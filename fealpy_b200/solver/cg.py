@@ -38,7 +38,7 @@ def cg(A, b, x0=None, M=None, *, batch_first=False, atol=1e-12, rtol=1e-8, maxit
     if not isinstance(A, CSRTensor):
         raise TypeError("fealpy_b200.solver.cg needs a fealpy_b200 CSRTensor (assemble with BilinearForm.assembly())")
     if b.ndim == 2:
-        raise NotImplementedError("batched right-hand sides are not on the accelerated path yet")
+        return _cg_batched(A, b, x0, M, batch_first, atol, rtol, maxit, returninfo)
     if b.device.type != "cuda" or b.dtype != torch.float64:
         raise RuntimeError("fealpy_b200.solver.cg needs float64 CUDA tensors; there is no CPU fallback")
     n = A.sparse_shape[0]
@@ -54,4 +54,52 @@ def cg(A, b, x0=None, M=None, *, batch_first=False, atol=1e-12, rtol=1e-8, maxit
               float(atol), float(rtol), -1 if maxit is None else int(maxit), 0, _lib.ptr(ws), C.byref(niter), C.byref(resid),
               _lib.stream())
     info = {"residual": resid.value, "niter": niter.value}
+    return (x, info) if returninfo else x
+
+
+def _cg_batched(A, b, x0, M, batch_first, atol, rtol, maxit, returninfo):
+    """b of shape (dof, batch) (or (batch, dof) with batch_first): per-column alpha/beta, joint stopping
+    test on sqrt(sum_k r_k.z_k) -- solver/cg.py:58-121.  Host-driven loop over fb2_csr_spmm + fb2_bcg_*."""
+    if b.device.type != "cuda" or b.dtype != torch.float64:
+        raise RuntimeError("fealpy_b200.solver.cg needs float64 CUDA tensors; there is no CPU fallback")
+    if batch_first:
+        b = b.swapaxes(0, 1)
+        x0 = None if x0 is None else x0.swapaxes(0, 1)
+    n, B = b.shape
+    if A.sparse_shape != (n, n):
+        raise ValueError("shape mismatch between A and b")
+    dev = b.device
+    bb = b.contiguous()
+    info = {"residual": 0.0, "niter": 0}
+    if float(torch.linalg.norm(bb)) < 1e-15:
+        x = torch.zeros_like(bb)
+    else:
+        minv = _minv_diag(M, n, dev)
+        pws = _lib.partial_ws(dev)
+        x = torch.zeros_like(bb) if x0 is None else x0.contiguous().clone()
+        r = bb - (A @ x)
+        z = r if minv is None else minv[:, None] * r
+        p = z.clone()
+        rTr = torch.empty(B, dtype=torch.float64, device=dev)
+        rTr_new = torch.empty_like(rTr)
+        pAp = torch.empty_like(rTr)
+        _lib.call("fb2_bcg_dots", n, B, _lib.ptr(r), _lib.ptr(z), _lib.ptr(rTr), _lib.ptr(pws), _lib.stream())
+        b_norm = float(torch.linalg.norm(bb))
+        it = 0
+        while True:
+            Ap = A @ p
+            _lib.call("fb2_bcg_dots", n, B, _lib.ptr(p), _lib.ptr(Ap), _lib.ptr(pAp), _lib.ptr(pws), _lib.stream())
+            _lib.call("fb2_bcg_update_xr", n, B, _lib.ptr(x), _lib.ptr(r), _lib.ptr(p), _lib.ptr(Ap), _lib.ptr(rTr), _lib.ptr(pAp),
+                      _lib.stream())
+            z = r if minv is None else minv[:, None] * r
+            _lib.call("fb2_bcg_dots", n, B, _lib.ptr(r), _lib.ptr(z), _lib.ptr(rTr_new), _lib.ptr(pws), _lib.stream())
+            r_norm = float(rTr_new.sum().sqrt())
+            it += 1
+            info["residual"], info["niter"] = r_norm, it
+            if r_norm < atol or r_norm < rtol * b_norm or (maxit is not None and it >= maxit):
+                break
+            _lib.call("fb2_bcg_update_p", n, B, _lib.ptr(p), _lib.ptr(r), _lib.ptr(minv), _lib.ptr(rTr_new), _lib.ptr(rTr), _lib.stream())
+            rTr, rTr_new = rTr_new, rTr
+    if batch_first:
+        x = x.swapaxes(0, 1)
     return (x, info) if returninfo else x

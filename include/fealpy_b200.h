@@ -179,6 +179,15 @@ int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const dou
 int fb2_cg_finalize(void* scalars, void* stream);
 int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, void* stream);
 
+/* batched right-hand sides, b of shape (n, nb) row-major (solver/cg.py:88-121): per-column dots,
+ * x/r update with alpha_k = rTr[k]/pAp[k], p update with beta_k = rTr_new[k]/rTr[k]; the host drives
+ * the loop with fb2_csr_spmm.  All scalar arrays live on the device. */
+int fb2_bcg_dots(int64_t n, int nb, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream);
+int fb2_bcg_update_xr(int64_t n, int nb, double* x, double* r, const double* p, const double* Ap, const double* rTr, const double* pAp,
+                      void* stream);
+int fb2_bcg_update_p(int64_t n, int nb, double* p, const double* r, const double* minv_diag, const double* rTr_new, const double* rTr,
+                     void* stream);
+
 /* ---- next rows: right-hand side and Dirichlet step ------------------------
  * replaces ScalarSourceIntegrator.assembly + LinearForm.assembly (fem/scalar_source_integrator.py:13-57,
  * fem/linear_form.py:36-86) and DirichletBC.apply (fem/dirichlet_bc.py:101-235). */

@@ -468,3 +468,27 @@ def test_config4_tet_p1_elasticity_full_size(U):
     x = torch.rand(A.shape[0], dtype=torch.float64, device="cuda")
     y = torch.rand(A.shape[0], dtype=torch.float64, device="cuda")
     assert abs(float(y @ (A @ x)) - float(x @ (A @ y))) <= 1e-9 * abs(float(y @ (A @ x)))
+
+
+@pytest.mark.parametrize("batch_first", [False, True])
+def test_batched_rhs_cg_matches_oracle(batch_first, U):
+    """b of shape (dof, batch): per-column alpha/beta, joint stopping test (solver/cg.py:58-121)"""
+    from oracle import fem_oracle as O
+    from fealpy_b200.solver import cg
+    case = C.by_name("tet_p2_3x2x1_diffmass")
+    gold = G.load(case["name"])
+    mesh, space, bform, _ = U.make_form(case, gold)
+    A = bform.assembly()
+    n = A.shape[0]
+    rng = np.random.default_rng(3)
+    Bm = rng.standard_normal((n, 3))
+    crow, col, val = gold["crow"], gold["col"], gold["values"]
+    xo, oinfo = O.cg(lambda v: np.stack([O.csr_matvec(crow, col, val, v[:, k]) for k in range(v.shape[1])], axis=1), Bm)
+    bt = U.t64(Bm.T.copy() if batch_first else Bm)
+    x, info = cg(A, bt, batch_first=batch_first, returninfo=True)
+    xg = x.cpu().numpy().T if batch_first else x.cpu().numpy()
+    assert abs(info["niter"] - oinfo["niter"]) <= 1
+    assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) <= 1e-10
+    y = (A @ U.t64(Bm)).cpu().numpy()                                     # SpMM against the oracle SpMV
+    ref = np.stack([O.csr_matvec(crow, col, val, Bm[:, k]) for k in range(3)], axis=1)
+    assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
