@@ -812,10 +812,9 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[(TD + 1
                                        const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
   constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1;
   using SR = SlotRec<SlotT, L>;
-#ifndef FB2_A4_JC
-#define FB2_A4_JC 2
-#endif
-  constexpr int JC = (L % FB2_A4_JC == 0) ? FB2_A4_JC : 1;
+  // columns in chunks of JC independent FMA chains.  (Tried and measured slower, profiles/r01_tune_asm_v4*.txt:
+  // smaller chunks separated by warp barriers to cap registers at 128 -- occupancy up, time up.)
+  constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
 #pragma unroll
   for (int j0 = 0; j0 < L; j0 += JC) {
     double val[JC];
@@ -834,7 +833,6 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[(TD + 1
     for (int jj = 0; jj < JC; ++jj) old[jj] = my[SR::get(sw, j0 + jj)];
 #pragma unroll
     for (int jj = 0; jj < JC; ++jj) my[SR::get(sw, j0 + jj)] = old[jj] + val[jj];
-    __syncwarp();      // all 32 lanes get here (padding lanes add zeros to a dummy slot): bounds the live range of a chunk
   }
 }
 
@@ -921,9 +919,7 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
     __syncwarp();
     const bool more = b + 1 < b1;
     if (more) fetch(b + 1);
-    // padding lanes (cell < 0) carry h = 0 and slot words 0: they add zeros to a private dummy slot, so the
-    // whole warp stays converged through the batch (the chunk barriers in a4_row need that)
-    a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, (cell >= 0) ? acc + base : acc + (a.tile + a.max_row - 1));
+    if (cell >= 0) a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, acc + base);
     if (more) stash();
   }
   __syncwarp();
