@@ -483,9 +483,10 @@ def test_batched_rhs_cg_matches_oracle(batch_first, U):
     rng = np.random.default_rng(3)
     Bm = rng.standard_normal((n, 3))
     crow, col, val = gold["crow"], gold["col"], gold["values"]
-    xo, oinfo = O.cg(lambda v: np.stack([O.csr_matvec(crow, col, val, v[:, k]) for k in range(v.shape[1])], axis=1), Bm)
+    xo, oinfo = O.cg(lambda v: np.stack([O.csr_matvec(crow, col, val, v[:, k]) for k in range(v.shape[1])], axis=1), Bm,
+                     atol=1e-14, rtol=1e-12)
     bt = U.t64(Bm.T.copy() if batch_first else Bm)
-    x, info = cg(A, bt, batch_first=batch_first, returninfo=True)
+    x, info = cg(A, bt, batch_first=batch_first, returninfo=True, atol=1e-14, rtol=1e-12)
     xg = x.cpu().numpy().T if batch_first else x.cpu().numpy()
     assert abs(info["niter"] - oinfo["niter"]) <= 1
     assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) <= 1e-10
