@@ -42,6 +42,17 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic():
+    """per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the two dominant kernels from the
+    committed `ncu --set full` capture of this same workload (profiles/r01_traffic.json), or {}"""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -301,6 +312,7 @@ def run_ours(args):
         nnz_glob, NC_glob, gdof_glob = nnz, NC, gdof
     if rank == 0:
         peak, peak_src = peaks()
+        traffic = measured_traffic()
         # algorithmic bytes, per launch == per step for both kernels
         b_asm = 4 * NC * 4 + 4 * NC * L + 8 * 3 * NN + 12 * nnz + 8 * (gdof + 1)
         b_it = 12 * nnz + 8 * (gdof + 1) + 104 * gdof
@@ -321,12 +333,17 @@ def run_ours(args):
             "assembly_ms": 1e3 * t_asm / args.steps,
             "cold": {"mesh_topology_ms": t_mesh, "symbolic_ms": t_sym, "first_assembly_ms": t_first,
                      "nnz_per_s_incl_symbolic": nnz / ((t_sym + t_first) * 1e-3)},
-            "roofline": {"bound": "hbm", "kernel": "spmv_kernel (CG iteration = spmv+dot, update_xr, update_p)",
-                         "achieved": cg_gbs, "peak": peak, "unit": "GB/s", "frac": cg_gbs / peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_iter": b_it},
-            "roofline_assembly": {"bound": "hbm", "kernel": "assemble_const_kernel", "achieved": asm_gbs, "peak": peak,
-                                  "unit": "GB/s", "frac": asm_gbs / peak, "traffic": None, "algorithmic_bytes": b_asm},
-            "e2e": e2e, "gpu_launches": args.steps * (1 + 3 * args.cg_iters + 4),
+            "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<8> (one CG iteration = spmv+dot, update_xr, update_p)",
+                         "achieved": cg_gbs, "peak": peak, "unit": "GB/s", "frac": cg_gbs / peak,
+                         "traffic": traffic.get("cg_iteration_bytes") if (n == 128 and p == 2) else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_iter": b_it,
+                         "note": "achieved = algorithmic bytes of one CG iteration x iterations / CUDA-event time of cg()"},
+            "roofline_assembly": {"bound": "hbm", "kernel": "cell_geometry4_kernel + assemble_const_v4_kernel", "achieved": asm_gbs,
+                                  "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
+                                  "traffic": traffic.get("assembly_bytes") if (n == 128 and p == 2) else None,
+                                  "algorithmic_bytes": b_asm,
+                                  "note": "warm pattern: col/crow are cached and not re-written; limiter is the L1/LSU data pipe (DESIGN.md)"},
+            "e2e": e2e, "gpu_launches": args.steps * (2 + 3 * args.cg_iters + 7),
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         if not args.no_cpu_baseline and world == 1:
