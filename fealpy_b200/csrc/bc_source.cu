@@ -163,3 +163,36 @@ int bc_vector(int64_t n, const uint8_t* isbd, const double* uh, double* f, cudaS
 }
 
 }  // namespace fb2
+
+// ---- matrix-free operator (row f4): v = sum_c P_c^T K_e[c] P_c u without the global matrix
+// (BilinearForm.__matmul__ before assembly, fem/bilinear_form.py:126-158).  Row-owner form: dof d
+// sums, over its (cell, i) pairs in canonical order, the dot of K_e's row i with u gathered at the
+// cell's dofs -- deterministic, no atomics.
+namespace fb2 {
+__global__ void __launch_bounds__(256) matfree_apply_kernel(int64_t gdof, int L, const int64_t* __restrict__ adj_ptr,
+                                                            const int* __restrict__ adj_pair, const int* __restrict__ c2d,
+                                                            const double* __restrict__ ke, const double* __restrict__ u,
+                                                            double* __restrict__ v) {
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < gdof; d += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int64_t q = adj_ptr[d]; q < adj_ptr[d + 1]; ++q) {
+      const int pair = adj_pair[q];
+      const int64_t c = pair / L;
+      const double* row = ke + (int64_t)pair * L;          // K_e[c][i][:] (pair = c*L + i)
+      const int* dofs = c2d + c * L;
+      double t = 0.0;
+      for (int j = 0; j < L; ++j) t += row[j] * u[dofs[j]];
+      s += t;
+    }
+    v[d] = s;
+  }
+}
+
+int matfree_apply(int64_t gdof, int L, const int64_t* adj_ptr, const int* adj_pair, const int* c2d, const double* ke, const double* u,
+                  double* v, cudaStream_t s) {
+  if (gdof <= 0) return OK;
+  matfree_apply_kernel<<<grid_for(gdof), 256, 0, s>>>(gdof, L, adj_ptr, adj_pair, c2d, ke, u, v);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+}  // namespace fb2

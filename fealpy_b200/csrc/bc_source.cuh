@@ -11,4 +11,6 @@ int bc_matrix_count(int64_t n, const int64_t* crow, const int* col, const uint8_
 int bc_matrix_fill(int64_t n, const int64_t* crow, const int* col, const double* val, const uint8_t* isbd, const int64_t* crow_new,
                    int* col_new, double* val_new, cudaStream_t s);
 int bc_vector(int64_t n, const uint8_t* isbd, const double* uh, double* f, cudaStream_t s);
+int matfree_apply(int64_t gdof, int L, const int64_t* adj_ptr, const int* adj_pair, const int* c2d, const double* ke, const double* u,
+                  double* v, cudaStream_t s);
 }  // namespace fb2

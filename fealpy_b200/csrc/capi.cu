@@ -280,6 +280,10 @@ int fb2_elem_source(int TD, int64_t NC, int ldof, int NQ, const double* node, co
 int fb2_gather_vector(int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair, const double* fe, double* F, void* stream) {
   return gather_vector(gdof, adj_ptr, adj_pair, fe, F, S(stream));
 }
+int fb2_matfree_apply(int64_t gdof, int ldof, const int64_t* adj_ptr, const int32_t* adj_pair, const int32_t* cell2dof,
+                      const double* Ke, const double* u, double* v, void* stream) {
+  return matfree_apply(gdof, ldof, adj_ptr, adj_pair, cell2dof, Ke, u, v, S(stream));
+}
 size_t fb2_bc_workspace_bytes(int64_t n) { return bc_workspace_bytes(n); }
 int fb2_bc_matrix_count(int64_t n, const int64_t* crow, const int32_t* col, const uint8_t* isbd, int64_t* crow_new,
                         int64_t* nnz_host, void* ws, void* stream) {

@@ -410,6 +410,18 @@ class BilinearForm:
         return self._M
 
     def __matmul__(self, u):
-        if self._M is None:
-            self.assembly()
-        return self._M @ u
+        """assembled product if assembly() was called, else matrix-free (fem/bilinear_form.py:126-158)"""
+        if self._M is not None:
+            return self._M @ u
+        if self._is_tensor_space():
+            raise NotImplementedError("matrix-free products on tensor spaces are not on the accelerated path; call assembly()")
+        if not isinstance(u, torch.Tensor) or u.ndim != 1 or u.dtype != torch.float64:
+            raise NotImplementedError("matrix-free products take a 1-D float64 CUDA tensor")
+        sym = symbolic_pattern(self.space)
+        if u.shape[0] != sym["gdof"]:
+            raise ValueError("shape mismatch")
+        ke = self._summed_ke()
+        v = torch.empty_like(u)
+        _lib.call("fb2_matfree_apply", sym["gdof"], sym["L"], _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
+                  _lib.ptr(self.space.cell_to_dof().contiguous()), _lib.ptr(ke), _lib.ptr(u.contiguous()), _lib.ptr(v), _lib.stream())
+        return v

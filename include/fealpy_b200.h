@@ -196,6 +196,10 @@ int fb2_elem_source(int TD, int64_t NC, int ldof, int NQ, const double* node, co
                     double scal, const double* f, double* out, void* stream);
 /* F[d] = sum of F_e over the (cell, i) pairs of dof d in ascending order (adjacency of fb2_sym_count) */
 int fb2_gather_vector(int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair, const double* fe, double* F, void* stream);
+/* matrix-free v = A u from the element matrices Ke (NC,l,l) (BilinearForm.__matmul__ before assembly,
+ * fem/bilinear_form.py:126-158): row-owner gather over the adjacency of fb2_sym_count, no atomics */
+int fb2_matfree_apply(int64_t gdof, int ldof, const int64_t* adj_ptr, const int32_t* adj_pair, const int32_t* cell2dof,
+                      const double* Ke, const double* u, double* v, void* stream);
 size_t fb2_bc_workspace_bytes(int64_t n);
 /* canonical CSR of the constrained matrix: boundary rows/columns removed, unit diagonal on boundary rows */
 int fb2_bc_matrix_count(int64_t n, const int64_t* crow, const int32_t* col, const uint8_t* isbd, int64_t* crow_new,

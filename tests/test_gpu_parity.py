@@ -181,8 +181,12 @@ def test_reference_bilinear_form_matmul(k, p, U):
     y = torch.zeros(gdof, dtype=torch.float64, device="cuda")
     y.index_add_(0, c2d.reshape(-1), torch.einsum("cij,cj->ci", Ke, x[c2d]).reshape(-1))
     bform = BilinearForm(space).add_integrator(I)
+    w = bform @ x                      # matrix-free (row f4): no global matrix yet
+    assert bform._M is None
     z = bform.assembly() @ x
-    assert float((y - z).norm()) < 1e-12
+    assert bform._M is not None
+    assert float((y - z).norm()) < 1e-12 and float((w - z).norm()) < 1e-12
+    assert float(((bform @ x) - z).norm()) == 0.0
 
 
 @pytest.mark.parametrize("mesh_kind,p,n", [("tri", 1, 96), ("tri", 3, 40), ("tet", 1, 20), ("tet", 2, 14), ("tet", 3, 6)])
