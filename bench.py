@@ -23,6 +23,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_emit = print
 METRIC = "assembled_nnz_per_s"
 UNIT = "nnz/s"
 
@@ -157,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------
@@ -353,14 +354,36 @@ def run_ours(args):
                                     "sample": f"tet P{p} from_box n={args.cpu_n} ({om.NC} cells, nnz {nz}), numpy oracle port of the "
                                               f"reference path, {ta:.1f}s assembly",
                                     "cg_iters_per_s": it / tc}
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class StdoutToStderr:
+    """Everything libraries print on fd 1 (e.g. NCCL's version banner) goes to stderr; only the final JSON
+    line is written to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    with StdoutToStderr() as out:
+        _emit = out.emit
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
