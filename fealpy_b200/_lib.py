@@ -47,7 +47,7 @@ SIGNATURES = {
     "fb2_sym_fill": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _i32, _p]),
     "fb2_slot_stride": (_i32, [_i32, _i32]),
     "fb2_assemble_scalar_const": (_i32, [_i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _i32, _i32, _p, _p,
-                                         _p, _p, _p, _f64, _p, _f64, _p, _p, _p]),
+                                         _f64, _p, _f64, _p, _p, _p]),
     "fb2_assemble_from_ke": (_i32, [_i64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _i32, _i32, _p, _p]),
     "fb2_asm4_workspace_bytes": (_sz, [_i32]),
     "fb2_asm4_plan_count": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p]),

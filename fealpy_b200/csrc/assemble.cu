@@ -407,148 +407,6 @@ __global__ void __launch_bounds__(128, FB2_ASM_MINBLOCKS) assemble_const_kernel(
   }
 }
 
-// -------------------------------------------------------------------------------------
-// v3: per-cell geometry precomputed once, element tables in the kernel parameter block
-// -------------------------------------------------------------------------------------
-// H[c] = ( kd_c * G_c[0..NG-1], km_c * vol_c ):  K_e[i][j] = sum_t Ms[i][j][t] H[t] + Mm[i][j] H[NG]
-template <int TD>
-__global__ void __launch_bounds__(256) cell_geometry_kernel(const double* __restrict__ node, const int* __restrict__ cell, int64_t NC,
-                                                            double scal_d, const double* __restrict__ coef_d, double scal_m,
-                                                            const double* __restrict__ coef_m, double* __restrict__ H) {
-  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2, NH = NG + 1;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < NC; c += (int64_t)gridDim.x * blockDim.x) {
-    int v[NV];
-    double x[NV][TD], cm, G[NG];
-    load_verts<TD>(cell, c, v);
-    load_coords<TD>(node, v, x);
-    geo_from_coords(x, cm, G);
-    const double kd = scal_d * (coef_d ? coef_d[c] : 1.0);
-    const double km = scal_m * (coef_m ? coef_m[c] : 1.0) * cm;
-    double* h = H + c * NH;
-#pragma unroll
-    for (int t = 0; t < NG; ++t) h[t] = kd * G[t];
-    h[NG] = km;
-  }
-}
-
-template <int NH>
-__device__ __forceinline__ void load_h(const double* __restrict__ H, int64_t c, double (&h)[NH]) {
-  const double* p = H + c * NH;
-#pragma unroll
-  for (int t = 0; t < NH; ++t) h[t] = p[t];
-}
-
-// one phase = all pairs whose local index is I: the table row T[I] sits at a compile-time offset
-// of the shared-memory table and is read with warp-uniform (broadcast) 128-bit loads
-template <int TD, int L, typename SlotT, int I>
-__device__ __forceinline__ void asm_phase(const AsmConstArgs& a, const double* __restrict__ sT, double* __restrict__ my, int64_t& q,
-                                          const int64_t q1, int& pair_cur, int& pair_nxt,
-                                          double (&h_cur)[(TD + 1) * (TD + 2) / 2 + 1], const uint32_t* __restrict__ slot_words) {
-  constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1;
-  constexpr int ROW = ((NH + 1) / 2) * 2;          // doubles per (I, j) record, padded to a double2 multiple
-  using SR = SlotRec<SlotT, L>;
-  bool mine = (q < q1) && (pair_cur % L == I);
-  while (__any_sync(0xffffffffu, mine)) {
-    if (mine) {
-      // prefetch the next pair of this row (clamped at the end of the list)
-      const int64_t qn = (q + 2 < q1) ? q + 2 : q1 - 1;
-      const int pair_nn = a.adj_pair[qn];
-      double h_nxt[NH];
-      load_h<NH>(a.H, pair_nxt / L, h_nxt);
-      uint32_t sw[SR::WORDS];
-#pragma unroll
-      for (int w = 0; w < SR::WORDS; ++w) sw[w] = slot_words[q * SR::WORDS + w];
-      // columns in chunks of JC: bounded live registers, still JC independent FMA chains
-      constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
-      static_assert(L % JC == 0, "chunk must divide ldof");
-#pragma unroll
-      for (int j0 = 0; j0 < L; j0 += JC) {
-        double val[JC];
-#pragma unroll
-        for (int jj = 0; jj < JC; ++jj) {
-          const double2* __restrict__ row = reinterpret_cast<const double2*>(sT + ((I * L) + j0 + jj) * ROW);
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int t = 0; t < ROW / 2; ++t) {
-            const double2 m = row[t];
-            s0 += m.x * h_cur[2 * t];
-            if (2 * t + 1 < NH) s1 += m.y * h_cur[2 * t + 1];
-          }
-          val[jj] = s0 + s1;
-        }
-        // the dofs of one cell are distinct, so are their slots: independent read-modify-writes
-        double old[JC];
-#pragma unroll
-        for (int jj = 0; jj < JC; ++jj) old[jj] = my[SR::get(sw, j0 + jj)];
-#pragma unroll
-        for (int jj = 0; jj < JC; ++jj) my[SR::get(sw, j0 + jj)] = old[jj] + val[jj];
-      }
-      ++q;
-      pair_cur = pair_nxt;
-      pair_nxt = pair_nn;
-#pragma unroll
-      for (int t = 0; t < NH; ++t) h_cur[t] = h_nxt[t];
-    }
-    mine = (q < q1) && (pair_cur % L == I);
-  }
-  if constexpr (I + 1 < L) asm_phase<TD, L, SlotT, I + 1>(a, sT, my, q, q1, pair_cur, pair_nxt, h_cur, slot_words);
-}
-
-#ifndef FB2_ASM3_MINBLOCKS
-#define FB2_ASM3_MINBLOCKS 4
-#endif
-template <int TD, int L, typename SlotT>
-__global__ void __launch_bounds__(128, FB2_ASM3_MINBLOCKS) assemble_const_v3_kernel(const __grid_constant__ AsmConstArgs a) {
-  constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1;
-  constexpr int ROW = ((NH + 1) / 2) * 2;
-  extern __shared__ __align__(16) double sm3[];
-  double* sT = sm3;                                             // [L][L][ROW]: (Ms[i][j][0..NG-1], Mm[i][j], pad)
-  double* acc = sT + L * L * ROW;                               // CTA tile of CSR values
-  for (int t = threadIdx.x; t < L * L * ROW; t += blockDim.x) {
-    const int ij = t / ROW, k = t - ij * ROW;
-    double v = 0.0;
-    if (k < NG) v = a.has_diff ? a.Ms[ij * NG + k] : 0.0;
-    else if (k == NG) v = a.has_mass ? a.Mm[ij] : 0.0;
-    sT[t] = v;
-  }
-  __shared__ int next_rows;
-  const int64_t r0 = a.blk_row[blockIdx.x], r1 = a.blk_row[blockIdx.x + 1];
-  const int64_t v0 = a.crow[r0];
-  const int nval = (int)(a.crow[r1] - v0);
-  for (int t = threadIdx.x; t < nval; t += blockDim.x) acc[t] = 0.0;
-  if (threadIdx.x == 0) next_rows = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const uint32_t* __restrict__ slot_words = static_cast<const uint32_t*>(a.slots);
-  while (true) {
-    int off = 0;
-    if (lane == 0) off = atomicAdd(&next_rows, 32);
-    off = __shfl_sync(0xffffffffu, off, 0);
-    const int64_t rb = r0 + off;
-    if (rb >= r1) break;
-    const int64_t r = rb + lane;
-    const bool act = r < r1;
-    int64_t q = act ? a.adj_ptr[r] : 0;
-    const int64_t q1 = act ? a.adj_ptr[r + 1] : 0;
-    double* my = acc + (act ? (a.crow[r] - v0) : 0);
-    int pair_cur = 0, pair_nxt = 0;
-    double h_cur[NH];
-#pragma unroll
-    for (int t = 0; t < NH; ++t) h_cur[t] = 0.0;
-    if (q < q1) {
-      pair_cur = a.adj_pair[q];
-      pair_nxt = a.adj_pair[(q + 1 < q1) ? q + 1 : q1 - 1];
-      load_h<NH>(a.H, pair_cur / L, h_cur);
-    }
-    asm_phase<TD, L, SlotT, 0>(a, sT, my, q, q1, pair_cur, pair_nxt, h_cur, slot_words);
-    __syncwarp();
-    const int64_t rend = (rb + 32 < r1) ? rb + 32 : r1;
-    const int s0 = (int)(a.crow[rb] - v0), s1 = (int)(a.crow[rend] - v0);
-    double* out = a.values + v0;
-    for (int t = s0 + lane; t < s1; t += 32) out[t] = acc[t];
-  }
-}
-
 // =====================================================================================
 // numeric: generic gather of precomputed element-matrix rows (any integrator, tensor spaces)
 //   one thread per output (tensor) row; scalar row r = row / ncomp (interleaved) or row % gdof
@@ -636,32 +494,8 @@ __global__ void __launch_bounds__(256) expand_col_kernel(int64_t gdof, int nc, i
 
 // ---- host dispatch --------------------------------------------------------------------
 template <int TD, int L>
-static int launch_asm_const_v3(AsmConstArgs a, int slot_bytes, int max_row, cudaStream_t s) {
-  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2, ROW = ((NG + 2) / 2) * 2;
-  const int64_t NC = a.NC;
-  cell_geometry_kernel<TD><<<grid_for(NC), 256, 0, s>>>(a.node, a.cell, NC, a.has_diff ? a.scal_d : 0.0, a.coef_d,
-                                                        a.has_mass ? a.scal_m : 0.0, a.coef_m, a.Hbuf);
-  a.H = a.Hbuf;
-  const size_t smem = ((size_t)L * L * ROW + (size_t)(a.tile + max_row)) * 8;
-  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble_const: row tile does not fit shared memory (max_row=%d)", max_row);
-  if (a.nblk <= 0) return OK;
-  if (slot_bytes == 1) {
-    auto k = assemble_const_v3_kernel<TD, L, uint8_t>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)a.nblk, 128, smem, s>>>(a);
-  } else {
-    auto k = assemble_const_v3_kernel<TD, L, uint16_t>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)a.nblk, 128, smem, s>>>(a);
-  }
-  FB2_LAUNCH_CHECK();
-  return OK;
-}
-
-template <int TD, int L>
 static int launch_asm_const(AsmConstArgs a, int slot_bytes, int max_row, cudaStream_t s) {
   constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;
-  if (a.Hbuf) return launch_asm_const_v3<TD, L>(a, slot_bytes, max_row, s);
   // must mirror MS_STRIDE / MM_STRIDE of assemble_const_kernel
   const size_t tab = ((a.has_diff ? (size_t)L * (L * NG + 2) : 0) + (a.has_mass ? (size_t)L * ((L + 3) & ~1) : 0)) * sizeof(double);
   if (a.threads <= 0) a.threads = 128;

@@ -21,10 +21,6 @@ struct AsmConstArgs {
   const int32_t* blk_row;     // (nblk+1) first row of every CTA tile (fb2_spmv_plan_build on crow)
   int nblk, tile, threads;    // tile = values per CTA the partition was built with
   int64_t NC;
-  const double* Ms_host;      // host copies of the tables (v3 kernel: parameter-block tables) or null
-  const double* Mm_host;
-  double* Hbuf;               // (NC, NG+1) per-cell geometry workspace (v3) or null
-  const double* H;
 };
 
 struct AsmKeArgs {

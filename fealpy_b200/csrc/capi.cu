@@ -123,9 +123,8 @@ int fb2_sym_fill(const int32_t* c2d, int64_t NC, int ldof, int64_t gdof, const i
 int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,
                               const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
                               const int64_t* crow, int32_t max_row, const int32_t* blk_row, int nblk, int tile,
-                              const double* Ms, const double* Mm, const double* Ms_host, const double* Mm_host, double* geom_ws,
-                              double scal_d, const double* coef_d, double scal_m, const double* coef_m, double* values,
-                              void* stream) {
+                              const double* Ms, const double* Mm, double scal_d, const double* coef_d, double scal_m,
+                              const double* coef_m, double* values, void* stream) {
   if (!Ms && !Mm) return fail(ERR_INVALID, "assemble_scalar_const: need a diffusion and/or a mass table");
   AsmConstArgs a{};
   a.node = node; a.cell = cell; a.gdof = gdof;
@@ -134,7 +133,7 @@ int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const dou
   a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.values = values;
   a.nnz = 0;
   a.blk_row = blk_row; a.nblk = nblk; a.tile = tile; a.threads = 0;
-  a.NC = NC; a.Ms_host = Ms_host; a.Mm_host = Mm_host; a.Hbuf = geom_ws; a.H = nullptr;
+  a.NC = NC;
   return assemble_const(TD, p, a, slot_bytes, max_row, S(stream));
 }
 int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int64_t gdof_scalar, const double* Ke,

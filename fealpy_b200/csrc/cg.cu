@@ -173,227 +173,6 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
   if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
 }
 
-// ---- SpMV, software-pipelined over tiles: while tile t is reduced out of shared memory, the
-// (val, col) stream of tile t+2 and the x gathers of tile t+1 are already in flight in registers,
-// so every DRAM / L2 round trip is issued a full tile ahead of its use.
-[[maybe_unused]] constexpr int SP_U = 9;                  // values per thread and tile: tile + max_row <= SP_U * 256
-[[maybe_unused]] constexpr int SP_ROWCAP = 768;           // rows of a tile staged in shared memory
-[[maybe_unused]] constexpr int SP_RU = SP_ROWCAP / CG_THREADS + 1;
-
-struct SpTile { int r0, r1, nval; int64_t v0; };
-
-template <int G>
-__global__ void __launch_bounds__(CG_THREADS, 2) spmv_pipe_kernel(int64_t n, const int64_t* __restrict__ crow,
-                                                                  const int32_t* __restrict__ col, const double* __restrict__ val,
-                                                                  const double* __restrict__ x, double* __restrict__ y,
-                                                                  const double* __restrict__ b, int mode,
-                                                                  const int32_t* __restrict__ blk_row,
-                                                                  const int64_t* __restrict__ blk_v0, int nblk, double* dot_out,
-                                                                  double* partials, unsigned int* counter, const CgScalars* sc,
-                                                                  OwnRange own) {
-  if (sc && sc->done) return;
-  __shared__ __align__(16) double prod[SP_U * CG_THREADS];
-  __shared__ int rowoff[SP_ROWCAP + 1];
-  const int tid = threadIdx.x;
-  const int g = tid % G, grp = tid / G;
-  constexpr int NGRP = CG_THREADS / G;
-  double dsum = 0.0;
-
-  auto tile_of = [&](int blk) {          // four independent (uniform) loads: no dependent chain
-    SpTile t;
-    t.r0 = blk_row[blk]; t.r1 = blk_row[blk + 1];
-    t.v0 = blk_v0[blk];
-    t.nval = (int)(blk_v0[blk + 1] - t.v0);
-    return t;
-  };
-  double vv1[SP_U], xx1[SP_U], vv2[SP_U];
-  int cc1[SP_U], cc2[SP_U], ro1[SP_RU], ro2[SP_RU];
-  auto load_raw = [&](const SpTile& t, double (&vv)[SP_U], int (&cc)[SP_U], int (&ro)[SP_RU]) {
-#pragma unroll
-    for (int u = 0; u < SP_U; ++u) {
-      const int k = tid + u * CG_THREADS;
-      const bool ok = k < t.nval;
-      vv[u] = ok ? ld_stream(val + t.v0 + k) : 0.0;
-      cc[u] = ok ? ld_stream(col + t.v0 + k) : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < SP_RU; ++u) {
-      const int k = tid + u * CG_THREADS;
-      ro[u] = (k <= t.r1 - t.r0 && k <= SP_ROWCAP) ? (int)(crow[t.r0 + k] - t.v0) : 0;
-    }
-  };
-  auto gather = [&](const SpTile& t, const int (&cc)[SP_U], double (&xx)[SP_U]) {
-#pragma unroll
-    for (int u = 0; u < SP_U; ++u) xx[u] = (tid + u * CG_THREADS < t.nval) ? x[cc[u]] : 0.0;
-  };
-  auto store_prod = [&](const SpTile& t, const double (&vv)[SP_U], const double (&xx)[SP_U], const int (&ro)[SP_RU]) {
-#pragma unroll
-    for (int u = 0; u < SP_U; ++u) {
-      const int k = tid + u * CG_THREADS;
-      if (k < t.nval) prod[k] = vv[u] * xx[u];
-    }
-#pragma unroll
-    for (int u = 0; u < SP_RU; ++u) {
-      const int k = tid + u * CG_THREADS;
-      if (k <= t.r1 - t.r0 && k <= SP_ROWCAP) rowoff[k] = ro[u];
-    }
-  };
-
-  int blk = blockIdx.x;
-  if (blk >= nblk) { if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; }); return; }
-  const int gs = (int)gridDim.x;
-  SpTile t0 = tile_of(blk), t1{}, t2{}, t3{};
-  // prologue: tile t0 into shared memory, raw stream of t1 in flight, metadata of t2 in flight
-  load_raw(t0, vv1, cc1, ro1);
-  gather(t0, cc1, xx1);
-  store_prod(t0, vv1, xx1, ro1);
-  const bool has1 = blk + gs < nblk;
-  if (has1) { t1 = tile_of(blk + gs); load_raw(t1, vv1, cc1, ro1); }
-  if (blk + 2 * gs < nblk) t2 = tile_of(blk + 2 * gs);
-  __syncthreads();
-  bool have_next = has1;
-  while (true) {
-    const bool has2 = have_next && blk + 2 * gs < nblk;
-    if (have_next) gather(t1, cc1, xx1);                         // cc1 arrived during the previous iteration
-    if (has2) load_raw(t2, vv2, cc2, ro2);                       // t2's metadata arrived during the previous iteration
-    if (blk + 3 * gs < nblk) t3 = tile_of(blk + 3 * gs);
-    // ---- reduce tile t0 out of shared memory
-    const int nrow = t0.r1 - t0.r0;
-    const bool staged = nrow <= SP_ROWCAP;
-    for (int base = 0; base < nrow; base += NGRP) {
-      const int rl = base + grp;
-      double acc = 0.0;
-      if (rl < nrow) {
-        int s, e;
-        if (staged) { s = rowoff[rl]; e = rowoff[rl + 1]; }
-        else { s = (int)(crow[t0.r0 + rl] - t0.v0); e = (int)(crow[t0.r0 + rl + 1] - t0.v0); }
-        for (int q = s + g; q < e; q += G) acc += prod[q];
-      }
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (rl < nrow && g == 0) {
-        const int64_t r = t0.r0 + rl;
-        const double yv = mode ? b[r] - acc : acc;
-        y[r] = yv;
-        if (dot_out && own.has(r)) dsum += x[r] * yv;
-      }
-    }
-    if (!have_next) break;
-    __syncthreads();
-    store_prod(t1, vv1, xx1, ro1);
-    __syncthreads();
-    // rotate
-    t0 = t1; blk += gs;
-    have_next = has2;
-    if (has2) {
-      t1 = t2; t2 = t3;
-#pragma unroll
-      for (int u = 0; u < SP_U; ++u) { vv1[u] = vv2[u]; cc1[u] = cc2[u]; }
-#pragma unroll
-      for (int u = 0; u < SP_RU; ++u) ro1[u] = ro2[u];
-    }
-  }
-  if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
-}
-
-// ---- SpMV with an asynchronous shared-memory ring: the (val, col) stream of the next tiles is
-// copied global->shared with cp.async (LDGSTS: no registers, no warps blocked) while the current
-// tile gathers x and is reduced.  Keeps full occupancy AND several tiles of DRAM traffic in flight.
-#ifndef FB2_SA_STAGES
-#define FB2_SA_STAGES 3
-#endif
-constexpr int SA_STAGES = FB2_SA_STAGES;
-
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-template <int G>
-__global__ void __launch_bounds__(CG_THREADS) spmv_async_kernel(int64_t n, const int64_t* __restrict__ crow,
-                                                                const int32_t* __restrict__ col, const double* __restrict__ val,
-                                                                const double* __restrict__ x, double* __restrict__ y,
-                                                                const double* __restrict__ b, int mode,
-                                                                const int32_t* __restrict__ blk_row,
-                                                                const int64_t* __restrict__ blk_v0, int nblk, int cap, double* dot_out,
-                                                                double* partials, unsigned int* counter, const CgScalars* sc,
-                                                                OwnRange own) {
-  if (sc && sc->done) return;
-  extern __shared__ __align__(16) unsigned char sa_raw[];
-  // per stage: cap doubles (values, overwritten in place by the products) + cap ints (columns)
-  auto sval = [&](int st) { return reinterpret_cast<double*>(sa_raw + (size_t)st * cap * 12); };
-  auto scol = [&](int st) { return reinterpret_cast<int*>(sa_raw + (size_t)st * cap * 12 + (size_t)cap * 8); };
-  const int tid = threadIdx.x;
-  const int g = tid % G, grp = tid / G;
-  constexpr int NGRP = CG_THREADS / G;
-  const int gs = (int)gridDim.x;
-  double dsum = 0.0;
-  auto issue = [&](int blk, int st) {
-    if (blk < nblk) {
-      const int64_t v0 = blk_v0[blk];
-      const int nval = (int)(blk_v0[blk + 1] - v0);
-      double* dv = sval(st);
-      int* dc = scol(st);
-      for (int k = tid; k < nval; k += CG_THREADS) { cp_async8(dv + k, val + v0 + k); cp_async4(dc + k, col + v0 + k); }
-    }
-    cp_async_commit();            // always commit so that group counting stays uniform
-  };
-  int blk = blockIdx.x;
-#pragma unroll
-  for (int s = 0; s < SA_STAGES - 1; ++s) issue(blk + s * gs, s);
-  int st = 0;
-  for (; blk < nblk; blk += gs) {
-    issue(blk + (SA_STAGES - 1) * gs, (st + SA_STAGES - 1) % SA_STAGES);
-    cp_async_wait<SA_STAGES - 1>();
-    __syncthreads();
-    const int r0 = blk_row[blk], r1 = blk_row[blk + 1];
-    const int64_t v0 = blk_v0[blk];
-    const int nval = (int)(blk_v0[blk + 1] - v0);
-    double* pv = sval(st);
-    const int* pc = scol(st);
-    {
-      int k = tid;
-      for (; k + 3 * CG_THREADS < nval; k += 4 * CG_THREADS) {
-        double xx[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) xx[u] = x[pc[k + u * CG_THREADS]];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) pv[k + u * CG_THREADS] *= xx[u];
-      }
-      for (; k < nval; k += CG_THREADS) pv[k] *= x[pc[k]];
-    }
-    __syncthreads();
-    const int nrow = r1 - r0;
-    for (int base = 0; base < nrow; base += NGRP) {
-      const int rl = base + grp;
-      double acc = 0.0;
-      if (rl < nrow) {
-        const int s = (int)(crow[r0 + rl] - v0), e = (int)(crow[r0 + rl + 1] - v0);
-        for (int q = s + g; q < e; q += G) acc += pv[q];
-      }
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (rl < nrow && g == 0) {
-        const int64_t r = (int64_t)r0 + rl;
-        const double yv = mode ? b[r] - acc : acc;
-        y[r] = yv;
-        if (dot_out && own.has(r)) dsum += x[r] * yv;
-      }
-    }
-    __syncthreads();              // the stage is recycled by the issue() of the next iteration
-    st = (st + 1) % SA_STAGES;
-  }
-  cp_async_wait<0>();
-  if (dot_out) grid_reduce(dsum, partials, counter, [=](double tot) { *dot_out = tot; });
-}
-
 __global__ void __launch_bounds__(256) partition_rows_kernel(const int64_t* __restrict__ crow, int64_t n, int tile, int nblk,
                                                              int32_t* __restrict__ blk_row, int64_t* __restrict__ blk_v0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -542,47 +321,6 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
                               unsigned int* counter, const CgScalars* sc, cudaStream_t s, OwnRange own) {
   const size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
-#ifdef FB2_SPMV_ASYNC        // cp.async ring variant: measured slower (2.9-4.4 vs 1.92 ms/iteration), kept for reference
-  if (plan.blk_v0) {
-    const int cap = (plan.tile + plan.max_row + 3) & ~3;
-    const size_t smem_a = (size_t)SA_STAGES * cap * 12;
-    if (smem_a <= 200 * 1024) {
-      const int per_sm_a = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem_a + 1024)));
-      int grida = std::min(plan.nblk, kNumSM * per_sm_a);
-      if (grida > CG_PARTIALS) grida = CG_PARTIALS;
-      if (grida < 1) grida = 1;
-#define FB2_SA(GV)                                                                                                   \
-  do {                                                                                                               \
-    auto kern = spmv_async_kernel<GV>;                                                                               \
-    if (smem_a > 48 * 1024) FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a)); \
-    kern<<<grida, CG_THREADS, smem_a, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.blk_v0, plan.nblk, cap, dot_out,   \
-                                           partials, counter, sc, own);                                              \
-  } while (0)
-      if (avg <= 6.0) FB2_SA(2);
-      else if (avg <= 12.0) FB2_SA(4);
-      else if (avg <= 48.0) FB2_SA(8);
-      else FB2_SA(16);
-#undef FB2_SA
-      FB2_LAUNCH_CHECK();
-      return OK;
-    }
-  }
-#endif
-#ifdef FB2_SPMV_REGPIPE      // register-pipelined variant: measured slower (2.59 vs 1.93 ms/iteration), kept for reference
-  if (plan.blk_v0 && plan.tile + plan.max_row <= SP_U * CG_THREADS) {
-    int gridp = std::min(plan.nblk, kNumSM * 2);
-    if (gridp > CG_PARTIALS) gridp = CG_PARTIALS;
-    if (gridp < 1) gridp = 1;
-#define FB2_SP(GV) spmv_pipe_kernel<GV><<<gridp, CG_THREADS, 0, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.blk_v0, plan.nblk, dot_out, partials, counter, sc, own)
-    if (avg <= 6.0) FB2_SP(2);
-    else if (avg <= 12.0) FB2_SP(4);
-    else if (avg <= 48.0) FB2_SP(8);
-    else FB2_SP(16);
-#undef FB2_SP
-    FB2_LAUNCH_CHECK();
-    return OK;
-  }
-#endif
   const int per_sm = (int)std::min<size_t>(8, (200 * 1024) / (smem + 1024));
   int grid = std::min(plan.nblk, kNumSM * std::max(per_sm, 1));
   if (grid > CG_PARTIALS) grid = CG_PARTIALS;

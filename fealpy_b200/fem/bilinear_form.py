@@ -300,20 +300,10 @@ class BilinearForm:
                       sym["slot_bytes"], hostp(dm, "Ms"), hostp(mm, "Mm"),
                       sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(geom), _lib.ptr(values), _lib.stream())
             return sym["crow"], sym["col"], values
-        geom = None
-        if kernel == "v3":     # per-cell geometry precompute with lane = row (kept for comparison)
-            geom = torch.empty((sym["NC"], NH), dtype=torch.float64, device=mesh.device)
-
-        def hostp(m, key):
-            if m is None:
-                return None
-            h = host_tables(mesh.TD, space.p, m["q"])[key]
-            return h.ctypes.data_as(C.c_void_p)
         _lib.call("fb2_assemble_scalar_const", mesh.TD, space.p, sym["NC"], sym["gdof"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
                   _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]), _lib.ptr(sym["slots"]), sym["slot_bytes"],
                   _lib.ptr(sym["crow"]), sym["max_row"], _lib.ptr(sym["blk_row"]), sym["nblk"], sym["tile"],
                   _lib.ptr(dm["tabs"]["Ms"]) if dm else None, _lib.ptr(mm["tabs"]["Mm"]) if mm else None,
-                  hostp(dm, "Ms"), hostp(mm, "Mm"), _lib.ptr(geom),
                   sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(values), _lib.stream())
         return sym["crow"], sym["col"], values
 

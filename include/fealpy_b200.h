@@ -103,16 +103,14 @@ int fb2_slot_stride(int ldof, int slot_bytes);
 int fb2_sym_fill(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair,
                  const int64_t* crow, int32_t* col, void* slots, int slot_bytes, void* stream);
 /* numeric, constant / per-cell coefficient scalar forms (diffusion and/or mass fused).
- * blk_row/nblk/tile: row tiling of crow from fb2_spmv_plan_build (one CTA per tile).
- * Ms_host/Mm_host: host copies of the tables, geom_ws: (NC, NG+1) doubles of device scratch --
- * when given (and the tables fit the 32 KB kernel parameter block) the tables ride in the
- * constant bank and the per-cell geometry is computed once; else the shared-memory-table kernel runs. */
+ * blk_row/nblk/tile: row tiling of crow from fb2_spmv_plan_build (one CTA per tile).  This is the
+ * "v2" kernel (lane = row, tables in shared memory); it also serves elements whose tables exceed the
+ * kernel parameter block of the v4 kernel below (tet P3). */
 int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,
                               const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
                               const int64_t* crow, int32_t max_row, const int32_t* blk_row, int nblk, int tile,
-                              const double* Ms, const double* Mm, const double* Ms_host, const double* Mm_host, double* geom_ws,
-                              double scal_d, const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* values,
-                              void* stream);
+                              const double* Ms, const double* Mm, double scal_d, const double* coef_d_cell, double scal_m,
+                              const double* coef_m_cell, double* values, void* stream);
 /* numeric, generic: gathers rows of a precomputed element-matrix block Ke (NC, lt, lt);
  * ncomp > 1 = tensor space over the scalar pattern (interleaved or dof-priority layout) */
 int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int64_t gdof_scalar, const double* Ke,
