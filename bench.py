@@ -231,9 +231,8 @@ def run_ours(args):
         def solve(A_, rhs):
             if part is None:
                 return cg(A_, rhs, atol=0.0, rtol=0.0, maxit=args.cg_iters, returninfo=True)
-            peer = (part.exchanges, None) if os.environ.get("FB2_HALO", "peer") == "peer" else None
-            return dist_cg(CudaCgOps(A_, part.own_ranges, peer=peer), rhs, torch.zeros_like(rhs), part.exchanges, atol=0.0,
-                           rtol=0.0, maxit=args.cg_iters, check_every=args.cg_iters)
+            return dist_cg(CudaCgOps(A_, part.own_ranges), rhs, torch.zeros_like(rhs), part.exchanges, atol=0.0, rtol=0.0,
+                           maxit=args.cg_iters, check_every=args.cg_iters)
 
         def step():
             s0, s1, s2 = ev(), ev(), ev()

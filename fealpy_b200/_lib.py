@@ -72,7 +72,6 @@ SIGNATURES = {
     "fb2_tet_box_slab": (_i32, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "fb2_cg_finalize": (_i32, [_p, _p]),
     "fb2_cg_update_p": (_i32, [_i64, _p, _p, _p, _p, _p]),
-    "fb2_cg_update_p_push": (_i32, [_i64, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "fb2_bcg_dots": (_i32, [_i64, _i32, _p, _p, _p, _p, _p]),
     "fb2_bcg_update_xr": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "fb2_bcg_update_p": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p]),

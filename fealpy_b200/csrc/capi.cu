@@ -248,10 +248,6 @@ int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const dou
                      void* partial_ws, int fuse_finalize, const int64_t own[4], void* stream) {
   return cg_update_xr(n, x, r, p, Ap, minv_diag, static_cast<CgScalars*>(scalars), partial_ws, fuse_finalize, S(stream), make_own(own));
 }
-int fb2_cg_update_p_push(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, int nslices,
-                         const int64_t* lo, const int64_t* hi, void* const* peer_base, const int64_t* peer_lo, void* stream) {
-  return cg_update_p_push(n, p, r, minv_diag, static_cast<CgScalars*>(scalars), nslices, lo, hi, peer_base, peer_lo, S(stream));
-}
 int64_t fb2_box_edges_before(int nx, int ny, int nz, int i, int j, int k) { return box_edges_before_host(nx, ny, nz, i, j, k); }
 int fb2_tet_box_slab(const double box[6], int nx, int ny, int nz, int cube_layer_lo, int cube_layer_hi, int p, double* node,
                      int32_t* cell, int32_t* cell2dof, void* stream) {

@@ -265,31 +265,6 @@ __global__ void __launch_bounds__(CG_THREADS) cg_update_p_kernel(int64_t n, doub
   }
 }
 
-// p update fused with the halo push: entries of the owned boundary slices are ALSO stored straight into the
-// neighbour ranks' halo slots through NVLink peer pointers (symmetric memory), so the exchange rides on the
-// kernel that produces the data instead of a separate pack / send / recv / unpack sequence.
-struct PeerSlices {
-  int n;
-  int64_t lo[4], hi[4], peer_lo[4];
-  double* peer[4];
-};
-
-__global__ void __launch_bounds__(CG_THREADS) cg_update_p_push_kernel(int64_t n, double* __restrict__ p, const double* __restrict__ r,
-                                                                      const double* __restrict__ minv, const CgScalars* sc,
-                                                                      PeerSlices ps) {
-  if (sc->done) return;
-  const double beta = sc->beta;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double ri = r[i];
-    const double v = (minv ? minv[i] * ri : ri) + beta * p[i];
-    p[i] = v;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (k < ps.n && i >= ps.lo[k] && i < ps.hi[k]) ps.peer[k][ps.peer_lo[k] + (i - ps.lo[k])] = v;
-  }
-  __threadfence_system();      // peer stores visible before the signal that follows on the stream
-}
-
 __global__ void cg_init_scalars_kernel(CgScalars* sc, double atol, double rtol, int maxit) {
   sc->rTr = sc->pAp = sc->rTr_new = sc->rnorm = sc->alpha = sc->beta = 0.0;
   sc->niter = 0;
@@ -461,17 +436,6 @@ int cg_finalize(CgScalars* sc, cudaStream_t s) {
 }
 int cg_update_p(int64_t n, double* p, const double* r, const double* minv, CgScalars* sc, cudaStream_t s) {
   cg_update_p_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, p, r, minv, sc);
-  FB2_LAUNCH_CHECK();
-  return OK;
-}
-
-int cg_update_p_push(int64_t n, double* p, const double* r, const double* minv, CgScalars* sc, int nslices, const int64_t* lo,
-                     const int64_t* hi, void* const* peer, const int64_t* peer_lo, cudaStream_t s) {
-  if (nslices < 0 || nslices > 4) return fail(ERR_INVALID, "cg_update_p_push: at most 4 boundary slices");
-  PeerSlices ps{};
-  ps.n = nslices;
-  for (int k = 0; k < nslices; ++k) { ps.lo[k] = lo[k]; ps.hi[k] = hi[k]; ps.peer_lo[k] = peer_lo[k]; ps.peer[k] = static_cast<double*>(peer[k]); }
-  cg_update_p_push_kernel<<<vec_grid(n), CG_THREADS, 0, s>>>(n, p, r, minv, sc, ps);
   FB2_LAUNCH_CHECK();
   return OK;
 }

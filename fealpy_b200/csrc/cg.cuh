@@ -53,8 +53,6 @@ int cg_update_xr(int64_t n, double* x, double* r, const double* p, const double*
                  void* partial_ws, int fuse_finalize, cudaStream_t s, OwnRange own = OwnRange{});
 int cg_finalize(CgScalars* sc, cudaStream_t s);
 int cg_update_p(int64_t n, double* p, const double* r, const double* minv, CgScalars* sc, cudaStream_t s);
-int cg_update_p_push(int64_t n, double* p, const double* r, const double* minv, CgScalars* sc, int nslices, const int64_t* lo,
-                     const int64_t* hi, void* const* peer, const int64_t* peer_lo, cudaStream_t s);
 
 // batched right-hand sides (row-major (n, B))
 int bcg_dots(int64_t n, int B, const double* a, const double* b, double* out, void* partial_ws, cudaStream_t s);

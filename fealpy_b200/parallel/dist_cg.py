@@ -38,13 +38,9 @@ def halo_exchange(v, exchanges, group=None):
 
 
 class CudaCgOps:
-    """CUDA backend of the distributed driver: kernels of csrc/cg.cu on the local window matrix.
+    """CUDA backend of the distributed driver: kernels of csrc/cg.cu on the local window matrix"""
 
-    With `peer=(exchanges, group)` the search direction p lives in symmetric memory and the p update
-    kernel stores the owned boundary slices straight into the neighbours' halo slots over NVLink
-    (fb2_cg_update_p_push); the per-iteration exchange then reduces to a signal handshake."""
-
-    def __init__(self, A, own, minv=None, peer=None):
+    def __init__(self, A, own, minv=None):
         self.A, self.n = A, A.sparse_shape[0]
         self.own = (C.c_int64 * 4)(*[int(v) for v in own])
         self.own_t = tuple(int(v) for v in own)
@@ -57,51 +53,6 @@ class CudaCgOps:
         self.Ap = torch.empty(self.n, dtype=torch.float64, device=dev)
         self.pws = _lib.partial_ws(dev)
         self.plan = A.spmv_plan()
-        self.peer = None
-        if peer is not None and peer[0]:
-            self._setup_peer(*peer)
-
-    def _setup_peer(self, exchanges, group):
-        import torch.distributed._symmetric_memory as symm_mem
-        grp = group if group is not None else dist.group.WORLD
-        nmax = torch.tensor([self.n], dtype=torch.int64, device=self.r.device)
-        dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=grp)          # symmetric allocations must have one size
-        buf = symm_mem.empty(int(nmax.item()), dtype=torch.float64, device=self.r.device)
-        hdl = symm_mem.rendezvous(buf, grp)
-        self.p = buf[: self.n]
-        # which slice of the neighbour's p my send slice lands in = the neighbour's matching recv slice
-        mine = [(ex.peer, lo, hi) for ex in exchanges for (lo, hi) in ex.send]
-        sizes = [hi - lo for (_, lo, hi) in mine]
-        recv_lo = {}
-        # every rank publishes its recv slices (peer, lo, size); neighbours look theirs up
-        world = dist.get_world_size(grp)
-        local = [(ex.peer, lo, hi - lo) for ex in exchanges for (lo, hi) in ex.recv]
-        allrecv = [None] * world
-        dist.all_gather_object(allrecv, local, group=grp)
-        me = dist.get_rank(grp)
-        lo_arr, hi_arr, plo_arr, ptr_arr = [], [], [], []
-        for (peer_rank, lo, hi) in mine:
-            cands = [(l, sz) for (src, l, sz) in allrecv[peer_rank] if src == me and sz == hi - lo]
-            # several slices of the same size to the same peer keep their order (nodes first, then edges)
-            k = recv_lo.get((peer_rank, hi - lo), 0)
-            recv_lo[(peer_rank, hi - lo)] = k + 1
-            lo_arr.append(lo); hi_arr.append(hi); plo_arr.append(cands[k][0]); ptr_arr.append(hdl.buffer_ptrs[peer_rank])
-        m = len(mine)
-        self.peer = dict(hdl=hdl, neighbours=sorted({ex.peer for ex in exchanges}), n=m,
-                         lo=(C.c_int64 * max(m, 1))(*lo_arr), hi=(C.c_int64 * max(m, 1))(*hi_arr),
-                         plo=(C.c_int64 * max(m, 1))(*plo_arr), ptr=(C.c_void_p * max(m, 1))(*ptr_arr))
-        assert m <= 4 and all(s > 0 for s in sizes)
-
-    def exchange_p(self, exchanges, group, first):
-        """make the halo entries of p current before the SpMV"""
-        if self.peer is None or first:
-            halo_exchange(self.p, exchanges, group)
-            return
-        hdl = self.peer["hdl"]
-        for nb in self.peer["neighbours"]:          # my pushes are complete (stream order) -> tell the neighbours
-            hdl.put_signal(nb)
-        for nb in self.peer["neighbours"]:
-            hdl.wait_signal(nb)
 
     def dot_owned(self, a, b):
         tot = 0.0
@@ -138,11 +89,6 @@ class CudaCgOps:
         _lib.call("fb2_cg_finalize", _lib.ptr(self.sc), _lib.stream())
 
     def update_p(self):
-        if self.peer is not None:
-            pr = self.peer
-            _lib.call("fb2_cg_update_p_push", self.n, _lib.ptr(self.p), _lib.ptr(self.r), _lib.ptr(self.minv), _lib.ptr(self.sc),
-                      pr["n"], pr["lo"], pr["hi"], pr["ptr"], pr["plo"], _lib.stream())
-            return
         _lib.call("fb2_cg_update_p", self.n, _lib.ptr(self.p), _lib.ptr(self.r), _lib.ptr(self.minv), _lib.ptr(self.sc), _lib.stream())
 
     def scalar(self, slot):
@@ -177,12 +123,8 @@ def dist_cg(ops, b, x0, exchanges, *, atol=1e-12, rtol=1e-8, maxit=10000, check_
     allreduce(ops.scalar(SC_RTR))
     it = 0
     limit = maxit if maxit is not None else 1 << 30
-    exchange_p = getattr(ops, "exchange_p", None)
     while True:
-        if exchange_p is not None:
-            exchange_p(exchanges, group, it == 0)
-        else:
-            halo_exchange(ops.p, exchanges, group)
+        halo_exchange(ops.p, exchanges, group)
         ops.spmv_dot()
         allreduce(ops.scalar(SC_PAP))
         ops.update_xr(x)

@@ -176,11 +176,6 @@ int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const dou
                      void* partial_ws, int fuse_finalize, const int64_t own[4], void* stream);
 int fb2_cg_finalize(void* scalars, void* stream);
 int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, void* stream);
-/* p update fused with the halo push over NVLink peer memory: entries in [lo[k], hi[k]) are also stored to
- * peer_base[k][peer_lo[k] + (i - lo[k])] (the neighbour's halo slots in ITS p vector; symmetric memory).
- * nslices <= 4; lo/hi/peer_base/peer_lo are host arrays. */
-int fb2_cg_update_p_push(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, int nslices,
-                         const int64_t* lo, const int64_t* hi, void* const* peer_base, const int64_t* peer_lo, void* stream);
 
 /* batched right-hand sides, b of shape (n, nb) row-major (solver/cg.py:88-121): per-column dots,
  * x/r update with alpha_k = rTr[k]/pAp[k], p update with beta_k = rTr_new[k]/rTr[k]; the host drives
