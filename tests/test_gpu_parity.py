@@ -497,3 +497,54 @@ def test_batched_rhs_cg_matches_oracle(batch_first, U):
     y = (A @ U.t64(Bm)).cpu().numpy()                                     # SpMM against the oracle SpMV
     ref = np.stack([O.csr_matvec(crow, col, val, Bm[:, k]) for k in range(3)], axis=1)
     assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def _relabelled_mesh(kind, dims, seed):
+    """from_box topology with a random node relabelling, shuffled cells and jittered geometry: nothing of the
+    closed-form numbering survives, the generic topology path must agree with the oracle"""
+    from oracle import fem_oracle as O
+    rng = np.random.default_rng(seed)
+    if kind == "tri":
+        node, cell = O.tri_from_box([0, 1, 0, 1], *dims)
+    else:
+        node, cell = O.tet_from_box([0, 1, 0, 1, 0, 1], *dims)
+    node = C.perturb(node, dims, seed)
+    perm = rng.permutation(len(node))                # new id of old node k
+    node2 = np.empty_like(node)
+    node2[perm] = node
+    cell2 = perm[cell][rng.permutation(len(cell))].astype(np.int32)
+    return node2, cell2
+
+
+@pytest.mark.parametrize("kind,dims,p", [("tri", (5, 4), 1), ("tri", (4, 5), 2), ("tri", (4, 3), 3),
+                                         ("tet", (3, 2, 2), 1), ("tet", (2, 3, 2), 2), ("tet", (2, 2, 2), 3),
+                                         ("tri", (1, 1), 3), ("tet", (1, 1, 1), 3)])
+def test_relabelled_mesh_matches_oracle(kind, dims, p, U):
+    from oracle import fem_oracle as O
+    from fealpy_b200.mesh import TriangleMesh, TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    from fealpy_b200.solver import cg
+    node, cell = _relabelled_mesh(kind, dims, seed=17 + p)
+    om = O.Mesh(node, cell)
+    mesh = (TriangleMesh if kind == "tri" else TetrahedronMesh)(U.t64(node), U.t64(cell))
+    space = LagrangeFESpace(mesh, p)
+    assert np.array_equal(mesh.edge.cpu().numpy(), om.edge)
+    c2d = om.cell_to_ipoint(p)
+    assert np.array_equal(space.cell_to_dof().cpu().numpy(), c2d)
+    gdof = om.number_of_global_ipoints(p)
+    assert space.number_of_global_dofs() == gdof
+    crow, col, val = O.assemble([(O.diffusion_element(om, p), c2d), (O.mass_element(om, p), c2d)], gdof)
+    for path in ("auto", "gather", "coo"):
+        bf = BilinearForm(space, assembly_path=path)
+        bf.add_integrator(ScalarDiffusionIntegrator())
+        bf.add_integrator(ScalarMassIntegrator())
+        A = bf.assembly()
+        assert np.array_equal(A.crow.cpu().numpy(), crow) and np.array_equal(A.col.cpu().numpy(), col), path
+        assert np.max(np.abs(A.values.cpu().numpy() - val)) <= 1e-12 * np.max(np.abs(val)), path
+    b = O.csr_matvec(crow, col, val, np.ones(gdof))
+    xo, oinfo = O.cg(lambda v: O.csr_matvec(crow, col, val, v), b, atol=1e-14, rtol=1e-12)
+    x, info = cg(A, U.t64(b), atol=1e-14, rtol=1e-12, returninfo=True)
+    assert abs(info["niter"] - oinfo["niter"]) <= 2
+    assert np.linalg.norm(x.cpu().numpy() - xo) / np.linalg.norm(xo) <= 1e-10
+    assert np.array_equal(space.is_boundary_dof().cpu().numpy(), O.boundary_dof_flag(om, p))
