@@ -331,10 +331,14 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
     if (smem > 48 * 1024) FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, CG_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own); \
   } while (0)
+#ifdef FB2_SPMV_G
+  FB2_ST(FB2_SPMV_G);
+#else
   if (avg <= 6.0) FB2_ST(2);
   else if (avg <= 12.0) FB2_ST(4);
   else if (avg <= 48.0) FB2_ST(8);
   else FB2_ST(16);
+#endif
 #undef FB2_ST
   FB2_LAUNCH_CHECK();
   return OK;
