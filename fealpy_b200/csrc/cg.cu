@@ -27,8 +27,7 @@ __device__ __forceinline__ void grid_reduce(double v, double* partials, unsigned
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < CG_THREADS / 32; ++w) t += red[w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     partials[blockIdx.x] = t;
     __threadfence();
     const unsigned int ticket = atomicInc(counter, gridDim.x - 1);   // wraps back to 0 for the next use
@@ -38,15 +37,14 @@ __device__ __forceinline__ void grid_reduce(double v, double* partials, unsigned
   if (!is_last) return;
   __threadfence();
   double t = 0.0;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += CG_THREADS) t += __ldcg(partials + i);
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += (int)blockDim.x) t += __ldcg(partials + i);
   t = warp_sum(t);
   __syncthreads();
   if (lane == 0) red[wid] = t;
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;
-#pragma unroll
-    for (int w = 0; w < CG_THREADS / 32; ++w) tot += red[w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
     finish(tot);
   }
 }
@@ -120,9 +118,13 @@ __global__ void __launch_bounds__(CG_THREADS) spmm_kernel(int64_t n, const int64
 // parks the products in shared memory; phase 2 reduces each row with G lanes.  Row sums and
 // the fused p.Ap partials are formed in a fixed order -> bitwise reproducible.
 constexpr int ST_UNROLL = 4;
+#ifndef FB2_ST_THREADS
+#define FB2_ST_THREADS 256
+#endif
+constexpr int ST_THREADS = FB2_ST_THREADS;     // threads per CTA of the streaming SpMV kernel
 
 template <int G>
-__global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, const int64_t* __restrict__ crow,
+__global__ void __launch_bounds__(ST_THREADS) spmv_stream_kernel(int64_t n, const int64_t* __restrict__ crow,
                                                                  const int32_t* __restrict__ col, const double* __restrict__ val,
                                                                  const double* __restrict__ x, double* __restrict__ y,
                                                                  const double* __restrict__ b, int mode,
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
   extern __shared__ __align__(16) double prod[];
   const int tid = threadIdx.x;
   const int g = tid % G, grp = tid / G;
-  constexpr int NGRP = CG_THREADS / G;
+  constexpr int NGRP = ST_THREADS / G;
   double dsum = 0.0;
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     const int r0 = blk_row[blk], r1 = blk_row[blk + 1];
@@ -143,15 +145,15 @@ __global__ void __launch_bounds__(CG_THREADS) spmv_stream_kernel(int64_t n, cons
     const double* __restrict__ vp = val + v0;
     const int32_t* __restrict__ cp = col + v0;
     int k = tid;
-    for (; k + (ST_UNROLL - 1) * CG_THREADS < nval; k += ST_UNROLL * CG_THREADS) {
+    for (; k + (ST_UNROLL - 1) * ST_THREADS < nval; k += ST_UNROLL * ST_THREADS) {
       double vv[ST_UNROLL];
       int cc[ST_UNROLL];
 #pragma unroll
-      for (int u = 0; u < ST_UNROLL; ++u) { vv[u] = ld_stream(vp + k + u * CG_THREADS); cc[u] = ld_stream(cp + k + u * CG_THREADS); }
+      for (int u = 0; u < ST_UNROLL; ++u) { vv[u] = ld_stream(vp + k + u * ST_THREADS); cc[u] = ld_stream(cp + k + u * ST_THREADS); }
 #pragma unroll
-      for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * CG_THREADS] = vv[u] * x[cc[u]];
+      for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * ST_THREADS] = vv[u] * x[cc[u]];
     }
-    for (; k < nval; k += CG_THREADS) prod[k] = ld_stream(vp + k) * x[ld_stream(cp + k)];
+    for (; k < nval; k += ST_THREADS) prod[k] = ld_stream(vp + k) * x[ld_stream(cp + k)];
     __syncthreads();
     for (int base = r0; base < r1; base += NGRP) {
       const int r = base + grp;
@@ -321,7 +323,7 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
                               unsigned int* counter, const CgScalars* sc, cudaStream_t s, OwnRange own) {
   const size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
-  const int per_sm = (int)std::min<size_t>(8, (200 * 1024) / (smem + 1024));
+  const int per_sm = (int)std::min<size_t>(2048 / ST_THREADS, (200 * 1024) / (smem + 1024));
   int grid = std::min(plan.nblk, kNumSM * std::max(per_sm, 1));
   if (grid > CG_PARTIALS) grid = CG_PARTIALS;
   if (grid < 1) grid = 1;
@@ -329,15 +331,15 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
   do {                                                                                                         \
     auto kern = spmv_stream_kernel<GV>;                                                                        \
     if (smem > 48 * 1024) FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, CG_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own); \
+    kern<<<grid, ST_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own); \
   } while (0)
+  // lanes per row in the reduce phase: ONE (a thread sums its row sequentially out of shared memory) measured
+  // best by a wide margin -- 1.60 ms/iteration against 1.92 with 8 lanes + shuffles (profiles/r01_tune_spmv.txt)
 #ifdef FB2_SPMV_G
   FB2_ST(FB2_SPMV_G);
 #else
-  if (avg <= 6.0) FB2_ST(2);
-  else if (avg <= 12.0) FB2_ST(4);
-  else if (avg <= 48.0) FB2_ST(8);
-  else FB2_ST(16);
+  if (avg <= 160.0) FB2_ST(1);
+  else FB2_ST(4);
 #endif
 #undef FB2_ST
   FB2_LAUNCH_CHECK();
@@ -375,7 +377,7 @@ struct PartialWs {
 
 // values per SpMV tile inside fb2_cg (FB2_SPMV_TILE overrides, for tuning)
 static int cg_tile() {
-  static int t = [] { const char* e = getenv("FB2_SPMV_TILE"); const int v = e ? atoi(e) : 0; return v >= 256 ? v : 2048; }();
+  static int t = [] { const char* e = getenv("FB2_SPMV_TILE"); const int v = e ? atoi(e) : 0; return v >= 256 ? v : 2560; }();
   return t;
 }
 #define CG_TILE cg_tile()

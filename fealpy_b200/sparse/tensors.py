@@ -86,7 +86,7 @@ class CSRTensor:
 
     __matmul__ = matmul
 
-    SPMV_TILE = int(__import__('os').environ.get('FB2_SPMV_TILE', '2048'))
+    SPMV_TILE = int(__import__('os').environ.get('FB2_SPMV_TILE', '2560'))
 
     def spmv_plan(self):
         """row-aligned nnz tiling used by the streaming SpMV kernel; built once per pattern"""
