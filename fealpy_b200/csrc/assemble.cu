@@ -569,18 +569,23 @@ int expand_pattern(int64_t gdof, int nc, int prio, const int64_t* crow_s, const 
 // `tile` values, owned by ONE warp) into a list of 32-entry batches such that
 //   * all entries of a batch share the local index i      -> the table row T[i] is warp-uniform,
 //   * all entries of a batch belong to different rows      -> conflict-free accumulation,
-//   * per row, entries appear in (i, cell) order           -> fixed, reproducible summation order.
+//   * per row, entries appear in (i, cell) order           -> fixed summation order, independent of the tiling.
 // The numeric kernel is then a flat loop over batches with every lane busy: lane = one
 // (row, cell) pair; geometry comes precomputed per cell (H), the element row is 11 FMAs per
 // column against broadcast table reads, the result is added into the warp's private tile.
 // =====================================================================================
 namespace fb2 {
 
-constexpr int A4_ROWCHUNK = 128;     // rows scheduled together (conflict mask width)
 
-struct A4Entry { int cell; int q; unsigned short base; };
+// one thread per tile; COUNT pass returns the number of batches, FILL pass writes them.
+// Within a tile the entries of local index i (n of them, at most m in any one row) are dealt
+// round-robin over B = max(ceil(n/32), m) batches in adjacency order (row-major): entry k goes to
+// batch k mod B, position k / B.  A row's entries are consecutive k and there are at most m <= B of
+// them, so they land in different batches; every batch gets at most ceil(n/B) <= 32 entries; and B
+// is the minimum possible.  Per row the cells stay in ascending order (see the rotation below).  (The first version closed a batch whenever a row repeated: 65-70 % of
+// the lanes carried work on tet P2; this one reaches 81-85 % with the same tile.)
+constexpr int A4_MAXL = 32;
 
-// one thread per tile; COUNT pass returns the number of batches, FILL pass writes them
 template <bool FILL>
 __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int32_t* __restrict__ blk_row, const int64_t* __restrict__ crow,
                                                             const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair, int L,
@@ -592,59 +597,99 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
   if (t >= ntile) return;
   const int64_t r0 = blk_row[t], r1 = blk_row[t + 1];
   const int64_t v0 = crow[r0];
-  int64_t nb = 0;                                  // batches emitted so far (tile-local)
-  const int64_t b0 = FILL ? batch_ptr[t] : 0;
-  int64_t cursor[A4_ROWCHUNK];
-  for (int64_t c0 = r0; c0 < r1; c0 += A4_ROWCHUNK) {
-    const int nr = (int)((r1 - c0) < A4_ROWCHUNK ? (r1 - c0) : A4_ROWCHUNK);
-    for (int k = 0; k < nr; ++k) cursor[k] = adj_ptr[c0 + k];
-    for (int i = 0; i < L; ++i) {
-      int fill = 0;                                // entries in the open batch
-      uint32_t mask[A4_ROWCHUNK / 32] = {0, 0, 0, 0};
-      bool any = true;
-      while (any) {
-        any = false;
-        for (int k = 0; k < nr; ++k) {
-          const int64_t q = cursor[k];
-          if (q >= adj_ptr[c0 + k + 1]) continue;
-          const int pair = adj_pair[q];
-          if (pair % L != i) continue;
-          any = true;
-          if (fill == 32 || (mask[k >> 5] >> (k & 31)) & 1u) {       // full, or this row is already in the batch
-            if (FILL) for (int z = fill; z < 32; ++z) ent_cell[(b0 + nb) * 32 + z] = -1;
-            ++nb; fill = 0;
-            mask[0] = mask[1] = mask[2] = mask[3] = 0;
-          }
-          if (FILL) {
-            const int64_t e = (b0 + nb) * 32 + fill;
-            if (fill == 0) batch_i[b0 + nb] = (unsigned char)i;
-            ent_cell[e] = pair / L;
-            ent_base[e] = (unsigned short)(crow[c0 + k] - v0);
-            for (int w = 0; w < slot_nwords; ++w) ent_slots[e * slot_nwords + w] = slot_words[q * slot_nwords + w];
-          }
-          mask[k >> 5] |= 1u << (k & 31);
-          ++fill;
-          cursor[k] = q + 1;
-        }
-      }
-      if (fill > 0) {                              // close the batch at the end of the i-group
-        if (FILL) for (int z = fill; z < 32; ++z) ent_cell[(b0 + nb) * 32 + z] = -1;
-        ++nb;
-      }
+  int cnt[A4_MAXL], mult[A4_MAXL];               // per local index: entries in the tile, longest run inside one row
+  for (int i = 0; i < L; ++i) { cnt[i] = 0; mult[i] = 0; }
+  for (int64_t r = r0; r < r1; ++r) {
+    int prev = -1, run = 0;
+    for (int64_t q = adj_ptr[r]; q < adj_ptr[r + 1]; ++q) {
+      const int i = adj_pair[q] % L;
+      run = (i == prev) ? run + 1 : 1;
+      prev = i;
+      ++cnt[i];
+      if (run > mult[i]) mult[i] = run;
     }
   }
-  if (!FILL) nbatch_of_tile[t] = (int)nb;
+  int nb = 0;
+  int off[A4_MAXL], nbi[A4_MAXL];                // first batch (tile-local) and number of batches of every local index
+  for (int i = 0; i < L; ++i) {
+    const int B = cnt[i] == 0 ? 0 : max((cnt[i] + 31) / 32, mult[i]);
+    off[i] = nb; nbi[i] = B; nb += B;
+  }
+  if (!FILL) { nbatch_of_tile[t] = nb; return; }
+  const int64_t b0 = batch_ptr[t];
+  for (int i = 0; i < L; ++i)
+    for (int j = 0; j < nbi[i]; ++j) {
+      batch_i[b0 + off[i] + j] = (unsigned char)i;
+      const int have = (cnt[i] - j + nbi[i] - 1) / nbi[i];         // entries k = j, j+B, j+2B, ... < cnt
+      for (int z = have; z < 32; ++z) ent_cell[(b0 + off[i] + j) * 32 + z] = -1;
+    }
+  int seen[A4_MAXL];
+  for (int i = 0; i < L; ++i) seen[i] = 0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const unsigned short base = (unsigned short)(crow[r] - v0);
+    const int64_t qe = adj_ptr[r + 1];
+    for (int64_t q = adj_ptr[r]; q < qe;) {
+      const int i = adj_pair[q] % L;
+      int m = 1;                                   // the row's run of local index i (adjacency is sorted by (i, cell))
+      while (q + m < qe && adj_pair[q + m] % L == i) ++m;
+      const int B = nbi[i], k0 = seen[i];
+      seen[i] += m;
+      // the run takes the deal numbers k0 .. k0+m-1; when they wrap around the B batches the numbers
+      // are handed out rotated, so that the row still meets its cells in ascending batch order:
+      // every row is summed in (i, cell) order whatever the tiling (single- and multi-GPU bit-identical)
+      const int wrap = max(0, k0 % B + m - B);
+      for (int t = 0; t < m; ++t) {
+        const int k = t < wrap ? k0 + (m - wrap) + t : k0 + (t - wrap);
+        const int64_t e = (b0 + off[i] + k % B) * 32 + k / B;
+        ent_cell[e] = adj_pair[q + t] / L;
+        ent_base[e] = base;
+        for (int w = 0; w < slot_nwords; ++w) ent_slots[e * slot_nwords + w] = slot_words[(q + t) * slot_nwords + w];
+      }
+      q += m;
+    }
+  }
 }
 
 // element tables in the kernel parameter block: operands come through the constant / uniform
-// datapath and cost no LSU (shared-memory) wavefronts -- the LSU data pipe is this kernel's limiter
+// datapath and cost no LSU (shared-memory) wavefronts -- the LSU data pipe is this kernel's limiter.
+//
+// Reduced geometry.  sum_k grad(lambda_k) = 0, so the (TD+1)(TD+2)/2 products g_kl = |K| grad(lambda_k).grad(lambda_l)
+// are linear in the TD(TD+1)/2 with k, l >= 1:  g_0l = -sum_m g_ml,  g_00 = sum_mn g_mn.  Folding that
+// into the table (a4_reduced_table) leaves  Ke[i][j] = sum_{1<=m<=n} Tr[i][j][mn] g_mn + Mm[i][j] |K|:
+// 7 instead of 11 values per cell and per FMA chain on tetrahedra, 4 instead of 7 on triangles.
+template <int TD>
+struct A4Geo {
+  static constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;   // full upper triangle (tables arrive in this layout)
+  static constexpr int NR = TD * (TD + 1) / 2;                // reduced: 1 <= m <= n <= TD
+  static constexpr int NH = NR + 1;                           // + the mass factor
+  static constexpr int HS = ((NH + 1) / 2) * 2;               // record length in doubles (16-byte units)
+  static constexpr int QP = HS / 2;                           // 16-byte units per record: 4 (tet), 2 (tri)
+  __host__ __device__ static constexpr int full(int k, int l) { return k * NV - k * (k - 1) / 2 + (l - k); }   // k <= l
+};
 template <int L, int NH>
-struct A4Tables { double T[L][L][NH]; };     // T[i][j] = (Ms[i][j][0..NG-1], Mm[i][j])
+struct A4Tables { double T[L][L][NH]; };     // T[i][j] = (Tr[i][j][0..NR-1], Mm[i][j])
+
+template <int TD, int L>
+static void a4_reduced_table(const double* Ms, const double* Mm, A4Tables<L, A4Geo<TD>::NH>& tb) {
+  using GEO = A4Geo<TD>;
+  for (int i = 0; i < L; ++i)
+    for (int j = 0; j < L; ++j) {
+      const double* ms = Ms ? Ms + (size_t)(i * L + j) * GEO::NG : nullptr;
+      int t = 0;
+      for (int m = 1; m <= TD; ++m)
+        for (int n = m; n <= TD; ++n, ++t) {
+          if (!ms) { tb.T[i][j][t] = 0.0; continue; }
+          const double m00 = ms[GEO::full(0, 0)], m0m = ms[GEO::full(0, m)], m0n = ms[GEO::full(0, n)];
+          tb.T[i][j][t] = m == n ? (ms[GEO::full(m, m)] + m00) - m0m : (ms[GEO::full(m, n)] + 2.0 * m00) - (m0m + m0n);
+        }
+      tb.T[i][j][GEO::NR] = Mm ? Mm[i * L + j] : 0.0;
+    }
+}
 
 template <int TD, int L, typename SlotT, int I, typename TabT>
-__device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[(TD + 1) * (TD + 2) / 2 + 1],
+__device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[A4Geo<TD>::NH],
                                        const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
-  constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1;
+  constexpr int NH = A4Geo<TD>::NH;
   using SR = SlotRec<SlotT, L>;
   // columns in chunks of JC independent FMA chains.  (Tried and measured slower, profiles/r01_tune_asm_v4*.txt:
   // smaller chunks separated by warp barriers to cap registers at 128 -- occupancy up, time up.)
@@ -671,7 +716,7 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[(TD + 1
 }
 
 template <int TD, int L, typename SlotT, int I, typename TabT>
-__device__ __forceinline__ void a4_dispatch(int i, const TabT& tb, const double (&h)[(TD + 1) * (TD + 2) / 2 + 1],
+__device__ __forceinline__ void a4_dispatch(int i, const TabT& tb, const double (&h)[A4Geo<TD>::NH],
                                             const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
   if (i == I) a4_row<TD, L, SlotT, I, TabT>(tb, h, sw, my);
   else if constexpr (I + 1 < L) a4_dispatch<TD, L, SlotT, I + 1, TabT>(i, tb, h, sw, my);
@@ -684,89 +729,153 @@ __device__ __forceinline__ void a4_dispatch(int i, const TabT& tb, const double 
 #define FB2_ASM4_MINBLOCKS 2
 #endif
 
-// H rows are padded to HS doubles (multiple of 2) so that they are read with 128-bit loads
-template <int TD, int L, typename SlotT>
+// ---- v4 numeric kernel: asynchronous-copy pipeline ------------------------------------
+// How a batch's operands reach the warp.  A first version prefetched ONE batch ahead through
+// registers: ncu showed 8 resident warps per SM, each stalled ~85 % of the time on the DEPENDENT pair
+// of global round trips (entry -> cell id -> geometry record).  Here both streams are cp.async rings
+// in the warp's private shared memory -- no registers held by data in flight, so the look-ahead is a
+// template parameter: entries run 2*D batches ahead, geometry records D batches ahead
+// (group G_b = {entries(b+2D), H(b+D)}; at the top of iteration b `wait_group D-1` retires G_{b-D},
+// which delivered H(b) and the cell ids needed to issue H(b+D)).  7.0 -> 5.0 ms on tet P2 128^3.
+//
+// Geometry stage layout.  A record is QP 16-byte units (4 on tetrahedra, 2 on triangles).  The 32
+// records of a batch are copied COOPERATIVELY -- consecutive lanes copy consecutive units, so one
+// cp.async instruction touches 8 / 16 records (few L1 tag look-ups) -- and then read back one record
+// per lane with LDS.128.  Records are packed (no padding) and unit p of record r sits at
+//     r*QP + ((p + (r*QP/8)) mod QP)
+// which makes BOTH sides conflict-free: a quarter-warp of the copy writes 8 consecutive units (a
+// rotation inside a record keeps them distinct), a quarter-warp of the read-back hits 8 distinct
+// 16-byte bank groups.  (With padded records the copy side cost 11 wavefronts per instruction
+// instead of 4 and was 43 % of the kernel's shared-memory traffic.)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int QP>
+__device__ __forceinline__ int a4_unit(int rec, int part) {      // swizzled 16-byte unit of (record, part)
+  static_assert(QP == 2 || QP == 4 || QP == 8, "record size must divide the 128-byte bank row");
+  return rec * QP + ((part + (rec * QP) / 8) & (QP - 1));
+}
+
+template <int TD, int L, typename SlotT, int D>
 __global__ void __launch_bounds__(FB2_ASM4_WARPS * 32, FB2_ASM4_MINBLOCKS)
-assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_constant__ A4Tables<L, (TD + 1) * (TD + 2) / 2 + 1> tb) {
-  constexpr int NG = (TD + 1) * (TD + 2) / 2, NH = NG + 1, ROW = ((NH + 1) / 2) * 2, HS = ROW;
+assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_constant__ A4Tables<L, A4Geo<TD>::NH> tb) {
+  using GEO = A4Geo<TD>;
+  constexpr int NH = GEO::NH, HS = GEO::HS, QP = GEO::QP;
   using SR = SlotRec<SlotT, L>;
+  constexpr int NHST = D + 1, NEST = 2 * D + 1;                 // ring depths: geometry stages, entry slots
+  constexpr int ENT_BYTES = 192 + 128 * SR::WORDS;              // 32 x (cell int32 | base uint16 | slot words)
+  constexpr int ENT_CHUNKS = ENT_BYTES / 16;
   extern __shared__ __align__(16) double sm4[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int tile = blockIdx.x * FB2_ASM4_WARPS + wid;
   if (tile >= a.ntile) return;
-  constexpr int QP = HS / 2;                                    // 16-byte quarters per geometry record
-  constexpr int HSP = HS + 2;                                   // padded record stride in the stage (conflict-free LDS.128)
-  double* acc = sm4 + (size_t)wid * (a.acc_stride + 32 * HSP);  // this warp's private tile ...
-  double* hst = acc + a.acc_stride;                             // ... and its 32-record geometry stage
+  const size_t per_warp = (size_t)a.acc_stride + NHST * 32 * HS + NEST * (ENT_BYTES / 8);
+  double* acc = sm4 + (size_t)wid * per_warp;                   // this warp's private tile ...
+  double* hring = acc + a.acc_stride;                           // ... its geometry stages ...
+  unsigned char* ering = reinterpret_cast<unsigned char*>(hring + NHST * 32 * HS);   // ... and its entry slots
   const int64_t r0 = a.blk_row[tile], r1 = a.blk_row[tile + 1];
   const int64_t v0 = a.crow[r0];
   const int nval = (int)(a.crow[r1] - v0);
-  for (int t = lane; t < nval; t += 32) acc[t] = 0.0;
-  __syncwarp();
   const int64_t b0 = a.batch_ptr[tile], b1 = a.batch_ptr[tile + 1];
-  // software pipeline: entry + geometry of batch b+1 are in flight while batch b is computed.
-  // The 32 geometry records of a batch are fetched COOPERATIVELY: consecutive lanes read
-  // consecutive 16-byte quarters of the same record (one LSU wavefront per record instead of
-  // one per lane and quarter), then the records are transposed through the shared-memory stage.
-  int cell_n = -1, base_n = 0, i_n = 0;
-  uint32_t sw_n[SR::WORDS];
-  double2 hq[QP];
-  auto fetch = [&](int64_t b) {
-    const int64_t e = b * 32 + lane;
-    cell_n = a.ent_cell[e];
-    base_n = a.ent_base[e];
-    i_n = a.batch_i[b];
+
+  auto issue_entries = [&](int64_t b, int slot) {               // 36 x 16 B for tet P2: two cp.async per lane
+    unsigned char* dst = ering + slot * ENT_BYTES;
 #pragma unroll
-    for (int w = 0; w < SR::WORDS; ++w) sw_n[w] = a.ent_slots[e * SR::WORDS + w];
-#pragma unroll
-    for (int r = 0; r < QP; ++r) {
-      const int idx = r * 32 + lane, rec = idx / QP, part = idx - rec * QP;
-      const int c = __shfl_sync(0xffffffffu, cell_n, rec);
-      hq[r] = (c >= 0) ? *reinterpret_cast<const double2*>(a.H + (int64_t)c * HS + 2 * part) : make_double2(0.0, 0.0);
-    }
-  };
-  auto stash = [&]() {
-#pragma unroll
-    for (int r = 0; r < QP; ++r) {
-      const int idx = r * 32 + lane, rec = idx / QP, part = idx - rec * QP;
-      *reinterpret_cast<double2*>(hst + rec * HSP + 2 * part) = hq[r];
-    }
-  };
-  if (b0 < b1) { fetch(b0); stash(); }
-  for (int64_t b = b0; b < b1; ++b) {
-    const int cell = cell_n, base = base_n, i = i_n;
-    uint32_t sw[SR::WORDS];
-    double h[NH];
-#pragma unroll
-    for (int w = 0; w < SR::WORDS; ++w) sw[w] = sw_n[w];
-    __syncwarp();
-    {
-      double hh[HS];
-#pragma unroll
-      for (int t = 0; t < QP; ++t) {
-        const double2 v = *reinterpret_cast<const double2*>(hst + lane * HSP + 2 * t);
-        hh[2 * t] = v.x; hh[2 * t + 1] = v.y;
+    for (int q0 = 0; q0 < ENT_CHUNKS; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < ENT_CHUNKS) {
+        const unsigned char* src;
+        if (q < 8) src = reinterpret_cast<const unsigned char*>(a.ent_cell + b * 32) + q * 16;
+        else if (q < 12) src = reinterpret_cast<const unsigned char*>(a.ent_base + b * 32) + (q - 8) * 16;
+        else src = reinterpret_cast<const unsigned char*>(a.ent_slots + b * 32 * SR::WORDS) + (q - 12) * 16;
+        cp_async16(dst + q * 16, src);
       }
-#pragma unroll
-      for (int t = 0; t < NH; ++t) h[t] = hh[t];
     }
-    __syncwarp();
-    const bool more = b + 1 < b1;
-    if (more) fetch(b + 1);
-    if (cell >= 0) a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, acc + base);
-    if (more) stash();
+  };
+  auto issue_geometry = [&](int eslot, int hslot) {
+    const int* cells = reinterpret_cast<const int*>(ering + eslot * ENT_BYTES);
+    double* dst = hring + hslot * 32 * HS;
+#pragma unroll
+    for (int r = 0; r < QP; ++r) {
+      const int idx = r * 32 + lane, rec = idx / QP, part = idx % QP;
+      const int c = cells[rec];
+      if (c >= 0) cp_async16(dst + 2 * a4_unit<QP>(rec, part), a.H + (int64_t)c * HS + 2 * part);
+    }
+  };
+
+  // prologue: entries of the first 2D batches, then the geometry of the first D
+  for (int k = 0; k < 2 * D; ++k)
+    if (b0 + k < b1) issue_entries(b0 + k, k);
+  cp_async_commit();
+  for (int t = lane; t < nval; t += 32) acc[t] = 0.0;
+  int iq[D];                                                    // local index i of batches b .. b+D-1
+#pragma unroll
+  for (int k = 0; k < D; ++k) iq[k] = (b0 + k < b1) ? a.batch_i[b0 + k] : 0;
+  cp_async_wait<0>();
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    if (b0 + k < b1) issue_geometry(k, k);
+    cp_async_commit();
   }
+  int hs = 0, es = 0;                                           // ring positions of batch b
+  for (int64_t b = b0; b < b1; ++b) {
+    cp_async_wait<D - 1>();
+    __syncwarp();                                               // G_{b-D} visible to all lanes; everyone is done with batch b-1
+    {
+      int hn = hs + D; if (hn >= NHST) hn -= NHST;              // == stage of batch b-1: free
+      int en = es + D; if (en >= NEST) en -= NEST;
+      int e2 = es + 2 * D; if (e2 >= NEST) e2 -= NEST;          // == slot of batch b-1: free
+      if (b + 2 * D < b1) issue_entries(b + 2 * D, e2);
+      if (b + D < b1) issue_geometry(en, hn);
+      cp_async_commit();
+    }
+    const int i = iq[0];
+#pragma unroll
+    for (int k = 0; k + 1 < D; ++k) iq[k] = iq[k + 1];
+    iq[D - 1] = (b + D < b1) ? a.batch_i[b + D] : 0;
+    const unsigned char* ent = ering + es * ENT_BYTES;
+    const int cell = reinterpret_cast<const int*>(ent)[lane];
+    if (cell >= 0) {
+      const int base = reinterpret_cast<const unsigned short*>(ent + 128)[lane];
+      uint32_t sw[SR::WORDS];
+#pragma unroll
+      for (int w = 0; w < SR::WORDS; ++w) sw[w] = reinterpret_cast<const uint32_t*>(ent + 192)[lane * SR::WORDS + w];
+      double h[NH];
+      {
+        const double* hst = hring + hs * 32 * HS;
+        double hh[HS];
+#pragma unroll
+        for (int t = 0; t < QP; ++t) {
+          const double2 v = *reinterpret_cast<const double2*>(hst + 2 * a4_unit<QP>(lane, t));
+          hh[2 * t] = v.x; hh[2 * t + 1] = v.y;
+        }
+#pragma unroll
+        for (int t = 0; t < NH; ++t) h[t] = hh[t];
+      }
+      a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, acc + base);
+    }
+    if (++hs == NHST) hs = 0;
+    if (++es == NEST) es = 0;
+  }
+  cp_async_wait<0>();
   __syncwarp();
   double* out = a.values + v0;
   for (int t = lane; t < nval; t += 32) out[t] = acc[t];
 }
 
-// H rows padded to a multiple of 2 doubles
+// per-cell record H = (kd * g_mn for 1 <= m <= n <= TD, km * |K|), padded to a multiple of 2 doubles
 template <int TD>
 __global__ void __launch_bounds__(256) cell_geometry4_kernel(const double* __restrict__ node, const int* __restrict__ cell, int64_t NC,
                                                              double scal_d, const double* __restrict__ coef_d, double scal_m,
                                                              const double* __restrict__ coef_m, double* __restrict__ H) {
-  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2, NH = NG + 1, HS = ((NH + 1) / 2) * 2;
+  using GEO = A4Geo<TD>;
+  constexpr int NV = TD + 1, NG = GEO::NG, NR = GEO::NR, NH = GEO::NH, HS = GEO::HS;
   __shared__ double stage[256 * HS];
   const int64_t c0 = (int64_t)blockIdx.x * 256;
   const int64_t c = c0 + threadIdx.x;
@@ -779,9 +888,12 @@ __global__ void __launch_bounds__(256) cell_geometry4_kernel(const double* __res
     const double kd = scal_d * (coef_d ? coef_d[c] : 1.0);
     const double km = scal_m * (coef_m ? coef_m[c] : 1.0) * cm;
     double* h = stage + threadIdx.x * HS;
+    int t = 0;
 #pragma unroll
-    for (int t = 0; t < NG; ++t) h[t] = kd * G[t];
-    h[NG] = km;
+    for (int m = 1; m <= TD; ++m)
+#pragma unroll
+      for (int n = m; n <= TD; ++n) h[t++] = kd * G[GEO::full(m, n)];
+    h[NR] = km;
     if (HS > NH) h[NH] = 0.0;
   }
   __syncthreads();
@@ -821,38 +933,40 @@ int asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const
 
 template <int TD, int L>
 static int launch_asm4(Asm4Args a, int slot_bytes, cudaStream_t s) {
-  constexpr int NV = TD + 1, NG = NV * (NV + 1) / 2;
-  if constexpr (sizeof(A4Tables<L, NG + 1>) + sizeof(Asm4Args) >= 32000) {
-    return fail(ERR_UNSUPPORTED, "assemble v4: element tables exceed the kernel parameter block (ldof=%d)", L);
+  using GEO = A4Geo<TD>;
+  static_assert(sizeof(A4Tables<L, GEO::NH>) + sizeof(Asm4Args) < 32000, "element tables exceed the kernel parameter block");
+  static_assert(L <= A4_MAXL, "scheduler arrays too small");
+  cell_geometry4_kernel<TD><<<(unsigned)ceil_div(a.NC, 256), 256, 0, s>>>(a.node, a.cell, a.NC, a.Ms ? a.scal_d : 0.0, a.coef_d,
+                                                                         a.Mm ? a.scal_m : 0.0, a.coef_m, a.Hbuf);
+  a.H = a.Hbuf;
+  a.acc_stride = (a.tile + a.max_row + 1) & ~1;
+  A4Tables<L, GEO::NH> tb;
+  a4_reduced_table<TD, L>(a.Ms_host, a.Mm_host, tb);
+  static const int depth = [] { const char* e = getenv("FB2_ASM4_DEPTH"); const int d = e ? atoi(e) : 1; return d == 2 ? 2 : 1; }();
+  if (a.tile + a.max_row > 65535) return fail(ERR_UNSUPPORTED, "assemble v4: tile offsets exceed 16 bits");
+  const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
+  if (grid == 0) return OK;
+  const int words = slot_stride(L, slot_bytes) * slot_bytes / 4;
+  // per warp: accumulator tile + (D+1) geometry stages + (2D+1) entry slots
+  const size_t per_warp = (size_t)(a.acc_stride + (depth + 1) * 32 * GEO::HS) * 8 + (size_t)(2 * depth + 1) * (192 + 128 * words);
+  const size_t smem = (size_t)FB2_ASM4_WARPS * per_warp;
+  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble v4: tiles do not fit shared memory (tile=%d max_row=%d)", a.tile, a.max_row);
+#define FB2_A4_LAUNCH(KERN)                                                                          \
+  do {                                                                                               \
+    auto k = KERN;                                                                                   \
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a, tb);                                                \
+  } while (0)
+  if (slot_bytes == 1) {
+    if (depth == 1) FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint8_t, 1>));
+    else FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint8_t, 2>));
   } else {
-    cell_geometry4_kernel<TD><<<(unsigned)ceil_div(a.NC, 256), 256, 0, s>>>(a.node, a.cell, a.NC, a.Ms ? a.scal_d : 0.0, a.coef_d,
-                                                                           a.Mm ? a.scal_m : 0.0, a.coef_m, a.Hbuf);
-    a.H = a.Hbuf;
-    a.acc_stride = (a.tile + a.max_row + 1) & ~1;
-    A4Tables<L, NG + 1> tb;
-    for (int i = 0; i < L; ++i)
-      for (int j = 0; j < L; ++j) {
-        for (int t = 0; t < NG; ++t) tb.T[i][j][t] = a.Ms_host ? a.Ms_host[(i * L + j) * NG + t] : 0.0;
-        tb.T[i][j][NG] = a.Mm_host ? a.Mm_host[i * L + j] : 0.0;
-      }
-    constexpr int HSP4 = ((NG + 2) / 2) * 2 + 2;
-    const size_t smem = ((size_t)FB2_ASM4_WARPS * (a.acc_stride + 32 * HSP4)) * 8;
-    if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble v4: tiles do not fit shared memory (tile=%d max_row=%d)", a.tile, a.max_row);
-    if (a.tile + a.max_row > 65535) return fail(ERR_UNSUPPORTED, "assemble v4: tile offsets exceed 16 bits");
-    const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
-    if (grid == 0) return OK;
-    if (slot_bytes == 1) {
-      auto k = assemble_const_v4_kernel<TD, L, uint8_t>;
-      FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a, tb);
-    } else {
-      auto k = assemble_const_v4_kernel<TD, L, uint16_t>;
-      FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a, tb);
-    }
-    FB2_LAUNCH_CHECK();
-    return OK;
+    if (depth == 1) FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint16_t, 1>));
+    else FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint16_t, 2>));
   }
+#undef FB2_A4_LAUNCH
+  FB2_LAUNCH_CHECK();
+  return OK;
 }
 
 int assemble_v4(int TD, int p, const Asm4Args& a, int slot_bytes, cudaStream_t s) {

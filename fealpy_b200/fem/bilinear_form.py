@@ -119,7 +119,7 @@ def row_tiling(crow, nrow, nnz, tile):
     return blk_row, nblk
 
 
-ASM4_TILE = int(_os.environ.get("FB2_ASM4_TILE", "2560"))     # values per WARP tile of the v4 kernel
+ASM4_TILE = int(_os.environ.get("FB2_ASM4_TILE", "2304"))     # values per WARP tile of the v4 kernel
 
 
 def asm4_plan(space):
@@ -288,9 +288,7 @@ class BilinearForm:
             h = host_tables(mesh.TD, space.p, m["q"])[key]
             return h.ctypes.data_as(C.c_void_p)
         kernel = _os.environ.get("FB2_ASM_KERNEL", "v4")
-        NH = NV * (NV + 1) // 2 + 1
-        if kernel == "v4" and sym["L"] * sym["L"] * NH * 8 > 30000:
-            kernel = "v2"          # tables do not fit the kernel parameter block (tet P3)
+        NH = mesh.TD * (mesh.TD + 1) // 2 + 1          # reduced geometry record (csrc/assemble.cu A4Geo)
         if kernel == "v4":
             pl = asm4_plan(space)
             geom = torch.empty((sym["NC"], (NH + 1) // 2 * 2), dtype=torch.float64, device=mesh.device)

@@ -120,9 +120,10 @@ int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int6
 /* "v4" numeric kernel for the same forms: the symbolic phase additionally turns every warp tile
  * (rows holding <= tile values; fb2_spmv_plan_build) into 32-entry batches that share the local
  * index (warp-uniform element-table row) and touch 32 different rows (conflict-free adds);
- * geom_ws = NC * 2*ceil((NG+1)/2) doubles of scratch for the per-cell geometry.  The element tables
- * are HOST pointers here: they travel in the kernel parameter block (constant bank), which costs no
- * load/store-unit bandwidth; FB2_ERR_UNSUPPORTED if they exceed it (ldof = 20). */
+ * geom_ws = NC * 2*ceil((TD*(TD+1)/2+1)/2) doubles of scratch for the per-cell geometry (8 per
+ * tetrahedron, 4 per triangle).  The element tables are HOST pointers here: they travel in the kernel
+ * parameter block (constant bank), which costs no load/store-unit bandwidth.  Pad entries of a
+ * batch carry ent_cell = -1. */
 size_t fb2_asm4_workspace_bytes(int ntile);
 int fb2_asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
                         int ldof, int64_t* batch_ptr, int64_t* nbatch_host, void* ws, void* stream);
