@@ -693,7 +693,11 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[A4Geo<T
   using SR = SlotRec<SlotT, L>;
   // columns in chunks of JC independent FMA chains.  (Tried and measured slower, profiles/r01_tune_asm_v4*.txt:
   // smaller chunks separated by warp barriers to cap registers at 128 -- occupancy up, time up.)
+#ifdef FB2_ASM4_JC
+  constexpr int JC = (L % FB2_ASM4_JC == 0) ? FB2_ASM4_JC : ((L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3));
+#else
   constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
+#endif
 #pragma unroll
   for (int j0 = 0; j0 < L; j0 += JC) {
     double val[JC];

@@ -119,7 +119,7 @@ def row_tiling(crow, nrow, nnz, tile):
     return blk_row, nblk
 
 
-ASM4_TILE = int(_os.environ.get("FB2_ASM4_TILE", "2304"))     # values per WARP tile of the v4 kernel
+ASM4_TILE = int(_os.environ.get("FB2_ASM4_TILE", "2560"))     # values per WARP tile of the v4 kernel
 
 
 def asm4_plan(space):
