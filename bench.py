@@ -334,7 +334,7 @@ def run_ours(args):
             "assembly_ms": 1e3 * t_asm / args.steps,
             "cold": {"mesh_topology_ms": t_mesh, "symbolic_ms": t_sym, "first_assembly_ms": t_first,
                      "nnz_per_s_incl_symbolic": nnz / ((t_sym + t_first) * 1e-3)},
-            "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<8> (one CG iteration = spmv+dot, update_xr, update_p)",
+            "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<1> (one CG iteration = spmv+dot, update_xr, update_p)",
                          "achieved": cg_gbs, "peak": peak, "unit": "GB/s", "frac": cg_gbs / peak,
                          "traffic": traffic.get("cg_iteration_bytes") if (n == 128 and p == 2) else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_iter": b_it,
