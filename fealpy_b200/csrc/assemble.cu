@@ -577,13 +577,16 @@ int expand_pattern(int64_t gdof, int nc, int prio, const int64_t* crow_s, const 
 namespace fb2 {
 
 
-// one thread per tile; COUNT pass returns the number of batches, FILL pass writes them.
+// one WARP per tile; COUNT pass returns the number of batches, FILL pass writes them.
 // Within a tile the entries of local index i (n of them, at most m in any one row) are dealt
 // round-robin over B = max(ceil(n/32), m) batches in adjacency order (row-major): entry k goes to
 // batch k mod B, position k / B.  A row's entries are consecutive k and there are at most m <= B of
 // them, so they land in different batches; every batch gets at most ceil(n/B) <= 32 entries; and B
-// is the minimum possible.  Per row the cells stay in ascending order (see the rotation below).  (The first version closed a batch whenever a row repeated: 65-70 % of
-// the lanes carried work on tet P2; this one reaches 81-85 % with the same tile.)
+// is the minimum possible.  Per row the cells stay in ascending order (see the rotation below).
+// (The first version closed a batch whenever a row repeated: 65-70 % of the lanes carried work on
+// tet P2; this one reaches 81-85 % with the same tile.)
+// Lane = row while walking the adjacency (sorted by (i, cell) per row, so the run of local index i
+// is found by advancing a per-lane cursor); lane i keeps the totals of local index i.
 constexpr int A4_MAXL = 32;
 
 template <bool FILL>
@@ -593,57 +596,69 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
                                                             unsigned char* __restrict__ batch_i, int* __restrict__ ent_cell,
                                                             unsigned short* __restrict__ ent_base, uint32_t* __restrict__ ent_slots,
                                                             const uint32_t* __restrict__ slot_words, int slot_nwords) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (t >= ntile) return;
   const int64_t r0 = blk_row[t], r1 = blk_row[t + 1];
   const int64_t v0 = crow[r0];
-  int cnt[A4_MAXL], mult[A4_MAXL];               // per local index: entries in the tile, longest run inside one row
-  for (int i = 0; i < L; ++i) { cnt[i] = 0; mult[i] = 0; }
-  for (int64_t r = r0; r < r1; ++r) {
-    int prev = -1, run = 0;
-    for (int64_t q = adj_ptr[r]; q < adj_ptr[r + 1]; ++q) {
-      const int i = adj_pair[q] % L;
-      run = (i == prev) ? run + 1 : 1;
-      prev = i;
-      ++cnt[i];
-      if (run > mult[i]) mult[i] = run;
-    }
-  }
-  int nb = 0;
-  int off[A4_MAXL], nbi[A4_MAXL];                // first batch (tile-local) and number of batches of every local index
-  for (int i = 0; i < L; ++i) {
-    const int B = cnt[i] == 0 ? 0 : max((cnt[i] + 31) / 32, mult[i]);
-    off[i] = nb; nbi[i] = B; nb += B;
-  }
-  if (!FILL) { nbatch_of_tile[t] = nb; return; }
-  const int64_t b0 = batch_ptr[t];
-  for (int i = 0; i < L; ++i)
-    for (int j = 0; j < nbi[i]; ++j) {
-      batch_i[b0 + off[i] + j] = (unsigned char)i;
-      const int have = (cnt[i] - j + nbi[i] - 1) / nbi[i];         // entries k = j, j+B, j+2B, ... < cnt
-      for (int z = have; z < 32; ++z) ent_cell[(b0 + off[i] + j) * 32 + z] = -1;
-    }
-  int seen[A4_MAXL];
-  for (int i = 0; i < L; ++i) seen[i] = 0;
-  for (int64_t r = r0; r < r1; ++r) {
-    const unsigned short base = (unsigned short)(crow[r] - v0);
-    const int64_t qe = adj_ptr[r + 1];
-    for (int64_t q = adj_ptr[r]; q < qe;) {
-      const int i = adj_pair[q] % L;
-      int m = 1;                                   // the row's run of local index i (adjacency is sorted by (i, cell))
+  int cnt = 0, mult = 0;                         // lane i: entries of local index i in the tile, longest run inside one row
+  for (int64_t rb = r0; rb < r1; rb += 32) {
+    const int64_t r = rb + lane;
+    int64_t q = 0, qe = 0;
+    if (r < r1) { q = adj_ptr[r]; qe = adj_ptr[r + 1]; }
+    for (int i = 0; i < L; ++i) {
+      int m = 0;
       while (q + m < qe && adj_pair[q + m] % L == i) ++m;
-      const int B = nbi[i], k0 = seen[i];
-      seen[i] += m;
-      // the run takes the deal numbers k0 .. k0+m-1; when they wrap around the B batches the numbers
-      // are handed out rotated, so that the row still meets its cells in ascending batch order:
-      // every row is summed in (i, cell) order whatever the tiling (single- and multi-GPU bit-identical)
-      const int wrap = max(0, k0 % B + m - B);
-      for (int t = 0; t < m; ++t) {
-        const int k = t < wrap ? k0 + (m - wrap) + t : k0 + (t - wrap);
-        const int64_t e = (b0 + off[i] + k % B) * 32 + k / B;
-        ent_cell[e] = adj_pair[q + t] / L;
-        ent_base[e] = base;
-        for (int w = 0; w < slot_nwords; ++w) ent_slots[e * slot_nwords + w] = slot_words[(q + t) * slot_nwords + w];
+      q += m;
+      const int s = __reduce_add_sync(FULL, m), mx = __reduce_max_sync(FULL, m);
+      if (lane == i) { cnt += s; mult = max(mult, mx); }
+    }
+  }
+  const int B = cnt == 0 ? 0 : max((cnt + 31) / 32, mult);     // batches of local index `lane`
+  int off = B;                                                 // -> first batch (tile-local) of local index `lane`
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, off, o); if (lane >= o) off += v; }
+  const int nb = __shfl_sync(FULL, off, 31);
+  off -= B;
+  if (!FILL) { if (lane == 0) nbatch_of_tile[t] = nb; return; }
+  const int64_t b0 = batch_ptr[t];
+  for (int i = 0; i < L; ++i) {
+    const int Bi = __shfl_sync(FULL, B, i), offi = __shfl_sync(FULL, off, i), ci = __shfl_sync(FULL, cnt, i);
+    for (int j = 0; j < Bi; ++j) {
+      const int have = (ci - j + Bi - 1) / Bi;                 // entries k = j, j+B, j+2B, ... < cnt
+      if (lane == 0) batch_i[b0 + offi + j] = (unsigned char)i;
+      if (lane >= have) ent_cell[(b0 + offi + j) * 32 + lane] = -1;
+    }
+  }
+  int dealt = 0;                                               // lane i: entries of local index i dealt so far
+  for (int64_t rb = r0; rb < r1; rb += 32) {
+    const int64_t r = rb + lane;
+    int64_t q = 0, qe = 0;
+    unsigned short base = 0;
+    if (r < r1) { q = adj_ptr[r]; qe = adj_ptr[r + 1]; base = (unsigned short)(crow[r] - v0); }
+    for (int i = 0; i < L; ++i) {
+      int m = 0;                                 // this row's run of local index i
+      while (q + m < qe && adj_pair[q + m] % L == i) ++m;
+      int ex = m;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, ex, o); if (lane >= o) ex += v; }
+      const int total = __shfl_sync(FULL, ex, 31);
+      const int Bi = __shfl_sync(FULL, B, i), offi = __shfl_sync(FULL, off, i);
+      const int k0 = __shfl_sync(FULL, dealt, i) + ex - m;     // rows are dealt in order: row-major deal numbers
+      if (lane == i) dealt += total;
+      if (m > 0) {
+        // the run takes the deal numbers k0 .. k0+m-1; when they wrap around the Bi batches the numbers
+        // are handed out rotated, so that the row still meets its cells in ascending batch order:
+        // every row is summed in (i, cell) order whatever the tiling (single- and multi-GPU bit-identical)
+        const int wrap = max(0, k0 % Bi + m - Bi);
+        for (int u = 0; u < m; ++u) {
+          const int k = u < wrap ? k0 + (m - wrap) + u : k0 + (u - wrap);
+          const int64_t e = (b0 + offi + k % Bi) * 32 + k / Bi;
+          ent_cell[e] = adj_pair[q + u] / L;
+          ent_base[e] = base;
+          for (int w = 0; w < slot_nwords; ++w) ent_slots[e * slot_nwords + w] = slot_words[(q + u) * slot_nwords + w];
+        }
       }
       q += m;
     }
@@ -914,7 +929,7 @@ int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, cons
   int* cnt = c.take<int>(ntile + 1);
   void* scan_ws = c.take<char>(scan_workspace_bytes(ntile + 1));
   if (ntile > 0)
-    asm4_schedule_kernel<false><<<(unsigned)ceil_div(ntile, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, cnt, nullptr,
+    asm4_schedule_kernel<false><<<(unsigned)ceil_div((int64_t)ntile * 32, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, cnt, nullptr,
                                                                                nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   FB2_LAUNCH_CHECK();
   FB2_TRY(exclusive_scan_i32(cnt, batch_ptr, ntile, true, scan_ws, s));
@@ -928,7 +943,7 @@ int asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const
                    const void* slots, int slot_bytes, cudaStream_t s) {
   if (ntile <= 0) return OK;
   const int nwords = slot_stride(L, slot_bytes) * slot_bytes / 4;
-  asm4_schedule_kernel<true><<<(unsigned)ceil_div(ntile, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, nullptr, batch_ptr,
+  asm4_schedule_kernel<true><<<(unsigned)ceil_div((int64_t)ntile * 32, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, nullptr, batch_ptr,
                                                                             batch_i, ent_cell, ent_base, ent_slots,
                                                                             static_cast<const uint32_t*>(slots), nwords);
   FB2_LAUNCH_CHECK();

@@ -548,3 +548,56 @@ def test_relabelled_mesh_matches_oracle(kind, dims, p, U):
     assert abs(info["niter"] - oinfo["niter"]) <= 2
     assert np.linalg.norm(x.cpu().numpy() - xo) / np.linalg.norm(xo) <= 1e-10
     assert np.array_equal(space.is_boundary_dof().cpu().numpy(), O.boundary_dof_flag(om, p))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,dims,p,tile", [("tet", (6, 5, 4), 2, 2560), ("tet", (5, 4, 3), 3, 2560), ("tri", (31, 17), 1, 512),
+                                              ("tri", (9, 8), 3, 640), ("tet", (7, 6, 5), 1, 256)])
+def test_asm4_schedule_invariants(kind, dims, p, tile, U, monkeypatch):
+    """the batch schedule of the v4 numeric kernel (csrc/assemble.cu asm4_schedule_kernel), checked entry by entry:
+    every (row, cell, i) pair of the mesh exactly once; a batch holds one local index and 32 DIFFERENT rows;
+    every row meets its cells in (i, cell) order; and the number of batches per (tile, i) is the minimum
+    max(ceil(n/32), longest run in one row)."""
+    from fealpy_b200.mesh import TetrahedronMesh, TriangleMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import bilinear_form as bfm
+    monkeypatch.setattr(bfm, "ASM4_TILE", tile)
+    mesh = (TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], *dims) if kind == "tet" else TriangleMesh.from_box([0, 1, 0, 1], *dims))
+    space = LagrangeFESpace(mesh, p)
+    sym = bfm.symbolic_pattern(space)
+    pl = bfm.asm4_plan(space)
+    c2d = space.cell_to_dof().cpu().numpy()
+    NC, L = c2d.shape
+    crow = sym["crow"].cpu().numpy()
+    blk_row = pl["blk_row"].cpu().numpy()[:pl["ntile"] + 1]
+    batch_ptr = pl["batch_ptr"].cpu().numpy()
+    batch_i = pl["batch_i"].cpu().numpy()
+    ent_cell = pl["ent_cell"].cpu().numpy().reshape(-1, 32)
+    ent_base = pl["ent_base"].cpu().numpy().astype(np.uint16).reshape(-1, 32)
+    assert batch_ptr[0] == 0 and batch_ptr[-1] == ent_cell.shape[0] == batch_i.shape[0]
+    seen = np.zeros((NC, L), dtype=int)
+    for t in range(pl["ntile"]):
+        r0, r1 = blk_row[t], blk_row[t + 1]
+        v0 = crow[r0]
+        base_to_row = {int(crow[r] - v0): r for r in range(r0, r1) if crow[r + 1] > crow[r]}
+        last = {}                                   # (row, i) -> last cell seen, in batch order
+        per_i = {}
+        for b in range(batch_ptr[t], batch_ptr[t + 1]):
+            i = int(batch_i[b])
+            live = ent_cell[b] >= 0
+            assert live.any(), "empty batch"
+            cells, bases = ent_cell[b][live], ent_base[b][live]
+            rows = np.array([base_to_row[int(x)] for x in bases])
+            assert len(set(rows.tolist())) == rows.size, "a row twice in one batch"
+            assert np.array_equal(c2d[cells, i], rows), "entry does not belong to its row / local index"
+            seen[cells, i] += 1
+            for r, c in zip(rows.tolist(), cells.tolist()):
+                assert last.get((r, i), -1) < c, "cells of a row out of order"
+                last[(r, i)] = c
+            per_i.setdefault(i, []).append(rows)
+        assert sorted(per_i) == sorted(set(per_i)), "batches of one local index are contiguous"
+        for i, lst in per_i.items():
+            allr = np.concatenate(lst)
+            mult = np.unique(allr, return_counts=True)[1].max()
+            assert len(lst) == max(-(-allr.size // 32), mult), "not the minimum number of batches"
+    assert np.all(seen == 1), "every (cell, local index) pair exactly once"
