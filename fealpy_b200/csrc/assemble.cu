@@ -701,56 +701,47 @@ static void a4_reduced_table(const double* Ms, const double* Mm, A4Tables<L, A4G
     }
 }
 
-// columns [J0, J1) of element row I for one (row, cell) entry
-template <int TD, int L, typename SlotT, int I, int J0, int J1, typename TabT>
+template <int TD, int L, typename SlotT, int I, typename TabT>
 __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[A4Geo<TD>::NH],
                                        const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
   constexpr int NH = A4Geo<TD>::NH;
   using SR = SlotRec<SlotT, L>;
-  // columns in chunks of JC independent FMA chains.  (Tried and measured, profiles/r01_tune_asm_v4*.txt:
-  // chunks of 2, 5 or 10 make no difference; chunks separated by warp barriers to cap registers are slower.)
-  constexpr int NJ = J1 - J0;
-  constexpr int JC = (NJ % 5 == 0) ? 5 : ((NJ % 4 == 0) ? 4 : (NJ < 3 ? NJ : 3));
+  // columns in chunks of JC independent FMA chains.  (Tried and measured, profiles/r01_tune_asm_v4*.txt: chunks
+  // of 2, 5 or 10 make no difference; chunks separated by warp barriers to cap registers at 128 are slower;
+  // a PAIR of warps per tile, each on half of the columns (commit 16a3237: 16 warps/SM, 128 registers),
+  // runs in the same time -- the LSU data pipe goes from 58 % to 73 % busy because both warps read the
+  // entry and geometry records.  The kernel is bound by shared-memory wavefronts, not by latency.)
+#ifdef FB2_ASM4_JC
+  constexpr int JC = (L % FB2_ASM4_JC == 0) ? FB2_ASM4_JC : ((L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3));
+#else
+  constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
+#endif
 #pragma unroll
-  for (int j0 = J0; j0 < J1; j0 += JC) {
+  for (int j0 = 0; j0 < L; j0 += JC) {
     double val[JC];
 #pragma unroll
     for (int jj = 0; jj < JC; ++jj) {
       double s0 = 0.0, s1 = 0.0;
-      if (j0 + jj < J1) {
 #pragma unroll
-        for (int t = 0; t < NH; t += 2) {
-          s0 += tb.T[I][j0 + jj][t] * h[t];
-          if (t + 1 < NH) s1 += tb.T[I][j0 + jj][t + 1] * h[t + 1];
-        }
+      for (int t = 0; t < NH; t += 2) {
+        s0 += tb.T[I][j0 + jj][t] * h[t];
+        if (t + 1 < NH) s1 += tb.T[I][j0 + jj][t + 1] * h[t + 1];
       }
       val[jj] = s0 + s1;
     }
     double old[JC];
 #pragma unroll
-    for (int jj = 0; jj < JC; ++jj)
-      if (j0 + jj < J1) old[jj] = my[SR::get(sw, j0 + jj)];
+    for (int jj = 0; jj < JC; ++jj) old[jj] = my[SR::get(sw, j0 + jj)];
 #pragma unroll
-    for (int jj = 0; jj < JC; ++jj)
-      if (j0 + jj < J1) my[SR::get(sw, j0 + jj)] = old[jj] + val[jj];
+    for (int jj = 0; jj < JC; ++jj) my[SR::get(sw, j0 + jj)] = old[jj] + val[jj];
   }
 }
 
-// S warps share a tile: warp `part` of the group handles the columns [part*CH, (part+1)*CH) of every entry
-template <int TD, int L, typename SlotT, int S, int I, typename TabT>
-__device__ __forceinline__ void a4_dispatch(int i, int part, const TabT& tb, const double (&h)[A4Geo<TD>::NH],
+template <int TD, int L, typename SlotT, int I, typename TabT>
+__device__ __forceinline__ void a4_dispatch(int i, const TabT& tb, const double (&h)[A4Geo<TD>::NH],
                                             const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
-  if (i == I) {
-    if constexpr (S == 1) {
-      a4_row<TD, L, SlotT, I, 0, L, TabT>(tb, h, sw, my);
-    } else {
-      constexpr int CH = (L + 1) / 2;
-      if (part == 0) a4_row<TD, L, SlotT, I, 0, CH, TabT>(tb, h, sw, my);
-      else a4_row<TD, L, SlotT, I, CH, L, TabT>(tb, h, sw, my);
-    }
-  } else if constexpr (I + 1 < L) {
-    a4_dispatch<TD, L, SlotT, S, I + 1, TabT>(i, part, tb, h, sw, my);
-  }
+  if (i == I) a4_row<TD, L, SlotT, I, TabT>(tb, h, sw, my);
+  else if constexpr (I + 1 < L) a4_dispatch<TD, L, SlotT, I + 1, TabT>(i, tb, h, sw, my);
 }
 
 #ifndef FB2_ASM4_WARPS
@@ -792,15 +783,8 @@ __device__ __forceinline__ int a4_unit(int rec, int part) {      // swizzled 16-
   return rec * QP + ((part + (rec * QP) / 8) & (QP - 1));
 }
 
-// Warp groups.  The tile (accumulators + rings) is what limits residency: 8 tiles of ~28 KB per SM,
-// i.e. 8 warps with one warp per tile -- two per scheduler, issue slots 41 % busy, every kind of
-// latency exposed.  With S = 2 a PAIR of warps owns the tile and works on the SAME batch, each
-// warp on half of the columns of every entry: the two never touch the same accumulator (a batch
-// holds 32 different rows, and the columns of one entry are distinct), so the only coupling is
-// one 64-thread named barrier per batch, which also publishes the cp.async data (warp 0 of the pair
-// feeds the entry ring, warp 1 the geometry ring).  16 warps per SM at <= 128 registers.
-template <int TD, int L, typename SlotT, int D, int S>
-__global__ void __launch_bounds__(FB2_ASM4_WARPS * S * 32, FB2_ASM4_MINBLOCKS)
+template <int TD, int L, typename SlotT, int D>
+__global__ void __launch_bounds__(FB2_ASM4_WARPS * 32, FB2_ASM4_MINBLOCKS)
 assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_constant__ A4Tables<L, A4Geo<TD>::NH> tb) {
   using GEO = A4Geo<TD>;
   constexpr int NH = GEO::NH, HS = GEO::HS, QP = GEO::QP;
@@ -810,12 +794,10 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
   constexpr int ENT_CHUNKS = ENT_BYTES / 16;
   extern __shared__ __align__(16) double sm4[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int grp = wid / S, part = wid - grp * S;                // tile slot inside the CTA, role inside the group
-  const int tile = blockIdx.x * FB2_ASM4_WARPS + grp;
-  if (tile >= a.ntile) return;                                  // whole group leaves together
-  const bool feeds_entries = part == 0, feeds_geometry = part == S - 1;
-  const size_t per_tile = (size_t)a.acc_stride + NHST * 32 * HS + NEST * (ENT_BYTES / 8);
-  double* acc = sm4 + (size_t)grp * per_tile;                   // this group's private tile ...
+  const int tile = blockIdx.x * FB2_ASM4_WARPS + wid;
+  if (tile >= a.ntile) return;
+  const size_t per_warp = (size_t)a.acc_stride + NHST * 32 * HS + NEST * (ENT_BYTES / 8);
+  double* acc = sm4 + (size_t)wid * per_warp;                   // this warp's private tile ...
   double* hring = acc + a.acc_stride;                           // ... its geometry stages ...
   unsigned char* ering = reinterpret_cast<unsigned char*>(hring + NHST * 32 * HS);   // ... and its entry slots
   const int64_t r0 = a.blk_row[tile], r1 = a.blk_row[tile + 1];
@@ -823,10 +805,6 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
   const int nval = (int)(a.crow[r1] - v0);
   const int64_t b0 = a.batch_ptr[tile], b1 = a.batch_ptr[tile + 1];
 
-  auto group_sync = [&]() {
-    __syncwarp();
-    if constexpr (S > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(S * 32) : "memory");
-  };
   auto issue_entries = [&](int64_t b, int slot) {               // 36 x 16 B for tet P2: two cp.async per lane
     unsigned char* dst = ering + slot * ENT_BYTES;
 #pragma unroll
@@ -846,42 +824,38 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
     double* dst = hring + hslot * 32 * HS;
 #pragma unroll
     for (int r = 0; r < QP; ++r) {
-      const int idx = r * 32 + lane, rec = idx / QP, prt = idx % QP;
+      const int idx = r * 32 + lane, rec = idx / QP, part = idx % QP;
       const int c = cells[rec];
-      if (c >= 0) cp_async16(dst + 2 * a4_unit<QP>(rec, prt), a.H + (int64_t)c * HS + 2 * prt);
+      if (c >= 0) cp_async16(dst + 2 * a4_unit<QP>(rec, part), a.H + (int64_t)c * HS + 2 * part);
     }
   };
 
   // prologue: entries of the first 2D batches, then the geometry of the first D
-  if (feeds_entries) {
-    for (int k = 0; k < 2 * D; ++k)
-      if (b0 + k < b1) issue_entries(b0 + k, k);
-    cp_async_commit();
-  }
-  for (int t = part * 32 + lane; t < nval; t += 32 * S) acc[t] = 0.0;
+  for (int k = 0; k < 2 * D; ++k)
+    if (b0 + k < b1) issue_entries(b0 + k, k);
+  cp_async_commit();
+  for (int t = lane; t < nval; t += 32) acc[t] = 0.0;
   int iq[D];                                                    // local index i of batches b .. b+D-1
 #pragma unroll
   for (int k = 0; k < D; ++k) iq[k] = (b0 + k < b1) ? a.batch_i[b0 + k] : 0;
   cp_async_wait<0>();
-  group_sync();
-  if (feeds_geometry) {
+  __syncwarp();
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-      if (b0 + k < b1) issue_geometry(k, k);
-      cp_async_commit();
-    }
+  for (int k = 0; k < D; ++k) {
+    if (b0 + k < b1) issue_geometry(k, k);
+    cp_async_commit();
   }
   int hs = 0, es = 0;                                           // ring positions of batch b
   for (int64_t b = b0; b < b1; ++b) {
-    cp_async_wait<D - 1>();                                     // (a warp without groups in flight passes through)
-    group_sync();                                               // G_{b-D} visible to the group; everyone is done with batch b-1
+    cp_async_wait<D - 1>();
+    __syncwarp();                                               // G_{b-D} visible to all lanes; everyone is done with batch b-1
     {
       int hn = hs + D; if (hn >= NHST) hn -= NHST;              // == stage of batch b-1: free
       int en = es + D; if (en >= NEST) en -= NEST;
       int e2 = es + 2 * D; if (e2 >= NEST) e2 -= NEST;          // == slot of batch b-1: free
-      if (feeds_entries && b + 2 * D < b1) issue_entries(b + 2 * D, e2);
-      if (feeds_geometry && b + D < b1) issue_geometry(en, hn);
-      if (feeds_entries || feeds_geometry) cp_async_commit();
+      if (b + 2 * D < b1) issue_entries(b + 2 * D, e2);
+      if (b + D < b1) issue_geometry(en, hn);
+      cp_async_commit();
     }
     const int i = iq[0];
 #pragma unroll
@@ -906,15 +880,15 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
 #pragma unroll
         for (int t = 0; t < NH; ++t) h[t] = hh[t];
       }
-      a4_dispatch<TD, L, SlotT, S, 0>(i, part, tb, h, sw, acc + base);
+      a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, acc + base);
     }
     if (++hs == NHST) hs = 0;
     if (++es == NEST) es = 0;
   }
   cp_async_wait<0>();
-  group_sync();
+  __syncwarp();
   double* out = a.values + v0;
-  for (int t = part * 32 + lane; t < nval; t += 32 * S) out[t] = acc[t];
+  for (int t = lane; t < nval; t += 32) out[t] = acc[t];
 }
 
 // per-cell record H = (kd * g_mn for 1 <= m <= n <= TD, km * |K|), padded to a multiple of 2 doubles
@@ -991,29 +965,27 @@ static int launch_asm4(Asm4Args a, int slot_bytes, cudaStream_t s) {
   A4Tables<L, GEO::NH> tb;
   a4_reduced_table<TD, L>(a.Ms_host, a.Mm_host, tb);
   static const int depth = [] { const char* e = getenv("FB2_ASM4_DEPTH"); const int d = e ? atoi(e) : 1; return d == 2 ? 2 : 1; }();
-  static const int split = [] { const char* e = getenv("FB2_ASM4_SPLIT"); const int d = e ? atoi(e) : 2; return d == 1 ? 1 : 2; }();
   if (a.tile + a.max_row > 65535) return fail(ERR_UNSUPPORTED, "assemble v4: tile offsets exceed 16 bits");
   const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
   if (grid == 0) return OK;
   const int words = slot_stride(L, slot_bytes) * slot_bytes / 4;
-  // per tile: accumulators + (D+1) geometry stages + (2D+1) entry slots
-  const size_t per_tile = (size_t)(a.acc_stride + (depth + 1) * 32 * GEO::HS) * 8 + (size_t)(2 * depth + 1) * (192 + 128 * words);
-  const size_t smem = (size_t)FB2_ASM4_WARPS * per_tile;
+  // per warp: accumulator tile + (D+1) geometry stages + (2D+1) entry slots
+  const size_t per_warp = (size_t)(a.acc_stride + (depth + 1) * 32 * GEO::HS) * 8 + (size_t)(2 * depth + 1) * (192 + 128 * words);
+  const size_t smem = (size_t)FB2_ASM4_WARPS * per_warp;
   if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble v4: tiles do not fit shared memory (tile=%d max_row=%d)", a.tile, a.max_row);
-#define FB2_A4_LAUNCH(SLOT, DD, SS)                                                                  \
+#define FB2_A4_LAUNCH(KERN)                                                                          \
   do {                                                                                               \
-    auto k = assemble_const_v4_kernel<TD, L, SLOT, DD, SS>;                                          \
+    auto k = KERN;                                                                                   \
     FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    k<<<grid, FB2_ASM4_WARPS * SS * 32, smem, s>>>(a, tb);                                           \
+    k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a, tb);                                                \
   } while (0)
-#define FB2_A4_PICK(SLOT)                                                                            \
-  do {                                                                                               \
-    if (split == 2) { if (depth == 1) FB2_A4_LAUNCH(SLOT, 1, 2); else FB2_A4_LAUNCH(SLOT, 2, 2); }   \
-    else { if (depth == 1) FB2_A4_LAUNCH(SLOT, 1, 1); else FB2_A4_LAUNCH(SLOT, 2, 1); }              \
-  } while (0)
-  if (slot_bytes == 1) FB2_A4_PICK(uint8_t);
-  else FB2_A4_PICK(uint16_t);
-#undef FB2_A4_PICK
+  if (slot_bytes == 1) {
+    if (depth == 1) FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint8_t, 1>));
+    else FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint8_t, 2>));
+  } else {
+    if (depth == 1) FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint16_t, 1>));
+    else FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint16_t, 2>));
+  }
 #undef FB2_A4_LAUNCH
   FB2_LAUNCH_CHECK();
   return OK;
