@@ -43,8 +43,8 @@ SIGNATURES = {
     "fb2_coo_fill": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _i32, _p, _p]),
     "fb2_coo_reduce": (_i32, [_p, _p, _i64, _p, _p, _p]),
     "fb2_sym_workspace_bytes": (_sz, [_i64, _i32, _i64]),
-    "fb2_sym_count": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _p]),
-    "fb2_sym_fill": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _i32, _p]),
+    "fb2_sym_count": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fb2_sym_fill": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "fb2_slot_stride": (_i32, [_i32, _i32]),
     "fb2_assemble_scalar_const": (_i32, [_i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _i32, _i32, _p, _p,
                                          _f64, _p, _f64, _p, _p, _p]),

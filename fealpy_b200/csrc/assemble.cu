@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
                                                                   const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair,
                                                                   const int64_t* __restrict__ crow, int* __restrict__ rowlen,
                                                                   int* __restrict__ col, SlotT* __restrict__ slots, int slot_stride,
-                                                                  int* __restrict__ err) {
+                                                                  int* __restrict__ err, uint32_t* __restrict__ stash) {
   __shared__ uint64_t buf_all[SYM_WARPS][SYM_CAP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint64_t* buf = buf_all[wid];
@@ -122,17 +122,45 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
         head = (k == 0) || ((key >> SYM_KBITS) != (buf[k - 1] >> SYM_KBITS));
       }
       const uint32_t hb = __ballot_sync(0xffffffffu, head);
-      if (FILL && k < ncand) {
+      if (k < ncand) {
         const int rank = running + __popc(hb & lt) + (head ? 1 : 0) - 1;
-        if (head) col[cbase + rank] = (int)(key >> SYM_KBITS);
         const int kk = (int)(key & ((1u << SYM_KBITS) - 1u));      // candidate index = pair_local * L + j
-        const int pl = kk / L;
-        slots[(a0 + pl) * slot_stride + (kk - pl * L)] = (SlotT)rank;
+        if (FILL) {
+          if (head) col[cbase + rank] = (int)(key >> SYM_KBITS);
+          const int pl = kk / L;
+          slots[(a0 + pl) * slot_stride + (kk - pl * L)] = (SlotT)rank;
+        } else if (stash) {                        // sorted order kept for sym_replay_kernel: the fill pass need not sort again
+          stash[a0 * L + k] = ((uint32_t)rank << SYM_KBITS) | (uint32_t)kk;
+        }
       }
       running += __popc(hb);
     }
     if (!FILL && lane == 0) rowlen[r] = running;
     __syncwarp();
+  }
+}
+
+// fill pass from the stash of the count pass: (rank, candidate) in sorted order per row -- no sort,
+// one warp per row, coalesced reads; the column of a head candidate is re-gathered from cell2dof
+template <typename SlotT>
+__global__ void __launch_bounds__(256) sym_replay_kernel(const int* __restrict__ c2d, int L, int64_t gdof, const int64_t* __restrict__ adj_ptr,
+                                                         const int* __restrict__ adj_pair, const int64_t* __restrict__ crow,
+                                                         const uint32_t* __restrict__ stash, int* __restrict__ col,
+                                                         SlotT* __restrict__ slots, int slot_stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < gdof; r += nwarp) {
+    const int64_t a0 = adj_ptr[r];
+    const int ncand = (int)(adj_ptr[r + 1] - a0) * L;
+    const int64_t cbase = crow[r];
+    const uint32_t* st = stash + a0 * L;
+    for (int k = lane; k < ncand; k += 32) {
+      const uint32_t e = st[k];
+      const int rank = (int)(e >> SYM_KBITS), kk = (int)(e & ((1u << SYM_KBITS) - 1u));
+      const int pl = kk / L, j = kk - pl * L;
+      slots[(a0 + pl) * slot_stride + j] = (SlotT)rank;
+      if (k == 0 || (int)(st[k - 1] >> SYM_KBITS) != rank) col[cbase + rank] = c2d[(int64_t)(adj_pair[a0 + pl] / L) * L + j];
+    }
   }
 }
 
@@ -155,7 +183,7 @@ size_t sym_workspace_bytes(int64_t NC, int L, int64_t gdof) {
 }
 
 int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, int64_t* crow, int64_t* nnz_host,
-              int* max_row_host, void* ws, cudaStream_t s) {
+              int* max_row_host, uint32_t* stash, void* ws, cudaStream_t s) {
   const int64_t npair = NC * L;
   if (npair >= ((int64_t)1 << 31)) return fail(ERR_UNSUPPORTED, "sym_count: NC*ldof=%lld exceeds int32 pair ids", (long long)npair);
   Carver c(ws);
@@ -175,7 +203,7 @@ int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr,
   int* rowlen = deg;
   const unsigned nb = (unsigned)std::min<int64_t>(ceil_div(gdof, SYM_WARPS), (int64_t)kNumSM * 16);
   if (gdof > 0) {
-    sym_rows_kernel<false, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, nullptr, rowlen, nullptr, nullptr, 0, cursor);
+    sym_rows_kernel<false, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, nullptr, rowlen, nullptr, nullptr, 0, cursor, stash);
     max_kernel<<<grid_for(gdof), 256, 0, s>>>(rowlen, gdof, cursor + 1);
   }
   FB2_LAUNCH_CHECK();
@@ -190,14 +218,23 @@ int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr,
 }
 
 int sym_fill(const int* c2d, int64_t NC, int L, int64_t gdof, const int64_t* adj_ptr, const int* adj_pair, const int64_t* crow,
-             int* col, void* slots, int slot_bytes, cudaStream_t s) {
+             int* col, void* slots, int slot_bytes, const uint32_t* stash, cudaStream_t s) {
   if (gdof <= 0) return OK;
+  if (stash) {
+    if (slot_bytes != 1 && slot_bytes != 2) return fail(ERR_INVALID, "sym_fill: slot_bytes must be 1 or 2");
+    const int st = slot_stride(L, slot_bytes);
+    const unsigned g = (unsigned)std::min<int64_t>(ceil_div(gdof, 8), (int64_t)kNumSM * 8);
+    if (slot_bytes == 1) sym_replay_kernel<uint8_t><<<g, 256, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, stash, col, (uint8_t*)slots, st);
+    else sym_replay_kernel<uint16_t><<<g, 256, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, stash, col, (uint16_t*)slots, st);
+    FB2_LAUNCH_CHECK();
+    return OK;
+  }
   const unsigned nb = (unsigned)std::min<int64_t>(ceil_div(gdof, SYM_WARPS), (int64_t)kNumSM * 16);
   const int stride = slot_stride(L, slot_bytes);
   if (slot_bytes == 1)
-    sym_rows_kernel<true, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint8_t*)slots, stride, nullptr);
+    sym_rows_kernel<true, uint8_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint8_t*)slots, stride, nullptr, nullptr);
   else if (slot_bytes == 2)
-    sym_rows_kernel<true, uint16_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint16_t*)slots, stride, nullptr);
+    sym_rows_kernel<true, uint16_t><<<nb, SYM_WARPS * 32, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, nullptr, col, (uint16_t*)slots, stride, nullptr, nullptr);
   else
     return fail(ERR_INVALID, "sym_fill: slot_bytes must be 1 or 2");
   FB2_LAUNCH_CHECK();

@@ -90,14 +90,19 @@ def symbolic_pattern(space):
     crow = torch.empty(gdof + 1, dtype=torch.int64, device=dev)
     ws = _lib.workspace(lib.fb2_sym_workspace_bytes(NC, L, gdof), dev)
     nnz, max_row = C.c_int64(0), C.c_int32(0)
+    try:        # scratch for the sorted candidate order (4 bytes per (cell, i, j)): the fill pass then need not sort again
+        stash = torch.empty(NC * L * L, dtype=torch.int32, device=dev)
+    except torch.cuda.OutOfMemoryError:
+        stash = None
     _lib.call("fb2_sym_count", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow),
-              C.byref(nnz), C.byref(max_row), _lib.ptr(ws), _lib.stream())
+              C.byref(nnz), C.byref(max_row), _lib.ptr(stash), _lib.ptr(ws), _lib.stream())
     slot_bytes = 1 if max_row.value <= 255 else 2
     col = torch.empty(nnz.value, dtype=torch.int32, device=dev)
     stride = lib.fb2_slot_stride(L, slot_bytes)
     slots = torch.zeros(NC * L * stride, dtype=torch.uint8 if slot_bytes == 1 else torch.int16, device=dev)
     _lib.call("fb2_sym_fill", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow), _lib.ptr(col),
-              _lib.ptr(slots), slot_bytes, _lib.stream())
+              _lib.ptr(slots), slot_bytes, _lib.ptr(stash), _lib.stream())
+    del stash
     blk_row, nblk = row_tiling(crow, gdof, nnz.value, ASM_TILE)
     cache = dict(adj_ptr=adj_ptr, adj_pair=adj_pair, crow=crow, col=col, slots=slots, slot_bytes=slot_bytes,
                  max_row=max_row.value, nnz=nnz.value, NC=NC, L=L, gdof=gdof, blk_row=blk_row, nblk=nblk, tile=ASM_TILE)
