@@ -625,14 +625,16 @@ namespace fb2 {
 // Lane = row while walking the adjacency (sorted by (i, cell) per row, so the run of local index i
 // is found by advancing a per-lane cursor); lane i keeps the totals of local index i.
 constexpr int A4_MAXL = 32;
+constexpr int A4_BASE_BITS = 12;     // entry word = tile offset of the row (12 bits) | first-touch mask (ldof <= 20 bits)
+constexpr int A4_MAXROW = 1024;      // longest row the first-touch bitmap covers (SYM_CAP bounds a row anyway)
 
 template <bool FILL>
 __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int32_t* __restrict__ blk_row, const int64_t* __restrict__ crow,
                                                             const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair, int L,
                                                             int* __restrict__ nbatch_of_tile, const int64_t* __restrict__ batch_ptr,
                                                             unsigned char* __restrict__ batch_i, int* __restrict__ ent_cell,
-                                                            unsigned short* __restrict__ ent_base, uint32_t* __restrict__ ent_slots,
-                                                            const uint32_t* __restrict__ slot_words, int slot_nwords) {
+                                                            uint32_t* __restrict__ ent_base, uint32_t* __restrict__ ent_slots,
+                                                            const uint32_t* __restrict__ slot_words, int slot_nwords, int slot_bytes) {
   constexpr unsigned FULL = 0xffffffffu;
   const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
@@ -672,8 +674,14 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
   for (int64_t rb = r0; rb < r1; rb += 32) {
     const int64_t r = rb + lane;
     int64_t q = 0, qe = 0;
-    unsigned short base = 0;
-    if (r < r1) { q = adj_ptr[r]; qe = adj_ptr[r + 1]; base = (unsigned short)(crow[r] - v0); }
+    uint32_t base = 0;
+    if (r < r1) { q = adj_ptr[r]; qe = adj_ptr[r + 1]; base = (uint32_t)(crow[r] - v0); }
+    // first-touch flags: the lane walks its row in execution order ((i, cell), see the rotation below), so it knows
+    // which (entry, column) is the first contribution to a value -- the numeric kernel stores that one instead of
+    // load-add-store, and the tile needs no zero fill
+    uint32_t touched[A4_MAXROW / 32];
+#pragma unroll
+    for (int w = 0; w < A4_MAXROW / 32; ++w) touched[w] = 0;
     for (int i = 0; i < L; ++i) {
       int m = 0;                                 // this row's run of local index i
       while (q + m < qe && adj_pair[q + m] % L == i) ++m;
@@ -693,8 +701,14 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
           const int k = u < wrap ? k0 + (m - wrap) + u : k0 + (u - wrap);
           const int64_t e = (b0 + offi + k % Bi) * 32 + k / Bi;
           ent_cell[e] = adj_pair[q + u] / L;
-          ent_base[e] = base;
+          uint32_t first = 0;
           for (int w = 0; w < slot_nwords; ++w) ent_slots[e * slot_nwords + w] = slot_words[(q + u) * slot_nwords + w];
+          for (int j = 0; j < L; ++j) {
+            const uint32_t wd = slot_words[(q + u) * slot_nwords + (slot_bytes == 1 ? (j >> 2) : (j >> 1))];
+            const int sl = slot_bytes == 1 ? (wd >> ((j & 3) * 8)) & 0xffu : (wd >> ((j & 1) * 16)) & 0xffffu;
+            if (!((touched[sl >> 5] >> (sl & 31)) & 1u)) { first |= 1u << j; touched[sl >> 5] |= 1u << (sl & 31); }
+          }
+          ent_base[e] = base | (first << A4_BASE_BITS);
         }
       }
       q += m;
@@ -740,7 +754,7 @@ static void a4_reduced_table(const double* Ms, const double* Mm, A4Tables<L, A4G
 
 template <int TD, int L, typename SlotT, int I, typename TabT>
 __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[A4Geo<TD>::NH],
-                                       const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
+                                       const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], uint32_t first, double* __restrict__ my) {
   constexpr int NH = A4Geo<TD>::NH;
   using SR = SlotRec<SlotT, L>;
   // columns in chunks of JC independent FMA chains.  (Tried and measured, profiles/r01_tune_asm_v4*.txt: chunks
@@ -768,7 +782,7 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[A4Geo<T
     }
     double old[JC];
 #pragma unroll
-    for (int jj = 0; jj < JC; ++jj) old[jj] = my[SR::get(sw, j0 + jj)];
+    for (int jj = 0; jj < JC; ++jj) old[jj] = ((first >> (j0 + jj)) & 1u) ? 0.0 : my[SR::get(sw, j0 + jj)];
 #pragma unroll
     for (int jj = 0; jj < JC; ++jj) my[SR::get(sw, j0 + jj)] = old[jj] + val[jj];
   }
@@ -776,9 +790,9 @@ __device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[A4Geo<T
 
 template <int TD, int L, typename SlotT, int I, typename TabT>
 __device__ __forceinline__ void a4_dispatch(int i, const TabT& tb, const double (&h)[A4Geo<TD>::NH],
-                                            const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], double* __restrict__ my) {
-  if (i == I) a4_row<TD, L, SlotT, I, TabT>(tb, h, sw, my);
-  else if constexpr (I + 1 < L) a4_dispatch<TD, L, SlotT, I + 1, TabT>(i, tb, h, sw, my);
+                                            const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], uint32_t first, double* __restrict__ my) {
+  if (i == I) a4_row<TD, L, SlotT, I, TabT>(tb, h, sw, first, my);
+  else if constexpr (I + 1 < L) a4_dispatch<TD, L, SlotT, I + 1, TabT>(i, tb, h, sw, first, my);
 }
 
 #ifndef FB2_ASM4_WARPS
@@ -827,7 +841,7 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
   constexpr int NH = GEO::NH, HS = GEO::HS, QP = GEO::QP;
   using SR = SlotRec<SlotT, L>;
   constexpr int NHST = D + 1, NEST = 2 * D + 1;                 // ring depths: geometry stages, entry slots
-  constexpr int ENT_BYTES = 192 + 128 * SR::WORDS;              // 32 x (cell int32 | base uint16 | slot words)
+  constexpr int ENT_BYTES = 256 + 128 * SR::WORDS;              // 32 x (cell int32 | base+first-touch uint32 | slot words)
   constexpr int ENT_CHUNKS = ENT_BYTES / 16;
   extern __shared__ __align__(16) double sm4[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -850,8 +864,8 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
       if (q < ENT_CHUNKS) {
         const unsigned char* src;
         if (q < 8) src = reinterpret_cast<const unsigned char*>(a.ent_cell + b * 32) + q * 16;
-        else if (q < 12) src = reinterpret_cast<const unsigned char*>(a.ent_base + b * 32) + (q - 8) * 16;
-        else src = reinterpret_cast<const unsigned char*>(a.ent_slots + b * 32 * SR::WORDS) + (q - 12) * 16;
+        else if (q < 16) src = reinterpret_cast<const unsigned char*>(a.ent_base + b * 32) + (q - 8) * 16;
+        else src = reinterpret_cast<const unsigned char*>(a.ent_slots + b * 32 * SR::WORDS) + (q - 16) * 16;
         cp_async16(dst + q * 16, src);
       }
     }
@@ -870,8 +884,7 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
   // prologue: entries of the first 2D batches, then the geometry of the first D
   for (int k = 0; k < 2 * D; ++k)
     if (b0 + k < b1) issue_entries(b0 + k, k);
-  cp_async_commit();
-  for (int t = lane; t < nval; t += 32) acc[t] = 0.0;
+  cp_async_commit();                                            // (no zero fill of the tile: first-touch entries store)
   int iq[D];                                                    // local index i of batches b .. b+D-1
 #pragma unroll
   for (int k = 0; k < D; ++k) iq[k] = (b0 + k < b1) ? a.batch_i[b0 + k] : 0;
@@ -901,10 +914,11 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
     const unsigned char* ent = ering + es * ENT_BYTES;
     const int cell = reinterpret_cast<const int*>(ent)[lane];
     if (cell >= 0) {
-      const int base = reinterpret_cast<const unsigned short*>(ent + 128)[lane];
+      const uint32_t bw = reinterpret_cast<const uint32_t*>(ent + 128)[lane];
+      const int base = (int)(bw & ((1u << A4_BASE_BITS) - 1u));
       uint32_t sw[SR::WORDS];
 #pragma unroll
-      for (int w = 0; w < SR::WORDS; ++w) sw[w] = reinterpret_cast<const uint32_t*>(ent + 192)[lane * SR::WORDS + w];
+      for (int w = 0; w < SR::WORDS; ++w) sw[w] = reinterpret_cast<const uint32_t*>(ent + 256)[lane * SR::WORDS + w];
       double h[NH];
       {
         const double* hst = hring + hs * 32 * HS;
@@ -917,7 +931,7 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
 #pragma unroll
         for (int t = 0; t < NH; ++t) h[t] = hh[t];
       }
-      a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, acc + base);
+      a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, bw >> A4_BASE_BITS, acc + base);
     }
     if (++hs == NHST) hs = 0;
     if (++es == NEST) es = 0;
@@ -970,7 +984,7 @@ int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, cons
   void* scan_ws = c.take<char>(scan_workspace_bytes(ntile + 1));
   if (ntile > 0)
     asm4_schedule_kernel<false><<<(unsigned)ceil_div((int64_t)ntile * 32, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, cnt, nullptr,
-                                                                               nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+                                                                               nullptr, nullptr, nullptr, nullptr, nullptr, 0, 1);
   FB2_LAUNCH_CHECK();
   FB2_TRY(exclusive_scan_i32(cnt, batch_ptr, ntile, true, scan_ws, s));
   FB2_CUDA(cudaMemcpyAsync(nbatch_host, batch_ptr + ntile, 8, cudaMemcpyDeviceToHost, s));
@@ -979,13 +993,13 @@ int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, cons
 }
 
 int asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
-                   const int64_t* batch_ptr, unsigned char* batch_i, int* ent_cell, unsigned short* ent_base, uint32_t* ent_slots,
+                   const int64_t* batch_ptr, unsigned char* batch_i, int* ent_cell, uint32_t* ent_base, uint32_t* ent_slots,
                    const void* slots, int slot_bytes, cudaStream_t s) {
   if (ntile <= 0) return OK;
   const int nwords = slot_stride(L, slot_bytes) * slot_bytes / 4;
   asm4_schedule_kernel<true><<<(unsigned)ceil_div((int64_t)ntile * 32, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, nullptr, batch_ptr,
                                                                             batch_i, ent_cell, ent_base, ent_slots,
-                                                                            static_cast<const uint32_t*>(slots), nwords);
+                                                                            static_cast<const uint32_t*>(slots), nwords, slot_bytes);
   FB2_LAUNCH_CHECK();
   return OK;
 }
@@ -1002,12 +1016,13 @@ static int launch_asm4(Asm4Args a, int slot_bytes, cudaStream_t s) {
   A4Tables<L, GEO::NH> tb;
   a4_reduced_table<TD, L>(a.Ms_host, a.Mm_host, tb);
   static const int depth = [] { const char* e = getenv("FB2_ASM4_DEPTH"); const int d = e ? atoi(e) : 1; return d == 2 ? 2 : 1; }();
-  if (a.tile + a.max_row > 65535) return fail(ERR_UNSUPPORTED, "assemble v4: tile offsets exceed 16 bits");
+  if (a.tile + a.max_row >= (1 << A4_BASE_BITS) || a.max_row > A4_MAXROW)
+    return fail(ERR_UNSUPPORTED, "assemble v4: tile offsets exceed %d bits (tile=%d max_row=%d)", A4_BASE_BITS, a.tile, a.max_row);
   const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
   if (grid == 0) return OK;
   const int words = slot_stride(L, slot_bytes) * slot_bytes / 4;
   // per warp: accumulator tile + (D+1) geometry stages + (2D+1) entry slots
-  const size_t per_warp = (size_t)(a.acc_stride + (depth + 1) * 32 * GEO::HS) * 8 + (size_t)(2 * depth + 1) * (192 + 128 * words);
+  const size_t per_warp = (size_t)(a.acc_stride + (depth + 1) * 32 * GEO::HS) * 8 + (size_t)(2 * depth + 1) * (256 + 128 * words);
   const size_t smem = (size_t)FB2_ASM4_WARPS * per_warp;
   if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble v4: tiles do not fit shared memory (tile=%d max_row=%d)", a.tile, a.max_row);
 #define FB2_A4_LAUNCH(KERN)                                                                          \

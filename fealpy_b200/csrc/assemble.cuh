@@ -49,7 +49,7 @@ struct Asm4Args {
   const int64_t* batch_ptr;     // (ntile+1)
   const unsigned char* batch_i; // (nbatch) local index shared by the batch
   const int* ent_cell;          // (nbatch*32) cell id or -1 (padding)
-  const unsigned short* ent_base;   // (nbatch*32) offset of the entry's row inside the tile
+  const uint32_t* ent_base;         // (nbatch*32) offset of the entry's row inside the tile (12 bits) | first-touch column mask
   const uint32_t* ent_slots;    // (nbatch*32, words) packed slot record
   const double* Ms;             // device tables (null = term absent)
   const double* Mm;
@@ -66,7 +66,7 @@ size_t asm4_workspace_bytes(int ntile);
 int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
                     int64_t* batch_ptr, int64_t* nbatch_host, void* ws, cudaStream_t s);
 int asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
-                   const int64_t* batch_ptr, unsigned char* batch_i, int* ent_cell, unsigned short* ent_base, uint32_t* ent_slots,
+                   const int64_t* batch_ptr, unsigned char* batch_i, int* ent_cell, uint32_t* ent_base, uint32_t* ent_slots,
                    const void* slots, int slot_bytes, cudaStream_t s);
 int assemble_v4(int TD, int p, const Asm4Args& a, int slot_bytes, cudaStream_t s);
 size_t sym_workspace_bytes(int64_t NC, int L, int64_t gdof);

@@ -154,14 +154,14 @@ int fb2_asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, 
   return asm4_plan_count(ntile, blk_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, nbatch_host, ws, S(stream));
 }
 int fb2_asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
-                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, int32_t* ent_cell, uint16_t* ent_base,
+                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, int32_t* ent_cell, uint32_t* ent_base,
                        uint32_t* ent_slots, const void* slots, int slot_bytes, void* stream) {
   return asm4_plan_fill(ntile, blk_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, batch_i, ent_cell, ent_base, ent_slots, slots,
                         slot_bytes, S(stream));
 }
 int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
                                  const int32_t* blk_row, int ntile, int tile, int32_t max_row, const int64_t* batch_ptr,
-                                 const uint8_t* batch_i, const int32_t* ent_cell, const uint16_t* ent_base, const uint32_t* ent_slots,
+                                 const uint8_t* batch_i, const int32_t* ent_cell, const uint32_t* ent_base, const uint32_t* ent_slots,
                                  int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d, const double* coef_d,
                                  double scal_m, const double* coef_m, double* geom_ws, double* values, void* stream) {
   const double *Ms = Ms_host, *Mm = Mm_host;      // only their presence matters on the device side

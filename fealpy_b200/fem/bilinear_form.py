@@ -144,7 +144,7 @@ def asm4_plan(space):
     nwords = lib.fb2_slot_stride(sym["L"], sym["slot_bytes"]) * sym["slot_bytes"] // 4
     batch_i = torch.empty(nb, dtype=torch.uint8, device=dev)
     ent_cell = torch.empty(nb * 32, dtype=torch.int32, device=dev)
-    ent_base = torch.zeros(nb * 32, dtype=torch.int16, device=dev)
+    ent_base = torch.zeros(nb * 32, dtype=torch.int32, device=dev)
     ent_slots = torch.zeros(nb * 32 * nwords, dtype=torch.int32, device=dev)
     _lib.call("fb2_asm4_plan_fill", ntile, _lib.ptr(blk_row), _lib.ptr(sym["crow"]), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
               sym["L"], _lib.ptr(batch_ptr), _lib.ptr(batch_i), _lib.ptr(ent_cell), _lib.ptr(ent_base), _lib.ptr(ent_slots),

@@ -126,16 +126,18 @@ int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int6
  * geom_ws = NC * 2*ceil((TD*(TD+1)/2+1)/2) doubles of scratch for the per-cell geometry (8 per
  * tetrahedron, 4 per triangle).  The element tables are HOST pointers here: they travel in the kernel
  * parameter block (constant bank), which costs no load/store-unit bandwidth.  Pad entries of a
- * batch carry ent_cell = -1. */
+ * batch carry ent_cell = -1.  ent_base[e] = offset of the entry's row inside its tile (low 12 bits:
+ * tile + max_row < 4096) | mask of the columns whose value this entry is the FIRST to touch (bit j + 12):
+ * those are stored, the others load-add-stored, so the accumulator tile needs no zero fill. */
 size_t fb2_asm4_workspace_bytes(int ntile);
 int fb2_asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
                         int ldof, int64_t* batch_ptr, int64_t* nbatch_host, void* ws, void* stream);
 int fb2_asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
-                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, int32_t* ent_cell, uint16_t* ent_base,
+                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, int32_t* ent_cell, uint32_t* ent_base,
                        uint32_t* ent_slots, const void* slots, int slot_bytes, void* stream);
 int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
                                  const int32_t* blk_row, int ntile, int tile, int32_t max_row, const int64_t* batch_ptr,
-                                 const uint8_t* batch_i, const int32_t* ent_cell, const uint16_t* ent_base, const uint32_t* ent_slots,
+                                 const uint8_t* batch_i, const int32_t* ent_cell, const uint32_t* ent_base, const uint32_t* ent_slots,
                                  int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d,
                                  const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* geom_ws, double* values,
                                  void* stream);

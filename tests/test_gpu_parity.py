@@ -556,8 +556,8 @@ def test_relabelled_mesh_matches_oracle(kind, dims, p, U):
 def test_asm4_schedule_invariants(kind, dims, p, tile, U, monkeypatch):
     """the batch schedule of the v4 numeric kernel (csrc/assemble.cu asm4_schedule_kernel), checked entry by entry:
     every (row, cell, i) pair of the mesh exactly once; a batch holds one local index and 32 DIFFERENT rows;
-    every row meets its cells in (i, cell) order; and the number of batches per (tile, i) is the minimum
-    max(ceil(n/32), longest run in one row)."""
+    every row meets its cells in (i, cell) order; the number of batches per (tile, i) is the minimum
+    max(ceil(n/32), longest run in one row); and the first-touch masks mark exactly the first write of every value."""
     from fealpy_b200.mesh import TetrahedronMesh, TriangleMesh
     from fealpy_b200.functionspace import LagrangeFESpace
     from fealpy_b200.fem import bilinear_form as bfm
@@ -573,8 +573,12 @@ def test_asm4_schedule_invariants(kind, dims, p, tile, U, monkeypatch):
     batch_ptr = pl["batch_ptr"].cpu().numpy()
     batch_i = pl["batch_i"].cpu().numpy()
     ent_cell = pl["ent_cell"].cpu().numpy().reshape(-1, 32)
-    ent_base = pl["ent_base"].cpu().numpy().astype(np.uint16).reshape(-1, 32)
+    ent_word = pl["ent_base"].cpu().numpy().astype(np.uint32).reshape(-1, 32)
+    ent_base, ent_first = ent_word & 0xfff, ent_word >> 12
     assert batch_ptr[0] == 0 and batch_ptr[-1] == ent_cell.shape[0] == batch_i.shape[0]
+    sb = sym["slot_bytes"]
+    raw = pl["ent_slots"].cpu().numpy().view(np.uint8 if sb == 1 else np.uint16)
+    ent_slot = raw.reshape(ent_cell.shape[0], 32, -1)[:, :, :L].astype(np.int64)     # (batch, lane, column) -> position in the row
     seen = np.zeros((NC, L), dtype=int)
     for t in range(pl["ntile"]):
         r0, r1 = blk_row[t], blk_row[t + 1]
@@ -582,6 +586,7 @@ def test_asm4_schedule_invariants(kind, dims, p, tile, U, monkeypatch):
         base_to_row = {int(crow[r] - v0): r for r in range(r0, r1) if crow[r + 1] > crow[r]}
         last = {}                                   # (row, i) -> last cell seen, in batch order
         per_i = {}
+        touched = np.zeros(int(crow[r1] - v0), dtype=bool)
         for b in range(batch_ptr[t], batch_ptr[t + 1]):
             i = int(batch_i[b])
             live = ent_cell[b] >= 0
@@ -591,10 +596,16 @@ def test_asm4_schedule_invariants(kind, dims, p, tile, U, monkeypatch):
             assert len(set(rows.tolist())) == rows.size, "a row twice in one batch"
             assert np.array_equal(c2d[cells, i], rows), "entry does not belong to its row / local index"
             seen[cells, i] += 1
+            pos = bases.astype(np.int64)[:, None] + ent_slot[b][live]                  # tile-local value index of every column
+            first = ((ent_first[b][live][:, None] >> np.arange(L)) & 1).astype(bool)
+            assert np.array_equal(first, ~touched[pos]), "first-touch mask != (value not yet written in execution order)"
+            assert np.unique(pos).size == pos.size
+            touched[pos] = True
             for r, c in zip(rows.tolist(), cells.tolist()):
                 assert last.get((r, i), -1) < c, "cells of a row out of order"
                 last[(r, i)] = c
             per_i.setdefault(i, []).append(rows)
+        assert touched.all(), "a value of the tile is never written (the kernel does not zero-fill)"
         assert sorted(per_i) == sorted(set(per_i)), "batches of one local index are contiguous"
         for i, lst in per_i.items():
             allr = np.concatenate(lst)
