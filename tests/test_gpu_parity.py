@@ -612,3 +612,30 @@ def test_asm4_schedule_invariants(kind, dims, p, tile, U, monkeypatch):
             mult = np.unique(allr, return_counts=True)[1].max()
             assert len(lst) == max(-(-allr.size // 32), mult), "not the minimum number of batches"
     assert np.all(seen == 1), "every (cell, local index) pair exactly once"
+
+
+def test_sparse_edge_cases(U):
+    """ragged / degenerate COO inputs through K2 (sort + segmented reduce) against the oracle's coalesce/tocsr:
+    no entries at all, one entry repeated, empty leading / trailing / interior rows, a single dense row."""
+    from oracle import fem_oracle as O
+    from fealpy_b200.sparse import COOTensor
+    rng = np.random.default_rng(5)
+    cases = {
+        "empty": (np.zeros(0, int), np.zeros(0, int), np.zeros(0), (4, 4)),
+        "one_entry_x100": (np.full(100, 2), np.full(100, 1), rng.standard_normal(100), (3, 5)),
+        "ragged": (np.array([5, 5, 2, 2, 2, 7, 5]), np.array([0, 9, 3, 3, 1, 8, 0]), rng.standard_normal(7), (10, 10)),
+        "dense_row": (np.full(4097, 1), rng.permutation(4097), rng.standard_normal(4097), (3, 4097)),
+        "1x1": (np.zeros(3, int), np.zeros(3, int), np.array([1.0, 2.0, 4.0]), (1, 1)),
+    }
+    for name, (r, c, v, shape) in cases.items():
+        idx = torch.tensor(np.stack([r, c]), dtype=torch.int32, device="cuda")       # col keeps the index dtype (coo_tensor.py:137-157)
+        coo = COOTensor(idx, U.t64(v), shape, is_coalesced=False)
+        A = coo.tocsr()
+        crow, col, val = O.tocsr(*O.coalesce(r, c, v), shape[0])
+        assert A.shape == shape and A.nnz == len(col), name
+        assert np.array_equal(A.crow.cpu().numpy(), crow), name
+        assert np.array_equal(A.col.cpu().numpy(), col), name
+        assert np.array_equal(A.values.cpu().numpy(), val), name            # same left-to-right order as np.add.at: bit-exact
+        x = rng.standard_normal(shape[1])
+        y = (A @ U.t64(x)).cpu().numpy()
+        assert np.allclose(y, O.csr_matvec(crow, col, val, x), rtol=0, atol=1e-13 * (1 + np.abs(val).sum())), name
