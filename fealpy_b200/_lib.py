@@ -43,6 +43,9 @@ SIGNATURES = {
     "fb2_coo_fill": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _i32, _p, _p]),
     "fb2_coo_reduce": (_i32, [_p, _p, _i64, _p, _p, _p]),
     "fb2_sym_workspace_bytes": (_sz, [_i64, _i32, _i64]),
+    "fb2_bc_to_points": (_i32, [_i32, _i64, _i32, _p, _p, _p, _p, _p]),
+    "fb2_assemble_elasticity_p1": (_i32, [_i32, _i64, _p, _p, _i32, _i64, _f64, _f64, _f64, _f64, _p, _p, _p, _i32, _p, _i32, _p, _p, _i32,
+                                          _i32, _p, _p, _p]),
     "fb2_sym_count": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "fb2_sym_fill": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "fb2_slot_stride": (_i32, [_i32, _i32]),

@@ -446,41 +446,105 @@ __global__ void __launch_bounds__(128, FB2_ASM_MINBLOCKS) assemble_const_kernel(
 
 // =====================================================================================
 // numeric: generic gather of precomputed element-matrix rows (any integrator, tensor spaces)
-//   one thread per output (tensor) row; scalar row r = row / ncomp (interleaved) or row % gdof
+//   lanes = columns: a group of lt = ldof*ncomp lanes owns one output (tensor) row at a time and walks
+//   its (cell, i) pairs in order; every pair is ONE coalesced read of an element-matrix row (lt
+//   doubles) and lt adds at distinct positions of the row's segment in the CTA tile; eight pairs are
+//   in flight per group.  (The first version had one THREAD per row chasing 8-byte loads.)
+//   scalar row r = row / ncomp (interleaved) or row % gdof (dof_priority)
 // =====================================================================================
-template <typename SlotT>
+//   ETD > 0: P1 linear elasticity on the fly (ldof = ETD+1, ncomp = ETD): the element-matrix entry is
+//   |K| w (d_lam D_i[a] D_j[b] + d_shear D_i[b] D_j[a]) (a != b) resp. |K| w (d_diag D_i[a] D_j[a] + d_shear sum_{z != a}
+//   D_i[z] D_j[z]) from a 13-double (7 in 2-D) per-cell record of grad lambda -- the 1152-byte K_e per cell is never written
+//   or read (fem/linear_elasticity_integrator.py:159-179 with grad phi_i = grad lambda_i)
+template <int N>
+__device__ __forceinline__ double pick(const double (&d)[N], int k) {
+  double v = d[0];
+#pragma unroll
+  for (int z = 1; z < N; ++z) v = (k == z) ? d[z] : v;
+  return v;
+}
+
+template <typename SlotT, int ETD, int NC>
 __global__ void __launch_bounds__(128) assemble_from_ke_kernel(AsmKeArgs a) {
   extern __shared__ __align__(16) double acc[];
-  const int L = a.L, nc = a.ncomp, lt = L * nc;
+  const int L = ETD > 0 ? ETD + 1 : a.L;                   // lanes per group: one per local (scalar) column dof j
+  const int lt = L * NC;
   const int64_t R0 = a.blk_row[blockIdx.x], R1 = a.blk_row[blockIdx.x + 1];
   const int64_t v0 = a.crow_out[R0];
   const int nval = (int)(a.crow_out[R1] - v0);
   for (int t = threadIdx.x; t < nval; t += blockDim.x) acc[t] = 0.0;
   __syncthreads();
   const SlotT* __restrict__ slots = static_cast<const SlotT*>(a.slots);
-  for (int64_t R = R0 + threadIdx.x; R < R1; R += blockDim.x) {
-    int64_t r;
-    int comp;
-    if (nc == 1) { r = R; comp = 0; }
-    else if (a.dof_priority) { comp = (int)(R / a.gdof); r = R - (int64_t)comp * a.gdof; }
-    else { r = R / nc; comp = (int)(R - r * nc); }
-    const int len = (int)(a.crow_s[r + 1] - a.crow_s[r]);
-    double* my = acc + (a.crow_out[R] - v0);
-    const int64_t q0 = a.adj_ptr[r], q1 = a.adj_ptr[r + 1];
-    for (int64_t q = q0; q < q1; ++q) {
-      const int pair = a.adj_pair[q];
-      const int64_t c = pair / L;
-      const int i = pair - (int)c * L;
-      const int lrow = a.dof_priority ? comp * L + i : i * nc + comp;
-      const double* krow = a.Ke + (c * lt + lrow) * (int64_t)lt;
-      const SlotT* sl = slots + q * a.slot_stride;
-      for (int j = 0; j < L; ++j) {
-        const int s = sl[j];
-        for (int b = 0; b < nc; ++b) {
-          const int lcol = a.dof_priority ? b * L + j : j * nc + b;
-          const int pos = a.dof_priority ? b * len + s : s * nc + b;
-          my[pos] += krow[lcol];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int G = 32 / L;                                    // output rows in flight per warp (L <= 20)
+  const int g = lane / L, j = lane - g * L;                // this lane's row group and column dof
+  const uint32_t gmask = ((1u << L) - 1u) << (g * L);
+  if (g < G) {
+    for (int64_t R = R0 + (int64_t)wid * G + g; R < R1; R += (int64_t)nw * G) {
+      int64_t r;
+      int comp;
+      if (NC == 1) { r = R; comp = 0; }
+      else if (a.dof_priority) { comp = (int)(R / a.gdof); r = R - (int64_t)comp * a.gdof; }
+      else { r = R / NC; comp = (int)(R - r * NC); }
+      const int len = (int)(a.crow_s[r + 1] - a.crow_s[r]);
+      double* my = acc + (a.crow_out[R] - v0);
+      const int64_t q0 = a.adj_ptr[r], q1 = a.adj_ptr[r + 1];
+      // the NC entries (row (i, comp), columns (j, b), b < NC) of one (cell, i) pair, and where the first goes
+      auto operand = [&](int64_t q, int pair, double (&kv)[NC], int& sl) {
+        const int64_t c = pair / L;
+        const int i = pair - (int)c * L;
+        if constexpr (ETD > 0) {
+          constexpr int RS = (ETD + 1) * ETD + 1;
+          const double* rec = a.geo + c * RS;
+          double Di[ETD], Dj[ETD];
+#pragma unroll
+          for (int z = 0; z < ETD; ++z) { Di[z] = rec[i * ETD + z]; Dj[z] = rec[j * ETD + z]; }
+          const double cm = rec[RS - 1], dic = pick(Di, comp), djc = pick(Dj, comp);
+          double oth = 0.0;
+#pragma unroll
+          for (int z = 0; z < ETD; ++z) oth += (z == comp) ? 0.0 : a.wsum * (Di[z] * Dj[z]);
+#pragma unroll
+          for (int bb = 0; bb < NC; ++bb) {
+            const double v = (bb == comp) ? a.d_diag * (a.wsum * (dic * djc)) + a.d_shear * oth
+                                          : a.d_lam * (a.wsum * (dic * Dj[bb])) + a.d_shear * (a.wsum * (Di[bb] * djc));
+            kv[bb] = v * cm;
+          }
+        } else {
+          const int lrow = a.dof_priority ? comp * L + i : i * NC + comp;
+          const double* krow = a.Ke + (c * lt + lrow) * (int64_t)lt;
+#pragma unroll
+          for (int bb = 0; bb < NC; ++bb) kv[bb] = krow[a.dof_priority ? bb * L + j : j * NC + bb];
         }
+        sl = slots[q * a.slot_stride + j];
+      };
+      // pairs in chunks of U: the element-matrix rows of a chunk are independent loads (memory-level
+      // parallelism), the adds then run in pair order; the next chunk's pair ids are fetched meanwhile
+      constexpr int U = NC == 1 ? 8 : 4;
+      int pr[U], prn[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) pr[u] = q0 + u < q1 ? a.adj_pair[q0 + u] : 0;
+      for (int64_t q = q0; q < q1; q += U) {
+        double kv[U][NC];
+        int sl[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          sl[u] = 0;
+#pragma unroll
+          for (int bb = 0; bb < NC; ++bb) kv[u][bb] = 0.0;
+          if (q + u < q1) operand(q + u, pr[u], kv[u], sl[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) prn[u] = q + U + u < q1 ? a.adj_pair[q + U + u] : 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (q + u < q1) {
+#pragma unroll
+            for (int bb = 0; bb < NC; ++bb) my[a.dof_priority ? bb * len + sl[u] : sl[u] * NC + bb] += kv[u][bb];
+          }
+          __syncwarp(gmask);                               // the next pair may hit the same entry from another lane
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) pr[u] = prn[u];
       }
     }
   }
@@ -567,6 +631,21 @@ int assemble_const(int TD, int p, const AsmConstArgs& a, int slot_bytes, int max
   }
 }
 
+template <int ETD, int NC>
+static int launch_gather(const AsmKeArgs& a, int slot_bytes, size_t smem, cudaStream_t s) {
+  if (slot_bytes == 1) {
+    auto k = assemble_from_ke_kernel<uint8_t, ETD, NC>;
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)a.nblk, 128, smem, s>>>(a);
+  } else {
+    auto k = assemble_from_ke_kernel<uint16_t, ETD, NC>;
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)a.nblk, 128, smem, s>>>(a);
+  }
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
 int assemble_from_ke(AsmKeArgs a, int slot_bytes, int max_row, cudaStream_t s) {
   if (a.gdof <= 0) return OK;
   const int max_out_row = max_row * a.ncomp;
@@ -575,19 +654,25 @@ int assemble_from_ke(AsmKeArgs a, int slot_bytes, int max_row, cudaStream_t s) {
   a.slot_stride = slot_stride(a.L, slot_bytes);
   const int64_t nb = a.nblk;
   if (nb <= 0) return OK;
-  if (slot_bytes == 1) {
-    auto k = assemble_from_ke_kernel<uint8_t>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)nb, 128, smem, s>>>(a);
-  } else if (slot_bytes == 2) {
-    auto k = assemble_from_ke_kernel<uint16_t>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)nb, 128, smem, s>>>(a);
-  } else {
-    return fail(ERR_INVALID, "assemble_from_ke: slot_bytes must be 1 or 2");
+  if (slot_bytes != 1 && slot_bytes != 2) return fail(ERR_INVALID, "assemble_from_ke: slot_bytes must be 1 or 2");
+  if (a.L > 32) return fail(ERR_UNSUPPORTED, "assemble_from_ke: ldof=%d exceeds a warp", a.L);
+  switch (a.ncomp) {
+    case 1: return launch_gather<0, 1>(a, slot_bytes, smem, s);
+    case 2: return launch_gather<0, 2>(a, slot_bytes, smem, s);
+    case 3: return launch_gather<0, 3>(a, slot_bytes, smem, s);
+    default: return fail(ERR_UNSUPPORTED, "assemble_from_ke: ncomp=%d (1..3 supported)", a.ncomp);
   }
-  FB2_LAUNCH_CHECK();
-  return OK;
+}
+
+int assemble_elasticity_p1(int TD, AsmKeArgs a, int slot_bytes, int max_row, cudaStream_t s) {
+  if (a.gdof <= 0 || a.nblk <= 0) return OK;
+  if (TD != 2 && TD != 3) return fail(ERR_UNSUPPORTED, "assemble_elasticity_p1: TD must be 2 or 3");
+  if (slot_bytes != 1 && slot_bytes != 2) return fail(ERR_INVALID, "assemble_elasticity_p1: slot_bytes must be 1 or 2");
+  a.L = TD + 1; a.ncomp = TD; a.Ke = nullptr;
+  const size_t smem = (size_t)(a.tile + max_row * a.ncomp) * 8;
+  if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble_elasticity_p1: row tile does not fit shared memory (max_row=%d)", max_row);
+  a.slot_stride = slot_stride(a.L, slot_bytes);
+  return TD == 2 ? launch_gather<2, 2>(a, slot_bytes, smem, s) : launch_gather<3, 3>(a, slot_bytes, smem, s);
 }
 
 int expand_pattern(int64_t gdof, int nc, int prio, const int64_t* crow_s, const int* col_s, int64_t* crow_out, int* col_out,

@@ -36,9 +36,13 @@ struct AsmKeArgs {
   double* values;
   const int32_t* blk_row;     // (nblk+1) tiling of the OUTPUT rows (crow_out)
   int nblk, tile, slot_stride;
+  // fused P1 linear elasticity (Ke == nullptr): per-cell (grad lambda, measure) records instead of element matrices
+  const double* geo;
+  double d_diag, d_lam, d_shear, wsum;
 };
 
 int slot_stride(int L, int slot_bytes);
+int assemble_elasticity_p1(int TD, AsmKeArgs a, int slot_bytes, int max_row, cudaStream_t s);
 struct Asm4Args {
   const double* node;
   const int* cell;

@@ -195,4 +195,41 @@ int matfree_apply(int64_t gdof, int L, const int64_t* adj_ptr, const int* adj_pa
   FB2_LAUNCH_CHECK();
   return OK;
 }
+
+// ---- bc_to_point -------------------------------------------------------------------------
+// one thread per (cell, point): consecutive threads write consecutive points (coalesced), the
+// vertices of a cell are shared through L1 by the NQ threads that need them
+template <int TD>
+__global__ void __launch_bounds__(256) bc_to_points_kernel(int64_t NC, int NQ, const double* __restrict__ node, const int* __restrict__ cell,
+                                                           const double* __restrict__ bcs, double* __restrict__ out) {
+  const int64_t total = NC * NQ;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / NQ;
+    const int q = (int)(t - c * NQ);
+    double x[TD];
+#pragma unroll
+    for (int m = 0; m < TD; ++m) x[m] = 0.0;
+#pragma unroll
+    for (int j = 0; j <= TD; ++j) {
+      const int v = cell[c * (TD + 1) + j];
+      const double b = bcs[q * (TD + 1) + j];
+#pragma unroll
+      for (int m = 0; m < TD; ++m) x[m] += b * node[(int64_t)v * TD + m];      // same j-ascending order as the reference's einsum
+    }
+#pragma unroll
+    for (int m = 0; m < TD; ++m) out[t * TD + m] = x[m];
+  }
+}
+
+int bc_to_points(int TD, int64_t NC, int NQ, const double* node, const int* cell, const double* bcs, double* out, cudaStream_t s) {
+  if (NC <= 0 || NQ <= 0) return OK;
+  const int64_t total = NC * NQ;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSM * 32);
+  if (TD == 2) bc_to_points_kernel<2><<<grid, 256, 0, s>>>(NC, NQ, node, cell, bcs, out);
+  else if (TD == 3) bc_to_points_kernel<3><<<grid, 256, 0, s>>>(NC, NQ, node, cell, bcs, out);
+  else return fail(ERR_UNSUPPORTED, "bc_to_points: TD must be 2 or 3");
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
 }  // namespace fb2

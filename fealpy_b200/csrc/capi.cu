@@ -148,6 +148,18 @@ int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int6
   a.blk_row = blk_row; a.nblk = nblk; a.tile = tile;
   return assemble_from_ke(a, slot_bytes, max_row, S(stream));
 }
+int fb2_assemble_elasticity_p1(int TD, int64_t NC, const double* node, const int32_t* cell, int dof_priority, int64_t gdof_scalar,
+                               double d_diag, double d_lam, double d_shear, double wsum, const int64_t* adj_ptr,
+                               const int32_t* adj_pair, const void* slots, int slot_bytes, const int64_t* crow_scalar, int32_t max_row,
+                               const int64_t* crow_out, const int32_t* blk_row, int nblk, int tile, double* geo_ws, double* values,
+                               void* stream) {
+  FB2_TRY(cell_gradients(TD, NC, node, cell, geo_ws, S(stream)));
+  AsmKeArgs a{};
+  a.gdof = gdof_scalar; a.dof_priority = dof_priority; a.adj_ptr = adj_ptr; a.adj_pair = adj_pair; a.slots = slots;
+  a.crow_s = crow_scalar; a.crow_out = crow_out; a.values = values; a.blk_row = blk_row; a.nblk = nblk; a.tile = tile;
+  a.geo = geo_ws; a.d_diag = d_diag; a.d_lam = d_lam; a.d_shear = d_shear; a.wsum = wsum;
+  return assemble_elasticity_p1(TD, a, slot_bytes, max_row, S(stream));
+}
 size_t fb2_asm4_workspace_bytes(int ntile) { return asm4_workspace_bytes(ntile); }
 int fb2_asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
                         int ldof, int64_t* batch_ptr, int64_t* nbatch_host, void* ws, void* stream) {
@@ -275,6 +287,9 @@ int fb2_elem_source(int TD, int64_t NC, int ldof, int NQ, const double* node, co
                     double scal, const double* f, double* out, void* stream) {
   if (kind < 0 || kind > 2) return fail(ERR_INVALID, "elem_source: kind must be 0 (scalar), 1 (NC,) or 2 (NC,NQ)");
   return elem_source(TD, NC, ldof, NQ, node, cell, phiw, kind, scal, f, out, S(stream));
+}
+int fb2_bc_to_points(int TD, int64_t NC, int NQ, const double* node, const int32_t* cell, const double* bcs, double* out, void* stream) {
+  return bc_to_points(TD, NC, NQ, node, cell, bcs, out, S(stream));
 }
 int fb2_gather_vector(int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair, const double* fe, double* F, void* stream) {
   return gather_vector(gdof, adj_ptr, adj_pair, fe, F, S(stream));

@@ -295,57 +295,107 @@ __global__ void __launch_bounds__(128) elem_quad_kernel(ElemQuadArgs a) {
 //   KK(i a, j b) = d_lam * A_ab + d_shear * A_ba                       (a != b)
 //   layout: interleaved row = GD*i + a (dof_priority False) or blocked row = a*L + i (True)
 // -------------------------------------------------------------------------------------
+// One thread per cell computes; the TD rows of local index i (TD*LD values per cell) are parked in a
+// per-warp shared-memory stage (odd stride: conflict-free) and written out cooperatively, so the
+// stores are contiguous runs of TD*LD (interleaved) or LD (dof_priority) doubles instead of one
+// scattered 8-byte store per thread (the first version wrote 16.1 GB at 1.1 TB/s for config 4).
 template <int TD, int L>
 __global__ void __launch_bounds__(128) elem_elasticity_kernel(ElemElasticityArgs a) {
-  constexpr int NV = TD + 1, LD = L * TD;
+  constexpr int NV = TD + 1, LD = L * TD, ROWS = TD * LD, STRIDE = ROWS + 1;
   extern __shared__ __align__(16) double sm[];
+  double* stage = sm + L * L * NV * NV + (threadIdx.x >> 5) * 32 * STRIDE;
   for (int i = threadIdx.x; i < L * L * NV * NV; i += blockDim.x) sm[i] = a.M4[i];
   __syncthreads();
+  const int lane = threadIdx.x & 31;
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.NC) return;
+  const int64_t cw = c - lane;                              // first cell of this warp
+  const bool live = c < a.NC;
   Geo<TD> g;
-  load_geo(a.node, a.cell, c, g);
-  double* out = a.out + c * (int64_t)LD * LD;
+  if (live) load_geo(a.node, a.cell, c, g);
+  double* mine = stage + lane * STRIDE;
 #pragma unroll 1
   for (int i = 0; i < L; ++i) {
+    if (live) {
 #pragma unroll 1
-    for (int j = 0; j < L; ++j) {
-      const double* m = sm + (i * L + j) * NV * NV;
-      double A[TD][TD];
+      for (int j = 0; j < L; ++j) {
+        const double* m = sm + (i * L + j) * NV * NV;
+        double A[TD][TD];
 #pragma unroll
-      for (int x = 0; x < TD; ++x)
+        for (int x = 0; x < TD; ++x)
 #pragma unroll
-        for (int y = 0; y < TD; ++y) A[x][y] = 0.0;
+          for (int y = 0; y < TD; ++y) A[x][y] = 0.0;
 #pragma unroll
-      for (int k = 0; k < NV; ++k)
+        for (int k = 0; k < NV; ++k)
 #pragma unroll
-        for (int l = 0; l < NV; ++l) {
-          const double mv = m[k * NV + l];
+          for (int l = 0; l < NV; ++l) {
+            const double mv = m[k * NV + l];
 #pragma unroll
-          for (int x = 0; x < TD; ++x)
+            for (int x = 0; x < TD; ++x)
 #pragma unroll
-            for (int y = 0; y < TD; ++y) A[x][y] += mv * (g.D[k][x] * g.D[l][y]);
-        }
-#pragma unroll
-      for (int x = 0; x < TD; ++x)
-#pragma unroll
-        for (int y = 0; y < TD; ++y) {
-          double v;
-          if (x == y) {
-            double oth = 0.0;
-#pragma unroll
-            for (int z = 0; z < TD; ++z) if (z != x) oth += A[z][z];
-            v = a.d_diag * A[x][x] + a.d_shear * oth;
-          } else {
-            v = a.d_lam * A[x][y] + a.d_shear * A[y][x];
+              for (int y = 0; y < TD; ++y) A[x][y] += mv * (g.D[k][x] * g.D[l][y]);
           }
-          v *= g.cm;
-          const int row = a.dof_priority ? x * L + i : i * TD + x;
-          const int col = a.dof_priority ? y * L + j : j * TD + y;
-          out[row * LD + col] = v;
-        }
+#pragma unroll
+        for (int x = 0; x < TD; ++x)
+#pragma unroll
+          for (int y = 0; y < TD; ++y) {
+            double v;
+            if (x == y) {
+              double oth = 0.0;
+#pragma unroll
+              for (int z = 0; z < TD; ++z) if (z != x) oth += A[z][z];
+              v = a.d_diag * A[x][x] + a.d_shear * oth;
+            } else {
+              v = a.d_lam * A[x][y] + a.d_shear * A[y][x];
+            }
+            v *= g.cm;
+            const int col = a.dof_priority ? y * L + j : j * TD + y;
+            mine[x * LD + col] = v;
+          }
+      }
     }
+    __syncwarp();
+    for (int idx = lane; idx < 32 * ROWS; idx += 32) {
+      const int cl = idx / ROWS, k = idx - cl * ROWS;
+      if (cw + cl < a.NC) {
+        const int x = k / LD, col = k - x * LD;
+        const int row = a.dof_priority ? x * L + i : i * TD + x;
+        a.out[(cw + cl) * (int64_t)LD * LD + row * LD + col] = stage[cl * STRIDE + k];
+      }
+    }
+    __syncwarp();
   }
+}
+
+// per-cell record (grad lambda (NV x TD), signed measure) for the fused P1 elasticity assembly
+template <int TD>
+__global__ void __launch_bounds__(256) cell_gradients_kernel(const double* __restrict__ node, const int* __restrict__ cell, int64_t NC,
+                                                             double* __restrict__ out) {
+  constexpr int NV = TD + 1, RS = NV * TD + 1;
+  __shared__ double stage[256 * RS];
+  const int64_t c0 = (int64_t)blockIdx.x * 256, c = c0 + threadIdx.x;
+  if (c < NC) {
+    Geo<TD> g;
+    load_geo(node, cell, c, g);
+    double* h = stage + threadIdx.x * RS;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int x = 0; x < TD; ++x) h[k * TD + x] = g.D[k][x];
+    h[NV * TD] = g.cm;
+  }
+  __syncthreads();
+  const int64_t ncell = (NC - c0) < 256 ? (NC - c0) : 256;
+  for (int64_t t = threadIdx.x; t < ncell * RS; t += 256) out[c0 * RS + t] = stage[t];
+}
+
+int cell_gradients(int TD, int64_t NC, const double* node, const int* cell, double* out, cudaStream_t s) {
+  if (NC <= 0) return OK;
+  const unsigned grid = (unsigned)ceil_div(NC, 256);
+  if (TD == 2) cell_gradients_kernel<2><<<grid, 256, 0, s>>>(node, cell, NC, out);
+  else if (TD == 3) cell_gradients_kernel<3><<<grid, 256, 0, s>>>(node, cell, NC, out);
+  else return fail(ERR_UNSUPPORTED, "cell_gradients: TD must be 2 or 3");
+  FB2_LAUNCH_CHECK();
+  return OK;
 }
 
 // -------------------------------------------------------------------------------------
@@ -388,7 +438,7 @@ static int launch_quad(const ElemQuadArgs& a, cudaStream_t s) {
 template <int TD, int L>
 static int launch_elast(const ElemElasticityArgs& a, cudaStream_t s) {
   constexpr int NV = TD + 1;
-  size_t smem = (size_t)L * L * NV * NV * sizeof(double);
+  size_t smem = ((size_t)L * L * NV * NV + (size_t)4 * 32 * (TD * L * TD + 1)) * sizeof(double);      // M4 table + 4 warp stages
   auto kern = elem_elasticity_kernel<TD, L>;
   FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)ceil_div(a.NC, 128), 128, smem, s>>>(a);

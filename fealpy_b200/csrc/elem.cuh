@@ -42,6 +42,8 @@ struct ElemElasticityArgs {
 
 int elem_const(int TD, int p, const ElemConstArgs& a, cudaStream_t s);
 int elem_quad(int TD, int p, const ElemQuadArgs& a, cudaStream_t s);
+// out[c] = (grad lambda_k[x] for k, x; signed measure): (TD+1)*TD + 1 doubles per cell
+int cell_gradients(int TD, int64_t NC, const double* node, const int* cell, double* out, cudaStream_t s);
 int elem_elasticity(int TD, int p, const ElemElasticityArgs& a, cudaStream_t s);
 
 }  // namespace fb2

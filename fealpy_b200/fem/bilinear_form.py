@@ -320,6 +320,35 @@ class BilinearForm:
             ke = k if ke is None else ke.add_(k)
         return ke.contiguous()
 
+    def _plan_elasticity_p1(self):
+        """one LinearElasticityIntegrator on a P1 tensor space: grad(phi) is cell-constant, the element matrix is a
+        closed form of grad(lambda) and the gather computes its entries on the fly (no K_e block in HBM)"""
+        its = self._flat_integrators()
+        if not self._is_tensor_space() or len(its) != 1 or getattr(its[0], "KIND", None) != "elasticity":
+            return None
+        space, it = self.space, its[0]
+        sspace = space.scalar_space
+        mesh = sspace.mesh
+        if getattr(sspace, "p", None) != 1 or space.dof_numel != mesh.geo_dimension() or mesh.TD not in (2, 3):
+            return None
+        q = sspace.p + 3 if it.q is None else it.q
+        wsum = float(host_tables(mesh.TD, 1, q)["M4"][0, 0, 0, 0])
+        return dict(coef=it.coefficients(space), wsum=wsum)
+
+    def _assemble_elasticity_p1(self, plan):
+        space = self.space
+        sspace, mesh = space.scalar_space, space.scalar_space.mesh
+        sym, pat = symbolic_pattern(sspace), tensor_pattern(space)
+        TD, NC = mesh.TD, sym["NC"]
+        d_diag, d_lam, d_shear = plan["coef"]
+        geo = torch.empty((NC, (TD + 1) * TD + 1), dtype=torch.float64, device=mesh.device)
+        values = torch.empty(pat["col"].shape[0], dtype=torch.float64, device=mesh.device)
+        _lib.call("fb2_assemble_elasticity_p1", TD, NC, _lib.ptr(mesh.node), _lib.ptr(mesh.cell), int(space.dof_priority), sym["gdof"],
+                  d_diag, d_lam, d_shear, plan["wsum"], _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]), _lib.ptr(sym["slots"]),
+                  sym["slot_bytes"], _lib.ptr(sym["crow"]), sym["max_row"], _lib.ptr(pat["crow"]), _lib.ptr(pat["blk_row"]), pat["nblk"],
+                  pat["tile"], _lib.ptr(geo), _lib.ptr(values), _lib.stream())
+        return pat["crow"], pat["col"], values
+
     def _assemble_gather(self):
         space = self.space
         ke = self._summed_ke()
@@ -385,11 +414,15 @@ class BilinearForm:
         plan = None
         if path in ("auto", "fused"):
             plan = self._plan_fused()
-            if plan is None and path == "fused":
+            if plan is None and path == "fused" and self._plan_elasticity_p1() is None:
                 raise NotImplementedError("the fused path needs constant / per-cell scalar coefficients on a scalar space")
+        eplan = self._plan_elasticity_p1() if (plan is None and path in ("auto", "fused")) else None
         if plan is not None:
             crow, col, values = self._assemble_fused(plan)
             self.last_path = "fused"
+        elif eplan is not None:
+            crow, col, values = self._assemble_elasticity_p1(eplan)
+            self.last_path = "fused-elasticity-p1"
         elif path == "coo":
             crow, col, values = self._assemble_coo()
             self.last_path = "coo"

@@ -157,9 +157,14 @@ class SimplexMesh:
 
     def bc_to_point(self, bcs, index=None):
         """physical points of barycentric points, (NC, NQ, GD) (mesh_base.py bc_to_point)."""
-        cell = self.cell if index is None else self.cell[index]
-        b = torch.as_tensor(bcs, dtype=torch.float64, device=self.device)
-        return torch.einsum("cjk,qj->cqk", self.node[cell.long()], b)
+        cell = (self.cell if index is None else self.cell[index]).contiguous()
+        b = torch.as_tensor(bcs, dtype=torch.float64, device=self.device).contiguous()
+        if b.ndim != 2 or b.shape[1] != self.TD + 1:
+            raise ValueError(f"bc_to_point: barycentric points must be (NQ, {self.TD + 1})")
+        out = torch.empty((cell.shape[0], b.shape[0], self.TD), dtype=torch.float64, device=self.device)
+        _lib.call("fb2_bc_to_points", self.TD, cell.shape[0], b.shape[0], _lib.ptr(self.node), _lib.ptr(cell), _lib.ptr(b),
+                  _lib.ptr(out), _lib.stream())
+        return out
 
     def interpolation_points(self, p):
         """(gdof, GD) coordinates of the global interpolation points."""

@@ -120,6 +120,16 @@ int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int6
                          const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
                          const int64_t* crow_scalar, int32_t max_row, const int64_t* crow_out, const int32_t* blk_row, int nblk,
                          int tile, double* values, void* stream);
+/* LinearElasticityIntegrator on a P1 tensor space, fused: grad(phi_i) = grad(lambda_i) is constant per cell, so the
+ * element-matrix entry is a closed form of a (TD+1)*TD+1-double per-cell record (geo_ws: that many doubles per
+ * cell of scratch) and the gather never materialises K_e (fem/linear_elasticity_integrator.py:159-179);
+ * d_diag / d_lam / d_shear as in fb2_elem_elasticity, wsum = sum of the quadrature weights (M4[0,0,0,0]);
+ * pattern arguments as in fb2_assemble_from_ke with ncomp = TD */
+int fb2_assemble_elasticity_p1(int TD, int64_t NC, const double* node, const int32_t* cell, int dof_priority, int64_t gdof_scalar,
+                               double d_diag, double d_lam, double d_shear, double wsum, const int64_t* adj_ptr,
+                               const int32_t* adj_pair, const void* slots, int slot_bytes, const int64_t* crow_scalar, int32_t max_row,
+                               const int64_t* crow_out, const int32_t* blk_row, int nblk, int tile, double* geo_ws, double* values,
+                               void* stream);
 /* "v4" numeric kernel for the same forms: the symbolic phase additionally turns every warp tile
  * (rows holding <= tile values; fb2_spmv_plan_build) into 32-entry batches that share the local
  * index (warp-uniform element-table row) and touch 32 different rows (conflict-free adds);
@@ -198,6 +208,9 @@ int fb2_bcg_update_p(int64_t n, int nb, double* p, const double* r, const double
 /* F_e (NC,l) = vol_c * scal * sum_q phiw[q][i] f_cq; kind 0: f = 1, 1: f (NC,), 2: f (NC,NQ) */
 int fb2_elem_source(int TD, int64_t NC, int ldof, int NQ, const double* node, const int32_t* cell, const double* phiw, int kind,
                     double scal, const double* f, double* out, void* stream);
+/* physical points of NQ barycentric points (bcs: NQ x (TD+1), device) in every cell, out (NC, NQ, TD):
+ * mesh.bc_to_point (mesh/mesh_base.py), where callable coefficients / sources are evaluated */
+int fb2_bc_to_points(int TD, int64_t NC, int NQ, const double* node, const int32_t* cell, const double* bcs, double* out, void* stream);
 /* F[d] = sum of F_e over the (cell, i) pairs of dof d in ascending order (adjacency of fb2_sym_count) */
 int fb2_gather_vector(int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair, const double* fe, double* F, void* stream);
 /* matrix-free v = A u from the element matrices Ke (NC,l,l) (BilinearForm.__matmul__ before assembly,

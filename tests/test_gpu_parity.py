@@ -630,7 +630,10 @@ def test_sparse_edge_cases(U):
     for name, (r, c, v, shape) in cases.items():
         idx = torch.tensor(np.stack([r, c]), dtype=torch.int32, device="cuda")       # col keeps the index dtype (coo_tensor.py:137-157)
         coo = COOTensor(idx, U.t64(v), shape, is_coalesced=False)
-        A = coo.tocsr()
+        if len(r) > len(set(zip(r.tolist(), c.tolist()))):
+            with pytest.raises(ValueError):          # duplicates: the reference requires coalesce() before tocsr()
+                coo.tocsr()
+        A = coo.coalesce().tocsr()
         crow, col, val = O.tocsr(*O.coalesce(r, c, v), shape[0])
         assert A.shape == shape and A.nnz == len(col), name
         assert np.array_equal(A.crow.cpu().numpy(), crow), name
@@ -638,4 +641,6 @@ def test_sparse_edge_cases(U):
         assert np.array_equal(A.values.cpu().numpy(), val), name            # same left-to-right order as np.add.at: bit-exact
         x = rng.standard_normal(shape[1])
         y = (A @ U.t64(x)).cpu().numpy()
-        assert np.allclose(y, O.csr_matvec(crow, col, val, x), rtol=0, atol=1e-13 * (1 + np.abs(val).sum())), name
+        yref = np.zeros(shape[0])
+        np.add.at(yref, np.repeat(np.arange(shape[0]), np.diff(crow)), val * x[col])
+        assert np.allclose(y, yref, rtol=0, atol=1e-13 * (1 + np.abs(val).sum())), name
