@@ -323,7 +323,8 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
                               unsigned int* counter, const CgScalars* sc, cudaStream_t s, OwnRange own) {
   const size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
-  const int per_sm = (int)std::min<size_t>(2048 / ST_THREADS, (200 * 1024) / (smem + 1024));
+  static const int per_sm_cap = [] { const char* e = getenv("FB2_SPMV_PERSM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2048 / ST_THREADS; }();
+  const int per_sm = (int)std::min<size_t>(per_sm_cap, (200 * 1024) / (smem + 1024));
   int grid = std::min(plan.nblk, kNumSM * std::max(per_sm, 1));
   if (grid > CG_PARTIALS) grid = CG_PARTIALS;
   if (grid < 1) grid = 1;
