@@ -64,24 +64,62 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """SM clocks / throttle reasons sampled DURING the timed region.  In-process NVML (a 100 ms thread) when
+    nvidia_ml_py is importable -- an external `nvidia-smi -lms` loop was seen to stall this process's CUDA calls by
+    ~30 ms per step on some boxes -- else nvidia-smi."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index, self.proc, self.path = index, None, None
+        self.thread, self.stop_flag, self.samples = None, None, []
+
+    def _nvml_loop(self, nv, h):
+        R = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+             "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                bits = (getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons)(h)
+                self.samples.append((float(sm), float(mx), {k for k, v in R.items() if bits & v}))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                h = nv.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid))
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
                                           "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=statistics.median(x[0] for x in self.samples), sm_max_mhz=max(x[1] for x in self.samples),
+                           reasons=sorted(set().union(*(x[2] for x in self.samples))), samples=len(self.samples), source="nvml")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
