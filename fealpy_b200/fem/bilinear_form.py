@@ -293,6 +293,8 @@ class BilinearForm:
             h = host_tables(mesh.TD, space.p, m["q"])[key]
             return h.ctypes.data_as(C.c_void_p)
         kernel = _os.environ.get("FB2_ASM_KERNEL", "v4")
+        if kernel == "v4" and (ASM4_TILE + sym["max_row"] >= 4096 or sym["max_row"] > 1024 or sym["L"] > 20):
+            kernel = "v2"          # very long rows (high-valence meshes): tile offsets / first-touch bitmap of v4 do not cover them
         NH = mesh.TD * (mesh.TD + 1) // 2 + 1          # reduced geometry record (csrc/assemble.cu A4Geo)
         if kernel == "v4":
             pl = asm4_plan(space)
