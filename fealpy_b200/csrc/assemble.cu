@@ -693,8 +693,8 @@ int expand_pattern(int64_t gdof, int nc, int prio, const int64_t* crow_s, const 
 //   * all entries of a batch belong to different rows      -> conflict-free accumulation,
 //   * per row, entries appear in (i, cell) order           -> fixed summation order, independent of the tiling.
 // The numeric kernel is then a flat loop over batches with every lane busy: lane = one
-// (row, cell) pair; geometry comes precomputed per cell (H), the element row is 11 FMAs per
-// column against broadcast table reads, the result is added into the warp's private tile.
+// (row, cell) pair; geometry comes precomputed per cell (H, reduced form: 7 values per tetrahedron), the
+// element row is 7 FMAs per column against uniform table operands, the result is added into the warp's private tile.
 // =====================================================================================
 namespace fb2 {
 

@@ -107,8 +107,8 @@ int fb2_sym_fill(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, co
                  const int64_t* crow, int32_t* col, void* slots, int slot_bytes, const uint32_t* stash, void* stream);
 /* numeric, constant / per-cell coefficient scalar forms (diffusion and/or mass fused).
  * blk_row/nblk/tile: row tiling of crow from fb2_spmv_plan_build (one CTA per tile).  This is the
- * "v2" kernel (lane = row, tables in shared memory); it also serves elements whose tables exceed the
- * kernel parameter block of the v4 kernel below (tet P3). */
+ * "v2" kernel (lane = row, tables in shared memory); it also serves rows too long for the 12-bit tile
+ * offsets of the v4 kernel below. */
 int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,
                               const int64_t* adj_ptr, const int32_t* adj_pair, const void* slots, int slot_bytes,
                               const int64_t* crow, int32_t max_row, const int32_t* blk_row, int nblk, int tile,
