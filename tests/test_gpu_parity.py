@@ -644,3 +644,46 @@ def test_sparse_edge_cases(U):
         yref = np.zeros(shape[0])
         np.add.at(yref, np.repeat(np.arange(shape[0]), np.diff(crow)), val * x[col])
         assert np.allclose(y, yref, rtol=0, atol=1e-13 * (1 + np.abs(val).sum())), name
+
+
+@pytest.mark.parametrize("kind,n,prio,hypo", [("tet", 12, False, "3D"), ("tet", 9, True, "3D"), ("tri", 48, False, "plane_strain"),
+                                              ("tri", 40, True, "plane_stress")])
+def test_elasticity_p1_fused_agrees_with_ke_paths(kind, n, prio, hypo, U):
+    """LinearElasticityIntegrator on a P1 tensor space: the fused path (entries from per-cell grad-lambda records, no K_e in
+    HBM) against the K_e gather path and the literal COO pipeline at a size the golden cases do not reach; plus
+    the rigid-body null space (translations) and symmetry as size-independent properties."""
+    from fealpy_b200.mesh import TriangleMesh, TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace, TensorFunctionSpace
+    from fealpy_b200.fem import BilinearForm, LinearElasticityIntegrator
+    from fealpy_b200.material import LinearElasticMaterial
+    if kind == "tet":
+        mesh = TetrahedronMesh.from_box([0, 1, 0, 2, 0, 1], n, n + 1, n - 1)
+    else:
+        mesh = TriangleMesh.from_box([0, 2, 0, 1], n, n - 3)
+    GD = mesh.geo_dimension()
+    space = TensorFunctionSpace(LagrangeFESpace(mesh, 1), shape=(GD, -1) if prio else (-1, GD))
+    assert bool(space.dof_priority) == prio
+    mat = LinearElasticMaterial("m", elastic_modulus=2.0, poisson_ratio=0.27, hypo=hypo)
+    out = {}
+    for path in ("auto", "gather", "coo"):
+        bf = BilinearForm(space, assembly_path=path)
+        bf.add_integrator(LinearElasticityIntegrator(mat, q=3))
+        out[path] = (bf.assembly(), bf.last_path)
+    A, used = out["auto"]
+    assert used == "fused-elasticity-p1" and out["gather"][1] == "gather"
+    scale = float(A.values.abs().max())
+    for path in ("gather", "coo"):
+        B = out[path][0]
+        assert torch.equal(A.crow, B.crow) and torch.equal(A.col, B.col), path
+        assert float((A.values - B.values).abs().max()) <= 1e-12 * scale, path
+    gdof = space.scalar_space.number_of_global_dofs()
+    for a in range(GD):                          # a rigid translation produces no strain
+        t = torch.zeros(GD * gdof, dtype=torch.float64, device="cuda")
+        if prio:
+            t[a * gdof:(a + 1) * gdof] = 1.0
+        else:
+            t[a::GD] = 1.0
+        assert float((A @ t).abs().max()) <= 1e-11 * scale
+    x = torch.rand(GD * gdof, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    y = torch.rand(GD * gdof, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    assert abs(float(y @ (A @ x) - x @ (A @ y))) <= 1e-10 * scale * GD * gdof
