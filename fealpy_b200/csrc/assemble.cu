@@ -66,6 +66,62 @@ constexpr int SYM_CAP = 1024;       // max candidate columns (valence*ldof) per 
 constexpr int SYM_KBITS = 10;
 constexpr int SYM_WARPS = 4;
 
+// bitonic sort of 32*K keys held K per lane (element e = k*32 + lane): strides below 32 are lane exchanges
+// (shuffles), strides of 32 and more are register swaps -- no shared memory, no barriers
+template <int K>
+__device__ __forceinline__ void bitonic_sort_regs(uint64_t (&v)[K], int lane) {
+  constexpr int N = 32 * K;
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int ks = stride >> 5;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if ((k & ks) == 0) {
+            const bool up = (((k << 5) + lane) & size) == 0;
+            const uint64_t x = v[k], y = v[k | ks];
+            if ((x > y) == up) { v[k] = y; v[k | ks] = x; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const bool up = (((k << 5) + lane) & size) == 0;
+          const uint64_t x = v[k], y = __shfl_xor_sync(0xffffffffu, x, stride);
+          const bool lower = (lane & stride) == 0;
+          v[k] = (lower == up) ? (x < y ? x : y) : (x < y ? y : x);
+        }
+      }
+    }
+  }
+}
+
+// candidate keys of row positions k = it*32 + lane, sorted in registers, left in buf[] in ascending order
+template <int K>
+__device__ __forceinline__ void sym_sort_small(const int* __restrict__ c2d, const int* __restrict__ adj_pair, int64_t a0, int L, int ncand,
+                                               int lane, uint64_t* __restrict__ buf) {
+  uint64_t v[K];
+  int pr[K], jj[K];
+#pragma unroll
+  for (int it = 0; it < K; ++it) {
+    const int k = it * 32 + lane;
+    const int pl = k / L;
+    jj[it] = k - pl * L;
+    pr[it] = k < ncand ? adj_pair[a0 + pl] : 0;
+  }
+#pragma unroll
+  for (int it = 0; it < K; ++it) {
+    const int k = it * 32 + lane;
+    v[it] = k < ncand ? (((uint64_t)(uint32_t)c2d[(int64_t)(pr[it] / L) * L + jj[it]] << SYM_KBITS) | (uint64_t)k) : ~0ull;
+  }
+  bitonic_sort_regs<K>(v, lane);
+#pragma unroll
+  for (int it = 0; it < K; ++it) buf[it * 32 + lane] = v[it];
+  __syncwarp();
+}
+
 template <bool FILL, typename SlotT>
 __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __restrict__ c2d, int L, int64_t gdof,
                                                                   const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair,
@@ -88,27 +144,33 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
     }
     int n2 = 32;
     while (n2 < ncand) n2 <<= 1;
-    for (int k = lane; k < n2; k += 32) {
-      uint64_t key = ~0ull;
-      if (k < ncand) {
-        const int pl = k / L, j = k - pl * L;
-        const int pair = adj_pair[a0 + pl];
-        const int64_t c = pair / L;
-        key = ((uint64_t)(uint32_t)c2d[c * L + j] << SYM_KBITS) | (uint64_t)k;
-      }
-      buf[k] = key;
-    }
-    __syncwarp();
-    for (int size = 2; size <= n2; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int t = lane; t < (n2 >> 1); t += 32) {
-          const int i = 2 * t - (t & (stride - 1));
-          const int j = i + stride;
-          const bool up = (i & size) == 0;
-          const uint64_t x = buf[i], y = buf[j];
-          if ((x > y) == up) { buf[i] = y; buf[j] = x; }
+    if (n2 == 32) sym_sort_small<1>(c2d, adj_pair, a0, L, ncand, lane, buf);
+    else if (n2 == 64) sym_sort_small<2>(c2d, adj_pair, a0, L, ncand, lane, buf);
+    else if (n2 == 128) sym_sort_small<4>(c2d, adj_pair, a0, L, ncand, lane, buf);
+    else if (n2 == 256) sym_sort_small<8>(c2d, adj_pair, a0, L, ncand, lane, buf);
+    else {
+      for (int k = lane; k < n2; k += 32) {
+        uint64_t key = ~0ull;
+        if (k < ncand) {
+          const int pl = k / L, j = k - pl * L;
+          const int pair = adj_pair[a0 + pl];
+          const int64_t c = pair / L;
+          key = ((uint64_t)(uint32_t)c2d[c * L + j] << SYM_KBITS) | (uint64_t)k;
         }
-        __syncwarp();
+        buf[k] = key;
+      }
+      __syncwarp();
+      for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int t = lane; t < (n2 >> 1); t += 32) {
+            const int i = 2 * t - (t & (stride - 1));
+            const int j = i + stride;
+            const bool up = (i & size) == 0;
+            const uint64_t x = buf[i], y = buf[j];
+            if ((x > y) == up) { buf[i] = y; buf[j] = x; }
+          }
+          __syncwarp();
+        }
       }
     }
     int running = 0;
