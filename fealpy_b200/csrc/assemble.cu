@@ -23,6 +23,17 @@ static inline unsigned grid_for(int64_t n, int threads = 256) {
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// exact division by a small run-time constant (ldof) without the ~25-instruction integer-divide sequence:
+// floor(n / d) = mulhi(n, floor(2^w / d) + 1) for n < 2^16 (w = 32) resp. n < 2^32 (w = 64), d >= 2
+struct FastDiv {
+  uint32_t m32;
+  uint64_t m64;
+  int d;
+  __device__ __forceinline__ explicit FastDiv(int dd) : m32(0xffffffffu / (uint32_t)dd + 1u), m64(~0ull / (uint64_t)dd + 1ull), d(dd) {}
+  __device__ __forceinline__ int small(int n) const { return d == 1 ? n : (int)__umulhi((uint32_t)n, m32); }        // 0 <= n < 65536
+  __device__ __forceinline__ int wide(int n) const { return d == 1 ? n : (int)__umul64hi((uint64_t)(uint32_t)n, m64); }   // 0 <= n < 2^31
+};
+
 // =====================================================================================
 // symbolic
 // =====================================================================================
@@ -100,21 +111,21 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t (&v)[K], int lane) {
 
 // candidate keys of row positions k = it*32 + lane, sorted in registers, left in buf[] in ascending order
 template <int K>
-__device__ __forceinline__ void sym_sort_small(const int* __restrict__ c2d, const int* __restrict__ adj_pair, int64_t a0, int L, int ncand,
-                                               int lane, uint64_t* __restrict__ buf) {
+__device__ __forceinline__ void sym_sort_small(const int* __restrict__ c2d, const int* __restrict__ adj_pair, int64_t a0, int L,
+                                               const FastDiv& fd, int ncand, int lane, uint64_t* __restrict__ buf) {
   uint64_t v[K];
   int pr[K], jj[K];
 #pragma unroll
   for (int it = 0; it < K; ++it) {
     const int k = it * 32 + lane;
-    const int pl = k / L;
+    const int pl = fd.small(k);
     jj[it] = k - pl * L;
     pr[it] = k < ncand ? adj_pair[a0 + pl] : 0;
   }
 #pragma unroll
   for (int it = 0; it < K; ++it) {
     const int k = it * 32 + lane;
-    v[it] = k < ncand ? (((uint64_t)(uint32_t)c2d[(int64_t)(pr[it] / L) * L + jj[it]] << SYM_KBITS) | (uint64_t)k) : ~0ull;
+    v[it] = k < ncand ? (((uint64_t)(uint32_t)c2d[(int64_t)fd.wide(pr[it]) * L + jj[it]] << SYM_KBITS) | (uint64_t)k) : ~0ull;
   }
   bitonic_sort_regs<K>(v, lane);
 #pragma unroll
@@ -133,6 +144,7 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
   uint64_t* buf = buf_all[wid];
   const int64_t nwarp = (int64_t)gridDim.x * SYM_WARPS;
   const uint32_t lt = (1u << lane) - 1u;
+  const FastDiv fd(L);
   for (int64_t r = (int64_t)blockIdx.x * SYM_WARPS + wid; r < gdof; r += nwarp) {
     const int64_t a0 = adj_ptr[r];
     const int deg = (int)(adj_ptr[r + 1] - a0);
@@ -144,17 +156,17 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
     }
     int n2 = 32;
     while (n2 < ncand) n2 <<= 1;
-    if (n2 == 32) sym_sort_small<1>(c2d, adj_pair, a0, L, ncand, lane, buf);
-    else if (n2 == 64) sym_sort_small<2>(c2d, adj_pair, a0, L, ncand, lane, buf);
-    else if (n2 == 128) sym_sort_small<4>(c2d, adj_pair, a0, L, ncand, lane, buf);
-    else if (n2 == 256) sym_sort_small<8>(c2d, adj_pair, a0, L, ncand, lane, buf);
+    if (n2 == 32) sym_sort_small<1>(c2d, adj_pair, a0, L, fd, ncand, lane, buf);
+    else if (n2 == 64) sym_sort_small<2>(c2d, adj_pair, a0, L, fd, ncand, lane, buf);
+    else if (n2 == 128) sym_sort_small<4>(c2d, adj_pair, a0, L, fd, ncand, lane, buf);
+    else if (n2 == 256) sym_sort_small<8>(c2d, adj_pair, a0, L, fd, ncand, lane, buf);
     else {
       for (int k = lane; k < n2; k += 32) {
         uint64_t key = ~0ull;
         if (k < ncand) {
-          const int pl = k / L, j = k - pl * L;
+          const int pl = fd.small(k), j = k - pl * L;
           const int pair = adj_pair[a0 + pl];
-          const int64_t c = pair / L;
+          const int64_t c = fd.wide(pair);
           key = ((uint64_t)(uint32_t)c2d[c * L + j] << SYM_KBITS) | (uint64_t)k;
         }
         buf[k] = key;
@@ -189,7 +201,7 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
         const int kk = (int)(key & ((1u << SYM_KBITS) - 1u));      // candidate index = pair_local * L + j
         if (FILL) {
           if (head) col[cbase + rank] = (int)(key >> SYM_KBITS);
-          const int pl = kk / L;
+          const int pl = fd.small(kk);
           slots[(a0 + pl) * slot_stride + (kk - pl * L)] = (SlotT)rank;
         } else if (stash) {                        // sorted order kept for sym_replay_kernel: the fill pass need not sort again
           stash[a0 * L + k] = ((uint32_t)rank << SYM_KBITS) | (uint32_t)kk;
@@ -211,6 +223,7 @@ __global__ void __launch_bounds__(256) sym_replay_kernel(const int* __restrict__
                                                          SlotT* __restrict__ slots, int slot_stride) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const FastDiv fd(L);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < gdof; r += nwarp) {
     const int64_t a0 = adj_ptr[r];
     const int ncand = (int)(adj_ptr[r + 1] - a0) * L;
@@ -219,9 +232,9 @@ __global__ void __launch_bounds__(256) sym_replay_kernel(const int* __restrict__
     for (int k = lane; k < ncand; k += 32) {
       const uint32_t e = st[k];
       const int rank = (int)(e >> SYM_KBITS), kk = (int)(e & ((1u << SYM_KBITS) - 1u));
-      const int pl = kk / L, j = kk - pl * L;
+      const int pl = fd.small(kk), j = kk - pl * L;
       slots[(a0 + pl) * slot_stride + j] = (SlotT)rank;
-      if (k == 0 || (int)(st[k - 1] >> SYM_KBITS) != rank) col[cbase + rank] = c2d[(int64_t)(adj_pair[a0 + pl] / L) * L + j];
+      if (k == 0 || (int)(st[k - 1] >> SYM_KBITS) != rank) col[cbase + rank] = c2d[(int64_t)fd.wide(adj_pair[a0 + pl]) * L + j];
     }
   }
 }
@@ -786,6 +799,8 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
   const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= ntile) return;
+  const FastDiv fd(L);
+  auto local_index = [&](int pair) { return pair - fd.wide(pair) * L; };
   const int64_t r0 = blk_row[t], r1 = blk_row[t + 1];
   const int64_t v0 = crow[r0];
   int cnt = 0, mult = 0;                         // lane i: entries of local index i in the tile, longest run inside one row
@@ -795,7 +810,7 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
     if (r < r1) { q = adj_ptr[r]; qe = adj_ptr[r + 1]; }
     for (int i = 0; i < L; ++i) {
       int m = 0;
-      while (q + m < qe && adj_pair[q + m] % L == i) ++m;
+      while (q + m < qe && local_index(adj_pair[q + m]) == i) ++m;
       q += m;
       const int s = __reduce_add_sync(FULL, m), mx = __reduce_max_sync(FULL, m);
       if (lane == i) { cnt += s; mult = max(mult, mx); }
@@ -831,7 +846,7 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
     for (int w = 0; w < A4_MAXROW / 32; ++w) touched[w] = 0;
     for (int i = 0; i < L; ++i) {
       int m = 0;                                 // this row's run of local index i
-      while (q + m < qe && adj_pair[q + m] % L == i) ++m;
+      while (q + m < qe && local_index(adj_pair[q + m]) == i) ++m;
       int ex = m;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, ex, o); if (lane >= o) ex += v; }
@@ -847,7 +862,7 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
         for (int u = 0; u < m; ++u) {
           const int k = u < wrap ? k0 + (m - wrap) + u : k0 + (u - wrap);
           const int64_t e = (b0 + offi + k % Bi) * 32 + k / Bi;
-          ent_cell[e] = adj_pair[q + u] / L;
+          ent_cell[e] = fd.wide(adj_pair[q + u]);
           uint32_t first = 0;
           for (int w = 0; w < slot_nwords; ++w) ent_slots[e * slot_nwords + w] = slot_words[(q + u) * slot_nwords + w];
           for (int j = 0; j < L; ++j) {
