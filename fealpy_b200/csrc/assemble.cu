@@ -109,28 +109,32 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t (&v)[K], int lane) {
   }
 }
 
-// candidate keys of row positions k = it*32 + lane, sorted in registers, left in buf[] in ascending order
+// ---- rows of up to SYM_HASH_CAP candidates: deduplicate first, sort only the unique columns --------
+// A row's candidates are heavily duplicated (tet P2: 50-240 candidates, 28-80 distinct columns), and the
+// sort is what the symbolic phase spends its instructions on.  So: (1) every candidate is inserted
+// into a small open-addressing hash set in shared memory (atomicCAS; the inserting candidate is the
+// column's representative), (2) the representatives' (column, table slot) keys are compacted and
+// sorted in registers, (3) the sorted position = rank is written back to the table slot, where every
+// candidate of that column picks it up.
+constexpr int SYM_HASH_CAP = 256;           // candidates per row on this path
+constexpr int SYM_HASH_SIZE = 512;          // table entries (load factor <= 0.5)
+constexpr uint32_t SYM_EMPTY = 0xffffffffu;
+
 template <int K>
-__device__ __forceinline__ void sym_sort_small(const int* __restrict__ c2d, const int* __restrict__ adj_pair, int64_t a0, int L,
-                                               const FastDiv& fd, int ncand, int lane, uint64_t* __restrict__ buf) {
+__device__ __forceinline__ void sym_sort_unique(const uint64_t* __restrict__ ulist, int nu, int lane, uint32_t* __restrict__ trank,
+                                                int* __restrict__ col_out) {
   uint64_t v[K];
-  int pr[K], jj[K];
 #pragma unroll
-  for (int it = 0; it < K; ++it) {
-    const int k = it * 32 + lane;
-    const int pl = fd.small(k);
-    jj[it] = k - pl * L;
-    pr[it] = k < ncand ? adj_pair[a0 + pl] : 0;
-  }
-#pragma unroll
-  for (int it = 0; it < K; ++it) {
-    const int k = it * 32 + lane;
-    v[it] = k < ncand ? (((uint64_t)(uint32_t)c2d[(int64_t)fd.wide(pr[it]) * L + jj[it]] << SYM_KBITS) | (uint64_t)k) : ~0ull;
-  }
+  for (int it = 0; it < K; ++it) { const int p = it * 32 + lane; v[it] = p < nu ? ulist[p] : ~0ull; }
   bitonic_sort_regs<K>(v, lane);
 #pragma unroll
-  for (int it = 0; it < K; ++it) buf[it * 32 + lane] = v[it];
-  __syncwarp();
+  for (int it = 0; it < K; ++it) {
+    const int p = it * 32 + lane;
+    if (p < nu) {
+      trank[(int)(v[it] & (SYM_HASH_SIZE - 1))] = (uint32_t)p;
+      if (col_out) col_out[p] = (int)(v[it] >> SYM_KBITS);
+    }
+  }
 }
 
 template <bool FILL, typename SlotT>
@@ -138,13 +142,15 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
                                                                   const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair,
                                                                   const int64_t* __restrict__ crow, int* __restrict__ rowlen,
                                                                   int* __restrict__ col, SlotT* __restrict__ slots, int slot_stride,
-                                                                  int* __restrict__ err, uint32_t* __restrict__ stash) {
+                                                                  int* __restrict__ err, uint16_t* __restrict__ stash) {
   __shared__ uint64_t buf_all[SYM_WARPS][SYM_CAP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint64_t* buf = buf_all[wid];
   const int64_t nwarp = (int64_t)gridDim.x * SYM_WARPS;
   const uint32_t lt = (1u << lane) - 1u;
   const FastDiv fd(L);
+  for (int t = lane; t < SYM_HASH_SIZE; t += 32) reinterpret_cast<uint32_t*>(buf)[t] = SYM_EMPTY;
+  __syncwarp();
   for (int64_t r = (int64_t)blockIdx.x * SYM_WARPS + wid; r < gdof; r += nwarp) {
     const int64_t a0 = adj_ptr[r];
     const int deg = (int)(adj_ptr[r + 1] - a0);
@@ -154,13 +160,72 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
       if (!FILL && lane == 0) rowlen[r] = 0;
       continue;
     }
+    if (ncand <= SYM_HASH_CAP) {
+      // shared-memory carve-up of this warp's 8 KB: hash table | rank per table slot | unique keys
+      uint32_t* tab = reinterpret_cast<uint32_t*>(buf);
+      uint32_t* trank = tab + SYM_HASH_SIZE;
+      uint64_t* ulist = buf + SYM_HASH_SIZE;                     // (2 * SYM_HASH_SIZE u32 = SYM_HASH_SIZE u64 in)
+      constexpr int KMAX = SYM_HASH_CAP / 32;
+      int hs[KMAX];                                              // per candidate: table slot << 1 | representative
+      int nu = 0;
+#pragma unroll
+      for (int it = 0; it < KMAX; ++it) {
+        hs[it] = 0;
+        if (it * 32 < ncand) {                                   // warp-uniform
+          const int k = it * 32 + lane;
+          bool rep = false;
+          uint32_t cv = 0;
+          int h = 0;
+          if (k < ncand) {
+            const int pl = fd.small(k), j = k - pl * L;
+            cv = (uint32_t)c2d[(int64_t)fd.wide(adj_pair[a0 + pl]) * L + j];
+            h = (int)((cv * 2654435761u) >> 23);                 // 9 bits
+            while (true) {
+              const uint32_t prev = atomicCAS(tab + h, SYM_EMPTY, cv);
+              if (prev == SYM_EMPTY) { rep = true; break; }
+              if (prev == cv) break;
+              h = (h + 1) & (SYM_HASH_SIZE - 1);
+            }
+            hs[it] = (h << 1) | (rep ? 1 : 0);
+          }
+          const uint32_t rb = __ballot_sync(0xffffffffu, rep);
+          if (rep) ulist[nu + __popc(rb & lt)] = ((uint64_t)cv << SYM_KBITS) | (uint64_t)h;
+          nu += __popc(rb);
+        }
+      }
+      __syncwarp();
+      const int64_t cbase = FILL ? crow[r] : 0;
+      int* cout = FILL ? col + cbase : nullptr;
+      if (nu <= 32) sym_sort_unique<1>(ulist, nu, lane, trank, cout);
+      else if (nu <= 64) sym_sort_unique<2>(ulist, nu, lane, trank, cout);
+      else if (nu <= 128) sym_sort_unique<4>(ulist, nu, lane, trank, cout);
+      else sym_sort_unique<8>(ulist, nu, lane, trank, cout);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < KMAX; ++it) {
+        const int k = it * 32 + lane;
+        if (k < ncand) {
+          const int h = hs[it] >> 1, rank = (int)trank[h];
+          if (FILL) {
+            const int pl = fd.small(k);
+            slots[(a0 + pl) * slot_stride + (k - pl * L)] = (SlotT)rank;
+          } else if (stash) {
+            stash[a0 * L + k] = (uint16_t)((rank << 1) | (hs[it] & 1));
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < KMAX; ++it)
+        if ((hs[it] & 1) && it * 32 + lane < ncand) tab[hs[it] >> 1] = SYM_EMPTY;      // leave the table empty for the next row
+      if (!FILL && lane == 0) rowlen[r] = nu;
+      __syncwarp();
+      continue;
+    }
+    // ---- long rows: bitonic sort of all (column, candidate) keys in shared memory -----------
     int n2 = 32;
     while (n2 < ncand) n2 <<= 1;
-    if (n2 == 32) sym_sort_small<1>(c2d, adj_pair, a0, L, fd, ncand, lane, buf);
-    else if (n2 == 64) sym_sort_small<2>(c2d, adj_pair, a0, L, fd, ncand, lane, buf);
-    else if (n2 == 128) sym_sort_small<4>(c2d, adj_pair, a0, L, fd, ncand, lane, buf);
-    else if (n2 == 256) sym_sort_small<8>(c2d, adj_pair, a0, L, fd, ncand, lane, buf);
-    else {
+    {
       for (int k = lane; k < n2; k += 32) {
         uint64_t key = ~0ull;
         if (k < ncand) {
@@ -203,23 +268,25 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
           if (head) col[cbase + rank] = (int)(key >> SYM_KBITS);
           const int pl = fd.small(kk);
           slots[(a0 + pl) * slot_stride + (kk - pl * L)] = (SlotT)rank;
-        } else if (stash) {                        // sorted order kept for sym_replay_kernel: the fill pass need not sort again
-          stash[a0 * L + k] = ((uint32_t)rank << SYM_KBITS) | (uint32_t)kk;
+        } else if (stash) {                        // rank and representative flag per candidate for sym_replay_kernel
+          stash[a0 * L + kk] = (uint16_t)((rank << 1) | (head ? 1 : 0));
         }
       }
       running += __popc(hb);
     }
     if (!FILL && lane == 0) rowlen[r] = running;
     __syncwarp();
+    for (int t = lane; t < SYM_HASH_SIZE; t += 32) reinterpret_cast<uint32_t*>(buf)[t] = SYM_EMPTY;      // the sort used the table's memory
+    __syncwarp();
   }
 }
 
-// fill pass from the stash of the count pass: (rank, candidate) in sorted order per row -- no sort,
-// one warp per row, coalesced reads; the column of a head candidate is re-gathered from cell2dof
+// fill pass from the stash of the count pass: per candidate (rank << 1 | representative) -- no sort, one
+// warp per row, coalesced reads; the column of a representative is re-gathered from cell2dof
 template <typename SlotT>
 __global__ void __launch_bounds__(256) sym_replay_kernel(const int* __restrict__ c2d, int L, int64_t gdof, const int64_t* __restrict__ adj_ptr,
                                                          const int* __restrict__ adj_pair, const int64_t* __restrict__ crow,
-                                                         const uint32_t* __restrict__ stash, int* __restrict__ col,
+                                                         const uint16_t* __restrict__ stash, int* __restrict__ col,
                                                          SlotT* __restrict__ slots, int slot_stride) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -228,13 +295,12 @@ __global__ void __launch_bounds__(256) sym_replay_kernel(const int* __restrict__
     const int64_t a0 = adj_ptr[r];
     const int ncand = (int)(adj_ptr[r + 1] - a0) * L;
     const int64_t cbase = crow[r];
-    const uint32_t* st = stash + a0 * L;
+    const uint16_t* st = stash + a0 * L;
     for (int k = lane; k < ncand; k += 32) {
-      const uint32_t e = st[k];
-      const int rank = (int)(e >> SYM_KBITS), kk = (int)(e & ((1u << SYM_KBITS) - 1u));
-      const int pl = fd.small(kk), j = kk - pl * L;
+      const int e = st[k], rank = e >> 1;
+      const int pl = fd.small(k), j = k - pl * L;
       slots[(a0 + pl) * slot_stride + j] = (SlotT)rank;
-      if (k == 0 || (int)(st[k - 1] >> SYM_KBITS) != rank) col[cbase + rank] = c2d[(int64_t)fd.wide(adj_pair[a0 + pl]) * L + j];
+      if (e & 1) col[cbase + rank] = c2d[(int64_t)fd.wide(adj_pair[a0 + pl]) * L + j];
     }
   }
 }
@@ -258,7 +324,7 @@ size_t sym_workspace_bytes(int64_t NC, int L, int64_t gdof) {
 }
 
 int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, int64_t* crow, int64_t* nnz_host,
-              int* max_row_host, uint32_t* stash, void* ws, cudaStream_t s) {
+              int* max_row_host, uint16_t* stash, void* ws, cudaStream_t s) {
   const int64_t npair = NC * L;
   if (npair >= ((int64_t)1 << 31)) return fail(ERR_UNSUPPORTED, "sym_count: NC*ldof=%lld exceeds int32 pair ids", (long long)npair);
   Carver c(ws);
@@ -293,7 +359,7 @@ int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr,
 }
 
 int sym_fill(const int* c2d, int64_t NC, int L, int64_t gdof, const int64_t* adj_ptr, const int* adj_pair, const int64_t* crow,
-             int* col, void* slots, int slot_bytes, const uint32_t* stash, cudaStream_t s) {
+             int* col, void* slots, int slot_bytes, const uint16_t* stash, cudaStream_t s) {
   if (gdof <= 0) return OK;
   if (stash) {
     if (slot_bytes != 1 && slot_bytes != 2) return fail(ERR_INVALID, "sym_fill: slot_bytes must be 1 or 2");

@@ -75,9 +75,9 @@ int asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const
 int assemble_v4(int TD, int p, const Asm4Args& a, int slot_bytes, cudaStream_t s);
 size_t sym_workspace_bytes(int64_t NC, int L, int64_t gdof);
 int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, int64_t* crow, int64_t* nnz_host,
-              int* max_row_host, uint32_t* stash, void* ws, cudaStream_t s);
+              int* max_row_host, uint16_t* stash, void* ws, cudaStream_t s);
 int sym_fill(const int* c2d, int64_t NC, int L, int64_t gdof, const int64_t* adj_ptr, const int* adj_pair, const int64_t* crow,
-             int* col, void* slots, int slot_bytes, const uint32_t* stash, cudaStream_t s);
+             int* col, void* slots, int slot_bytes, const uint16_t* stash, cudaStream_t s);
 int assemble_const(int TD, int p, const AsmConstArgs& a, int slot_bytes, int max_row, cudaStream_t s);
 int assemble_from_ke(AsmKeArgs a, int slot_bytes, int max_row, cudaStream_t s);
 int expand_pattern(int64_t gdof, int nc, int prio, const int64_t* crow_s, const int* col_s, int64_t* crow_out, int* col_out,

@@ -113,11 +113,11 @@ int fb2_coo_reduce(const uint32_t* perm, const int64_t* seg_start, int64_t nnz, 
 size_t fb2_sym_workspace_bytes(int64_t NC, int ldof, int64_t gdof) { return sym_workspace_bytes(NC, ldof, gdof); }
 int fb2_slot_stride(int ldof, int slot_bytes) { return slot_stride(ldof, slot_bytes); }
 int fb2_sym_count(const int32_t* c2d, int64_t NC, int ldof, int64_t gdof, int64_t* adj_ptr, int32_t* adj_pair, int64_t* crow,
-                  int64_t* nnz_host, int32_t* max_row_host, uint32_t* stash, void* ws, void* stream) {
+                  int64_t* nnz_host, int32_t* max_row_host, uint16_t* stash, void* ws, void* stream) {
   return sym_count(c2d, NC, ldof, gdof, adj_ptr, adj_pair, crow, nnz_host, max_row_host, stash, ws, S(stream));
 }
 int fb2_sym_fill(const int32_t* c2d, int64_t NC, int ldof, int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair,
-                 const int64_t* crow, int32_t* col, void* slots, int slot_bytes, const uint32_t* stash, void* stream) {
+                 const int64_t* crow, int32_t* col, void* slots, int slot_bytes, const uint16_t* stash, void* stream) {
   return sym_fill(c2d, NC, ldof, gdof, adj_ptr, adj_pair, crow, col, slots, slot_bytes, stash, S(stream));
 }
 int fb2_assemble_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,

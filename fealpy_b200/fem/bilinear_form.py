@@ -90,8 +90,8 @@ def symbolic_pattern(space):
     crow = torch.empty(gdof + 1, dtype=torch.int64, device=dev)
     ws = _lib.workspace(lib.fb2_sym_workspace_bytes(NC, L, gdof), dev)
     nnz, max_row = C.c_int64(0), C.c_int32(0)
-    try:        # scratch for the sorted candidate order (4 bytes per (cell, i, j)): the fill pass then need not sort again
-        stash = torch.empty(NC * L * L, dtype=torch.int32, device=dev)
+    try:        # scratch for the candidates' ranks (2 bytes per (cell, i, j)): the fill pass then need not rank them again
+        stash = torch.empty(NC * L * L, dtype=torch.int16, device=dev)
     except torch.cuda.OutOfMemoryError:
         stash = None
     _lib.call("fb2_sym_count", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow),

@@ -95,16 +95,16 @@ int fb2_coo_reduce(const uint32_t* perm, const int64_t* seg_start, int64_t nnz, 
  * sums its incident cells in ascending cell order (numeric). */
 size_t fb2_sym_workspace_bytes(int64_t NC, int ldof, int64_t gdof);
 /* step 1: dof -> (cell, local index) adjacency, row lengths; returns nnz and max row length.
- * stash (optional, NC*ldof*ldof uint32 of scratch, may be NULL): the count pass has to sort every
- * row's candidate columns anyway; with a stash it keeps (rank, candidate) in sorted order and
- * fb2_sym_fill given the same stash replays it instead of sorting a second time. */
+ * stash (optional, NC*ldof*ldof uint16 of scratch, may be NULL): the count pass has to rank every
+ * row's candidate columns anyway; with a stash it keeps (rank << 1 | representative) per candidate and
+ * fb2_sym_fill given the same stash replays it instead of ranking a second time. */
 int fb2_sym_count(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, int64_t* adj_ptr, int32_t* adj_pair, int64_t* crow,
-                  int64_t* nnz_host, int32_t* max_row_host, uint32_t* stash, void* ws, void* stream);
+                  int64_t* nnz_host, int32_t* max_row_host, uint16_t* stash, void* ws, void* stream);
 /* step 2: col (nnz) and slot map: NC*ldof records of fb2_slot_stride(ldof, slot_bytes) elements
  * (uint8 when max_row<=255 else uint16; records padded to 4-byte multiples) */
 int fb2_slot_stride(int ldof, int slot_bytes);
 int fb2_sym_fill(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair,
-                 const int64_t* crow, int32_t* col, void* slots, int slot_bytes, const uint32_t* stash, void* stream);
+                 const int64_t* crow, int32_t* col, void* slots, int slot_bytes, const uint16_t* stash, void* stream);
 /* numeric, constant / per-cell coefficient scalar forms (diffusion and/or mass fused).
  * blk_row/nblk/tile: row tiling of crow from fb2_spmv_plan_build (one CTA per tile).  This is the
  * "v2" kernel (lane = row, tables in shared memory); it also serves rows too long for the 12-bit tile
