@@ -72,7 +72,7 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.proc, self.path = index, None, None
-        self.thread, self.stop_flag, self.samples = None, None, []
+        self.thread, self.stop_flag, self.samples, self.skip = None, None, [], 0
 
     def _nvml_loop(self, nv, h):
         R = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
@@ -111,6 +111,15 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """start of the timed region: forget what was sampled before"""
+        self.samples.clear()
+        if self.proc is not None and self.path:
+            try:
+                self.skip = sum(1 for _ in open(self.path))
+            except Exception:
+                self.skip = 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.thread is not None:
@@ -129,7 +138,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         try:
-            for line in open(self.path):
+            for ln, line in enumerate(open(self.path)):
+                if ln < self.skip:
+                    continue
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
@@ -281,12 +292,16 @@ def run_ours(args):
             s2.record()
             return s0, s1, s2, info["niter"], x
 
-        for _ in range(max(args.warmup, 3)):
-            step()
-        barrier()
+        # the clock sampler starts BEFORE the warm-up: NVML (or nvidia-smi) initialisation was seen to stall this
+        # process's CUDA calls for ~100 ms once, which must not land in the first timed step; samples taken during
+        # the warm-up are dropped
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        sampler.mark()
         t_wall0 = time.perf_counter()
         recs = [step() for _ in range(args.steps)]
         barrier()
@@ -370,6 +385,7 @@ def run_ours(args):
             "cg": {"iters_per_s": iters / t_cg, "iters_per_step": args.cg_iters, "ms_per_iter": 1e3 * t_cg / iters,
                    "x_err_vs_exact": xerr},
             "assembly_ms": 1e3 * t_asm / args.steps,
+            "assembly_ms_steps": [round(r[0].elapsed_time(r[1]), 3) for r in recs],      # this rank's per-step times (diagnostic)
             "cold": {"mesh_topology_ms": t_mesh, "symbolic_ms": t_sym, "first_assembly_ms": t_first,
                      "nnz_per_s_incl_symbolic": nnz / ((t_sym + t_first) * 1e-3)},
             "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<1> (one CG iteration = spmv+dot, update_xr, update_p)",

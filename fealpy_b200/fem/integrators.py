@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from ..basis import device_tables, number_of_local_dofs
+from ..basis import device_tables, host_tables, number_of_local_dofs
 
 
 class _Variant:
@@ -110,7 +110,8 @@ class _ScalarCellIntegrator(Integrator):
         if self.KIND == "diffusion" and self.assembly.get_key() == "fast":
             kind, payload = "scalar", 1.0      # the reference's 'fast' variant ignores coef (:65-79)
         else:
-            kind, payload = process_coef(self.coef, mesh, tabs["bcs"].cpu().numpy(), self.batched)
+            # host copy of the quadrature points (cached numpy table): no device->host copy / sync on the assembly path
+            kind, payload = process_coef(self.coef, mesh, host_tables(mesh.TD, space.p, q)["bcs"], self.batched)
         if kind == "matrix" and self.KIND == "mass":
             raise RuntimeError("matrix coefficients are not valid for the mass integrator")
         return dict(kind=self.KIND, q=q, coef_kind=kind, coef=payload, tabs=tabs)
@@ -180,7 +181,9 @@ class LinearElasticityIntegrator(Integrator):
         self.assembly = _Variant(self, {None: self._assembly_default})
 
     def coefficients(self, space):
-        D = self.material.elastic_matrix()[0, 0].cpu()
+        D = getattr(self.material, "_D", None)          # host copy: no device round trip on the assembly path
+        if D is None:
+            D = self.material.elastic_matrix()[0, 0].cpu()
         GD = space.mesh.geo_dimension()
         if GD == 2:
             D00, D01, Dss = float(D[0, 0]), float(D[0, 1]), float(D[2, 2])

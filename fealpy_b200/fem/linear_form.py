@@ -12,7 +12,7 @@ from collections.abc import Sequence
 import torch
 
 from .. import _lib
-from ..basis import device_tables, number_of_local_dofs
+from ..basis import device_tables, host_tables, number_of_local_dofs
 from ..sparse import CSRTensor
 from .bilinear_form import symbolic_pattern
 from .integrators import Integrator, _Variant, _check_space, process_coef
@@ -41,7 +41,7 @@ class ScalarSourceIntegrator(Integrator):
             tabs["phiw"] = (tabs["ws"][:, None] * tabs["phi"]).contiguous()
         if self.source is None:
             raise ValueError("ScalarSourceIntegrator needs a source")
-        kind, val = process_coef(self.source, mesh, tabs["bcs"].cpu().numpy(), self.batched)
+        kind, val = process_coef(self.source, mesh, host_tables(TD, p, q)["bcs"], self.batched)
         if kind == "matrix":
             raise RuntimeError("source must be scalar-valued")
         code = {"scalar": 0, "cell": 1, "quad": 2}[kind]
