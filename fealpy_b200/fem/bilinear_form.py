@@ -298,7 +298,9 @@ class BilinearForm:
         NH = mesh.TD * (mesh.TD + 1) // 2 + 1          # reduced geometry record (csrc/assemble.cu A4Geo)
         if kernel == "v4":
             pl = asm4_plan(space)
-            geom = torch.empty((sym["NC"], (NH + 1) // 2 * 2), dtype=torch.float64, device=mesh.device)
+            geom = getattr(self, "_asm4_geom", None)      # per-cell geometry scratch, kept with the form (no allocator churn per assembly)
+            if geom is None or geom.shape[0] != sym["NC"] or geom.device != mesh.device:
+                geom = self._asm4_geom = torch.empty((sym["NC"], (NH + 1) // 2 * 2), dtype=torch.float64, device=mesh.device)
             _lib.call("fb2_assemble_scalar_const_v4", mesh.TD, space.p, sym["NC"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
                       _lib.ptr(sym["crow"]), _lib.ptr(pl["blk_row"]), pl["ntile"], pl["tile"], sym["max_row"], _lib.ptr(pl["batch_ptr"]),
                       _lib.ptr(pl["batch_i"]), _lib.ptr(pl["ent_cell"]), _lib.ptr(pl["ent_base"]), _lib.ptr(pl["ent_slots"]),
