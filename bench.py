@@ -22,12 +22,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# every step allocates a fresh 3.9 GB `values` array (the reference API returns a new matrix per assembly) next to
-# many small solver vectors; with the default allocator the big block is now and then split and the next assembly pays a
-# 10-150 ms cudaMalloc inside the timed region.  Expandable segments keep freed memory contiguous.  (FB2_BENCH_ALLOC_CONF=""
-# restores torch's default.)
-if os.environ.get("FB2_BENCH_ALLOC_CONF", "expandable_segments:True"):
-    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", os.environ.get("FB2_BENCH_ALLOC_CONF", "expandable_segments:True"))
 
 _emit = print
 METRIC = "assembled_nnz_per_s"
