@@ -18,6 +18,7 @@ identical for all three and bit-identical to the reference's coalesce().tocsr().
 from __future__ import annotations
 
 import ctypes as C
+import os as _os
 from collections.abc import Sequence
 
 import torch
@@ -91,7 +92,7 @@ def symbolic_pattern(space):
     ws = _lib.workspace(lib.fb2_sym_workspace_bytes(NC, L, gdof), dev)
     nnz, max_row = C.c_int64(0), C.c_int32(0)
     try:        # scratch for the candidates' ranks (2 bytes per (cell, i, j)): the fill pass then need not rank them again
-        stash = torch.empty(NC * L * L, dtype=torch.int16, device=dev)
+        stash = None if _os.environ.get("FB2_SYM_NO_STASH") else torch.empty(NC * L * L, dtype=torch.int16, device=dev)
     except torch.cuda.OutOfMemoryError:
         stash = None
     _lib.call("fb2_sym_count", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow),

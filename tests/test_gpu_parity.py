@@ -687,3 +687,20 @@ def test_elasticity_p1_fused_agrees_with_ke_paths(kind, n, prio, hypo, U):
     x = torch.rand(GD * gdof, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
     y = torch.rand(GD * gdof, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
     assert abs(float(y @ (A @ x) - x @ (A @ y))) <= 1e-10 * scale * GD * gdof
+
+
+@pytest.mark.parametrize("kind,dims,p", [("tet", (5, 4, 3), 2), ("tet", (3, 3, 2), 3), ("tri", (12, 9), 3)])
+def test_symbolic_without_stash_matches(kind, dims, p, U, monkeypatch):
+    """the symbolic phase ranks every row's candidate columns once and replays the ranks from a scratch buffer; when
+    that buffer cannot be allocated the fill pass ranks again -- both routes must give the same pattern and slot map"""
+    from fealpy_b200.mesh import TriangleMesh, TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import bilinear_form as bfm
+    Mesh = TetrahedronMesh if kind == "tet" else TriangleMesh
+    box = [0, 1, 0, 1, 0, 1] if kind == "tet" else [0, 1, 0, 1]
+    a = bfm.symbolic_pattern(LagrangeFESpace(Mesh.from_box(box, *dims), p))
+    monkeypatch.setenv("FB2_SYM_NO_STASH", "1")
+    b = bfm.symbolic_pattern(LagrangeFESpace(Mesh.from_box(box, *dims), p))
+    for k in ("crow", "col", "slots", "adj_ptr", "adj_pair"):
+        assert torch.equal(a[k], b[k]), k
+    assert a["nnz"] == b["nnz"] and a["max_row"] == b["max_row"] and a["slot_bytes"] == b["slot_bytes"]
