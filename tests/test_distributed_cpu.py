@@ -106,3 +106,47 @@ def test_distributed_cg_gloo_world2(p):
         assert err < 1e-10, (r, err)
         assert abs(niter - oniter) <= 1, (niter, oniter)
     assert out[0][1] == out[1][1], "all ranks stop at the same iteration"
+
+
+@pytest.mark.parametrize("p", [1, 2])
+@pytest.mark.parametrize("nx,world", [(16, 8), (13, 5), (16, 4), (19, 8), (128, 8)])
+def test_slab_partition_structure_many_ranks(nx, world, p):
+    """ownership and halo plan for the rank counts of the scaling run (structure only, no matrices): every global dof is
+    owned exactly once, window numbering is monotone in the global numbering, and every receive slice names exactly
+    the global ids of the peer's matching send slice"""
+    ny, nz = (3, 2) if nx < 100 else (4, 4)
+    parts = [BoxSlab(nx, ny, nz, p, world, r) for r in range(world)]
+    gdof = parts[0].gdof
+    assert sum(s.n_owned for s in parts) == gdof
+    seen = np.zeros(gdof, dtype=np.int64)
+    for s in parts:
+        l2g = s.local_to_global(np.arange(s.n_local))
+        assert l2g.min() >= 0 and l2g.max() < gdof and np.all(np.diff(l2g) > 0)
+        for lo, hi in (s.own_nodes, s.own_edges):
+            seen[l2g[lo:hi]] += 1
+        assert len(s.exchanges) == (s.rank > 0) + (s.rank < world - 1)
+        for ex in s.exchanges:
+            assert abs(ex.peer - s.rank) == 1
+            peer = parts[ex.peer]
+            back = [e for e in peer.exchanges if e.peer == s.rank]
+            assert len(back) == 1
+            assert len(ex.recv) == len(back[0].send) and len(ex.send) == len(back[0].recv)
+            for (rl, rh), (sl, sh) in zip(ex.recv, back[0].send):
+                assert rh - rl == sh - sl
+                assert np.array_equal(l2g[rl:rh], peer.local_to_global(np.arange(sl, sh)))
+                # what a rank receives it does not own; what it sends it owns
+                own = np.zeros(s.n_local, dtype=bool)
+                own[s.own_nodes[0]:s.own_nodes[1]] = True
+                own[s.own_edges[0]:s.own_edges[1]] = True
+                assert not own[rl:rh].any()
+            pown = np.zeros(peer.n_local, dtype=bool)
+            pown[peer.own_nodes[0]:peer.own_nodes[1]] = True
+            pown[peer.own_edges[0]:peer.own_edges[1]] = True
+            for sl, sh in back[0].send:
+                assert pown[sl:sh].all()
+    assert np.all(seen == 1)
+
+
+def test_slab_partition_rejects_too_many_ranks():
+    with pytest.raises(ValueError):
+        BoxSlab(8, 3, 2, 2, 8, 0)          # 9 node planes cannot give every rank two
