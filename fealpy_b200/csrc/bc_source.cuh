@@ -2,7 +2,7 @@
 #include "common.cuh"
 
 namespace fb2 {
-// physical points of NQ barycentric points in every cell: out (NC, NQ, TD) (mesh/mesh_base.py bc_to_point)
+// physical points of NQ barycentric points in every cell: out (NC, NQ, TD) (mesh/mesh_base.py:454-478, backend/numpy_backend.py:401-407)
 int bc_to_points(int TD, int64_t NC, int NQ, const double* node, const int* cell, const double* bcs, double* out, cudaStream_t s);
 int elem_source(int TD, int64_t NC, int L, int NQ, const double* node, const int* cell, const double* phiw, int kind, double scal,
                 const double* f, double* out, cudaStream_t s);

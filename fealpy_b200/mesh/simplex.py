@@ -156,7 +156,7 @@ class SimplexMesh:
         return simplex_quadrature(self.TD, q)
 
     def bc_to_point(self, bcs, index=None):
-        """physical points of barycentric points, (NC, NQ, GD) (mesh_base.py bc_to_point)."""
+        """physical points of barycentric points, (NC, NQ, GD) (mesh/mesh_base.py:454-478, backend/numpy_backend.py:401-407)."""
         cell = (self.cell if index is None else self.cell[index]).contiguous()
         b = torch.as_tensor(bcs, dtype=torch.float64, device=self.device).contiguous()
         if b.ndim != 2 or b.shape[1] != self.TD + 1:

@@ -209,7 +209,8 @@ int fb2_bcg_update_p(int64_t n, int nb, double* p, const double* r, const double
 int fb2_elem_source(int TD, int64_t NC, int ldof, int NQ, const double* node, const int32_t* cell, const double* phiw, int kind,
                     double scal, const double* f, double* out, void* stream);
 /* physical points of NQ barycentric points (bcs: NQ x (TD+1), device) in every cell, out (NC, NQ, TD):
- * mesh.bc_to_point (mesh/mesh_base.py), where callable coefficients / sources are evaluated */
+ * mesh.bc_to_point (mesh/mesh_base.py:454-478 -> bm.bc_to_points, backend/numpy_backend.py:401-407), where callable
+ * coefficients / sources are evaluated */
 int fb2_bc_to_points(int TD, int64_t NC, int NQ, const double* node, const int32_t* cell, const double* bcs, double* out, void* stream);
 /* F[d] = sum of F_e over the (cell, i) pairs of dof d in ascending order (adjacency of fb2_sym_count) */
 int fb2_gather_vector(int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_pair, const double* fe, double* F, void* stream);
