@@ -1,15 +1,22 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: P2 tetrahedral Poisson (diffusion + mass) global assembly to CSR
-plus CG, on synthetic `TetrahedronMesh.from_box` meshes (BASELINE.json configs[1]).
+"""Benchmark of the hot path `BilinearForm(...).assembly() -> CSRTensor -> cg` on synthetic `from_box` meshes.
 
-    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the CPU arm (oracle port of the reference)
+    python bench.py --gpus 1 --steps K --warmup W [--config 1..5]      # our CUDA path
+    python bench.py --impl reference --steps K --warmup W              # the UNMODIFIED reference on the host cores
 
-One "step" = one assembly() of the form (pattern cached per space = "warm") followed by a
-fixed number of CG iterations on A x = A 1.  `value` = assembled nnz/s with all inputs resident
-in HBM; `cg.iters_per_s` is reported beside it; `e2e` repeats the step through the public API
-with HOST (pinned) inputs: H2D of node/cell/cell2dof and of b, D2H of the CSR values and of x,
-all inside the timed region.  Prints ONE JSON line on rank 0.
+Configs (BASELINE.json `configs`, sizes of SURVEY.md section 8; default 2 = the one the metric is quoted on):
+  1  tri 1024^2  P1      diffusion(q=3) + mass(q=3)                       + CG
+  2  tet 128^3   P2      diffusion + mass (q=5)                           + CG      [x-slabs of a (128 N)x128x128 box at N GPUs]
+  3  tri 1024^2  P3      variable-coefficient diffusion (q=6) + mass(q=6) + CG
+  4  tet 128^3   P1 x 3  linear elasticity (q=4), Dirichlet face x=0      + Jacobi-preconditioned CG
+  5  tet 322^3   P2      diffusion + mass, ONE box row-partitioned over the N >= 2 GPUs (config 2's kernels)
+
+One "step" = one `assembly()` of the form (symbolic pattern cached per space = "warm") followed by a fixed number of CG
+iterations.  `value` = assembled nnz/s with all inputs resident in HBM (CUDA events on the launching stream, max over
+ranks); `cg` reports iterations/s; `cold` the one-time costs a single assembly on a fresh space pays; `e2e` repeats the
+step through the public API with HOST (pinned) inputs, the H2D / D2H copies inside the timed region.  At N > 1 every rank
+first runs the hardware parity check of fealpy_b200.parallel.verify (`verify`), and the run fails if it does.
+Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -27,6 +34,16 @@ _emit = print
 METRIC = "assembled_nnz_per_s"
 UNIT = "nnz/s"
 
+CONFIGS = {
+    1: dict(mesh="tri", n=1024, p=1, what="tri P1 Poisson: ScalarDiffusionIntegrator(q=3) + ScalarMassIntegrator(q=3)", cpu_rate=1.0e6),
+    2: dict(mesh="tet", n=128, p=2, what="tet P2 Poisson: ScalarDiffusionIntegrator + ScalarMassIntegrator (q=5)", cpu_rate=3.0e5),
+    3: dict(mesh="tri", n=1024, p=3, what="tri P3: ScalarDiffusionIntegrator(coef=kappa(x), q=6) + ScalarMassIntegrator(q=6)",
+            cpu_rate=4.0e5),
+    4: dict(mesh="tet", n=128, p=1, what="tet P1x3 LinearElasticityIntegrator(E=1, nu=0.3, q=4), Dirichlet face x=0, Jacobi CG",
+            cpu_rate=4.0e5),
+    5: dict(mesh="tet", n=322, p=2, what="tet P2 Poisson: ScalarDiffusionIntegrator + ScalarMassIntegrator (q=5)", cpu_rate=3.0e5),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -34,24 +51,36 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=128, help="cells per box edge (per GPU)")
-    ap.add_argument("--p", type=int, default=2)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--n", type=int, default=0, help="cells per box edge (0 = the config's size)")
     ap.add_argument("--cg-iters", type=int, default=100)
-    ap.add_argument("--cpu-n", type=int, default=20, help="box edge of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=0, help="box edge of the CPU sample (0 = sized from --cpu-budget-s)")
+    ap.add_argument("--cpu-budget-s", type=float, default=0.0, help="seconds of CPU work (0 = 20 s beside our arm, 200 s for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-existing-gpu", action="store_true")
+    ap.add_argument("--dist-mode", default=os.environ.get("FB2_DIST", "auto"), choices=["auto", "nccl", "peer"])
     return ap.parse_args()
 
 
-def measured_traffic():
-    """per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the two dominant kernels from the
-    committed `ncu --set full` capture of this same workload (profiles/r01_traffic.json), or {}"""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f)
-    except Exception:
-        return {}
+def workload(cfg_id, n, cg_iters, world):
+    c = CONFIGS[cfg_id]
+    box = f"TriangleMesh.from_box n={n}" if c["mesh"] == "tri" else f"TetrahedronMesh.from_box n={n}"
+    if cfg_id == 5:
+        box += f" (one {n}^3 box over {world} GPUs)"
+    elif world > 1:
+        box += " per GPU"
+    return f"config {cfg_id}: {c['what']} assembly to CSR + {cg_iters} CG iterations, {box}"
+
+
+def config_dict(cfg_id, n, cg_iters, world):
+    par = "single GPU" if world == 1 else (f"{world} x-slabs of one {n}^3 box" if cfg_id == 5 else
+                                           f"{world} x-slabs of one {n * world}x{n}x{n} box") + ": owned-row assembly + halo-exchange CG"
+    return {"workload": workload(cfg_id, n, cg_iters, world), "config_id": cfg_id,
+            "l2_policy": "inputs larger than L2 (multi-GB arrays per step)" if cfg_id in (2, 4, 5) else
+                         "inputs + outputs exceed L2 per step except config 1 (164 MB, flushed by the CG vectors between assemblies)",
+            "parallelism": par}
 
 
 def peaks():
@@ -61,6 +90,16 @@ def peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(cfg_id):
+    """per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels from the committed
+    `ncu --set full` capture of this workload (profiles/r02_traffic.json), or {}"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f).get(str(cfg_id), {})
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -91,6 +130,7 @@ class ClockSampler:
         try:
             import threading
             import pynvml as nv
+            import torch
             nv.nvmlInit()
             try:
                 h = nv.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid))
@@ -160,51 +200,198 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path on the host cores
+# CPU arm: the unmodified reference (baseline/_ref) on the host cores; the numpy oracle port only if it is absent
 # --------------------------------------------------------------------------------------
-def cpu_problem(n, p):
+def kappa_np(p):
+    import numpy as np
+    return 1.0 + 0.5 * np.sin(2 * np.pi * p[..., 0]) * np.cos(2 * np.pi * p[..., 1])
+
+
+def host_threads():
+    try:
+        import threadpoolctl
+        th = [d.get("num_threads", 1) for d in threadpoolctl.threadpool_info() if d.get("user_api") == "blas"]
+        return max(th) if th else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def est_nnz(cfg_id, n):
+    """nnz of the config's matrix at box edge n (closed forms of SURVEY.md section 8 scaled; used only to size samples)"""
+    full = {1: (7_346_177, 1024, 2), 2: (484_609_025, 128, 3), 3: (160_462_849, 1024, 2), 4: (286_222_473, 128, 3),
+            5: (7_693_153_161, 322, 3)}[cfg_id]
+    return full[0] * (n / full[1]) ** full[2]
+
+
+def sample_size(cfg_id, budget_s, steps):
+    """largest box edge whose `steps` reference steps fit the CPU budget"""
+    c = CONFIGS[cfg_id]
+    lo = 4
+    grid = [4, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024]
+    best = lo
+    for n in grid:
+        if n > c["n"]:
+            break
+        t = est_nnz(cfg_id, n) / c["cpu_rate"] * 1.25          # + CG / setup share
+        if t * max(steps, 1) <= budget_s:
+            best = n
+    return best
+
+
+class RefProblem:
+    """the config on the reference's own objects (numpy backend, or the reference's pytorch backend on `device`)"""
+
+    def __init__(self, cfg_id, n, backend="numpy", device=None):
+        from baseline import ref_loader
+        ref_loader.install()
+        from fealpy.backend import backend_manager as bm
+        bm.set_backend(backend)
+        from fealpy.mesh import TriangleMesh, TetrahedronMesh
+        from fealpy.functionspace import LagrangeFESpace, TensorFunctionSpace
+        from fealpy.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator, LinearElasticityIntegrator
+        from fealpy.decorator import cartesian
+        self.bm, self.cfg_id = bm, cfg_id
+        c = CONFIGS[cfg_id]
+        kw = {} if device is None else {"device": device}
+        if c["mesh"] == "tri":
+            mesh = TriangleMesh.from_box([0, 1, 0, 1], n, n, **kw)
+        else:
+            mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], n, n, n, **kw)
+        self.mesh = mesh
+        space = LagrangeFESpace(mesh, c["p"])
+        NC = mesh.number_of_cells()
+        split = 2 ** 18 if NC > 2 ** 18 else None           # chunk the element loop like fem/form.py:158-188 allows (bounds gphi)
+        self.BilinearForm = BilinearForm
+        if cfg_id == 4:
+            from fealpy.material.elastic_material import LinearElasticMaterial
+            space = TensorFunctionSpace(space, shape=(-1, 3))
+            mat = LinearElasticMaterial("m", elastic_modulus=1.0, poisson_ratio=0.3, hypo="3D")
+            self.groups = [([LinearElasticityIntegrator(mat, q=4)], split)]
+        elif cfg_id == 3:
+            if backend == "numpy":
+                kap = cartesian(lambda p: kappa_np(p))
+            else:
+                import torch
+                kap = cartesian(lambda p: 1.0 + 0.5 * torch.sin(2 * torch.pi * p[..., 0]) * torch.cos(2 * torch.pi * p[..., 1]))
+            self.groups = [([ScalarDiffusionIntegrator(coef=kap, q=6)], split), ([ScalarMassIntegrator(q=6)], None)]
+        elif cfg_id == 1:
+            self.groups = [([ScalarDiffusionIntegrator(q=3)], split), ([ScalarMassIntegrator(q=3)], None)]
+        else:
+            self.groups = [([ScalarDiffusionIntegrator()], split), ([ScalarMassIntegrator()], None)]
+        self.space = space
+        self.NC = NC
+
+    def assemble(self):
+        bf = self.BilinearForm(self.space)
+        for ints, split in self.groups:
+            bf.add_integrator(*ints, splitter=split) if split else bf.add_integrator(*ints)
+        return bf.assembly()
+
+    def rhs_and_system(self, A):
+        """(A_sys, b, M): config 4 constrains the face x = 0 through the reference's DirichletBC and uses its Jacobi
+        preconditioner; the others solve A x = A 1 unpreconditioned"""
+        bm = self.bm
+        gdof = A.shape[0]
+        ones = bm.ones(gdof, dtype=bm.float64, **({} if self.mesh.device in (None, "cpu") else {"device": self.mesh.device}))
+        b = A @ ones
+        if self.cfg_id != 4:
+            return A, b, None
+        from fealpy.fem import DirichletBC
+        from fealpy.sparse import CSRTensor
+        ip = self.space.interpolation_points()
+        sflag = ip[:, 0] < 1e-12
+        flag = bm.repeat(sflag, 3) if hasattr(bm, "repeat") else None
+        bc = DirichletBC(self.space, gd=bm.zeros(gdof, dtype=bm.float64), threshold=flag)
+        A2, b2 = bc.apply(A, b)
+        d = A2.diags()
+        return A2, b2, CSRTensor(d.crow, d.col, 1.0 / d.values, A2.shape)
+
+
+def ref_step(prob, cg_iters):
+    from fealpy.solver import cg
+    t0 = time.perf_counter()
+    A = prob.assemble()
+    t1 = time.perf_counter()
+    A2, b, M = prob.rhs_and_system(A)
+    t2 = time.perf_counter()
+    x, info = cg(A2, b, M=M, atol=0.0, rtol=0.0, maxit=cg_iters, returninfo=True)
+    t3 = time.perf_counter()
+    return A.nnz, t1 - t0, info["niter"], t3 - t2, A.shape[0]
+
+
+def oracle_step(n, p, cg_iters):
+    """fallback when baseline/_ref is absent: the numpy restatement of the reference path (config 2 shape only)"""
+    import numpy as np
     from oracle import fem_oracle as O
     node, cell = O.tet_from_box([0, 1, 0, 1, 0, 1], n, n, n)
     mesh = O.Mesh(node, cell)
     c2d = mesh.cell_to_ipoint(p)
-    return O, mesh, c2d, mesh.number_of_global_ipoints(p)
-
-
-def cpu_step(O, mesh, c2d, gdof, p, cg_iters):
+    gdof = mesh.number_of_global_ipoints(p)
     t0 = time.perf_counter()
-    groups = [(O.diffusion_element(mesh, p), c2d), (O.mass_element(mesh, p), c2d)]
-    crow, col, val = O.assemble(groups, gdof)
+    crow, col, val = O.assemble([(O.diffusion_element(mesh, p), c2d), (O.mass_element(mesh, p), c2d)], gdof)
     t1 = time.perf_counter()
-    b = O.csr_matvec(crow, col, val, __import__("numpy").ones(gdof))
+    b = O.csr_matvec(crow, col, val, np.ones(gdof))
     t2 = time.perf_counter()
     x, info = O.cg(lambda v: O.csr_matvec(crow, col, val, v), b, atol=0.0, rtol=0.0, maxit=cg_iters)
     t3 = time.perf_counter()
-    return len(val), t1 - t0, info["niter"], t3 - t2
+    return len(val), t1 - t0, info["niter"], t3 - t2, gdof
+
+
+def cpu_measure(cfg_id, n, steps, warmup, cg_iters):
+    """-> dict(kind, nnz/s, it/s, sample description) from `steps` timed reference steps at box edge n"""
+    from baseline import ref_loader
+    if ref_loader.available():
+        kind = "reference"
+        for _ in range(warmup):                                   # warm-up steps run the same code on an 8-cell-per-edge box
+            ref_step(RefProblem(cfg_id, min(8, n)), 3)
+        prob = RefProblem(cfg_id, n)
+        run = lambda: ref_step(prob, cg_iters)
+    else:
+        kind = "port"
+        if cfg_id not in (2, 5):
+            return None
+        for _ in range(min(warmup, 1)):
+            oracle_step(min(6, n), 2, 3)
+        run = lambda: oracle_step(n, 2, cg_iters)
+    t_asm = t_cg = 0.0
+    nnz = its = gdof = 0
+    for _ in range(steps):
+        nz, ta, it, tc, gdof = run()
+        nnz += nz; t_asm += ta; its += it; t_cg += tc
+    c = CONFIGS[cfg_id]
+    what = ("unmodified FEALPy 3.4.0 (baseline/_ref), numpy backend" if kind == "reference" else "numpy oracle port of the reference path")
+    sample = (f"{what}: {c['what']} on from_box n={n} (gdof {gdof}, nnz {nnz // max(steps, 1)}), {steps} step(s) of "
+              f"assembly() [{t_asm / max(steps, 1):.1f} s each] + {cg_iters} cg iterations; the full config is n={c['n']}: the "
+              f"reference's nnz/s is flat in n (3.0e5 / 3.3e5 / 3.6e5 at 8^3 / 16^3 / 32^3 for config 2, profiles/r02_reference_cpu_sizes.json), "
+              f"so the sample rate is the extrapolation to the full size; its CG rate is NOT size-independent (see cg_same_matrix)")
+    return dict(kind=kind, value=nnz / t_asm, cg_iters_per_s=its / t_cg if t_cg > 0 else None, n=n, gdof=gdof, sample=sample,
+                ms_per_step=1e3 * (t_asm + t_cg) / max(steps, 1), cores=host_threads())
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    O, mesh, c2d, gdof = cpu_problem(args.cpu_n, args.p)
-    for _ in range(min(args.warmup, 1)):
-        cpu_step(O, mesh, c2d, gdof, args.p, 5)
-    t_asm = t_cg = 0.0
-    nnz = its = 0
-    for _ in range(args.steps):
-        nz, ta, it, tc = cpu_step(O, mesh, c2d, gdof, args.p, args.cg_iters)
-        nnz += nz; t_asm += ta; its += it; t_cg += tc
-    val = nnz / t_asm
-    sample = f"tet P{args.p} from_box n={args.cpu_n} ({mesh.NC} cells, gdof {gdof}), diffusion+mass q={args.p + 3}, numpy oracle port"
+    cfg_id = args.config
+    n_full = args.n or CONFIGS[cfg_id]["n"]
+    budget = args.cpu_budget_s or 200.0
+    n = args.cpu_n or sample_size(cfg_id, budget, args.steps)
+    cg_iters = min(args.cg_iters, 10)
+    m = cpu_measure(cfg_id, min(n, n_full), args.steps, args.warmup, cg_iters)
+    if m is None:
+        _emit(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed and the oracle port covers config 2 only"}))
+        return
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * (t_asm + t_cg) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"tet P{args.p} Poisson diffusion+mass assembly + CG, from_box n=128 per GPU (CPU arm: bounded sample)"},
-        "cg": {"iters_per_s": its / t_cg, "iters_per_step": args.cg_iters},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "cg_iters_per_s": its / t_cg},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": config_dict(cfg_id, n_full, args.cg_iters, args.gpus),
+        "cg": {"iters_per_s": m["cg_iters_per_s"], "iters_per_step": cg_iters, "gdof": m["gdof"],
+               "note": "CG on the SAMPLE matrix (cache-resident at small n): compare with cpu_baseline.cg_same_matrix of our arm instead"},
+        "cpu_baseline": {"value": m["value"], "unit": UNIT, "cores": m["cores"], "kind": m["kind"], "sample": m["sample"],
+                         "cores_note": "threads OpenBLAS may use inside einsum; the path is otherwise single-threaded numpy",
+                         "cg_iters_per_s": m["cg_iters_per_s"]},
+        "e2e": {"value": m["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(json.dumps(line))
@@ -213,6 +400,89 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+class Problem:
+    """the config on fealpy_b200 objects; `solver` is persistent (no allocation inside the timed region)"""
+
+    def __init__(self, cfg_id, n, dev, world, rank, dist_mode="auto"):
+        import torch
+        from fealpy_b200.mesh import TriangleMesh, TetrahedronMesh
+        from fealpy_b200.functionspace import LagrangeFESpace, TensorFunctionSpace
+        from fealpy_b200.fem import (BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator, LinearElasticityIntegrator)
+        self.cfg_id, self.dev, self.world, self.rank = cfg_id, dev, world, rank
+        c = CONFIGS[cfg_id]
+        self.part = None
+        if world > 1:
+            if cfg_id not in (2, 5):
+                raise SystemExit("multi-GPU runs use config 2 (weak scaling) or 5 (one 322^3 box)")
+            from fealpy_b200.parallel import SlabProblem
+            nx = n * world if cfg_id == 2 else n
+            sp = SlabProblem([0, world if cfg_id == 2 else 1, 0, 1, 0, 1], nx, n, n, c["p"], world, rank, device=dev)
+            self.mesh, self.space, self.part = sp.mesh, sp.space, sp.part
+        elif c["mesh"] == "tri":
+            self.mesh = TriangleMesh.from_box([0, 1, 0, 1], n, n, device=dev)
+            self.space = LagrangeFESpace(self.mesh, c["p"])
+        else:
+            self.mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], n, n, n, device=dev)
+            self.space = LagrangeFESpace(self.mesh, c["p"])
+        self.sspace = self.space
+        bf_space = self.space
+        if cfg_id == 4:
+            from fealpy_b200.material import LinearElasticMaterial
+            bf_space = TensorFunctionSpace(self.space, shape=(-1, 3))
+            ints = [[LinearElasticityIntegrator(LinearElasticMaterial("m", elastic_modulus=1.0, poisson_ratio=0.3, hypo="3D"), q=4)]]
+        elif cfg_id == 3:
+            def kappa(p):
+                return 1.0 + 0.5 * torch.sin(2 * torch.pi * p[..., 0]) * torch.cos(2 * torch.pi * p[..., 1])
+            kappa.coordtype = "cartesian"
+            ints = [[ScalarDiffusionIntegrator(coef=kappa, q=6)], [ScalarMassIntegrator(q=6)]]
+        elif cfg_id == 1:
+            ints = [[ScalarDiffusionIntegrator(q=3)], [ScalarMassIntegrator(q=3)]]
+        else:
+            ints = [[ScalarDiffusionIntegrator()], [ScalarMassIntegrator()]]
+        self.bf_space = bf_space
+        self.bform = BilinearForm(bf_space)
+        for g in ints:
+            self.bform.add_integrator(*g)
+        self.values = None
+        self.dist_mode = dist_mode
+
+    def c2d(self):
+        return self.sspace.cell_to_dof()
+
+    def assemble(self):
+        A = self.bform.assembly(out=self.values)
+        self.values = A.values                     # every later assembly reuses this buffer
+        return A
+
+    def system(self, A):
+        """(A_sys, b, M) as solved by CG; built once (the BC / preconditioner setup is reported as `bc_ms`, not part of `value`)"""
+        import torch
+        gdof = A.shape[0]
+        ones = torch.ones(gdof, dtype=torch.float64, device=self.dev)
+        b = A @ ones
+        if self.cfg_id != 4:
+            return A, b, None
+        from fealpy_b200.fem import DirichletBC
+        from fealpy_b200.sparse import CSRTensor
+        sflag = self.sspace.interpolation_points()[:, 0] < 1e-12
+        flag = sflag.repeat_interleave(3)
+        bc = DirichletBC(self.bf_space, gd=torch.zeros(gdof, dtype=torch.float64, device=self.dev), threshold=flag)
+        A2, b2 = bc.apply(A, b)
+        d = A2.diags()
+        return A2, b2, CSRTensor(d.crow, d.col, 1.0 / d.values, A2.shape)
+
+
+def alg_bytes(cfg_id, NC, NN, L, nnz, gdof, TD, GD, NQ_coef):
+    """algorithmic bytes.  `survey`: cell + cell2dof + node + coef + values + col + crow, what ONE
+    cold assembly() must move.  `warm`: what the numeric phase must move when the pattern is cached and shared (the
+    default, BilinearForm(share_pattern=True)): cell + node + coef + values -- the figure `frac` uses."""
+    coef = 8 * NC * NQ_coef
+    survey = 4 * NC * (TD + 1) + 4 * NC * L + 8 * GD * NN + coef + 12 * nnz + 8 * (gdof + 1)
+    warm = 4 * NC * (TD + 1) + 8 * GD * NN + coef + 8 * nnz
+    it = 12 * nnz + 8 * (gdof + 1) + 104 * gdof
+    return survey, warm, it
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -224,13 +494,16 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from fealpy_b200.mesh import TetrahedronMesh
-    from fealpy_b200.functionspace import LagrangeFESpace
-    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
     from fealpy_b200.fem.bilinear_form import symbolic_pattern
     from fealpy_b200.solver import cg
 
-    n, p = args.n, args.p
+    cfg_id = args.config
+    if world > 1 and cfg_id not in (2, 5):
+        raise SystemExit("multi-GPU runs use --config 2 (weak scaling) or --config 5")
+    if cfg_id == 5 and world < 2:
+        raise SystemExit("config 5 (322^3, 200 M cells) is the multi-GPU configuration: run it with --gpus 2/4/8")
+    c = CONFIGS[cfg_id]
+    n = args.n or c["n"]
     stream = torch.cuda.Stream(device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -240,35 +513,39 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    verify = None
     with torch.cuda.stream(stream):
-        # ---- setup (not timed as part of the step; reported as cold costs) --------------------
+        # ---- hardware parity of the multi-GPU data plane, before anything is timed -------------------------------
+        if world > 1 and not args.no_verify:
+            from fealpy_b200.parallel import verify_slab, make_dist_solver
+            verify = verify_slab(world, rank, dev, solver_factory=lambda A_, part_, group=None: make_dist_solver(A_, part_, mode=args.dist_mode))
+            if not verify["ok"]:
+                if rank == 0:
+                    sys.stderr.write("bench: multi-GPU parity check FAILED: " + json.dumps(verify) + "\n")
+                dist.destroy_process_group()
+                sys.exit(3)
+        # ---- setup (not timed as part of the step; reported as cold costs) ----------------------------------------
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         e0.record()
-        part = None
-        if world == 1:
-            mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], n, n, n, device=dev)
-            space = LagrangeFESpace(mesh, p)
-        else:
-            # weak scaling: ONE global box of (n*world) x n x n cubes, row-partitioned into x-slabs;
-            # every rank assembles its owned rows (+1 ghost cell layer) and CG swaps halo planes over NCCL
-            from fealpy_b200.parallel import SlabProblem, CudaCgOps, dist_cg
-            sp = SlabProblem([0, world, 0, 1, 0, 1], n * world, n, n, p, world, rank, device=dev)
-            mesh, space, part = sp.mesh, sp.space, sp.part
-        c2d = space.cell_to_dof()
+        prob = Problem(cfg_id, n, dev, world, rank, args.dist_mode)
+        mesh, space, part, bform = prob.mesh, prob.sspace, prob.part, prob.bform
+        c2d = prob.c2d()
         e1.record()
         sym = symbolic_pattern(space)
         e2.record()
-        bform = BilinearForm(space)
-        bform.add_integrator(ScalarDiffusionIntegrator())
-        bform.add_integrator(ScalarMassIntegrator())
-        A = bform.assembly()
+        A = prob.assemble()
         e3.record()
         torch.cuda.synchronize(dev)
         t_mesh, t_sym, t_first = e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)
         nnz, gdof, NC, NN = A.nnz, A.shape[0], mesh.number_of_cells(), mesh.number_of_nodes()
         L = c2d.shape[1]
-        ones = torch.ones(gdof, dtype=torch.float64, device=dev)
-        b = A @ ones
+        eb0, eb1 = ev(), ev()
+        eb0.record()
+        A_sys, b, M = prob.system(A)
+        eb1.record()
+        torch.cuda.synchronize(dev)
+        t_bc = eb0.elapsed_time(eb1)
+        own_mask = None
         if part is not None:       # count only owned rows (halo rows are scratch)
             cr = A.crow
             (a0, a1), (b0, b1) = part.own_nodes, part.own_edges
@@ -276,19 +553,20 @@ def run_ours(args):
             own_mask = torch.zeros(gdof, dtype=torch.bool, device=dev)
             own_mask[a0:a1] = True
             own_mask[b0:b1] = True
+            from fealpy_b200.parallel import make_dist_solver
+            dsolver = make_dist_solver(A, part, mode=args.dist_mode)
 
-        def solve(A_, rhs):
+        def solve(A_, rhs, maxit, atol=0.0, rtol=0.0):
             if part is None:
-                return cg(A_, rhs, atol=0.0, rtol=0.0, maxit=args.cg_iters, returninfo=True)
-            return dist_cg(CudaCgOps(A_, part.own_ranges), rhs, torch.zeros_like(rhs), part.exchanges, atol=0.0, rtol=0.0,
-                           maxit=args.cg_iters, check_every=args.cg_iters)
+                return cg(A_, rhs, M=M, atol=atol, rtol=rtol, maxit=maxit, returninfo=True)
+            return dsolver.solve(rhs, atol=atol, rtol=rtol, maxit=maxit, check_every=min(maxit, 25))
 
         def step():
             s0, s1, s2 = ev(), ev(), ev()
             s0.record()
-            A_ = bform.assembly()
+            A_ = prob.assemble()
             s1.record()
-            x, info = solve(A_, b)
+            x, info = solve(A_sys if cfg_id == 4 else A_, b, args.cg_iters)
             s2.record()
             return s0, s1, s2, info["niter"], x
 
@@ -303,14 +581,12 @@ def run_ours(args):
         barrier()
         sampler.mark()
         # a generation-2 pass of Python's cyclic GC takes 10-100 ms in a process that has imported torch; when it
-        # fires between s0.record() and the kernel launch it shows up as "assembly time" (seen: one step of 15 ms
-        # among four of 4.3 ms).  Collect now, keep the collector off inside the timed regions.
+        # fires between s0.record() and the kernel launch it shows up as "assembly time".  Collect now, keep the
+        # collector off inside the timed regions.
         import gc
         gc.collect()
         gc.disable()
         t_wall0 = time.perf_counter()
-        # only the LAST solution is kept: holding every step's x (136 MB each) makes torch's caching allocator carve
-        # them out of the freed 3.9 GB `values` blocks, and every fifth assembly then pays a 150 ms cudaMalloc
         recs, last_x = [], None
         for _ in range(args.steps):
             r = step()
@@ -324,7 +600,21 @@ def run_ours(args):
         t_asm = sum(r[0].elapsed_time(r[1]) for r in recs) * 1e-3
         t_cg = sum(r[1].elapsed_time(r[2]) for r in recs) * 1e-3
         iters = sum(r[3] for r in recs)
-        xerr = float(((last_x - 1.0)[own_mask] if part is not None else (last_x - 1.0)).abs().max())
+
+        # ---- a CONVERGED solve (reference tolerances), outside the timed region: the error of the returned solution -----
+        xc, cinfo = solve(A_sys if cfg_id == 4 else A, b, 20000, atol=1e-12, rtol=1e-8)
+        if cfg_id == 4:
+            resid = b - A_sys @ xc
+            conv = {"niter": int(cinfo["niter"]), "rel_residual": float(resid.norm() / b.norm())}
+        else:
+            d = (xc - 1.0)
+            if own_mask is not None:
+                d = d[own_mask]
+            e_inf = d.abs().max().reshape(1)
+            if world > 1:
+                dist.all_reduce(e_inf, op=dist.ReduceOp.MAX)
+            conv = {"niter": int(cinfo["niter"]), "x_err_vs_exact": float(e_inf), "residual": float(cinfo["residual"])}
+        del xc
 
         # ---- e2e: host (pinned) inputs, copies inside the timed region ------------------------------
         e2e = None
@@ -340,11 +630,11 @@ def run_ours(args):
                 mesh.node.copy_(h_node, non_blocking=True)
                 mesh.cell.copy_(h_cell, non_blocking=True)
                 c2d.copy_(h_c2d, non_blocking=True)
-                A_ = bform.assembly()
+                A_ = prob.assemble()
                 h_vals.copy_(A_.values, non_blocking=True)
                 s1.record()
                 b.copy_(h_b, non_blocking=True)
-                x, info = solve(A_, b)
+                x, info = solve(A_sys if cfg_id == 4 else A_, b, args.cg_iters)
                 h_x.copy_(x, non_blocking=True)
                 s2.record()
                 return s0, s1, s2, info["niter"]
@@ -363,10 +653,10 @@ def run_ours(args):
                    "d2h_bytes_per_step": int(h_vals.nbytes + h_x.nbytes),
                    "cg_iters_per_s": sum(r[3] for r in er) / tc,
                    "note": "assembly: H2D node+cell+cell2dof -> assembly() -> D2H values; CG: H2D b -> cg -> D2H x"}
+            del h_vals, h_x, h_node, h_cell, h_c2d
 
     # ---- reduce over ranks (max time) ----------------------------------------------------------------
     times = torch.tensor([t_asm, t_cg, t_wall], dtype=torch.float64, device=dev)
-    nnz_local = nnz
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         tot = torch.tensor([nnz, NC, part.n_owned], dtype=torch.int64, device=dev)
@@ -377,57 +667,140 @@ def run_ours(args):
             dist.all_reduce(ev_, op=dist.ReduceOp.MAX)
             e2e["value"] = nnz_glob / float(ev_[0])
             e2e["cg_iters_per_s"] = 1.0 / float(ev_[1])
+    else:
+        nnz_glob, NC_glob, gdof_glob = nnz, NC, gdof
     t_asm, t_cg, t_wall = (float(v) for v in times)
 
-    if world == 1:
-        nnz_glob, NC_glob, gdof_glob = nnz, NC, gdof
     if rank == 0:
         peak, peak_src = peaks()
-        traffic = measured_traffic()
-        # algorithmic bytes, per launch == per step for both kernels
-        b_asm = 4 * NC * 4 + 4 * NC * L + 8 * 3 * NN + 12 * nnz + 8 * (gdof + 1)
-        b_it = 12 * nnz + 8 * (gdof + 1) + 104 * gdof
-        asm_gbs = b_asm * args.steps / t_asm / 1e9          # per GPU (rank 0's share of the bytes, max-over-ranks time)
+        traffic = measured_traffic(cfg_id)
+        TD = mesh.TD
+        GD = TD
+        NQ_coef = 21 if cfg_id == 3 else 0
+        ncomp = 3 if cfg_id == 4 else 1
+        b_survey, b_warm, b_it = alg_bytes(cfg_id, NC, NN, L * ncomp, nnz, A.shape[0], TD, GD, NQ_coef)
+        nsys, nnz_sys = (A_sys.shape[0], A_sys.nnz) if cfg_id == 4 else (gdof, A.nnz)
+        b_it = 12 * nnz_sys + 8 * (nsys + 1) + (104 + (16 if M is not None else 0)) * nsys
+        asm_gbs = b_warm * args.steps / t_asm / 1e9          # per GPU (rank 0's share of the bytes, max-over-ranks time)
         cg_gbs = b_it * iters / t_cg / 1e9
+        path = bform.last_path
+        asm_kernel = {"fused": "cell_geometry4_kernel + assemble_const_v4/v5_kernel", "gather": "elem_* (K1) + assemble_from_ke_kernel",
+                      "fused-elasticity-p1": "cell_gradients_kernel + assemble_from_ke_kernel<ETD=3>"}.get(path, path)
+        asm_launches = {"fused": 2, "fused-elasticity-p1": 2}.get(path, 6)
         line = {
             "metric": METRIC, "value": nnz_glob * args.steps / t_asm, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * (t_asm + t_cg) / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"tet P{p} Poisson: ScalarDiffusionIntegrator + ScalarMassIntegrator (q={p + 3}) assembly to CSR "
-                                   f"+ {args.cg_iters} CG iterations, TetrahedronMesh.from_box n={n} per GPU",
-                       "NC": NC_glob, "gdof": gdof_glob, "nnz": nnz_glob, "l2_policy": "inputs larger than L2 (multi-GB arrays per step)",
-                       "assembly_path": bform.last_path, "pattern": "warm (symbolic cached per space)",
-                       "parallelism": (f"{world} x-slabs of one {n * world}x{n}x{n} box: owned-row assembly + NCCL halo CG"
-                                       if world > 1 else "single GPU")},
+            "scaling": "weak" if cfg_id != 5 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(cfg_id, n, args.cg_iters, world),
+            "problem": {"NC": NC_glob, "gdof": gdof_glob, "nnz": nnz_glob, "assembly_path": path,
+                        "pattern": "warm (symbolic pattern cached per space, shared by the returned matrices: share_pattern=True)"},
             "cg": {"iters_per_s": iters / t_cg, "iters_per_step": args.cg_iters, "ms_per_iter": 1e3 * t_cg / iters,
-                   "x_err_vs_exact": xerr},
+                   "preconditioner": "jacobi" if M is not None else None, "converged_solve": conv,
+                   "dist_mode": getattr(dsolver, "mode", None) if part is not None else None},
             "assembly_ms": 1e3 * t_asm / args.steps,
             "assembly_ms_steps": [round(r[0].elapsed_time(r[1]), 3) for r in recs],      # this rank's per-step times (diagnostic)
-            "cold": {"mesh_topology_ms": t_mesh, "symbolic_ms": t_sym, "first_assembly_ms": t_first,
-                     "nnz_per_s_incl_symbolic": nnz / ((t_sym + t_first) * 1e-3)},
-            "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<1> (one CG iteration = spmv+dot, update_xr, update_p)",
+            "cold": {"mesh_topology_ms": t_mesh, "symbolic_ms": t_sym, "first_assembly_ms": t_first, "bc_setup_ms": t_bc,
+                     "nnz_per_s_incl_symbolic": nnz / ((t_sym + t_first) * 1e-3),
+                     "roofline_frac_cold": b_survey / ((t_sym + t_first) * 1e-3) / 1e9 / peak},
+            "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel (one CG iteration = spmv+dot, update_xr, update_p)",
                          "achieved": cg_gbs, "peak": peak, "unit": "GB/s", "frac": cg_gbs / peak,
-                         "traffic": traffic.get("cg_iteration_bytes") if (n == 128 and p == 2) else None,
+                         "traffic": traffic.get("cg_iteration_bytes"),
                          "peak_source": peak_src, "algorithmic_bytes_per_iter": b_it,
                          "note": "achieved = algorithmic bytes of one CG iteration x iterations / CUDA-event time of cg()"},
-            "roofline_assembly": {"bound": "hbm", "kernel": "cell_geometry4_kernel + assemble_const_v4_kernel", "achieved": asm_gbs,
+            "roofline_assembly": {"bound": "hbm", "kernel": asm_kernel, "achieved": asm_gbs,
                                   "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
-                                  "traffic": traffic.get("assembly_bytes") if (n == 128 and p == 2) else None,
-                                  "algorithmic_bytes": b_asm,
-                                  "note": "warm pattern: col/crow are cached and not re-written; limiter is the L1/LSU data pipe (DESIGN.md)"},
-            "e2e": e2e, "gpu_launches": args.steps * (2 + 3 * args.cg_iters + 7),
+                                  "traffic": traffic.get("assembly_bytes"),
+                                  "algorithmic_bytes": b_warm, "survey_bytes": b_survey,
+                                  "frac_survey_bytes": b_survey * args.steps / t_asm / 1e9 / peak,
+                                  "note": "algorithmic_bytes = cell + node + coef + values: what the warm numeric phase must move "
+                                          "(col/crow/cell2dof are consumed by the cached symbolic phase, not per assembly); "
+                                          "frac_survey_bytes keeps SURVEY 8(d)'s cold-assembly byte count for comparison with round 1"},
+            "e2e": e2e, "gpu_launches": args.steps * (asm_launches + 3 * args.cg_iters + 7),
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        if verify is not None:
+            line["verify"] = verify
         if not args.no_cpu_baseline and world == 1:
-            O, om, oc2d, ogdof = cpu_problem(args.cpu_n, p)
-            nz, ta, it, tc = cpu_step(O, om, oc2d, ogdof, p, min(args.cg_iters, 50))
-            line["cpu_baseline"] = {"value": nz / ta, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"tet P{p} from_box n={args.cpu_n} ({om.NC} cells, nnz {nz}), numpy oracle port of the "
-                                              f"reference path, {ta:.1f}s assembly",
-                                    "cg_iters_per_s": it / tc}
+            try:
+                line["cpu_baseline"] = cpu_baseline_leg(args, cfg_id, A_sys if cfg_id == 4 else A, b, M, t_cg / iters)
+            except Exception as e:          # the CPU leg must never cost the GPU line
+                line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+            if not args.no_existing_gpu:
+                try:
+                    line["existing_gpu_path"] = existing_gpu_leg(cfg_id, dev)
+                except Exception as e:
+                    line["existing_gpu_path"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
         _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline_leg(args, cfg_id, A, b, M, gpu_s_per_iter):
+    """rank 0, N = 1: the reference on the host cores on a bounded sample (~20 s), plus its CG on the SAME matrix as
+    the GPU line (copied to the host once)"""
+    budget = args.cpu_budget_s or 20.0
+    n = args.cpu_n or sample_size(cfg_id, budget, 1)
+    m = cpu_measure(cfg_id, n, 1, 0, 5)
+    if m is None:
+        return {"error": "no CPU baseline for this config without baseline/_ref"}
+    out = {"value": m["value"], "unit": UNIT, "cores": m["cores"], "kind": m["kind"], "sample": m["sample"],
+           "cg_iters_per_s_sample": m["cg_iters_per_s"],
+           "cores_note": "threads OpenBLAS may use inside einsum; the path is otherwise single-threaded numpy"}
+    if m["kind"] == "reference":
+        import numpy as np
+        from fealpy.backend import backend_manager as bm
+        bm.set_backend("numpy")
+        from fealpy.sparse import CSRTensor
+        from fealpy.solver import cg as ref_cg
+        t0 = time.perf_counter()
+        Ah = CSRTensor(A.crow.cpu().numpy(), A.col.cpu().numpy(), A.values.cpu().numpy(), spshape=A.sparse_shape)
+        Mh = None
+        if M is not None:
+            Mh = CSRTensor(M.crow.cpu().numpy(), M.col.cpu().numpy(), M.values.cpu().numpy(), spshape=M.sparse_shape)
+        bh = b.cpu().numpy()
+        t1 = time.perf_counter()
+        its = 3
+        x, info = ref_cg(Ah, bh, M=Mh, atol=0.0, rtol=0.0, maxit=its, returninfo=True)
+        t2 = time.perf_counter()
+        rate = info["niter"] / (t2 - t1)
+        out["cg_same_matrix"] = {"iters_per_s": rate, "iters": int(info["niter"]), "gdof": int(A.shape[0]), "nnz": int(A.nnz),
+                                 "d2h_s": t1 - t0, "gpu_over_cpu": (1.0 / gpu_s_per_iter) / rate,
+                                 "note": "fealpy.solver.cg (numpy backend -> scipy csr_matvec) on the GPU line's own matrix, host copy"}
+    return out
+
+
+def existing_gpu_leg(cfg_id, dev):
+    """the reference's own pytorch backend on this GPU ('the existing GPU path') at a size it fits"""
+    import torch
+    from baseline import ref_loader
+    if not ref_loader.available():
+        return {"unavailable": "baseline/_ref not installed"}
+    n = {1: 512, 2: 32, 3: 256, 4: 32, 5: 32}[cfg_id]
+    try:
+        prob = RefProblem(cfg_id, n, backend="pytorch", device=str(dev))
+        from fealpy.solver import cg
+        A = prob.assemble()                      # warm-up (cuda context of the reference's ops)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        A = prob.assemble()
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        out = {"kind": "reference pytorch backend, device=cuda", "n": n, "nnz": int(A.nnz), "value": A.nnz / (t1 - t0), "unit": UNIT,
+               "assembly_s": t1 - t0}
+        try:
+            A2, b, M = prob.rhs_and_system(A)
+            torch.cuda.synchronize(dev)
+            t2 = time.perf_counter()
+            x, info = cg(A2, b, M=M, atol=0.0, rtol=0.0, maxit=20, returninfo=True)
+            torch.cuda.synchronize(dev)
+            t3 = time.perf_counter()
+            out["cg_iters_per_s"] = info["niter"] / (t3 - t2)
+        except Exception as e:
+            out["cg_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+        return out
+    finally:
+        from fealpy.backend import backend_manager as bm
+        bm.set_backend("numpy")
 
 
 class StdoutToStderr:

@@ -89,6 +89,15 @@ int fb2_elem_elasticity(int TD, int p, int64_t NC, const double* node, const int
   return elem_elasticity(TD, p, a, S(stream));
 }
 
+// ---- public geometry / basis (rows a7, a9) ----------------------------------------------------
+int fb2_cell_gradients(int TD, int64_t NC, const double* node, const int32_t* cell, double* out, void* stream) {
+  return cell_gradients(TD, NC, node, cell, out, S(stream));
+}
+int fb2_grad_basis(int TD, int64_t NC, int NQ, int ldof, const double* cell_gradient_records, const double* R, double* out,
+                   void* stream) {
+  return grad_basis(TD, NC, NQ, ldof, cell_gradient_records, R, out, S(stream));
+}
+
 // ---- K2 -----------------------------------------------------------------------------------
 int fb2_coo_keys_from_c2d(const int32_t* rdof, const int32_t* cdof, int64_t NC, int lr, int lc, int col_bits, uint64_t* keys,
                           void* stream) {

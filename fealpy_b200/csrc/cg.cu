@@ -456,15 +456,20 @@ int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, co
   // graph capture is illegal on the legacy default stream: borrow a private stream, ordered after it
   cudaStream_t s = user_stream;
   if (user_stream == nullptr || user_stream == cudaStreamLegacy || user_stream == cudaStreamPerThread) {
-    static thread_local cudaStream_t priv = nullptr;
-    static thread_local cudaEvent_t ev = nullptr;
-    if (!priv) {
-      FB2_CUDA(cudaStreamCreateWithFlags(&priv, cudaStreamNonBlocking));
-      FB2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    // one private stream + event per (thread, device): a stream is bound to the device that was current at creation
+    constexpr int kMaxDev = 64;
+    static thread_local cudaStream_t priv_of[kMaxDev] = {};
+    static thread_local cudaEvent_t ev_of[kMaxDev] = {};
+    int dev = 0;
+    FB2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) return fail(ERR_UNSUPPORTED, "cg: device ordinal %d out of range", dev);
+    if (!priv_of[dev]) {
+      FB2_CUDA(cudaStreamCreateWithFlags(&priv_of[dev], cudaStreamNonBlocking));
+      FB2_CUDA(cudaEventCreateWithFlags(&ev_of[dev], cudaEventDisableTiming));
     }
-    FB2_CUDA(cudaEventRecord(ev, user_stream));
-    FB2_CUDA(cudaStreamWaitEvent(priv, ev, 0));
-    s = priv;
+    FB2_CUDA(cudaEventRecord(ev_of[dev], user_stream));
+    FB2_CUDA(cudaStreamWaitEvent(priv_of[dev], ev_of[dev], 0));
+    s = priv_of[dev];
   }
   Carver c(ws);
   char* pws = c.take<char>(PartialWs::bytes());
@@ -491,6 +496,7 @@ int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, co
   const double bnorm = std::sqrt(bb);
   if (bnorm < 1e-15) {
     FB2_CUDA(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), s));
+    FB2_CUDA(cudaStreamSynchronize(s));      // s may be the private stream: x must be zero before the caller's stream reads it
     return OK;
   }
   FB2_CUDA(cudaMemcpyAsync(&sc->bnorm, &bnorm, sizeof(double), cudaMemcpyHostToDevice, s));

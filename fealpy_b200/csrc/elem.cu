@@ -398,6 +398,42 @@ int cell_gradients(int TD, int64_t NC, const double* node, const int* cell, doub
   return OK;
 }
 
+// physical gradients of the basis functions, the (NC, NQ, ldof, GD) array of LagrangeFESpace.grad_basis /
+// mesh.grad_shape_function(variables='x') (mesh/mesh_base.py:713-749, mesh/triangle_mesh.py:142-153):
+//   gphi[c][q][i][m] = sum_b R[q][i][b] * Dlambda[c][b][m],  Dlambda from the records of cell_gradients
+// one thread per (c, q, i): consecutive threads write consecutive TD-vectors (coalesced)
+template <int TD>
+__global__ void __launch_bounds__(256) grad_basis_kernel(int64_t total, int NQL, const double* __restrict__ rec, const double* __restrict__ R,
+                                                         double* __restrict__ out) {
+  constexpr int NV = TD + 1, RS = NV * TD + 1;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / NQL;
+    const int qi = (int)(t - c * NQL);
+    const double* D = rec + c * RS;
+    const double* r = R + (int64_t)qi * NV;
+    double g[TD];
+#pragma unroll
+    for (int m = 0; m < TD; ++m) g[m] = 0.0;
+#pragma unroll
+    for (int b = 0; b < NV; ++b)
+#pragma unroll
+      for (int m = 0; m < TD; ++m) g[m] += r[b] * D[b * TD + m];
+#pragma unroll
+    for (int m = 0; m < TD; ++m) out[t * TD + m] = g[m];
+  }
+}
+
+int grad_basis(int TD, int64_t NC, int NQ, int L, const double* rec, const double* R, double* out, cudaStream_t s) {
+  if (NC <= 0 || NQ <= 0 || L <= 0) return OK;
+  const int64_t total = NC * NQ * L;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSM * 32);
+  if (TD == 2) grad_basis_kernel<2><<<grid, 256, 0, s>>>(total, NQ * L, rec, R, out);
+  else if (TD == 3) grad_basis_kernel<3><<<grid, 256, 0, s>>>(total, NQ * L, rec, R, out);
+  else return fail(ERR_UNSUPPORTED, "grad_basis: TD must be 2 or 3");
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
 // -------------------------------------------------------------------------------------
 // host-side dispatch
 // -------------------------------------------------------------------------------------

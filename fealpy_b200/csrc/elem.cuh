@@ -45,5 +45,7 @@ int elem_quad(int TD, int p, const ElemQuadArgs& a, cudaStream_t s);
 // out[c] = (grad lambda_k[x] for k, x; signed measure): (TD+1)*TD + 1 doubles per cell
 int cell_gradients(int TD, int64_t NC, const double* node, const int* cell, double* out, cudaStream_t s);
 int elem_elasticity(int TD, int p, const ElemElasticityArgs& a, cudaStream_t s);
+// gphi (NC, NQ, L, TD) = R (NQ, L, TD+1) . Dlambda, Dlambda from the records of cell_gradients
+int grad_basis(int TD, int64_t NC, int NQ, int L, const double* rec, const double* R, double* out, cudaStream_t s);
 
 }  // namespace fb2

@@ -174,7 +174,7 @@ def tensor_pattern(space):
 
 
 class BilinearForm:
-    def __init__(self, space, batch_size: int = 0, *, assembly_path: str = "auto"):
+    def __init__(self, space, batch_size: int = 0, *, assembly_path: str = "auto", share_pattern: bool = True):
         if isinstance(space, (tuple, list)):
             if len(space) != 1:
                 raise NotImplementedError("two-space (rectangular) forms are not on the accelerated path")
@@ -193,6 +193,10 @@ class BilinearForm:
             raise ValueError(f"unknown assembly_path {assembly_path!r}")
         self.assembly_path = assembly_path
         self.last_path = None
+        # The CSR pattern depends only on the space and is cached with it.  share_pattern=True (default): every matrix
+        # assembled on this space references the SAME crow/col tensors -- treat them as read-only (CSRTensor.copy()
+        # gives private ones).  share_pattern=False: each returned matrix owns fresh copies, as the reference's do.
+        self.share_pattern = bool(share_pattern)
 
     # ---- bookkeeping (fem/form.py:92-144) ----------------------------------------------------
     @property
@@ -274,10 +278,18 @@ class BilinearForm:
                 m["scal"] = 0.0
         return merged
 
-    def _assemble_fused(self, plan):
+    def _values_buffer(self, nnz, device, out):
+        if out is None:
+            return torch.empty(nnz, dtype=torch.float64, device=device)
+        if not (isinstance(out, torch.Tensor) and out.dtype == torch.float64 and out.is_contiguous()
+                and out.shape == (nnz,) and out.device == torch.device(device)):
+            raise ValueError(f"out must be a contiguous float64 tensor of shape ({nnz},) on {device}")
+        return out
+
+    def _assemble_fused(self, plan, out=None):
         space, mesh = self.space, self.space.mesh
         sym = symbolic_pattern(space)
-        values = torch.empty(sym["nnz"], dtype=torch.float64, device=mesh.device)
+        values = self._values_buffer(sym["nnz"], mesh.device, out)
         dm, mm = plan.get("diffusion"), plan.get("mass")
 
         def parts(m):
@@ -322,7 +334,7 @@ class BilinearForm:
             if not isinstance(k, torch.Tensor) or k.ndim != 3:
                 raise ValueError("Output of operator integrators should be 3D, "
                                  f"but got shape {tuple(getattr(k, 'shape', ()))}.")
-            ke = k if ke is None else ke.add_(k)
+            ke = k if ke is None else ke + k          # out of place: an integrator may return a cached block
         return ke.contiguous()
 
     def _plan_elasticity_p1(self):
@@ -340,21 +352,23 @@ class BilinearForm:
         wsum = float(host_tables(mesh.TD, 1, q)["M4"][0, 0, 0, 0])
         return dict(coef=it.coefficients(space), wsum=wsum)
 
-    def _assemble_elasticity_p1(self, plan):
+    def _assemble_elasticity_p1(self, plan, out=None):
         space = self.space
         sspace, mesh = space.scalar_space, space.scalar_space.mesh
         sym, pat = symbolic_pattern(sspace), tensor_pattern(space)
         TD, NC = mesh.TD, sym["NC"]
         d_diag, d_lam, d_shear = plan["coef"]
-        geo = torch.empty((NC, (TD + 1) * TD + 1), dtype=torch.float64, device=mesh.device)
-        values = torch.empty(pat["col"].shape[0], dtype=torch.float64, device=mesh.device)
+        geo = getattr(self, "_ep1_geo", None)            # per-cell gradient records, kept with the form (no allocator churn)
+        if geo is None or geo.shape[0] != NC or geo.device != mesh.device:
+            geo = self._ep1_geo = torch.empty((NC, (TD + 1) * TD + 1), dtype=torch.float64, device=mesh.device)
+        values = self._values_buffer(pat["col"].shape[0], mesh.device, out)
         _lib.call("fb2_assemble_elasticity_p1", TD, NC, _lib.ptr(mesh.node), _lib.ptr(mesh.cell), int(space.dof_priority), sym["gdof"],
                   d_diag, d_lam, d_shear, plan["wsum"], _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]), _lib.ptr(sym["slots"]),
                   sym["slot_bytes"], _lib.ptr(sym["crow"]), sym["max_row"], _lib.ptr(pat["crow"]), _lib.ptr(pat["blk_row"]), pat["nblk"],
                   pat["tile"], _lib.ptr(geo), _lib.ptr(values), _lib.stream())
         return pat["crow"], pat["col"], values
 
-    def _assemble_gather(self):
+    def _assemble_gather(self, out=None):
         space = self.space
         ke = self._summed_ke()
         if self._is_tensor_space():
@@ -368,7 +382,7 @@ class BilinearForm:
             crow, col, tiling = sym["crow"], sym["col"], sym
         if ke.shape != (sym["NC"], sym["L"] * nc, sym["L"] * nc):
             raise ValueError(f"entity_to_global.shape[0] != local_tensor.shape[0] or wrong local shape {tuple(ke.shape)}")
-        values = torch.empty(col.shape[0], dtype=torch.float64, device=ke.device)
+        values = self._values_buffer(col.shape[0], ke.device, out)
         _lib.call("fb2_assemble_from_ke", sym["NC"], sym["L"], nc, prio, sym["gdof"], _lib.ptr(ke), _lib.ptr(sym["adj_ptr"]),
                   _lib.ptr(sym["adj_pair"]), _lib.ptr(sym["slots"]), sym["slot_bytes"], _lib.ptr(sym["crow"]), sym["max_row"],
                   _lib.ptr(crow), _lib.ptr(tiling["blk_row"]), tiling["nblk"], tiling["tile"], _lib.ptr(values), _lib.stream())
@@ -409,8 +423,9 @@ class BilinearForm:
         _lib.call("fb2_coo_reduce", _lib.ptr(perm), _lib.ptr(seg), nnz, _lib.ptr(vals), _lib.ptr(values), _lib.stream())
         return crow, col, values
 
-    def assembly(self, *, format="csr"):
-        """fem/bilinear_form.py:83-105"""
+    def assembly(self, *, format="csr", out=None):
+        """fem/bilinear_form.py:83-105.  `out` (optional, beyond the reference signature): a float64 tensor of nnz entries
+        that receives the CSR values, so that repeated assemblies allocate nothing."""
         if format not in ("csr", "coo"):
             raise ValueError(f"Unsupported format {format}.")
         if not self.integrators:
@@ -423,17 +438,21 @@ class BilinearForm:
                 raise NotImplementedError("the fused path needs constant / per-cell scalar coefficients on a scalar space")
         eplan = self._plan_elasticity_p1() if (plan is None and path in ("auto", "fused")) else None
         if plan is not None:
-            crow, col, values = self._assemble_fused(plan)
+            crow, col, values = self._assemble_fused(plan, out)
             self.last_path = "fused"
         elif eplan is not None:
-            crow, col, values = self._assemble_elasticity_p1(eplan)
+            crow, col, values = self._assemble_elasticity_p1(eplan, out)
             self.last_path = "fused-elasticity-p1"
         elif path == "coo":
             crow, col, values = self._assemble_coo()
+            if out is not None:
+                values = self._values_buffer(values.shape[0], values.device, out).copy_(values)
             self.last_path = "coo"
         else:
-            crow, col, values = self._assemble_gather()
+            crow, col, values = self._assemble_gather(out)
             self.last_path = "gather"
+        if not self.share_pattern and self.last_path != "coo":
+            crow, col = crow.clone(), col.clone()
         M = CSRTensor(crow, col, values, self.shape)
         if self._transposed:
             raise NotImplementedError("transposed forms are not on the accelerated path")

@@ -89,7 +89,7 @@ class LinearForm:
             v = it.assembly(space)
             if not isinstance(v, torch.Tensor) or v.shape != (sym["NC"], sym["L"]):
                 raise ValueError(f"Output of source integrators should be (NC, ldof), but got {tuple(getattr(v, 'shape', ()))}.")
-            fe = v if fe is None else fe.add_(v)
+            fe = v if fe is None else fe + v          # out of place: an integrator may return a cached block
         F = torch.empty(sym["gdof"], dtype=torch.float64, device=fe.device)
         _lib.call("fb2_gather_vector", sym["gdof"], _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]), _lib.ptr(fe.contiguous()),
                   _lib.ptr(F), _lib.stream())
@@ -165,10 +165,48 @@ class DirichletBC:
         if uh is None:
             uh = torch.zeros_like(f)
         uh, _ = self.space.boundary_interpolate(gd=gd, uh=uh, threshold=self.threshold, method=self.method)
+        uh = uh.contiguous()
         blk, bv0, tile, mr = A.spmv_plan()
         out = torch.empty_like(f)
         n = A.shape[0]
-        _lib.call("fb2_cg_residual", n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(uh.contiguous()),
+        _lib.call("fb2_cg_residual", n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(uh),
                   _lib.ptr(f.contiguous()), _lib.ptr(out), _lib.ptr(blk), _lib.ptr(bv0), tile, mr, _lib.stream())      # out = f - A uh
         _lib.call("fb2_bc_vector", n, _lib.ptr(self._mask), _lib.ptr(uh), _lib.ptr(out), _lib.stream())
         return out
+
+
+class DirichletBCOperator:
+    """Matrix-free constrained operator (fem/dirichlet_bc_operator.py:13-67): `op @ u` applies the form to u with
+    the boundary entries masked out and passes the boundary entries of u through; `apply(F, uh)` builds the right-hand
+    side.  `form` is a BilinearForm (assembled or not) or any operator with `@` and `.shape`; usable as `A` in cg()."""
+
+    def __init__(self, form, gd=None, *, threshold=None, isDDof=None, left: bool = True):
+        self.form, self.gd = form, gd
+        space = form._spaces[0] if hasattr(form, "_spaces") else getattr(form, "space", None)
+        self.space = space
+        if isDDof is None:
+            if space is None:
+                raise ValueError("isDDof is required when the operator carries no space")
+            isDDof = space.is_boundary_dof(threshold=threshold)
+        self.is_boundary_dof = isDDof
+        self.boundary_dof_index = isDDof.nonzero().reshape(-1)
+        self.shape = tuple(form.shape)
+
+    def init_solution(self):
+        uh = torch.zeros(self.shape[1], dtype=torch.float64, device=self.is_boundary_dof.device)
+        self.space.boundary_interpolate(self.gd, uh, threshold=self.is_boundary_dof)
+        return uh
+
+    def apply(self, F, uh):
+        F = F - self.form @ uh
+        F[self.is_boundary_dof] = uh[self.is_boundary_dof]
+        return F
+
+    def __matmul__(self, u):
+        bd = self.is_boundary_dof
+        v = u.clone()
+        val = v[bd]
+        v[bd] = 0.0
+        v = self.form @ v
+        v[bd] = val
+        return v

@@ -46,15 +46,25 @@ class LagrangeFESpace:
     def geo_dimension(self): return self.GD
     def top_dimension(self): return self.TD
 
-    def is_boundary_dof(self, threshold=None, method=None):
-        """functionspace/dofs.py:23-55 (threshold callables are evaluated with torch ops)."""
+    def basis(self, bc, index=None):
+        """phi (1, NQ, ldof) (functionspace/lagrange_fe_space.py:146-148)"""
+        return self.mesh.shape_function(bc, self.p, index=index)[None, ...]
+
+    face_basis = basis
+    edge_basis = basis
+
+    def grad_basis(self, bc, index=None, variable="x"):
+        """(NC, NQ, ldof, GD) for variable='x', R (NQ, ldof, TD+1) for 'u' (functionspace/lagrange_fe_space.py:153-154)"""
+        return self.mesh.grad_shape_function(bc, self.p, index=index, variables=variable)
+
+    def _boundary_face_dofs(self, keep_face=None):
+        """flag of the dofs lying on boundary faces (optionally only the faces flagged in keep_face): the dofs of
+        local face lf of a cell are the multi-indices with a zero in position lf (= face_to_dof of that face)"""
         mesh, p = self.mesh, self.p
         gdof = self.number_of_global_dofs()
-        if isinstance(threshold, torch.Tensor):
-            if threshold.dtype == torch.bool and threshold.numel() == gdof:
-                return threshold
-            raise ValueError(f"Unknown threshold: {threshold}")
         bd_face = mesh.boundary_face_flag()
+        if keep_face is not None:
+            bd_face = bd_face & keep_face
         c2d = self.cell_to_dof().long()
         c2f = mesh.cell2face.long()
         mi = torch.as_tensor(mesh.multi_index_matrix(p), device=self.device)
@@ -64,12 +74,35 @@ class LagrangeFESpace:
             cells = bd_face[c2f[:, lf]].nonzero().reshape(-1)
             if cells.numel():
                 flag[c2d[cells][:, on_face].reshape(-1)] = True
-        if callable(threshold):
-            idx = flag.nonzero().reshape(-1)
-            keep = threshold(self.interpolation_points()[idx])
-            flag = torch.zeros_like(flag)
-            flag[idx[keep]] = True
         return flag
+
+    def is_boundary_dof(self, threshold=None, method=None):
+        """functionspace/dofs.py:23-55.  method None / 'centroid': a callable threshold is evaluated on the
+        barycentres of the boundary FACES and every dof of a kept face is marked; 'interp': it is evaluated on
+        the interpolation points of the boundary dofs.  (threshold callables run as torch ops.)"""
+        gdof = self.number_of_global_dofs()
+        if isinstance(threshold, torch.Tensor):
+            if threshold.dtype == torch.bool and threshold.numel() == gdof:
+                return threshold
+            raise ValueError(f"Unknown threshold: {threshold}")
+        if method is None or method == "centroid":
+            keep = None
+            if callable(threshold):
+                mesh = self.mesh
+                idx = mesh.boundary_face_index()
+                sel = torch.as_tensor(threshold(mesh.entity_barycenter("face", idx)), device=self.device).to(torch.bool)
+                keep = torch.zeros(mesh.number_of_faces(), dtype=torch.bool, device=self.device)
+                keep[idx[sel]] = True
+            return self._boundary_face_dofs(keep)
+        if method == "interp":
+            flag = self._boundary_face_dofs()
+            if callable(threshold):
+                idx = flag.nonzero().reshape(-1)
+                sel = torch.as_tensor(threshold(self.interpolation_points()[idx]), device=self.device).to(torch.bool)
+                flag = torch.zeros_like(flag)
+                flag[idx[sel]] = True
+            return flag
+        raise ValueError(f"Unknown method: {method}")
 
     def boundary_interpolate(self, gd, uh=None, *, threshold=None, method=None):
         """functionspace/lagrange_fe_space.py:111-142"""
@@ -148,3 +181,53 @@ class TensorFunctionSpace:
                       int(self.dof_priority), _lib.ptr(out), _lib.stream())
             self._c2d = out
         return self._c2d if index is None else self._c2d[index]
+
+    def interpolation_points(self):
+        return self.scalar_space.interpolation_points()
+
+    def is_boundary_dof(self, threshold=None, method="interp"):
+        """functionspace/tensor_space.py:159-188: the scalar flag repeated over the components (or one threshold per
+        component when a tuple is given)"""
+        s, n = self.scalar_space, self.dof_numel
+        if isinstance(threshold, torch.Tensor):
+            if threshold.dtype == torch.bool and threshold.numel() == self.number_of_global_dofs():
+                return threshold
+            raise ValueError("len(threshold) must equal tensorspace gdof")
+        if threshold is None or callable(threshold):
+            f = s.is_boundary_dof(threshold, method=method)
+            return f.repeat(n) if self.dof_priority else f.repeat_interleave(n)
+        if isinstance(threshold, tuple):
+            assert n == len(threshold)
+            fs = [s.is_boundary_dof(t, method=method) for t in threshold]
+            return torch.cat(fs) if self.dof_priority else torch.stack(fs, dim=1).reshape(-1)
+        raise ValueError(f"Unknown type of threshold {type(threshold)}")
+
+    def boundary_interpolate(self, gd, uh=None, *, threshold=None, method=None):
+        """functionspace/tensor_space.py:190-260 for the cases the path uses: gd a number, a full-size tensor, or a
+        callable returning (npoints, ncomp) values at the boundary interpolation points"""
+        s, n = self.scalar_space, self.dof_numel
+        gdof = self.number_of_global_dofs()
+        if uh is None:
+            uh = torch.zeros(gdof, dtype=self.ftype, device=self.device)
+        isbd = self.is_boundary_dof(threshold) if isinstance(threshold, torch.Tensor) else self.is_boundary_dof(threshold, method=method)
+        if isinstance(gd, (int, float)):
+            uh[isbd] = float(gd)          # (the reference writes uh[threshold] = gd here, :197-204, which only works for mask thresholds)
+        elif isinstance(gd, torch.Tensor):
+            assert gd.numel() == gdof
+            uh[isbd] = gd.reshape(-1)[isbd]
+        elif callable(gd):
+            if isinstance(threshold, (tuple, torch.Tensor)):
+                raise NotImplementedError("callable gd with per-component / tensor thresholds is not on the accelerated path")
+            sflag = s.is_boundary_dof(threshold, method=method)
+            val = gd(s.interpolation_points()[sflag])                 # (nbd, ncomp)
+            sg = s.number_of_global_dofs()
+            view = uh.view(n, sg) if self.dof_priority else uh.view(sg, n)
+            if self.dof_priority:
+                view[:, sflag] = val.T.to(view.dtype)
+            else:
+                view[sflag, :] = val.to(view.dtype)
+        else:
+            raise ValueError("Unsupported type for gd. Must be a callable, int, float, or tensor.")
+        return uh, isbd
+
+    set_dirichlet_bc = boundary_interpolate

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..basis import multi_index_matrix, number_of_local_dofs
+from ..basis import grad_shape_function, multi_index_matrix, number_of_local_dofs, shape_function
 from ..quadrature import simplex_quadrature
 
 
@@ -180,9 +180,92 @@ class SimplexMesh:
         cnt = torch.bincount(self.cell2face.reshape(-1).long(), minlength=self.number_of_faces())
         return cnt == 1
 
+    def boundary_face_index(self):
+        return self.boundary_face_flag().nonzero().reshape(-1)
+
+    def entity_barycenter(self, etype="cell", index=None):
+        """mean of the entity's vertices (mesh/mesh_base.py entity_barycenter)"""
+        if etype in ("node", 0):
+            return self.node if index is None else self.node[index]
+        ent = self.entity(etype)
+        ent = ent if index is None else ent[index]
+        return self.node[ent.long()].mean(dim=1)
+
+    # ---- cell geometry as public device arrays (SURVEY 8 row a9) ---------------------------------
+    # The arithmetic is the element kernels' own (csrc/elem.cu load_geo): one record per cell holds
+    # grad(lambda_k) for k = 0..TD and the signed measure.
+    def _cells(self, index):
+        if index is None or (isinstance(index, slice) and index == slice(None)):
+            return self.cell
+        return self.cell[index].reshape(-1, self.TD + 1).contiguous()
+
+    def cell_gradient_records(self, index=None):
+        """(NC, (TD+1)*TD + 1) float64: grad lambda (k-major) then the signed cell measure"""
+        cell = self._cells(index)
+        NC, TD = cell.shape[0], self.TD
+        out = torch.empty((NC, (TD + 1) * TD + 1), dtype=torch.float64, device=self.device)
+        _lib.call("fb2_cell_gradients", TD, NC, _lib.ptr(self.node), _lib.ptr(cell), _lib.ptr(out), _lib.stream())
+        return out
+
+    def entity_measure(self, etype="cell", index=None):
+        """mesh/triangle_mesh.py:45-70, mesh/tetrahedron_mesh.py:144-175 (signed cell measure, never abs'ed)"""
+        if etype in ("cell", self.TD):
+            return self.cell_gradient_records(index)[:, -1].contiguous()
+        if etype in ("node", 0):
+            return torch.zeros(1, dtype=torch.float64, device=self.device)
+        if etype in ("edge", 1):
+            e = self.edge if index is None else self.edge[index]
+            v = self.node[e[:, 1].long()] - self.node[e[:, 0].long()]
+            return torch.sqrt((v * v).sum(dim=1))
+        if etype in ("face", 2) and self.TD == 3:
+            f = self.face if index is None else self.face[index]
+            v01 = self.node[f[:, 1].long()] - self.node[f[:, 0].long()]
+            v02 = self.node[f[:, 2].long()] - self.node[f[:, 0].long()]
+            nv = torch.linalg.cross(v01, v02)
+            return torch.sqrt((nv * nv).sum(dim=1)) / 2.0
+        raise ValueError(f"entity type: {etype} is wrong!")
+
+    def grad_lambda(self, index=None, TD=None):
+        """(NC, TD+1, GD) gradients of the barycentric coordinates (mesh/triangle_mesh.py:115-129,
+        mesh/tetrahedron_mesh.py:208-219)"""
+        if TD is not None and TD != self.TD:
+            raise NotImplementedError("grad_lambda of sub-entities is not on the accelerated path")
+        rec = self.cell_gradient_records(index)
+        return rec[:, :-1].reshape(rec.shape[0], self.TD + 1, self.TD).contiguous()
+
+    def shape_function(self, bcs, p=1, *, index=None, mi=None):
+        """phi (NQ, ldof) at barycentric points (mesh/mesh_base.py:687-711 -> bm.simplex_shape_function);
+        cell independent, evaluated once on the host in float64 and uploaded"""
+        b = bcs.detach().cpu().numpy() if isinstance(bcs, torch.Tensor) else np.asarray(bcs, dtype=np.float64)
+        return torch.from_numpy(np.ascontiguousarray(shape_function(b, p))).to(self.device)
+
+    GRAD_SHAPE_DEFAULT = "u"
+
+    def grad_shape_function(self, bcs, p=1, *, index=None, variables=None, mi=None):
+        """variables='u': R (NQ, ldof, TD+1) = dphi/dlambda; 'x': (NC, NQ, ldof, GD) physical gradients
+        (mesh/mesh_base.py:713-749; TriangleMesh defaults to 'x', mesh/triangle_mesh.py:142-153)"""
+        variables = self.GRAD_SHAPE_DEFAULT if variables is None else variables
+        b = bcs.detach().cpu().numpy() if isinstance(bcs, torch.Tensor) else np.asarray(bcs, dtype=np.float64)
+        if b.ndim != 2 or b.shape[1] != self.TD + 1:
+            raise ValueError(f"barycentric points must be (NQ, {self.TD + 1})")
+        R = torch.from_numpy(np.ascontiguousarray(grad_shape_function(b, p))).to(self.device)
+        if variables == "u":
+            return R
+        if variables != "x":
+            raise ValueError(f"Variables type is expected to be 'u' or 'x', but got '{variables}'.")
+        rec = self.cell_gradient_records(index)
+        NC, NQ, L = rec.shape[0], R.shape[0], R.shape[1]
+        out = torch.empty((NC, NQ, L, self.TD), dtype=torch.float64, device=self.device)
+        _lib.call("fb2_grad_basis", self.TD, NC, NQ, L, _lib.ptr(rec), _lib.ptr(R), _lib.ptr(out), _lib.stream())
+        return out
+
 
 class TriangleMesh(SimplexMesh):
     TD = 2
+    GRAD_SHAPE_DEFAULT = "x"
+
+    def cell_area(self, index=None):
+        return self.entity_measure("cell", index)
 
     @classmethod
     def from_box(cls, box=(0, 1, 0, 1), nx=10, ny=10, *, threshold=None, itype=None, ftype=None, device="cuda"):
@@ -202,6 +285,9 @@ class TriangleMesh(SimplexMesh):
 
 class TetrahedronMesh(SimplexMesh):
     TD = 3
+
+    def cell_volume(self, index=None):
+        return self.entity_measure("cell", index)
 
     @classmethod
     def from_box(cls, box=(0, 1, 0, 1, 0, 1), nx=10, ny=10, nz=10, threshold=None, device="cuda"):

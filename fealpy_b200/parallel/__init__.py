@@ -1,6 +1,7 @@
 from .box_partition import BoxSlab, box_edges_before, box_number_of_edges, box_number_of_nodes
-from .dist_cg import dist_cg, halo_exchange, CudaCgOps
+from .dist_cg import dist_cg, halo_exchange, CudaCgOps, DistCG, make_dist_solver
 from .slab_problem import SlabProblem
+from .verify import verify_slab
 
 __all__ = ["BoxSlab", "box_edges_before", "box_number_of_edges", "box_number_of_nodes", "dist_cg", "halo_exchange",
-           "CudaCgOps", "SlabProblem"]
+           "CudaCgOps", "DistCG", "make_dist_solver", "SlabProblem", "verify_slab"]

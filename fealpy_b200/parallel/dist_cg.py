@@ -102,7 +102,7 @@ class CudaCgOps:
         return float(self.sc[SC_RNORM].item())
 
 
-def dist_cg(ops, b, x0, exchanges, *, atol=1e-12, rtol=1e-8, maxit=10000, check_every=8, group=None):
+def dist_cg(ops, b, x0, exchanges, *, atol=1e-12, rtol=1e-8, maxit=10000, check_every=8, group=None, x_out=None):
     """x (window-local vector; owned entries are the solution), info = {'residual', 'niter'}"""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
 
@@ -115,7 +115,11 @@ def dist_cg(ops, b, x0, exchanges, *, atol=1e-12, rtol=1e-8, maxit=10000, check_
     bnorm = math.sqrt(float(bb.item()))
     if bnorm < 1e-15:
         return torch.zeros_like(b), {"residual": 0.0, "niter": 0}
-    x = x0.clone()
+    if x_out is None:
+        x = torch.zeros_like(b) if x0 is None else x0.clone()
+    else:                                    # caller-owned solution buffer (persistent solver: no allocation per solve)
+        x = x_out
+        x.zero_() if x0 is None else x.copy_(x0)
     halo_exchange(x, exchanges, group)
     ops.init(atol, rtol, maxit, bnorm)
     ops.residual(x, b)                       # r = b - A x on every local row (halo rows are scratch)
@@ -138,3 +142,34 @@ def dist_cg(ops, b, x0, exchanges, *, atol=1e-12, rtol=1e-8, maxit=10000, check_
                 break
     niter, _ = ops.status()
     return x, {"residual": ops.residual_norm(), "niter": niter}
+
+
+class DistCG:
+    """Persistent distributed CG solver for one matrix: work vectors, the device scalar block and the SpMV plan are
+    allocated ONCE (nothing is allocated inside a timed solve), `solve()` can be called repeatedly.
+
+    part: any object with `own_ranges` (lo0, hi0, lo1, hi1 in local ids) and `exchanges` (list of Exchange)."""
+
+    mode = "nccl"
+
+    def __init__(self, A, part, minv=None, group=None):
+        self.A, self.part, self.group = A, part, group
+        self.ops = CudaCgOps(A, part.own_ranges, minv)
+        self.x = torch.empty(A.sparse_shape[0], dtype=torch.float64, device=A.device)
+
+    def solve(self, b, x0=None, *, atol=1e-12, rtol=1e-8, maxit=10000, check_every=8):
+        return dist_cg(self.ops, b, x0, self.part.exchanges, atol=atol, rtol=rtol, maxit=maxit, check_every=check_every,
+                       group=self.group, x_out=self.x)
+
+
+def make_dist_solver(A, part, minv=None, group=None, mode="auto"):
+    """'nccl': halo exchange + scalar all-reduces through torch.distributed; 'peer': the exchange and the reductions are
+    fused into the CG kernels over NVLink peer memory (parallel/peer_cg.py); 'auto' picks 'peer' when it can be set up"""
+    if mode in ("auto", "peer"):
+        try:
+            from .peer_cg import PeerCG
+            return PeerCG(A, part, minv=minv, group=group)
+        except Exception:
+            if mode == "peer":
+                raise
+    return DistCG(A, part, minv=minv, group=group)

@@ -27,6 +27,58 @@ def _minv_diag(M, n, device):
     raise NotImplementedError("only diagonal preconditioners (1-D tensor or diagonal CSRTensor) are on the accelerated path")
 
 
+def _cg_operator(A, b, x0, M, atol, rtol, maxit, returninfo):
+    """The reference recurrence (solver/cg.py:76-123) for operator-valued A (and M): the products are Python-level
+    `A @ p` calls, the vector updates and inner products are the library's kernels (fb2_dot, fb2_bcg_update_xr/p with a
+    batch of one); the stopping test reads one scalar per iteration, as the reference does."""
+    if b.device.type != "cuda" or b.dtype != torch.float64:
+        raise RuntimeError("fealpy_b200.solver.cg needs float64 CUDA tensors; there is no CPU fallback")
+    n, dev = b.shape[0], b.device
+    bb = b.contiguous()
+    pws = _lib.partial_ws(dev)
+    sc = torch.zeros(4, dtype=torch.float64, device=dev)         # rTr | pAp | rTr_new | tmp
+    rTr, pAp, rTr_new, tmp = (sc[k:k + 1] for k in range(4))
+
+    def dot(u, v, out):
+        _lib.call("fb2_dot", n, _lib.ptr(u), _lib.ptr(v), _lib.ptr(out), _lib.ptr(pws), _lib.stream())
+
+    def precond(v):
+        if M is None:
+            return v
+        if isinstance(M, torch.Tensor) and M.ndim == 1:        # the diagonal of M
+            return (M * v).contiguous()
+        return (M @ v).contiguous()
+
+    info = {"residual": 0.0, "niter": 0}
+    dot(bb, bb, tmp)
+    b_norm = float(tmp.item()) ** 0.5
+    if b_norm < 1e-15:
+        x = torch.zeros_like(bb)
+        return (x, info) if returninfo else x
+    x = torch.zeros_like(bb) if x0 is None else x0.clone().contiguous()
+    r = (bb - (A @ x)).contiguous()
+    z = precond(r)
+    p = z.clone()
+    dot(r, z, rTr)
+    it = 0
+    while True:
+        Ap = (A @ p).contiguous()
+        dot(p, Ap, pAp)
+        _lib.call("fb2_bcg_update_xr", n, 1, _lib.ptr(x), _lib.ptr(r), _lib.ptr(p), _lib.ptr(Ap), _lib.ptr(rTr), _lib.ptr(pAp),
+                  _lib.stream())
+        z = precond(r)
+        dot(r, z, rTr_new)
+        r_norm = float(rTr_new.item()) ** 0.5
+        it += 1
+        info["residual"], info["niter"] = r_norm, it
+        if r_norm < atol or r_norm < rtol * b_norm or (maxit is not None and it >= maxit):
+            break
+        # p = z + beta p ; fb2_bcg_update_p forms z = minv .* r itself, so a general z goes in as "r" with minv = NULL
+        _lib.call("fb2_bcg_update_p", n, 1, _lib.ptr(p), _lib.ptr(z), None, _lib.ptr(rTr_new), _lib.ptr(rTr), _lib.stream())
+        rTr.copy_(rTr_new)
+    return (x, info) if returninfo else x
+
+
 def cg(A, b, x0=None, M=None, *, batch_first=False, atol=1e-12, rtol=1e-8, maxit=10000, returninfo=False):
     assert isinstance(b, torch.Tensor), "b must be a Tensor"
     if x0 is not None:
@@ -35,10 +87,23 @@ def cg(A, b, x0=None, M=None, *, batch_first=False, atol=1e-12, rtol=1e-8, maxit
         raise ValueError("b must be a 1D or 2D dense tensor")
     if x0 is not None and x0.shape != b.shape:
         raise ValueError("x0 and b must have the same shape")
-    if not isinstance(A, CSRTensor):
-        raise TypeError("fealpy_b200.solver.cg needs a fealpy_b200 CSRTensor (assemble with BilinearForm.assembly())")
     if b.ndim == 2:
+        if not isinstance(A, CSRTensor):
+            raise NotImplementedError("batched right-hand sides need an assembled CSRTensor on the accelerated path")
         return _cg_batched(A, b, x0, M, batch_first, atol, rtol, maxit, returninfo)
+    minv, fused = None, isinstance(A, CSRTensor)
+    if fused:
+        try:
+            minv = _minv_diag(M, A.sparse_shape[0], b.device)
+        except NotImplementedError:
+            if not hasattr(M, "__matmul__"):
+                raise
+            fused = False
+    if not fused:
+        # any A / M with __matmul__ (solver/cg.py:10-14): matrix-free forms, DirichletBCOperator, user operators
+        if not hasattr(A, "__matmul__"):
+            raise TypeError("A must support `A @ x` (a CSRTensor, a BilinearForm or any operator with __matmul__)")
+        return _cg_operator(A, b, x0, M, atol, rtol, maxit, returninfo)
     if b.device.type != "cuda" or b.dtype != torch.float64:
         raise RuntimeError("fealpy_b200.solver.cg needs float64 CUDA tensors; there is no CPU fallback")
     n = A.sparse_shape[0]
@@ -47,7 +112,6 @@ def cg(A, b, x0=None, M=None, *, batch_first=False, atol=1e-12, rtol=1e-8, maxit
     lib = _lib.load()
     x = torch.zeros_like(b) if x0 is None else x0.clone().contiguous()   # inputs are never mutated
     bb = b.contiguous()
-    minv = _minv_diag(M, n, b.device)
     ws = _lib.workspace(lib.fb2_cg_workspace_bytes(n, A.nnz), b.device)
     niter, resid = C.c_int(0), C.c_double(0.0)
     _lib.call("fb2_cg", n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(bb), _lib.ptr(x), _lib.ptr(minv),

@@ -125,7 +125,19 @@ class CSRTensor:
         return out
 
     def diags(self):
-        """main diagonal as a dense vector (sparse/csr_tensor.py diags)"""
+        """the diagonal entries as a CSRTensor of the same shape (sparse/csr_tensor.py:467-475 -> partial(), :224-239);
+        the reference builds its Jacobi preconditioner from it: CSRTensor(d.crow, d.col, 1/d.values, A.shape)"""
+        n = self._spshape[0]
+        rows = self.row_indices()
+        mask = rows == self._col
+        cnt = torch.bincount(rows[mask].long(), minlength=n)
+        crow = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+        crow[1:] = torch.cumsum(cnt, dim=0)
+        return CSRTensor(crow, self._col[mask].clone(), None if self._values is None else self._values[..., mask].clone(),
+                         self._spshape)
+
+    def diagonal(self):
+        """main diagonal as a dense vector (absent entries are 0)"""
         n = min(self._spshape)
         rows = self.row_indices()
         mask = rows == self._col

@@ -73,6 +73,18 @@ int fb2_elem_scalar_quad(int TD, int p, int64_t NC, const double* node, const in
 int fb2_elem_elasticity(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const double* M4, double d_diag,
                         double d_lam, double d_shear, int dof_priority, double* out, void* stream);
 
+/* ---- cell geometry and basis gradients as public arrays ----------------------------------------
+ * replaces mesh.entity_measure('cell') / cell_volume / grad_lambda (mesh/triangle_mesh.py:45-70,115-129,
+ * mesh/tetrahedron_mesh.py:144-175,208-219 -> backend simplex_measure / triangle_grad_lambda_2d /
+ * tetrahedron_grad_lambda_3d, backend/numpy_backend.py:413-421,586-629) and
+ * mesh.grad_shape_function(variables='x') = LagrangeFESpace.grad_basis (mesh/mesh_base.py:713-749,
+ * functionspace/lagrange_fe_space.py:146-154).  The same device functions feed the element kernels.
+ * out (NC, (TD+1)*TD + 1): grad lambda_k[x] (k-major), then the signed measure. */
+int fb2_cell_gradients(int TD, int64_t NC, const double* node, const int32_t* cell, double* out, void* stream);
+/* out (NC, NQ, ldof, TD) = sum_b R[q][i][b] * Dlambda[c][b][m]; R (NQ, ldof, TD+1) device table (dphi/dlambda) */
+int fb2_grad_basis(int TD, int64_t NC, int NQ, int ldof, const double* cell_gradient_records, const double* R, double* out,
+                   void* stream);
+
 /* ---- K2: deterministic COO -> CSR ---------------------------------------------------------
  * replaces BilinearForm._scalar_assembly index build (fem/bilinear_form.py:46-75),
  * COOTensor.coalesce (sparse/coo_tensor.py:184-213) and COOTensor.tocsr (:137-157). */

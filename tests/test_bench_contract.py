@@ -1,5 +1,6 @@
-"""bench.py contract checks that need no GPU: the reference arm (CPU oracle port) prints ONE JSON line with the keys
-the driver reads; under a multi-rank launch only rank 0 prints; the clock sampler degrades gracefully."""
+"""bench.py contract checks that need no GPU: the reference arm (the unmodified reference from baseline/_ref, or the
+oracle port when it is absent) prints ONE JSON line with the keys the driver reads; under a multi-rank launch only rank
+0 prints; the clock sampler degrades gracefully; the config / byte-count helpers are consistent."""
 import json
 import os
 import subprocess
@@ -24,9 +25,39 @@ def test_reference_arm_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["value"] > 0 and d["gpu_launches"] == 0
     cb, e2e = d["cpu_baseline"], d["e2e"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    sys.path.insert(0, ROOT)
+    from baseline import ref_loader
+    assert cb["kind"] == ("reference" if ref_loader.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["config_id"] == 2
+
+
+def test_reference_arm_other_configs():
+    sys.path.insert(0, ROOT)
+    from baseline import ref_loader
+    if not ref_loader.available():
+        import pytest
+        pytest.skip("baseline/_ref not installed")
+    for cfg in (1, 3, 4):
+        r = _run(["--impl", "reference", "--config", str(cfg), "--steps", "1", "--warmup", "0", "--cpu-n", "4"])
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert d["config"]["config_id"] == cfg and d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference"
+
+
+def test_config_and_bytes_helpers():
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    # both arms print the same config for the same (config, n, iterations, world)
+    assert bench.config_dict(2, 128, 100, 1) == bench.config_dict(2, 128, 100, 1)
+    assert "per GPU" in bench.workload(2, 128, 100, 8) and "322^3" in bench.workload(5, 322, 100, 8)
+    # config 2 = 6.71 GB per assembly, 7.72 GB per CG iteration
+    survey, warm, it = bench.alg_bytes(2, 12_582_912, 129 ** 3, 10, 484_609_025, 16_974_593, 3, 3, 0)
+    assert abs(survey - 6.707e9) < 5e6 and abs(it - 7.716e9) < 5e6
+    assert warm == 16 * 12_582_912 + 24 * 129 ** 3 + 8 * 484_609_025
+    assert bench.sample_size(2, 20.0, 1) >= 12 and bench.sample_size(2, 200.0, 20) >= 12
 
 
 def test_reference_arm_other_ranks_are_silent():

@@ -99,8 +99,13 @@ def test_jacobi_preconditioned_cg_matches_oracle(U):
     gold = G.load(case["name"])
     mesh, space, bform, _ = U.make_form(case, gold)
     A = bform.assembly()
-    d = A.diags()
-    x, info = cg(A, U.t64(gold["b"]), M=1.0 / d, returninfo=True)
+    from fealpy_b200.sparse import CSRTensor
+    d = A.diags()                                                 # a CSRTensor, as in the reference (sparse/csr_tensor.py:467-475)
+    assert isinstance(d, CSRTensor) and d.nnz == A.shape[0]
+    M = CSRTensor(d.crow, d.col, 1.0 / d.values, A.shape)        # solver/iterative_solver_manger.py:273-280
+    x, info = cg(A, U.t64(gold["b"]), M=M, returninfo=True)
+    x2 = cg(A, U.t64(gold["b"]), M=1.0 / A.diagonal())            # the diagonal as a vector is accepted too
+    assert float((x - x2).abs().max()) == 0.0
     crow, col, val = gold["crow"], gold["col"], gold["values"]
     diag = O.csr_matvec(crow, col, val, np.ones(len(crow) - 1)) * 0
     rows = np.repeat(np.arange(len(crow) - 1), np.diff(crow))
