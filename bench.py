@@ -35,13 +35,13 @@ METRIC = "assembled_nnz_per_s"
 UNIT = "nnz/s"
 
 CONFIGS = {
-    1: dict(mesh="tri", n=1024, p=1, what="tri P1 Poisson: ScalarDiffusionIntegrator(q=3) + ScalarMassIntegrator(q=3)", cpu_rate=1.0e6),
-    2: dict(mesh="tet", n=128, p=2, what="tet P2 Poisson: ScalarDiffusionIntegrator + ScalarMassIntegrator (q=5)", cpu_rate=3.0e5),
+    1: dict(mesh="tri", n=1024, p=1, what="tri P1 Poisson: ScalarDiffusionIntegrator(q=3) + ScalarMassIntegrator(q=3)", cpu_rate=6.0e5),
+    2: dict(mesh="tet", n=128, p=2, what="tet P2 Poisson: ScalarDiffusionIntegrator + ScalarMassIntegrator (q=5)", cpu_rate=2.6e5),
     3: dict(mesh="tri", n=1024, p=3, what="tri P3: ScalarDiffusionIntegrator(coef=kappa(x), q=6) + ScalarMassIntegrator(q=6)",
-            cpu_rate=4.0e5),
+            cpu_rate=9.0e5),
     4: dict(mesh="tet", n=128, p=1, what="tet P1x3 LinearElasticityIntegrator(E=1, nu=0.3, q=4), Dirichlet face x=0, Jacobi CG",
-            cpu_rate=4.0e5),
-    5: dict(mesh="tet", n=322, p=2, what="tet P2 Poisson: ScalarDiffusionIntegrator + ScalarMassIntegrator (q=5)", cpu_rate=3.0e5),
+            cpu_rate=5.5e5),
+    5: dict(mesh="tet", n=322, p=2, what="tet P2 Poisson: ScalarDiffusionIntegrator + ScalarMassIntegrator (q=5)", cpu_rate=2.6e5),
 }
 
 
@@ -260,7 +260,11 @@ class RefProblem:
         self.mesh = mesh
         space = LagrangeFESpace(mesh, c["p"])
         NC = mesh.number_of_cells()
-        split = 2 ** 18 if NC > 2 ** 18 else None           # chunk the element loop like fem/form.py:158-188 allows (bounds gphi)
+        # No `splitter=`: the reference's chunked element loop (fem/form.py:158-188) yields K_e chunks against the FULL
+        # cell2dof in BilinearForm._scalar_assembly (fem/bilinear_form.py:69: "operands could not be broadcast ...
+        # (663552,10,1) and (262144,10,10)" at n = 48), so the unmodified reference can only assemble unchunked; the
+        # sample size is therefore also bounded by host memory (gphi = NC x NQ x ldof x GD doubles).
+        split = None
         self.BilinearForm = BilinearForm
         if cfg_id == 4:
             from fealpy.material.elastic_material import LinearElasticMaterial
@@ -362,7 +366,7 @@ def cpu_measure(cfg_id, n, steps, warmup, cg_iters):
     what = ("unmodified FEALPy 3.4.0 (baseline/_ref), numpy backend" if kind == "reference" else "numpy oracle port of the reference path")
     sample = (f"{what}: {c['what']} on from_box n={n} (gdof {gdof}, nnz {nnz // max(steps, 1)}), {steps} step(s) of "
               f"assembly() [{t_asm / max(steps, 1):.1f} s each] + {cg_iters} cg iterations; the full config is n={c['n']}: the "
-              f"reference's nnz/s is flat in n (3.0e5 / 3.3e5 / 3.6e5 at 8^3 / 16^3 / 32^3 for config 2, profiles/r02_reference_cpu_sizes.json), "
+              f"reference's nnz/s is flat in n (2.6e5 / 2.3e5 / 3.2e5 / 2.7e5 / 2.9e5 at n = 8 / 16 / 24 / 32 / 40 for config 2, profiles/r02_reference_cpu_sizes.json), "
               f"so the sample rate is the extrapolation to the full size; its CG rate is NOT size-independent (see cg_same_matrix)")
     return dict(kind=kind, value=nnz / t_asm, cg_iters_per_s=its / t_cg if t_cg > 0 else None, n=n, gdof=gdof, sample=sample,
                 ms_per_step=1e3 * (t_asm + t_cg) / max(steps, 1), cores=host_threads())

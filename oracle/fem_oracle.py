@@ -542,11 +542,32 @@ def source_vector(mesh: Mesh, p: int, f, q=None):
     return F
 
 
-def boundary_dof_flag(mesh: Mesh, p: int):
-    flag = np.zeros(mesh.number_of_global_ipoints(p), dtype=bool)
+def boundary_dof_flag(mesh: Mesh, p: int, threshold=None, method=None):
+    """functionspace/dofs.py:23-55.  method None / 'centroid': a callable threshold selects boundary FACES by their
+    barycentres and every dof of a kept face is flagged; 'interp': it selects boundary dofs by their interpolation points."""
+    gdof = mesh.number_of_global_ipoints(p)
+    flag = np.zeros(gdof, dtype=bool)
     f2d = mesh.face_to_ipoint(p)
-    flag[f2d[mesh.boundary_face_flag()].ravel()] = True
+    index = np.nonzero(mesh.boundary_face_flag())[0]
+    if method is None or method == "centroid":
+        if callable(threshold):
+            bc = mesh.node[mesh.face[index]].mean(axis=1)
+            index = index[threshold(bc)]
+        flag[f2d[index].ravel()] = True
+    elif method == "interp":
+        dofs = f2d[index].ravel()
+        if callable(threshold):
+            dofs = dofs[threshold(mesh.interpolation_points(p)[dofs])]
+        flag[dofs] = True
+    else:
+        raise ValueError(f"Unknown method: {method}")
     return flag
+
+
+def tensor_boundary_dof_flag(mesh: Mesh, p: int, ncomp: int, dof_priority: bool, threshold=None, method=None):
+    """functionspace/tensor_space.py:159-188 (one threshold for all components)"""
+    f = boundary_dof_flag(mesh, p, threshold, method)
+    return np.tile(f, ncomp) if dof_priority else np.repeat(f, ncomp)
 
 
 def dirichlet_apply(crow, col, val, F, uh, is_bd):

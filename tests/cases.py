@@ -100,11 +100,37 @@ CASES = [
          cg=False, elem=True),
 ]
 
+def thr_partial(p):
+    """partial-boundary predicate (x < 0.38 or y > 0.62): evaluated on face barycentres (method None / 'centroid') and on
+    interpolation points (method 'interp') it selects different dof sets along the border of the region"""
+    return (p[..., 0] < 0.38) | (p[..., 1] > 0.62)
+
+
+def gd_vector(p):
+    """vector-valued Dirichlet data (npoints, GD) for the elasticity case"""
+    return np.stack([0.1 * p[..., 1], -0.2 * p[..., 0] * p[..., -1], 0.05 + 0.0 * p[..., 0]], axis=-1)[..., :p.shape[-1]]
+
+
+THRESHOLDS = {"thr_partial": thr_partial}
+
 # Poisson problems with Dirichlet BC + source (rows f1/f2): -div(grad u) = f, u = g on the boundary
+# (threshold / method: the Dirichlet part of the boundary, functionspace/dofs.py:23-55; the rest is natural)
 BC_CASES = [
     dict(name="bc_tri_p1_8", mesh="tri", dims=(8, 8), p=1),
     dict(name="bc_tri_p2_6_jit", mesh="tri", dims=(6, 6), p=2, jitter=13),
     dict(name="bc_tet_p2_3", mesh="tet", dims=(3, 3, 3), p=2),
+    dict(name="bc_tri_p2_7_thr_centroid", mesh="tri", dims=(7, 7), p=2, threshold="thr_partial", method=None, reaction=True),
+    dict(name="bc_tet_p2_4_thr_interp", mesh="tet", dims=(4, 4, 4), p=2, threshold="thr_partial", method="interp", reaction=True),
+    dict(name="bc_tri_p3_5_thr_centroid", mesh="tri", dims=(5, 5), p=3, jitter=17, threshold="thr_partial", method="centroid",
+         reaction=True),
+]
+
+# linear elasticity with a clamped / displaced part of the boundary (TensorFunctionSpace boundary API) + Jacobi CG
+TENSOR_BC_CASES = [
+    dict(name="bc_tet_p1_4_elasticity", mesh="tet", dims=(4, 3, 3), p=1, dof_priority=False, threshold="thr_partial",
+         E=1.0, nu=0.3, hypo="3D", q=4),
+    dict(name="bc_tri_p2_5_elasticity_prio", mesh="tri", dims=(5, 5), p=2, dof_priority=True, threshold="thr_partial",
+         E=2.0, nu=0.25, hypo="plane_strain", q=None, jitter=21),
 ]
 
 
@@ -113,7 +139,7 @@ def box_of(case):
 
 
 def by_name(name):
-    for c in CASES + BC_CASES:
+    for c in CASES + BC_CASES + TENSOR_BC_CASES:
         if c["name"] == name:
             return c
     raise KeyError(name)

@@ -373,13 +373,23 @@ def test_poisson_source_dirichlet_cg(case, U):
     gold = G.load(case["name"])
     mesh = U.make_mesh(case, gold)
     space = LagrangeFESpace(mesh, case["p"])
-    A = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).assembly()
+    from fealpy_b200.fem import ScalarMassIntegrator
+    bform = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator())
+    if case.get("reaction"):
+        bform.add_integrator(ScalarMassIntegrator())
+    A = bform.assembly()
     U.assert_csr_matches(A, gold)
     F = LinearForm(space).add_integrator(ScalarSourceIntegrator(U.torch_coef_func(C.source_cart))).assembly()
     assert np.max(np.abs(F.cpu().numpy() - gold["F"])) <= 1e-13 * np.max(np.abs(gold["F"]))
-    assert np.array_equal(space.is_boundary_dof().cpu().numpy(), gold["isbd"])
+    thr = U.torch_coef_func(C.THRESHOLDS[case["threshold"]]) if case.get("threshold") else None
+    method = case.get("method")
+    assert np.array_equal(space.is_boundary_dof(threshold=thr, method=method).cpu().numpy(), gold["isbd"])
+    if thr is not None:       # the face-centroid and the interpolation-point selections differ on these cases
+        assert np.array_equal(space.is_boundary_dof(threshold=thr, method="interp").cpu().numpy(), gold["isbd_val"])
+        with pytest.raises(ValueError):
+            space.is_boundary_dof(threshold=thr, method="nonsense")
     np.testing.assert_allclose(space.interpolation_points().cpu().numpy(), gold["ipoints"], atol=1e-14)
-    bc = DirichletBC(space, gd=U.torch_coef_func(C.kappa_cart))
+    bc = DirichletBC(space, gd=U.torch_coef_func(C.kappa_cart), threshold=thr, method=method)
     A2, F2 = bc.apply(A, F)
     assert np.max(np.abs(F2.cpu().numpy() - gold["F_bc"])) <= 1e-12 * np.max(np.abs(gold["F_bc"]))
     S = A2.to_scipy()
@@ -709,3 +719,227 @@ def test_symbolic_without_stash_matches(kind, dims, p, U, monkeypatch):
     for k in ("crow", "col", "slots", "adj_ptr", "adj_pair"):
         assert torch.equal(a[k], b[k]), k
     assert a["nnz"] == b["nnz"] and a["max_row"] == b["max_row"] and a["slot_bytes"] == b["slot_bytes"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: public geometry / basis arrays of the CUDA code against the reference's OWN test vectors
+# (test/mesh/tetrahedron_mesh_data.py:1819,1994,2176, test/mesh/triangle_mesh_data.py:60,68,104,
+#  test/backend/backend_data.py:12,198, test/functionspace/lagrange_fe_space_data.py)
+# ---------------------------------------------------------------------------------------------------------------
+def test_reference_geometry_vectors_on_device(U):
+    from fealpy_b200.mesh import TriangleMesh, TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.quadrature import simplex_quadrature
+    RT = G.ref_testdata()
+    # backend primitives
+    m = TriangleMesh(U.t64(RT["bk_tri2d_node"]), U.t64(RT["bk_tri2d_cell"].astype(np.int32)))
+    p = int(RT["bk_tri2d_p"])
+    np.testing.assert_allclose(m.entity_measure("cell").cpu().numpy(), RT["bk_tri2d_simple_measure"], atol=1e-14)
+    np.testing.assert_allclose(m.cell_area().cpu().numpy(), RT["bk_tri2d_simple_measure"], atol=1e-14)
+    np.testing.assert_allclose(m.grad_lambda().cpu().numpy(), RT["bk_tri2d_triangle_grad_lambda_2d"], atol=1e-14)
+    np.testing.assert_allclose(m.shape_function(RT["bk_tri2d_bcs"], p).cpu().numpy(), RT["bk_tri2d_simple_shape_function"], atol=1e-14)
+    np.testing.assert_allclose(m.grad_shape_function(RT["bk_tri2d_bcs"], p, variables="u").cpu().numpy(),
+                               RT["bk_tri2d_simple_grad_shape_function"], atol=1e-14)
+    t = TetrahedronMesh(U.t64(RT["bk_tet_node"]), U.t64(RT["bk_tet_cell"].astype(np.int32)))
+    np.testing.assert_allclose(t.grad_lambda().cpu().numpy(), RT["bk_tet_tetrahedron_grad_lambda_3d"], atol=1e-14)
+    # tetrahedron mesh vectors on from_box(3, 2, 1)
+    t = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], 3, 2, 1)
+    np.testing.assert_allclose(t.cell_volume().cpu().numpy(), RT["tet_321_cm"], atol=1e-14)
+    np.testing.assert_allclose(t.entity_measure("cell").cpu().numpy(), RT["tet_321_cm"], atol=1e-14)
+    np.testing.assert_allclose(t.grad_lambda().cpu().numpy(), RT["tet_321_glambda"], atol=1e-14)
+    t1 = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], 1, 1, 1)
+    bcs, _ = simplex_quadrature(3, 3).get_quadrature_points_and_weights()
+    np.testing.assert_allclose(t1.grad_shape_function(bcs, 2).cpu().numpy(), RT["tet_111_gsf_u_p2_q3"], atol=1e-14)   # default 'u'
+    gx = t1.grad_shape_function(bcs, 2, variables="x").cpu().numpy()
+    np.testing.assert_allclose(np.transpose(gx, (1, 0, 2, 3)), RT["tet_111_gsf_x_p2_q3"], atol=1e-13)    # reference layout (NQ, NC, l, GD)
+    # triangle mesh vectors
+    m = TriangleMesh.from_box([0, 1, 0, 1], 2, 2)
+    bcs, _ = simplex_quadrature(2, 3).get_quadrature_points_and_weights()
+    np.testing.assert_allclose(m.grad_shape_function(bcs, 2).cpu().numpy(), RT["tri_22_gphi_p2_q3"], atol=1e-13)      # default 'x'
+    m2 = TriangleMesh.from_box([-1, 1, -1, 1], 2, 2)
+    np.testing.assert_allclose(m2.grad_lambda().cpu().numpy(), RT["tri_glambda_m11_22"], atol=1e-14)
+    # LagrangeFESpace.basis / grad_basis (test/functionspace/lagrange_fe_space_data.py)
+    m = TriangleMesh.from_box([0, 1, 0, 1], 1, 1)
+    space = LagrangeFESpace(m, 2)
+    bcs = RT["lfs_box1_p2_bcs"]
+    np.testing.assert_allclose(space.basis(bcs).cpu().numpy(), RT["lfs_box1_p2_basis"], atol=1e-14)
+    np.testing.assert_allclose(space.grad_basis(bcs).cpu().numpy(), RT["lfs_box1_p2_grad_basis"], atol=1e-13)
+    assert np.array_equal(space.is_boundary_dof().cpu().numpy(), RT["lfs_box1_p2_is_boundary_dof"])
+    # index= sub-selection and the oracle on a jittered mesh
+    from oracle import fem_oracle as O
+    case = C.by_name("tet_p2_4_diffmass_jit")
+    gold = G.load(case["name"])
+    mesh = U.make_mesh(case, gold)
+    om = O.Mesh(gold["node"], gold["cell"])
+    np.testing.assert_allclose(mesh.entity_measure("cell").cpu().numpy(), om.cell_measure(), rtol=1e-13)
+    np.testing.assert_allclose(mesh.grad_lambda().cpu().numpy(), om.grad_lambda(), rtol=1e-12, atol=1e-13)
+    idx = torch.tensor([5, 0, 17], device="cuda")
+    np.testing.assert_allclose(mesh.grad_lambda(index=idx).cpu().numpy(), om.grad_lambda()[[5, 0, 17]], rtol=1e-12, atol=1e-13)
+    bcs, _ = O.quadrature(3, 4)
+    np.testing.assert_allclose(LagrangeFESpace(mesh, 2).grad_basis(bcs).cpu().numpy(), O.grad_basis(om, 2, bcs), rtol=1e-11, atol=1e-12)
+
+
+def test_user_integrator_written_against_basis_api(U):
+    """plug-in point (i) of SURVEY 8(b): an integrator that only uses space.grad_basis / mesh.entity_measure /
+    quadrature_formula and returns (NC, l, l) -- assembled through the gather path, equal to the built-in one"""
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator
+    from fealpy_b200.fem.integrators import Integrator
+
+    class MyDiffusion(Integrator):
+        def assembly(self, space, indices=None):
+            mesh = space.mesh
+            bcs, ws = mesh.quadrature_formula(space.p + 3).get_quadrature_points_and_weights()
+            gphi = space.grad_basis(bcs, variable="x")                       # (NC, NQ, l, GD)
+            cm = mesh.entity_measure("cell")
+            w = torch.as_tensor(ws, device=gphi.device)
+            return torch.einsum("q,c,cqid,cqjd->cij", w, cm, gphi, gphi)
+
+    case = C.by_name("tet_p2_4_diffmass_jit")
+    gold = G.load(case["name"])
+    mesh, space, _, _ = U.make_form(case, gold)
+    A = BilinearForm(space).add_integrator(MyDiffusion()).assembly()
+    B = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).assembly()
+    assert torch.equal(A.col, B.col) and torch.equal(A.crow, B.crow)
+    assert float((A.values - B.values).abs().max()) <= 1e-12 * float(B.values.abs().max())
+
+
+@pytest.mark.parametrize("n", [16, 24])
+def test_tet_p2_against_oracle_full_values(n, U):
+    """every CSR value of a jittered tet P2 diffusion + mass matrix at 16^3 / 24^3 against the oracle (itself pinned to the
+    reference on the smaller golden cases): pattern bit-exact, values <= 1e-12 max|A|; CG solution <= 1e-10"""
+    from oracle import fem_oracle as O
+    from fealpy_b200.mesh import TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    from fealpy_b200.solver import cg
+    node, cell = O.tet_from_box([0, 1, 0, 1, 0, 1], n, n, n)
+    node = C.perturb(node, (n, n, n), seed=100 + n)
+    om = O.Mesh(node, cell)
+    c2d = om.cell_to_ipoint(2)
+    gdof = om.number_of_global_ipoints(2)
+    crow, col, val = O.assemble([(O.diffusion_element(om, 2), c2d), (O.mass_element(om, 2), c2d)], gdof)
+    mesh = TetrahedronMesh(U.t64(node), U.t64(cell.astype(np.int32)))
+    space = LagrangeFESpace(mesh, 2)
+    assert np.array_equal(space.cell_to_dof().cpu().numpy(), c2d)
+    for path in ("auto", "gather"):
+        bf = BilinearForm(space, assembly_path=path)
+        bf.add_integrator(ScalarDiffusionIntegrator())
+        bf.add_integrator(ScalarMassIntegrator())
+        A = bf.assembly()
+        assert np.array_equal(A.crow.cpu().numpy(), crow) and np.array_equal(A.col.cpu().numpy(), col)
+        got = A.values.cpu().numpy()
+        assert np.max(np.abs(got - val)) <= 1e-12 * np.max(np.abs(val)), path
+    if n == 16:
+        b = O.csr_matvec(crow, col, val, np.ones(gdof))
+        xo, oinfo = O.cg(lambda v: O.csr_matvec(crow, col, val, v), b)
+        x, info = cg(A, U.t64(b), returninfo=True)
+        assert abs(info["niter"] - oinfo["niter"]) <= 1
+        assert np.linalg.norm(x.cpu().numpy() - xo) / np.linalg.norm(xo) <= 1e-10
+
+
+def test_share_pattern_and_out_buffer(U):
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    case = C.by_name("tet_p2_3x2x1_diffmass")
+    gold = G.load(case["name"])
+    mesh, space, bform, _ = U.make_form(case, gold)
+    A1 = bform.assembly()
+    A2 = BilinearForm(space).add_integrator(ScalarMassIntegrator()).assembly()
+    assert A1.col.data_ptr() == A2.col.data_ptr()                   # default: the cached pattern is shared (documented)
+    bf = BilinearForm(space, share_pattern=False)
+    bf.add_integrator(ScalarDiffusionIntegrator())
+    bf.add_integrator(ScalarMassIntegrator())
+    A3 = bf.assembly()
+    assert A3.col.data_ptr() != A1.col.data_ptr() and A3.crow.data_ptr() != A1.crow.data_ptr()
+    A3.col.zero_()                                                  # a private copy: editing it must not touch the cache
+    U.assert_csr_matches(bform.assembly(), gold)
+    out = torch.empty(A1.nnz, dtype=torch.float64, device="cuda")
+    A4 = bform.assembly(out=out)
+    assert A4.values.data_ptr() == out.data_ptr()
+    U.assert_csr_matches(A4, gold)
+    with pytest.raises(ValueError):
+        bform.assembly(out=torch.empty(3, dtype=torch.float64, device="cuda"))
+
+
+def test_operator_cg_and_dirichlet_operator(U):
+    """cg with operator-valued A (solver/cg.py:10-14): the unassembled BilinearForm (matrix-free product), a user operator,
+    an operator-valued M; DirichletBCOperator (fem/dirichlet_bc_operator.py:13-67) against DirichletBC.apply"""
+    from fealpy_b200.fem import (BilinearForm, LinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator, ScalarSourceIntegrator,
+                                 DirichletBC, DirichletBCOperator)
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.solver import cg
+    case = C.by_name("tet_p2_3x2x1_diffmass")
+    gold = G.load(case["name"])
+    mesh, space, bform, _ = U.make_form(case, gold)
+    b = U.t64(gold["b"])
+    x_free, i_free = cg(bform, b, returninfo=True)                   # matrix-free: bform._M is None
+    assert bform._M is None
+    assert abs(i_free["niter"] - gold["info"]["niter"]) <= 1
+    assert np.linalg.norm(x_free.cpu().numpy() - gold["x"]) / np.linalg.norm(gold["x"]) <= 1e-10
+    A = bform.assembly()
+
+    class Op:
+        shape = A.shape
+
+        def __matmul__(self, v):
+            return A @ v
+
+    class JacobiOp:
+        def __init__(self, d): self.d = d
+        def __matmul__(self, v): return v / self.d
+
+    x_op, i_op = cg(Op(), b, returninfo=True)
+    x_csr, i_csr = cg(A, b, returninfo=True)
+    assert i_op["niter"] == i_csr["niter"] and float((x_op - x_csr).abs().max()) <= 1e-12
+    x_m, i_m = cg(A, b, M=JacobiOp(A.diagonal()), returninfo=True)
+    x_d, i_d = cg(A, b, M=1.0 / A.diagonal(), returninfo=True)
+    assert abs(i_m["niter"] - i_d["niter"]) <= 1 and float((x_m - x_d).abs().max()) <= 1e-10
+    with pytest.raises(TypeError):
+        cg(object(), b)
+    # DirichletBCOperator on a Poisson problem == DirichletBC.apply + cg
+    bcase = C.by_name("bc_tet_p2_3")
+    bgold = G.load(bcase["name"])
+    bmesh = U.make_mesh(bcase, bgold)
+    bspace = LagrangeFESpace(bmesh, bcase["p"])
+    form = BilinearForm(bspace).add_integrator(ScalarDiffusionIntegrator())
+    F = LinearForm(bspace).add_integrator(ScalarSourceIntegrator(U.torch_coef_func(C.source_cart))).assembly()
+    op = DirichletBCOperator(form, gd=U.torch_coef_func(C.kappa_cart))
+    uh = op.init_solution()
+    Fb = op.apply(F, uh)
+    assert np.max(np.abs(Fb.cpu().numpy() - bgold["F_bc"])) <= 1e-12 * np.max(np.abs(bgold["F_bc"]))
+    x, info = cg(op, Fb, returninfo=True, atol=1e-14, rtol=1e-11)
+    assert np.linalg.norm(x.cpu().numpy() - bgold["x"]) / np.linalg.norm(bgold["x"]) <= 1e-10
+
+
+@pytest.mark.parametrize("case", C.TENSOR_BC_CASES, ids=lambda c: c["name"])
+def test_elasticity_dirichlet_jacobi_cg(case, U):
+    """TensorFunctionSpace.is_boundary_dof / boundary_interpolate + DirichletBC + Jacobi-preconditioned cg against the
+    reference run (golden)"""
+    from fealpy_b200.mesh import TriangleMesh, TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace, TensorFunctionSpace
+    from fealpy_b200.fem import BilinearForm, LinearElasticityIntegrator, DirichletBC
+    from fealpy_b200.material import LinearElasticMaterial
+    from fealpy_b200.sparse import CSRTensor
+    from fealpy_b200.solver import cg
+    from scipy.sparse import csr_matrix
+    gold = G.load(case["name"])
+    mesh = U.make_mesh(case, gold)
+    GD = mesh.geo_dimension()
+    space = TensorFunctionSpace(LagrangeFESpace(mesh, case["p"]), shape=(GD, -1) if case["dof_priority"] else (-1, GD))
+    mat = LinearElasticMaterial("m", elastic_modulus=case["E"], poisson_ratio=case["nu"], hypo=case["hypo"])
+    A = BilinearForm(space).add_integrator(LinearElasticityIntegrator(mat, q=case["q"])).assembly()
+    U.assert_csr_matches(A, gold)
+    thr = U.torch_coef_func(C.THRESHOLDS[case["threshold"]])
+    bc = DirichletBC(space, gd=U.torch_coef_func(C.gd_vector), threshold=thr)
+    assert np.array_equal(bc.is_boundary_dof.cpu().numpy(), gold["isbd"])
+    uh, _ = space.boundary_interpolate(U.torch_coef_func(C.gd_vector), threshold=thr)
+    np.testing.assert_allclose(uh.cpu().numpy(), gold["uh"], atol=1e-15)
+    A2, F2 = bc.apply(A, U.t64(gold["F"]))
+    assert np.max(np.abs(F2.cpu().numpy() - gold["F_bc"])) <= 1e-12 * np.max(np.abs(gold["F_bc"]))
+    S = A2.to_scipy()
+    R = csr_matrix((gold["Abc_data"], gold["Abc_indices"], gold["Abc_indptr"]), shape=S.shape)
+    D = S - R
+    assert (abs(D).max() if D.nnz else 0.0) <= 1e-12 * np.max(np.abs(gold["Abc_data"]))
+    d = A2.diags()
+    x, info = cg(A2, F2, M=CSRTensor(d.crow, d.col, 1.0 / d.values, A2.shape), returninfo=True, atol=1e-14, rtol=1e-11)
+    assert np.linalg.norm(x.cpu().numpy() - gold["x"]) / np.linalg.norm(gold["x"]) <= 1e-10
+    assert abs(info["niter"] - gold["info"]["niter"]) <= 2

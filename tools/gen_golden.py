@@ -169,7 +169,9 @@ def run_case(case):
 
 
 def run_bc_case(case):
-    """Poisson with source + Dirichlet data (rows f1/f2): reference LinearForm / DirichletBC / cg."""
+    """Poisson with source + Dirichlet data (rows f1/f2): reference LinearForm / DirichletBC / cg.  `threshold` / `method`
+    restrict the Dirichlet part (functionspace/dofs.py:23-55); `reaction` adds a mass term so that the problem with a
+    partly natural boundary stays well conditioned."""
     name = case["name"]
     mesh = ref_mesh(case)
     p = case["p"]
@@ -178,23 +180,32 @@ def run_bc_case(case):
     gdof = space.number_of_global_dofs()
     f = cartesian(lambda pts: C.source_cart(pts))
     g = cartesian(lambda pts: C.kappa_cart(pts))
+    thr = C.THRESHOLDS[case["threshold"]] if case.get("threshold") else None
+    method = case.get("method")
     bform = BilinearForm(space)
     bform.add_integrator(ScalarDiffusionIntegrator())
+    if case.get("reaction"):
+        bform.add_integrator(ScalarMassIntegrator())
     A = bform.assembly()
     lform = LinearForm(space)
     lform.add_integrator(ScalarSourceIntegrator(f))
     F = np.asarray(lform.assembly())
     Fo = O.source_vector(mesh_o, p, C.source_cart)
     assert rel_err(Fo, F) < 1e-13, f"{name}: oracle source vector differs"
-    isbd = np.asarray(space.is_boundary_dof())
-    isbd_o = O.boundary_dof_flag(mesh_o, p)
+    isbd = np.asarray(space.is_boundary_dof(threshold=thr, method=method))
+    isbd_o = O.boundary_dof_flag(mesh_o, p, thr, method)
     assert np.array_equal(isbd, isbd_o), f"{name}: boundary flags differ"
+    if thr is not None:      # the two methods must really differ on this case, or it pins nothing
+        other = O.boundary_dof_flag(mesh_o, p, thr, "interp" if method in (None, "centroid") else None)
+        assert not np.array_equal(other, isbd_o), f"{name}: centroid and interp flags coincide"
+    # the values DirichletBC writes: boundary_interpolate always selects with method='interp' (lagrange_fe_space.py:131)
+    isbd_val = O.boundary_dof_flag(mesh_o, p, thr, "interp")
     ip = np.asarray(space.interpolation_points())
     ipo = mesh_o.interpolation_points(p)
     assert np.max(np.abs(ip - ipo)) < 1e-14, f"{name}: interpolation points differ"
-    A2, F2 = DirichletBC(space, gd=g).apply(A, F)
+    A2, F2 = DirichletBC(space, gd=g, threshold=thr, method=method).apply(A, F)
     uh = np.zeros(gdof)
-    uh[isbd_o] = C.kappa_cart(ipo[isbd_o])
+    uh[isbd_val] = C.kappa_cart(ipo[isbd_val])
     Ao, F2o = O.dirichlet_apply(np.asarray(A.crow), np.asarray(A.col), np.asarray(A.values), Fo, uh, isbd_o)
     assert rel_err(F2o, np.asarray(F2)) < 1e-13, f"{name}: BC rhs differs"
     x, cinfo = cg(A2, F2, returninfo=True, atol=1e-14, rtol=1e-11)     # tight: compare solutions, not stopping luck
@@ -205,12 +216,70 @@ def run_bc_case(case):
     A2s.eliminate_zeros()
     out = dict(node=np.asarray(mesh.node), cell=np.asarray(mesh.cell), cell2dof=np.asarray(space.cell_to_dof()),
                crow=np.asarray(A.crow), col=np.asarray(A.col), values=np.asarray(A.values),
-               F=F, isbd=isbd, ipoints=ip, F_bc=np.asarray(F2),
+               F=F, isbd=isbd, isbd_val=isbd_val, ipoints=ip, F_bc=np.asarray(F2),
                Abc_indptr=A2s.indptr.astype(np.int64), Abc_indices=A2s.indices.astype(np.int32), Abc_data=A2s.data,
                x=np.asarray(x),
                info=np.array(json.dumps(dict(gdof=int(gdof), niter=int(cinfo["niter"]), residual=float(cinfo["residual"])))))
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
-    print(f"{name:36s} gdof {gdof:7d} cg {cinfo['niter']}")
+    print(f"{name:36s} gdof {gdof:7d} cg {cinfo['niter']}  bd {int(isbd.sum())}")
+
+
+def run_tensor_bc_case(case):
+    """linear elasticity on a TensorFunctionSpace with a displaced part of the boundary: reference
+    TensorFunctionSpace.is_boundary_dof / boundary_interpolate (functionspace/tensor_space.py:159-260), DirichletBC, and
+    cg with the reference's Jacobi preconditioner CSRTensor(diags, 1/diag) (solver/iterative_solver_manger.py:273-280)"""
+    from fealpy.sparse import CSRTensor
+    name = case["name"]
+    mesh = ref_mesh(case)
+    p = case["p"]
+    sspace = LagrangeFESpace(mesh, p)
+    mesh_o = O.Mesh(np.asarray(mesh.node), np.asarray(mesh.cell))
+    GD = mesh_o.GD
+    prio = case["dof_priority"]
+    space = TensorFunctionSpace(sspace, shape=(GD, -1) if prio else (-1, GD))
+    gdof = space.number_of_global_dofs()
+    sg = sspace.number_of_global_dofs()
+    thr = C.THRESHOLDS[case["threshold"]]
+    mat = LinearElasticMaterial("m", elastic_modulus=case["E"], poisson_ratio=case["nu"], hypo=case["hypo"])
+    A = BilinearForm(space).add_integrator(LinearElasticityIntegrator(mat, q=case["q"])).assembly()
+    lam, mu = O.lame(case["E"], case["nu"])
+    D = O.elastic_matrix(lam, mu, case["hypo"], case["E"], case["nu"])
+    c2d_t = O.tensor_cell_to_dof(mesh_o.cell_to_ipoint(p), sg, GD, prio)
+    ocrow, ocol, oval = O.assemble([(O.elasticity_element(mesh_o, p, D, q=case["q"], dof_priority=prio), c2d_t)], gdof)
+    assert np.array_equal(np.asarray(A.crow), ocrow) and np.array_equal(np.asarray(A.col), ocol)
+    assert rel_err(oval, np.asarray(A.values)) < 1e-13
+    F = A @ np.ones(gdof)
+    gd = cartesian(lambda pts: C.gd_vector(pts))
+    bc = DirichletBC(space, gd=gd, threshold=thr)                      # method=None -> face-centroid selection
+    isbd = np.asarray(bc.is_boundary_dof)
+    isbd_o = O.tensor_boundary_dof_flag(mesh_o, p, GD, prio, thr, None)
+    assert np.array_equal(isbd, isbd_o), f"{name}: tensor boundary flags differ"
+    A2, F2 = bc.apply(A, F)
+    sflag = O.boundary_dof_flag(mesh_o, p, thr, None)
+    ipo = mesh_o.interpolation_points(p)
+    uh = np.zeros(gdof)
+    val = C.gd_vector(ipo[sflag])
+    if prio:
+        uh.reshape(GD, sg)[:, sflag] = val.T
+    else:
+        uh.reshape(sg, GD)[sflag, :] = val
+    Ao, F2o = O.dirichlet_apply(ocrow, ocol, np.asarray(A.values), np.asarray(F), uh, isbd_o)
+    assert rel_err(F2o, np.asarray(F2)) < 1e-13, f"{name}: tensor BC rhs differs"
+    dg = A2.diags()
+    M = CSRTensor(dg.crow, dg.col, 1.0 / dg.values, A2.shape)
+    x, cinfo = cg(A2, F2, M=M, returninfo=True, atol=1e-14, rtol=1e-11)
+    A2s = A2.to_scipy().tocsr().copy()
+    A2s.sum_duplicates(); A2s.sort_indices()
+    dd = (A2s - Ao)
+    assert (abs(dd).max() if dd.nnz else 0.0) < 1e-13, f"{name}: tensor BC matrix differs"
+    A2s.eliminate_zeros()
+    out = dict(node=np.asarray(mesh.node), cell=np.asarray(mesh.cell), crow=np.asarray(A.crow), col=np.asarray(A.col),
+               values=np.asarray(A.values), F=np.asarray(F), isbd=isbd, F_bc=np.asarray(F2), uh=uh,
+               Abc_indptr=A2s.indptr.astype(np.int64), Abc_indices=A2s.indices.astype(np.int32), Abc_data=A2s.data,
+               x=np.asarray(x),
+               info=np.array(json.dumps(dict(gdof=int(gdof), niter=int(cinfo["niter"]), residual=float(cinfo["residual"])))))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(f"{name:36s} gdof {gdof:7d} cg {cinfo['niter']}  bd {int(isbd.sum())}")
 
 
 if __name__ == "__main__":
@@ -221,5 +290,8 @@ if __name__ == "__main__":
     for case in C.BC_CASES:
         if not only or case["name"] in only:
             run_bc_case(case)
+    for case in C.TENSOR_BC_CASES:
+        if not only or case["name"] in only:
+            run_tensor_bc_case(case)
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print("golden dir bytes:", total)
