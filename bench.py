@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-existing-gpu", action="store_true")
     ap.add_argument("--dist-mode", default=os.environ.get("FB2_DIST", "auto"), choices=["auto", "nccl", "peer"])
+    ap.add_argument("--existing-gpu-child", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -296,10 +297,11 @@ class RefProblem:
         preconditioner; the others solve A x = A 1 unpreconditioned"""
         bm = self.bm
         gdof = A.shape[0]
-        ones = bm.ones(gdof, dtype=bm.float64, **({} if self.mesh.device in (None, "cpu") else {"device": self.mesh.device}))
-        b = A @ ones
+        kw = {} if self.mesh.device in (None, "cpu") else {"device": self.mesh.device}
         if self.cfg_id != 4:
-            return A, b, None
+            return A, A @ bm.ones(gdof, dtype=bm.float64, **kw), None
+        # elasticity: A 1 = 0 (rigid translation), so the right-hand side comes from a non-rigid vector
+        b = A @ (bm.sin(0.37 * bm.arange(gdof, dtype=bm.float64, **kw)) + 1.5)
         from fealpy.fem import DirichletBC
         from fealpy.sparse import CSRTensor
         ip = self.space.interpolation_points()
@@ -462,10 +464,10 @@ class Problem:
         """(A_sys, b, M) as solved by CG; built once (the BC / preconditioner setup is reported as `bc_ms`, not part of `value`)"""
         import torch
         gdof = A.shape[0]
-        ones = torch.ones(gdof, dtype=torch.float64, device=self.dev)
-        b = A @ ones
         if self.cfg_id != 4:
-            return A, b, None
+            return A, A @ torch.ones(gdof, dtype=torch.float64, device=self.dev), None
+        # elasticity: A 1 = 0 (rigid translation), so the right-hand side comes from a non-rigid vector
+        b = A @ (torch.sin(0.37 * torch.arange(gdof, dtype=torch.float64, device=self.dev)) + 1.5)
         from fealpy_b200.fem import DirichletBC
         from fealpy_b200.sparse import CSRTensor
         sflag = self.sspace.interpolation_points()[:, 0] < 1e-12
@@ -730,10 +732,7 @@ def run_ours(args):
             except Exception as e:          # the CPU leg must never cost the GPU line
                 line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
             if not args.no_existing_gpu:
-                try:
-                    line["existing_gpu_path"] = existing_gpu_leg(cfg_id, dev)
-                except Exception as e:
-                    line["existing_gpu_path"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+                line["existing_gpu_path"] = existing_gpu_subprocess(cfg_id)
         _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -791,6 +790,7 @@ def existing_gpu_leg(cfg_id, dev):
         t1 = time.perf_counter()
         out = {"kind": "reference pytorch backend, device=cuda", "n": n, "nnz": int(A.nnz), "value": A.nnz / (t1 - t0), "unit": UNIT,
                "assembly_s": t1 - t0}
+        _emit(json.dumps(dict(out, cg_error="the reference's torch-cuda cg did not return (CUDA fault)")))     # survives a fault below
         try:
             A2, b, M = prob.rhs_and_system(A)
             torch.cuda.synchronize(dev)
@@ -805,6 +805,20 @@ def existing_gpu_leg(cfg_id, dev):
     finally:
         from fealpy.backend import backend_manager as bm
         bm.set_backend("numpy")
+
+
+def existing_gpu_subprocess(cfg_id):
+    """the reference's own torch-cuda code runs in a CHILD process: a CUDA fault inside it (its cg hit an illegal memory
+    access on this stack) must not poison this process's context"""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--existing-gpu-child", "--config", str(cfg_id)],
+                           capture_output=True, text=True, timeout=240)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": f"child rc={r.returncode}: {r.stderr.strip()[-300:]}"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
 
 class StdoutToStderr:
@@ -831,7 +845,15 @@ if __name__ == "__main__":
     a = parse()
     with StdoutToStderr() as out:
         _emit = out.emit
-        if a.impl == "reference":
+        if a.existing_gpu_child:
+            import torch
+            try:
+                res = existing_gpu_leg(a.config, torch.device("cuda", 0))
+            except Exception as e:
+                res = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+            _emit(json.dumps(res))
+            os._exit(0)                       # skip torch's teardown: the context may be in an error state
+        elif a.impl == "reference":
             run_reference(a)
         else:
             run_ours(a)

@@ -194,6 +194,40 @@ int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, 
   a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.Hbuf = geom_ws; a.values = values;
   return assemble_v4(TD, p, a, slot_bytes, S(stream));
 }
+// ---- v5: conflict-free transposed tiles, bulk-copied entry blocks ---------------------------------------------
+size_t fb2_asm5_workspace_bytes(int64_t nrow, int ntile_max) { return asm5_workspace_bytes(nrow, ntile_max); }
+int fb2_asm5_entry_words(int ldof) { return 32 * (2 + slot_stride(ldof, 1) / 4); }
+int fb2_asm5_tiles_count(int64_t nrow, const int64_t* crow, int cap, int64_t* ntile_host, void* ws, void* stream) {
+  if (cap < 1024) return fail(ERR_INVALID, "asm5: tile capacity must be >= 1024 values");
+  return asm5_tiles_count(nrow, crow, cap, ntile_host, ws, S(stream));
+}
+int fb2_asm5_tiles_fill(int64_t nrow, const int64_t* crow, int cap, int64_t ntile, int32_t* tile_row, void* ws, void* stream) {
+  return asm5_tiles_fill(nrow, crow, cap, ntile, tile_row, ws, S(stream));
+}
+int fb2_asm5_plan_count(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
+                        int ldof, int64_t* batch_ptr, int64_t* nbatch_host, int32_t* max_pad_host, void* ws, void* stream) {
+  return asm5_plan_count(ntile, tile_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, nbatch_host, max_pad_host, ws, S(stream));
+}
+int fb2_asm5_plan_fill(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
+                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, uint32_t* ent, uint16_t* row_code, const void* slots,
+                       int slot_bytes, void* ws, void* stream) {
+  return asm5_plan_fill(ntile, tile_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, batch_i, ent, row_code, slots, slot_bytes, ws,
+                        S(stream));
+}
+int fb2_assemble_scalar_const_v5(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
+                                 const int32_t* tile_row, int ntile, int acc_stride, const int64_t* batch_ptr, const uint8_t* batch_i,
+                                 const uint32_t* ent, const uint16_t* row_code, const double* Ms_host, const double* Mm_host,
+                                 double scal_d, const double* coef_d, double scal_m, const double* coef_m, double* geom_ws,
+                                 double* values, int threads, void* stream) {
+  if (!Ms_host && !Mm_host) return fail(ERR_INVALID, "assemble_scalar_const_v5: need a diffusion and/or a mass table");
+  Asm4Args g{};
+  g.node = node; g.cell = cell; g.NC = NC; g.Ms_host = Ms_host; g.Mm_host = Mm_host;
+  g.scal_d = scal_d; g.scal_m = scal_m; g.coef_d = coef_d; g.coef_m = coef_m; g.Hbuf = geom_ws;
+  Asm5Args a{};
+  a.NC = NC; a.crow = crow; a.tile_row = tile_row; a.ntile = ntile; a.acc_stride = acc_stride; a.batch_ptr = batch_ptr;
+  a.batch_i = batch_i; a.ent = ent; a.row_code = row_code; a.values = values;
+  return assemble_v5(TD, p, g, a, threads, S(stream));
+}
 int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,
                        int64_t* crow_out, int32_t* col_out, void* stream) {
   return expand_pattern(gdof_scalar, ncomp, dof_priority, crow_scalar, col_scalar, crow_out, col_out, S(stream));

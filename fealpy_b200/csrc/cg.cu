@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(ST_THREADS) spmv_stream_kernel(int64_t n, cons
                                                                  const double* __restrict__ b, int mode,
                                                                  const int32_t* __restrict__ blk_row, int nblk, double* dot_out,
                                                                  double* partials, unsigned int* counter, const CgScalars* sc,
-                                                                 OwnRange own) {
+                                                                 OwnRange own, const int32_t* __restrict__ blk_end) {
   if (sc && sc->done) return;
   extern __shared__ __align__(16) double prod[];
   const int tid = threadIdx.x;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(ST_THREADS) spmv_stream_kernel(int64_t n, cons
   constexpr int NGRP = ST_THREADS / G;
   double dsum = 0.0;
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int r0 = blk_row[blk], r1 = blk_row[blk + 1];
+    const int r0 = blk_row[blk], r1 = blk_end ? blk_end[blk] : blk_row[blk + 1];
     if (r0 == r1) continue;
     const int64_t v0 = crow[r0];
     const int nval = (int)(crow[r1] - v0);
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) partition_rows_kernel(const int64_t* __re
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nblk) return;
   if (b == nblk) { blk_row[b] = (int32_t)n; if (blk_v0) blk_v0[b] = crow[n]; return; }
-  const int64_t target = (int64_t)b * tile;
+  const int64_t target = crow[0] + (int64_t)b * tile;        // crow may point into the middle of a matrix (a row range)
   int64_t lo = 0, hi = n;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
@@ -332,7 +332,7 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
   do {                                                                                                         \
     auto kern = spmv_stream_kernel<GV>;                                                                        \
     if (smem > 48 * 1024) FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, ST_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own); \
+    kern<<<grid, ST_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own, plan.blk_end); \
   } while (0)
   // lanes per row in the reduce phase: ONE (a thread sums its row sequentially out of shared memory) measured
   // best by a wide margin -- 1.60 ms/iteration against 1.92 with 8 lanes + shuffles (profiles/r01_tune_spmv.txt)

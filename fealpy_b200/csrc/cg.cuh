@@ -24,6 +24,7 @@ struct SpmvPlan {
   const int32_t* blk_row = nullptr;   // (nblk+1) first row of every tile
   const int64_t* blk_v0 = nullptr;    // (nblk+1) first value index of every tile (pipelined kernel) or null
   int nblk = 0, tile = 0, max_row = 0;
+  const int32_t* blk_end = nullptr;   // optional (nblk): one-past-last row of every tile -- tiles of SEVERAL row ranges in one plan
 };   // max blocks contributing partial sums per reduction
 
 size_t cg_workspace_bytes(int64_t n, int64_t nnz);
@@ -53,6 +54,28 @@ int cg_update_xr(int64_t n, double* x, double* r, const double* p, const double*
                  void* partial_ws, int fuse_finalize, cudaStream_t s, OwnRange own = OwnRange{});
 int cg_finalize(CgScalars* sc, cudaStream_t s);
 int cg_update_p(int64_t n, double* p, const double* r, const double* minv, CgScalars* sc, cudaStream_t s);
+
+// ---- multi-GPU CG over NVLink peer memory (csrc/peer.cu): the halo exchange and the scalar all-reduces of the CG iteration
+// are done by the CG kernels themselves with stores into the neighbours' memory + sequence flags -- no NCCL call per iteration.
+constexpr int PEER_MAXW = 16;
+struct PeerCtrl {                         // one per rank, at the start of the rank's symmetric buffer (same layout everywhere)
+  double red[2][2][PEER_MAXW];            // [kind: 0 = p.Ap, 1 = r.z][parity of the iteration][source rank] partial sums
+  unsigned long long rflag[2][PEER_MAXW]; // [kind][source rank] sequence number of the newest partial
+  unsigned long long hflag[PEER_MAXW];    // [source rank] sequence number of the newest halo pushed by that neighbour
+};
+struct PeerSlice { int64_t lo, hi, peer_lo; double* peer_p; };     // my owned p[lo, hi) -> the neighbour's p[peer_lo, ...)
+struct PeerPush {
+  int nslice, nnb, rank;
+  PeerSlice slice[4];
+  PeerCtrl* nb_ctrl[2];                   // control blocks of the (<= 2) neighbours
+  unsigned int* counter;                  // local last-block ticket
+  const unsigned long long* epoch;        // device scalar: base of this solve's sequence numbers
+};
+int peer_allreduce(PeerCtrl* mine, const unsigned long long* peer_base, int world, int rank, int kind, const double* src0,
+                   const double* src1, double* dst, CgScalars* sc, int finalize, const unsigned long long* epoch, cudaStream_t s);
+int peer_wait_halo(PeerCtrl* mine, int nnb, const int* nb_rank, const CgScalars* sc, const unsigned long long* epoch, cudaStream_t s);
+int cg_update_p_push(OwnRange own, double* p, const double* r, const double* minv, const CgScalars* sc, const PeerPush& push,
+                     cudaStream_t s);
 
 // batched right-hand sides (row-major (n, B))
 int bcg_dots(int64_t n, int B, const double* a, const double* b, double* out, void* partial_ws, cudaStream_t s);

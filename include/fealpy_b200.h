@@ -163,6 +163,27 @@ int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, 
                                  int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d,
                                  const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* geom_ws, double* values,
                                  void* stream);
+/* v5 of the fused numeric phase (default for scalar forms with rows <= 255 values).  Same scheduled batches as v4, but the
+ * warp's accumulator tile is stored transposed and XOR-swizzled so that the shared-memory accumulation is bank-conflict
+ * free, and every batch's entry block arrives with one bulk asynchronous copy.  Plan (once per space):
+ *   fb2_asm5_tiles_count/fill : tile_row (ntile+1) -- runs of rows holding <= cap values, row counts multiples of 16
+ *   fb2_asm5_plan_count       : batch_ptr (ntile+1), number of batches, largest padded tile (doubles)
+ *   fb2_asm5_plan_fill        : batch_i (nbatch), ent (nbatch x fb2_asm5_entry_words(ldof) uint32), row_code (nrow uint16)
+ * ws >= fb2_asm5_workspace_bytes(nrow, ntile).  geom_ws: (NC, 8 [tet] / 4 [tri]) doubles of scratch. */
+size_t fb2_asm5_workspace_bytes(int64_t nrow, int ntile_max);
+int fb2_asm5_entry_words(int ldof);
+int fb2_asm5_tiles_count(int64_t nrow, const int64_t* crow, int cap, int64_t* ntile_host, void* ws, void* stream);
+int fb2_asm5_tiles_fill(int64_t nrow, const int64_t* crow, int cap, int64_t ntile, int32_t* tile_row, void* ws, void* stream);
+int fb2_asm5_plan_count(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
+                        int ldof, int64_t* batch_ptr, int64_t* nbatch_host, int32_t* max_pad_host, void* ws, void* stream);
+int fb2_asm5_plan_fill(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
+                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, uint32_t* ent, uint16_t* row_code, const void* slots,
+                       int slot_bytes, void* ws, void* stream);
+int fb2_assemble_scalar_const_v5(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
+                                 const int32_t* tile_row, int ntile, int acc_stride, const int64_t* batch_ptr, const uint8_t* batch_i,
+                                 const uint32_t* ent, const uint16_t* row_code, const double* Ms_host, const double* Mm_host,
+                                 double scal_d, const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* geom_ws,
+                                 double* values, int threads, void* stream);
 /* expands the scalar pattern to the tensor-space pattern */
 int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,
                        int64_t* crow_out, int32_t* col_out, void* stream);
