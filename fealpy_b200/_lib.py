@@ -59,14 +59,6 @@ SIGNATURES = {
     "fb2_asm4_plan_fill": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "fb2_assemble_scalar_const_v4": (_i32, [_i32, _i32, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _p,
                                             _f64, _p, _f64, _p, _p, _p, _p]),
-    "fb2_asm5_workspace_bytes": (_sz, [_i64, _i32]),
-    "fb2_asm5_entry_words": (_i32, [_i32]),
-    "fb2_asm5_tiles_count": (_i32, [_i64, _p, _i32, _p, _p, _p]),
-    "fb2_asm5_tiles_fill": (_i32, [_i64, _p, _i32, _i64, _p, _p, _p]),
-    "fb2_asm5_plan_count": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
-    "fb2_asm5_plan_fill": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p]),
-    "fb2_assemble_scalar_const_v5": (_i32, [_i32, _i32, _i64, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p,
-                                            _f64, _p, _f64, _p, _p, _p, _i32, _p]),
     "fb2_expand_pattern": (_i32, [_i64, _i32, _i32, _p, _p, _p, _p, _p]),
     "fb2_partial_workspace_bytes": (_sz, []),
     "fb2_spmv_plan_blocks": (_i32, [_i64, _i32]),
@@ -85,6 +77,11 @@ SIGNATURES = {
     "fb2_tet_box_slab": (_i32, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "fb2_cg_finalize": (_i32, [_p, _p]),
     "fb2_cg_update_p": (_i32, [_i64, _p, _p, _p, _p, _p]),
+    "fb2_peer_ctrl_bytes": (_i32, []),
+    "fb2_cg_spmv_dot_ranges": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "fb2_peer_allreduce": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p]),
+    "fb2_peer_wait_halo": (_i32, [_p, _i32, _p, _p, _p, _p]),
+    "fb2_cg_update_p_push": (_i32, [_p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p]),
     "fb2_bcg_dots": (_i32, [_i64, _i32, _p, _p, _p, _p, _p]),
     "fb2_bcg_update_xr": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "fb2_bcg_update_p": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p]),

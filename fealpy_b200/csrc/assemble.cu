@@ -1068,7 +1068,12 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
   using GEO = A4Geo<TD>;
   constexpr int NH = GEO::NH, HS = GEO::HS, QP = GEO::QP;
   using SR = SlotRec<SlotT, L>;
-  constexpr int NHST = D + 1, NEST = 2 * D + 1;                 // ring depths: geometry stages, entry slots
+  // ring depths: geometry stages, entry slots.  Geometry runs D batches ahead, entries 2D + 1: the entry block of a batch
+  // is streamed from DRAM exactly once, and with only 2D batches of look-ahead inside the SAME cp.async group as the geometry
+  // ncu's source view put 10 % of all warp samples on the instruction after `DEPBAR` (cp.async.wait_group), profiles/
+  // r02_ncu_asm_experiments.txt.  Now every iteration commits two groups, {geometry(b+D)} then {entries(b+2D+1)}, and waits
+  // with wait_group<1>: the newest entry block may stay in flight for another iteration.
+  constexpr int NHST = D + 1, NEST = 2 * D + 2;
   constexpr int ENT_BYTES = 256 + 128 * SR::WORDS;              // 32 x (cell int32 | base+first-touch uint32 | slot words)
   constexpr int ENT_CHUNKS = ENT_BYTES / 16;
   extern __shared__ __align__(16) double sm4[];
@@ -1109,7 +1114,7 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
     }
   };
 
-  // prologue: entries of the first 2D batches, then the geometry of the first D
+  // prologue: entries of the first 2D batches, then the geometry of the first D, then (own group) the entries of batch 2D
   for (int k = 0; k < 2 * D; ++k)
     if (b0 + k < b1) issue_entries(b0 + k, k);
   cp_async_commit();                                            // (no zero fill of the tile: first-touch entries store)
@@ -1123,16 +1128,19 @@ assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
     if (b0 + k < b1) issue_geometry(k, k);
     cp_async_commit();
   }
+  if (b0 + 2 * D < b1) issue_entries(b0 + 2 * D, 2 * D);
+  cp_async_commit();
   int hs = 0, es = 0;                                           // ring positions of batch b
   for (int64_t b = b0; b < b1; ++b) {
-    cp_async_wait<D - 1>();
-    __syncwarp();                                               // G_{b-D} visible to all lanes; everyone is done with batch b-1
+    cp_async_wait<D>();                                         // all but the newest group ({entries(b+2D)}): geometry(b), entries(b+D) are in
+    __syncwarp();                                               // ... visible to all lanes; everyone is done with batch b-1
     {
       int hn = hs + D; if (hn >= NHST) hn -= NHST;              // == stage of batch b-1: free
       int en = es + D; if (en >= NEST) en -= NEST;
-      int e2 = es + 2 * D; if (e2 >= NEST) e2 -= NEST;          // == slot of batch b-1: free
-      if (b + 2 * D < b1) issue_entries(b + 2 * D, e2);
+      int e3 = es + 2 * D + 1; if (e3 >= NEST) e3 -= NEST;      // == slot of batch b-1: free
       if (b + D < b1) issue_geometry(en, hn);
+      cp_async_commit();
+      if (b + 2 * D + 1 < b1) issue_entries(b + 2 * D + 1, e3);
       cp_async_commit();
     }
     const int i = iq[0];
@@ -1249,8 +1257,8 @@ static int launch_asm4(Asm4Args a, int slot_bytes, cudaStream_t s) {
   const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
   if (grid == 0) return OK;
   const int words = slot_stride(L, slot_bytes) * slot_bytes / 4;
-  // per warp: accumulator tile + (D+1) geometry stages + (2D+1) entry slots
-  const size_t per_warp = (size_t)(a.acc_stride + (depth + 1) * 32 * GEO::HS) * 8 + (size_t)(2 * depth + 1) * (256 + 128 * words);
+  // per warp: accumulator tile + (D+1) geometry stages + (2D+2) entry slots
+  const size_t per_warp = (size_t)(a.acc_stride + (depth + 1) * 32 * GEO::HS) * 8 + (size_t)(2 * depth + 2) * (256 + 128 * words);
   const size_t smem = (size_t)FB2_ASM4_WARPS * per_warp;
   if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble v4: tiles do not fit shared memory (tile=%d max_row=%d)", a.tile, a.max_row);
 #define FB2_A4_LAUNCH(KERN)                                                                          \
@@ -1286,632 +1294,3 @@ int assemble_v4(int TD, int p, const Asm4Args& a, int slot_bytes, cudaStream_t s
 
 }  // namespace fb2
 
-// =====================================================================================
-// v5: v4's scheduled batches with a bank-conflict-free accumulator.
-//
-// ncu on v4 (profiles/r01_ncu_full_final_assemble_cg.txt): 546 M shared-memory wavefronts, a third of them bank
-// conflicts -- the 32 lanes of a batch add into 32 different rows whose segments start at arbitrary banks.  Here the
-// warp's tile is stored TRANSPOSED and XOR-swizzled: the rows of a tile are placed at positions pi = 16*g + c
-// (group g, class c = pi mod 16) and value `s` of row pi lives at
-//        acc[ gbase[g] + 16*s + ((c ^ s) & 15) ]                      (doubles; gbase[g] is a multiple of 16)
-// so the 8-byte bank of an access is (c ^ s) & 15: a half-warp whose 16 lanes hold 16 DIFFERENT classes is conflict
-// free whatever slots they touch, and the write-back of one row (16 consecutive s, fixed c) is conflict free too.  The
-// scheduler therefore (a) assigns every row a class so that the per-(class, local index) entry counts are balanced
-// (rows sorted by length, greedy "least increase of the per-index maxima"), (b) deals the entries of (class c, local
-// index i) round-robin over B_i = max(longest run inside one row, ceil(max_c n_ic / 2)) batches x 2 half-warps: entry k
-// goes to batch k mod B_i, lane 16*(k div B_i) + c.  Rows of one group share the group's padded length (rows are placed
-// in order of decreasing length, so the padding is ~8-10 %).
-// Entries of a batch are ONE contiguous block fetched with ONE bulk asynchronous copy (cp.async.bulk -> UBLKCP,
-// completion on an mbarrier) instead of 36 LDGSTS; the geometry records keep the cooperative cp.async ring of v4.
-// =====================================================================================
-namespace fb2 {
-
-constexpr int A5_CHUNK = 4096;      // rows per independently tiled chunk (tile boundaries never cross a chunk)
-constexpr int A5_MAXROWS = 512;     // rows per tile (bounds the scheduler's shared-memory arrays)
-constexpr int A5_SCHED_WARPS = 2;
-
-// ---- tiles: greedy runs of rows holding <= cap values, the row count rounded down to a multiple of 16 ------------------
-template <bool FILL>
-__global__ void __launch_bounds__(128) asm5_tile_kernel(int64_t nrow, const int64_t* __restrict__ crow, int cap, int nchunk,
-                                                        int* __restrict__ cnt, const int64_t* __restrict__ first,
-                                                        int32_t* __restrict__ tile_row, int64_t ntile_total) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= nchunk) return;
-  int64_t r = (int64_t)ch * A5_CHUNK;
-  const int64_t end = (r + A5_CHUNK < nrow) ? r + A5_CHUNK : nrow;
-  int k = 0;
-  const int64_t base = FILL ? first[ch] : 0;
-  while (r < end) {
-    const int64_t v0 = crow[r];
-    int64_t lo = r + 1, hi = (r + A5_MAXROWS < end) ? r + A5_MAXROWS : end;       // last row boundary e in [lo, hi] with crow[e] - v0 <= cap
-    while (lo < hi) {
-      const int64_t mid = (lo + hi + 1) >> 1;
-      if (crow[mid] - v0 <= cap) lo = mid; else hi = mid - 1;
-    }
-    int64_t nr = lo - r;
-    if (nr >= 16 && lo < end) nr = nr / 16 * 16;
-    if (FILL) tile_row[base + k] = (int32_t)r;
-    ++k;
-    r += nr;
-  }
-  if (!FILL) cnt[ch] = k;
-  else if (ch == nchunk - 1) tile_row[ntile_total] = (int32_t)nrow;
-}
-
-struct A5Sched {             // per-warp shared-memory scratch of the scheduler (dynamic, sized by L)
-  uint16_t* order;           // [A5_MAXROWS] tile-local row ids, by decreasing length (stable)
-  uint16_t* kth;             // [A5_MAXROWS] position of the row inside its class = its group
-  uint16_t* gl;              // [A5_MAXROWS] group lengths, then group bases / 16
-  uint16_t* k0;              // [A5_MAXROWS][L] entries of (class, i) dealt before this row
-  uint8_t* cls;              // [A5_MAXROWS]
-  int* bins;                 // [257]
-  int* Bi;                   // [32] batches of local index i
-  int* offi;                 // [32] first batch (tile-local) of local index i
-  __host__ __device__ static size_t bytes(int L) {
-    return (size_t)A5_MAXROWS * (2 + 2 + 2 + 2 * L + 1) + 257 * 4 + 64 * 4 + 64;
-  }
-  __device__ void carve(unsigned char* p, int L) {
-    order = reinterpret_cast<uint16_t*>(p); p += A5_MAXROWS * 2;
-    kth = reinterpret_cast<uint16_t*>(p); p += A5_MAXROWS * 2;
-    gl = reinterpret_cast<uint16_t*>(p); p += A5_MAXROWS * 2;
-    k0 = reinterpret_cast<uint16_t*>(p); p += (size_t)A5_MAXROWS * 2 * L;
-    bins = reinterpret_cast<int*>(p); p += 257 * 4;
-    Bi = reinterpret_cast<int*>(p); p += 32 * 4;
-    offi = reinterpret_cast<int*>(p); p += 32 * 4;
-    cls = p;
-  }
-};
-
-// entry block of a batch, ENT_WORDS(words) 32-bit words: cell[32] | code[32] | slot word w of lane l at 64 + 32*w + l
-__host__ __device__ constexpr int a5_ent_words(int slot_words) { return 32 * (2 + slot_words); }
-
-template <bool FILL>
-__global__ void __launch_bounds__(A5_SCHED_WARPS * 32) asm5_schedule_kernel(
-    int ntile, const int32_t* __restrict__ tile_row, const int64_t* __restrict__ crow, const int64_t* __restrict__ adj_ptr,
-    const int* __restrict__ adj_pair, int L, int* __restrict__ nbatch_of_tile, int* __restrict__ pad_of_tile,
-    const int64_t* __restrict__ batch_ptr, unsigned char* __restrict__ batch_i, uint32_t* __restrict__ ent,
-    uint16_t* __restrict__ row_code, const uint32_t* __restrict__ slot_words, int slot_nwords, int* __restrict__ err) {
-  constexpr unsigned FULL = 0xffffffffu;
-  extern __shared__ __align__(16) unsigned char sm5[];
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * A5_SCHED_WARPS + wid;
-  if (t >= ntile) return;
-  A5Sched S;
-  S.carve(sm5 + (size_t)wid * ((A5Sched::bytes(L) + 15) / 16 * 16), L);
-  const FastDiv fd(L);
-  auto local_index = [&](int pair) { return pair - fd.wide(pair) * L; };
-  const int64_t r0 = tile_row[t], r1 = tile_row[t + 1];
-  const int nr = (int)(r1 - r0);
-  const uint32_t lt = (1u << lane) - 1u;
-
-  // (1) rows by decreasing length: stable counting sort on min(len, 255)
-  for (int k = lane; k < 257; k += 32) S.bins[k] = 0;
-  __syncwarp();
-  for (int rho = lane; rho < nr; rho += 32) {
-    const int len = (int)(crow[r0 + rho + 1] - crow[r0 + rho]);
-    atomicAdd(&S.bins[255 - (len < 255 ? len : 255)], 1);
-  }
-  __syncwarp();
-  {
-    int run = 0;                                   // exclusive scan of the 256 bins, 8 per lane
-    int v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { v[k] = S.bins[lane * 8 + k]; run += v[k]; }
-    int ex = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, ex, o); if (lane >= o) ex += u; }
-    ex -= run;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { S.bins[lane * 8 + k] = ex; ex += v[k]; }
-  }
-  __syncwarp();
-  for (int rb = 0; rb < nr; rb += 32) {
-    const int rho = rb + lane;
-    const bool act = rho < nr;
-    int key = 256;
-    if (act) { const int len = (int)(crow[r0 + rho + 1] - crow[r0 + rho]); key = 255 - (len < 255 ? len : 255); }
-    const unsigned peers = __match_any_sync(FULL, key);
-    const int start = S.bins[key];
-    __syncwarp();
-    if (act) {
-      S.order[start + __popc(peers & lt)] = (uint16_t)rho;
-      if ((peers & lt) == 0) S.bins[key] = start + __popc(peers);
-    }
-    __syncwarp();
-  }
-  for (int k = lane; k < nr; k += 32) S.gl[k] = 0;
-  __syncwarp();
-
-  // (2) classes: lane c < 16 keeps load[c][i] = entries of (class c, local index i) so far
-  int load[A4_MAXL], curmax[A4_MAXL];
-#pragma unroll
-  for (int i = 0; i < A4_MAXL; ++i) { load[i] = 0; curmax[i] = 0; }
-  int rows_in_class = 0, mrun = 0;                 // lane c: rows of class c;  lane i: longest run of local index i inside one row
-  for (int q = 0; q < nr; ++q) {
-    const int rho = S.order[q];
-    const int64_t r = r0 + rho;
-    const int64_t a0 = adj_ptr[r], a1 = adj_ptr[r + 1];
-    int mycnt = 0;                                 // lane i: entries of this row with local index i
-    for (int64_t b = a0; b < a1; b += 32) {
-      const int64_t idx = b + lane;
-      const int li = idx < a1 ? local_index(adj_pair[idx]) : -1;
-      for (int i = 0; i < L; ++i) {
-        const unsigned bal = __ballot_sync(FULL, li == i);
-        if (lane == i) mycnt += __popc(bal);
-      }
-    }
-    mrun = max(mrun, mycnt);
-    long long key = 0x7fffffffffffffffLL;
-    {
-      long long inc = 0, mx = 0, sum = 0;
-#pragma unroll
-      for (int i = 0; i < A4_MAXL; ++i) {
-        if (i < L) {
-          const int ci = __shfl_sync(FULL, mycnt, i);
-          const int nl = load[i] + ci;
-          inc += max(nl - curmax[i], 0);
-          mx = max(mx, (long long)nl);
-          sum += nl;
-        }
-      }
-      if (lane < 16) key = (((inc << 20) | mx) << 20 | sum) << 5 | lane;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const long long u = __shfl_xor_sync(FULL, key, o); key = u < key ? u : key; }
-    const int cstar = (int)(key & 31);
-    const int kthv = __shfl_sync(FULL, rows_in_class, cstar);
-#pragma unroll
-    for (int i = 0; i < A4_MAXL; ++i) {
-      if (i < L) {
-        const int before = __shfl_sync(FULL, load[i], cstar);
-        const int ci = __shfl_sync(FULL, mycnt, i);
-        if (lane == i) S.k0[rho * L + i] = (uint16_t)before;
-        if (lane == cstar) load[i] = before + ci;
-        curmax[i] = max(curmax[i], before + ci);
-      }
-    }
-    if (lane == cstar) ++rows_in_class;
-    if (lane == 0) {
-      S.cls[rho] = (uint8_t)cstar;
-      S.kth[rho] = (uint16_t)kthv;
-      const int len = (int)(crow[r + 1] - crow[r]);
-      if (len > S.gl[kthv]) S.gl[kthv] = (uint16_t)len;
-    }
-  }
-  __syncwarp();
-
-  // (3) batches per local index, group bases
-  int myB = 0;
-#pragma unroll
-  for (int i = 0; i < A4_MAXL; ++i)
-    if (i < L && lane == i) myB = curmax[i] == 0 ? 0 : max(mrun, (curmax[i] + 1) >> 1);
-  int off = myB;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, off, o); if (lane >= o) off += v; }
-  const int nb = __shfl_sync(FULL, off, 31);
-  off -= myB;
-  int ng = rows_in_class;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ng = max(ng, __shfl_xor_sync(FULL, ng, o));
-  int padded = 0;                                  // gl[g] <- gbase[g] / 16 (running sum of the group lengths)
-  bool too_big = false;
-  for (int gb = 0; gb < ng; gb += 32) {
-    const int g = gb + lane;
-    const int len = g < ng ? S.gl[g] : 0;
-    int ex = len;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, ex, o); if (lane >= o) ex += v; }
-    if (g < ng) S.gl[g] = (uint16_t)(padded + ex - len);
-    const bool fits = (g >= ng) || (padded + ex - len <= 255);  // gbase / 16 must fit the 8 bits of the row code
-    if (!__all_sync(FULL, fits)) too_big = true;
-    padded += __shfl_sync(FULL, ex, 31);
-  }
-  __syncwarp();
-  if (!FILL) {
-    if (lane == 0) { nbatch_of_tile[t] = nb; pad_of_tile[t] = too_big ? (1 << 30) : padded * 16; }      // the host rejects the plan then
-    return;
-  }
-  if (too_big && lane == 0) atomicExch(err, 1);
-  S.Bi[lane] = myB;
-  S.offi[lane] = off;
-  __syncwarp();
-  const int64_t b0 = batch_ptr[t];
-  const int EW = a5_ent_words(slot_nwords);
-  for (int i = 0; i < L; ++i) {
-    const int Bi = S.Bi[i], offi = S.offi[i];
-    for (int j = lane; j < Bi; j += 32) batch_i[b0 + offi + j] = (unsigned char)i;
-  }
-  for (int64_t e = lane; e < (int64_t)nb * 32; e += 32) ent[(b0 + (e >> 5)) * EW + (e & 31)] = 0xffffffffu;      // cell = -1: empty lane
-
-  // (4) entries: lane = row, every lane walks its adjacency in execution order ((i, cell))
-  for (int rb = 0; rb < nr; rb += 32) {
-    const int rho = rb + lane;
-    int64_t q = 0, qe = 0;
-    uint32_t rc = 0;
-    int c = 0;
-    if (rho < nr) {
-      const int64_t r = r0 + rho;
-      q = adj_ptr[r]; qe = adj_ptr[r + 1];
-      c = S.cls[rho];
-      rc = ((uint32_t)S.gl[S.kth[rho]] << 4) | (uint32_t)c;
-      row_code[r] = (uint16_t)rc;
-    }
-    uint32_t touched[A4_MAXROW / 32];
-#pragma unroll
-    for (int w = 0; w < A4_MAXROW / 32; ++w) touched[w] = 0;
-    for (int i = 0; i < L; ++i) {
-      int m = 0;
-      while (q + m < qe && local_index(adj_pair[q + m]) == i) ++m;
-      if (m > 0) {
-        const int Bi = S.Bi[i], offi = S.offi[i];
-        const int k0 = S.k0[rho * L + i];
-        const int wrap = max(0, k0 % Bi + m - Bi);
-        for (int u = 0; u < m; ++u) {
-          const int k = u < wrap ? k0 + (m - wrap) + u : k0 + (u - wrap);
-          const int half = k / Bi;
-          const int pos = half * 16 + c;
-          uint32_t* blk = ent + (b0 + offi + (k - half * Bi)) * EW;
-          if (half > 1) { atomicExch(err, 2); continue; }
-          blk[pos] = (uint32_t)fd.wide(adj_pair[q + u]);
-          uint32_t first = 0;
-          for (int w = 0; w < slot_nwords; ++w) blk[64 + 32 * w + pos] = slot_words[(q + u) * slot_nwords + w];
-          for (int j = 0; j < L; ++j) {
-            const uint32_t wd = slot_words[(q + u) * slot_nwords + (j >> 2)];
-            const int sl = (wd >> ((j & 3) * 8)) & 0xffu;
-            if (!((touched[sl >> 5] >> (sl & 31)) & 1u)) { first |= 1u << j; touched[sl >> 5] |= 1u << (sl & 31); }
-          }
-          blk[32 + pos] = rc | (first << A4_BASE_BITS);
-        }
-      }
-      q += m;
-    }
-  }
-}
-
-// ---- numeric kernel -------------------------------------------------------------------------------------------------
-// accumulate one lane's element row `v` into the warp's transposed tile: value `s` of the row sits at
-// my[16 s + ((c ^ s) & 15)]  (my = group base, c = class); first-touch columns are stored, the others load-add-stored
-template <int L>
-__device__ __forceinline__ void a5_accumulate(const double (&v)[L], const uint32_t (&sw)[SlotRec<uint8_t, L>::WORDS], uint32_t cw, bool act,
-                                              double* __restrict__ accd) {
-  using SR = SlotRec<uint8_t, L>;
-  constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
-  const uint32_t rc = cw & ((1u << A4_BASE_BITS) - 1u), first = cw >> A4_BASE_BITS;
-  double* __restrict__ my = accd + (rc >> 4) * 16;
-  const int c = (int)(rc & 15u);
-#pragma unroll
-  for (int j0 = 0; j0 < L; j0 += JC) {
-    int idx[JC];
-#pragma unroll
-    for (int jj = 0; jj < JC; ++jj) { const int sl = SR::get(sw, j0 + jj); idx[jj] = (sl << 4) | ((sl ^ c) & 15); }
-    double old[JC];
-#pragma unroll
-    for (int jj = 0; jj < JC; ++jj) old[jj] = (!act || ((first >> (j0 + jj)) & 1u)) ? 0.0 : my[idx[jj]];
-#pragma unroll
-    for (int jj = 0; jj < JC; ++jj)
-      if (act) my[idx[jj]] = old[jj] + v[j0 + jj];
-  }
-}
-
-// One step of the software pipeline: the element row of THIS batch (70 FMAs on tet P2, table operands warp-uniform) is
-// computed while the row of the PREVIOUS batch is added into the tile -- two independent instruction streams in one basic
-// block, so the FP64 chain and the shared-memory round trips overlap instead of following each other (ncu on v4: 46 % of
-// the warp samples were `wait` / `short_scoreboard` stalls of exactly that dependent chain, with 2 warps per scheduler).
-template <int TD, int L, int I, typename TabT>
-__device__ __forceinline__ void a5_row(const TabT& tb, const double (&h)[A4Geo<TD>::NH], double (&v)[L],
-                                       const uint32_t (&psw)[SlotRec<uint8_t, L>::WORDS], uint32_t pcw, bool pact, double* __restrict__ accd) {
-  constexpr int NH = A4Geo<TD>::NH;
-  double nv[L];
-#pragma unroll
-  for (int j = 0; j < L; ++j) {
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int t = 0; t < NH; t += 2) {
-      s0 += tb.T[I][j][t] * h[t];
-      if (t + 1 < NH) s1 += tb.T[I][j][t + 1] * h[t + 1];
-    }
-    nv[j] = s0 + s1;
-  }
-  a5_accumulate<L>(v, psw, pcw, pact, accd);
-#pragma unroll
-  for (int j = 0; j < L; ++j) v[j] = nv[j];
-}
-
-template <int TD, int L, int I, typename TabT>
-__device__ __forceinline__ void a5_dispatch(int i, const TabT& tb, const double (&h)[A4Geo<TD>::NH], double (&v)[L],
-                                            const uint32_t (&psw)[SlotRec<uint8_t, L>::WORDS], uint32_t pcw, bool pact,
-                                            double* __restrict__ accd) {
-  if (i == I) a5_row<TD, L, I, TabT>(tb, h, v, psw, pcw, pact, accd);
-  else if constexpr (I + 1 < L) a5_dispatch<TD, L, I + 1, TabT>(i, tb, h, v, psw, pcw, pact, accd);
-}
-
-template <int TD, int L, int D>
-__global__ void __launch_bounds__(FB2_ASM4_WARPS * 32, FB2_ASM4_MINBLOCKS)
-assemble_const_v5_kernel(const __grid_constant__ Asm5Args a, const __grid_constant__ A4Tables<L, A4Geo<TD>::NH> tb) {
-  // The batch loop is v4's (cp.async rings for the entry block and the geometry records) with the transposed accumulator.
-  // (A first version fetched the entry block with one cp.async.bulk per batch and an mbarrier: the UBLKCP operands and the
-  // phase bookkeeping pushed the loop -- whose element-table operands live in uniform registers -- into uniform-register
-  // spills, 719 instead of 393 warp instructions per batch, 6.3 ms instead of 4.0: profiles/r02_ncu_asm_v5_bulk.txt.)
-  using GEO = A4Geo<TD>;
-  constexpr int NH = GEO::NH, HS = GEO::HS, QP = GEO::QP;
-  using SR = SlotRec<uint8_t, L>;
-  constexpr int NHST = D + 1, NEST = 2 * D + 1;
-  constexpr int ENT_BYTES = 4 * a5_ent_words(SR::WORDS);        // cell[32] | code[32] | slot word w of lane l at 64 + 32 w + l
-  constexpr int ENT_CHUNKS = ENT_BYTES / 16;
-  extern __shared__ __align__(16) double sm5n[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int tile = blockIdx.x * FB2_ASM4_WARPS + wid;
-  if (tile >= a.ntile) return;
-  const size_t per_warp = (size_t)a.acc_stride + NHST * 32 * HS + NEST * (ENT_BYTES / 8);
-  double* accd = sm5n + (size_t)wid * per_warp;
-  double* hring = accd + a.acc_stride;
-  unsigned char* ering = reinterpret_cast<unsigned char*>(hring + NHST * 32 * HS);
-  const int64_t r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
-  const int64_t b0 = a.batch_ptr[tile], b1 = a.batch_ptr[tile + 1];
-
-  auto issue_entries = [&](int64_t b, int slot) {               // the batch's entry block is contiguous: 40 x 16 B for tet P2
-    unsigned char* dst = ering + slot * ENT_BYTES;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.ent + b * (ENT_BYTES / 4));
-#pragma unroll
-    for (int q0 = 0; q0 < ENT_CHUNKS; q0 += 32) {
-      const int q = q0 + lane;
-      if (q < ENT_CHUNKS) cp_async16(dst + q * 16, src + q * 16);
-    }
-  };
-  auto issue_geometry = [&](int eslot, int hslot) {
-    const int* cells = reinterpret_cast<const int*>(ering + eslot * ENT_BYTES);
-    double* dst = hring + hslot * 32 * HS;
-#pragma unroll
-    for (int r = 0; r < QP; ++r) {
-      const int idx = r * 32 + lane, rec = idx / QP, part = idx % QP;
-      const int c = cells[rec];
-      if (c >= 0) cp_async16(dst + 2 * a4_unit<QP>(rec, part), a.H + (int64_t)c * HS + 2 * part);
-    }
-  };
-
-  for (int k = 0; k < 2 * D; ++k)
-    if (b0 + k < b1) issue_entries(b0 + k, k);
-  cp_async_commit();
-  // local index of every batch: lane k holds batch_i of batch b0 + 32 c + k for the current (bi_cur) and the next (bi_nxt)
-  // chunk of 32 batches, handed out by a shuffle.  (v4 loaded batch_i[b + D] inside the loop and consumed it one iteration
-  // later: ncu's source view showed that single dependent global load as the largest stall of the kernel -- 10 % of all
-  // samples on the move that reads it, profiles/r02_ncu_asm_v4_source_top.txt.)
-  int bi_cur = (b0 + lane < b1) ? a.batch_i[b0 + lane] : 0;
-  int bi_nxt = (b0 + 32 + lane < b1) ? a.batch_i[b0 + 32 + lane] : 0;
-  cp_async_wait<0>();
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    if (b0 + k < b1) issue_geometry(k, k);
-    cp_async_commit();
-  }
-  int hs = 0, es = 0;
-  double pv[L];                                                 // the previous batch: its element row, slot words, code word
-  uint32_t psw[SR::WORDS], pcw = 0;
-  bool pact = false;
-#pragma unroll
-  for (int j = 0; j < L; ++j) pv[j] = 0.0;
-#pragma unroll
-  for (int w = 0; w < SR::WORDS; ++w) psw[w] = 0;
-  for (int64_t b = b0; b < b1; ++b) {
-    cp_async_wait<D - 1>();
-    __syncwarp();
-    {
-      int hn = hs + D; if (hn >= NHST) hn -= NHST;
-      int en = es + D; if (en >= NEST) en -= NEST;
-      int e2 = es + 2 * D; if (e2 >= NEST) e2 -= NEST;
-      if (b + 2 * D < b1) issue_entries(b + 2 * D, e2);
-      if (b + D < b1) issue_geometry(en, hn);
-      cp_async_commit();
-    }
-    const int kb = (int)(b - b0) & 31;
-    if (kb == 0 && b != b0) {                                   // next chunk of 32 batches (warp-uniform)
-      bi_cur = bi_nxt;
-      bi_nxt = (b + 32 + lane < b1) ? a.batch_i[b + 32 + lane] : 0;
-    }
-    const int i = __shfl_sync(0xffffffffu, bi_cur, kb);
-    const unsigned char* ent = ering + es * ENT_BYTES;
-    const int cell = reinterpret_cast<const int*>(ent)[lane];
-    const uint32_t cw = reinterpret_cast<const uint32_t*>(ent + 128)[lane];
-    uint32_t sw[SR::WORDS];
-#pragma unroll
-    for (int w = 0; w < SR::WORDS; ++w) sw[w] = reinterpret_cast<const uint32_t*>(ent + 256)[32 * w + lane];
-    double h[NH];
-    {
-      const double* hst = hring + hs * 32 * HS;                 // (an empty lane reads a stale record: its row is never used)
-      double hh[HS];
-#pragma unroll
-      for (int t = 0; t < QP; ++t) {
-        const double2 v = *reinterpret_cast<const double2*>(hst + 2 * a4_unit<QP>(lane, t));
-        hh[2 * t] = v.x; hh[2 * t + 1] = v.y;
-      }
-#pragma unroll
-      for (int t = 0; t < NH; ++t) h[t] = hh[t];
-    }
-    a5_dispatch<TD, L, 0>(i, tb, h, pv, psw, pcw, pact, accd);      // row of batch b  ||  accumulate row of batch b - 1
-#pragma unroll
-    for (int w = 0; w < SR::WORDS; ++w) psw[w] = sw[w];
-    pcw = cw;
-    pact = cell >= 0;
-    if (++hs == NHST) hs = 0;
-    if (++es == NEST) es = 0;
-  }
-  a5_accumulate<L>(pv, psw, pcw, pact, accd);                   // the last batch
-  cp_async_wait<0>();
-  __syncwarp();
-  // write-back: one row per half-warp, 16 consecutive values per step (128-byte global segments).  The metadata of 32
-  // rows is loaded at once (lane = row) and parked in the (now idle) entry ring: one global-load latency per 32 rows.  Lane
-  // hl of a half-warp reads values hl, hl + 16, ...: (c ^ s) & 15 = (c ^ hl) & 15 is a per-lane constant, the loop a stride.
-  // (Handing the metadata over with 64-bit shuffles instead changed the register allocation of the WHOLE kernel: 143
-  // instead of 198 registers, the element-table operands of the batch loop spilled out of the uniform register file --
-  // 402 MOV.SPILL, 1254 UMOV in the SASS -- and the kernel ran 6.3 ms instead of 4.)
-  {
-    const int hw = lane >> 4, hl = lane & 15;
-    int64_t* mv0 = reinterpret_cast<int64_t*>(ering);            // [32] first value index
-    int* mlen = reinterpret_cast<int*>(ering + 256);             // [32] row length
-    int* mrc = reinterpret_cast<int*>(ering + 384);              // [32] row code
-    int64_t v0l = 0;
-    int lenl = 0, rcl = 0;
-    if (r0 + lane < r1) { v0l = a.crow[r0 + lane]; lenl = (int)(a.crow[r0 + lane + 1] - v0l); rcl = a.row_code[r0 + lane]; }
-    for (int64_t rb = r0; rb < r1; rb += 32) {
-      __syncwarp();
-      mv0[lane] = v0l; mlen[lane] = lenl; mrc[lane] = rcl;
-      __syncwarp();
-      {                                                          // metadata of the next 32 rows: in flight while these are written
-        const int64_t r = rb + 32 + lane;
-        v0l = 0; lenl = 0; rcl = 0;
-        if (r < r1) { v0l = a.crow[r]; lenl = (int)(a.crow[r + 1] - v0l); rcl = a.row_code[r]; }
-      }
-      for (int k = hw; k < 32; k += 2) {
-        const int len = mlen[k];                                 // 0 for a row past the end
-        const int rc = mrc[k];
-        const double* g = accd + (rc >> 4) * 16 + 16 * hl + (((rc & 15) ^ hl) & 15);
-        double* out = a.values + mv0[k] + hl;
-        for (int s = hl; s < len; s += 64, g += 1024, out += 64) {      // 4 values per lane in flight
-          double v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = (s + 16 * u < len) ? g[256 * u] : 0.0;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (s + 16 * u < len) out[16 * u] = v[u];
-        }
-      }
-    }
-  }
-}
-
-// ---- host side --------------------------------------------------------------------------------------------------------
-size_t asm5_workspace_bytes(int64_t nrow, int ntile_max) {
-  const int64_t nchunk = ceil_div(nrow > 0 ? nrow : 1, A5_CHUNK);
-  const int64_t m = std::max<int64_t>(nchunk, ntile_max) + 1;
-  return 2 * align_up((size_t)m * 4) + align_up((size_t)(nchunk + 1) * 8) + scan_workspace_bytes(m) + 1024;
-}
-
-// step 1: number of tiles (host value)
-int asm5_tiles_count(int64_t nrow, const int64_t* crow, int cap, int64_t* ntile_host, void* ws, cudaStream_t s) {
-  if (nrow >= ((int64_t)1 << 31)) return fail(ERR_UNSUPPORTED, "asm5: more than 2^31 rows");
-  const int nchunk = (int)ceil_div(nrow > 0 ? nrow : 1, A5_CHUNK);
-  Carver c(ws);
-  int* cnt = c.take<int>(nchunk + 1);
-  c.take<int>(nchunk + 1);
-  int64_t* first = c.take<int64_t>(nchunk + 1);
-  void* scan_ws = c.take<char>(scan_workspace_bytes(nchunk + 1));
-  asm5_tile_kernel<false><<<(unsigned)ceil_div(nchunk, 128), 128, 0, s>>>(nrow, crow, cap, nchunk, cnt, nullptr, nullptr, 0);
-  FB2_LAUNCH_CHECK();
-  FB2_TRY(exclusive_scan_i32(cnt, first, nchunk, true, scan_ws, s));
-  FB2_CUDA(cudaMemcpyAsync(ntile_host, first + nchunk, 8, cudaMemcpyDeviceToHost, s));
-  FB2_CUDA(cudaStreamSynchronize(s));
-  return OK;
-}
-// step 2 (same ws, right after step 1): tile_row (ntile + 1)
-int asm5_tiles_fill(int64_t nrow, const int64_t* crow, int cap, int64_t ntile, int32_t* tile_row, void* ws, cudaStream_t s) {
-  const int nchunk = (int)ceil_div(nrow > 0 ? nrow : 1, A5_CHUNK);
-  Carver c(ws);
-  c.take<int>(nchunk + 1);
-  c.take<int>(nchunk + 1);
-  const int64_t* first = c.take<int64_t>(nchunk + 1);
-  asm5_tile_kernel<true><<<(unsigned)ceil_div(nchunk, 128), 128, 0, s>>>(nrow, crow, cap, nchunk, nullptr, first, tile_row, ntile);
-  FB2_LAUNCH_CHECK();
-  return OK;
-}
-
-static int asm5_sched_launch(bool fill, int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr,
-                             const int* adj_pair, int L, int* nb_of_tile, int* pad_of_tile, const int64_t* batch_ptr,
-                             unsigned char* batch_i, uint32_t* ent, uint16_t* row_code, const uint32_t* slot_words, int slot_nwords,
-                             int* err, cudaStream_t s) {
-  const size_t per_warp = (A5Sched::bytes(L) + 15) / 16 * 16;
-  const size_t smem = per_warp * A5_SCHED_WARPS;
-  const unsigned grid = (unsigned)ceil_div(ntile, A5_SCHED_WARPS);
-  if (fill) {
-    auto k = asm5_schedule_kernel<true>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, A5_SCHED_WARPS * 32, smem, s>>>(ntile, tile_row, crow, adj_ptr, adj_pair, L, nb_of_tile, pad_of_tile, batch_ptr, batch_i, ent,
-                                             row_code, slot_words, slot_nwords, err);
-  } else {
-    auto k = asm5_schedule_kernel<false>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, A5_SCHED_WARPS * 32, smem, s>>>(ntile, tile_row, crow, adj_ptr, adj_pair, L, nb_of_tile, pad_of_tile, batch_ptr, batch_i, ent,
-                                             row_code, slot_words, slot_nwords, err);
-  }
-  FB2_LAUNCH_CHECK();
-  return OK;
-}
-
-// step 3: batches per tile -> batch_ptr, total number of batches and the largest padded tile (host values)
-int asm5_plan_count(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
-                    int64_t* batch_ptr, int64_t* nbatch_host, int* max_pad_host, void* ws, cudaStream_t s) {
-  if (L > A4_MAXL) return fail(ERR_UNSUPPORTED, "asm5: ldof=%d exceeds %d", L, A4_MAXL);
-  Carver c(ws);
-  int* nb = c.take<int>(ntile + 1);
-  int* pad = c.take<int>(ntile + 1);
-  c.take<int64_t>(1);
-  void* scan_ws = c.take<char>(scan_workspace_bytes(ntile + 1));
-  if (ntile > 0) FB2_TRY(asm5_sched_launch(false, ntile, tile_row, crow, adj_ptr, adj_pair, L, nb, pad, nullptr, nullptr, nullptr, nullptr,
-                                           nullptr, 0, nullptr, s));
-  FB2_TRY(exclusive_scan_i32(nb, batch_ptr, ntile, true, scan_ws, s));
-  FB2_CUDA(cudaMemsetAsync(nb, 0, 4, s));
-  if (ntile > 0) max_kernel<<<grid_for(ntile), 256, 0, s>>>(pad, ntile, nb);
-  FB2_LAUNCH_CHECK();
-  FB2_CUDA(cudaMemcpyAsync(nbatch_host, batch_ptr + ntile, 8, cudaMemcpyDeviceToHost, s));
-  FB2_CUDA(cudaMemcpyAsync(max_pad_host, nb, 4, cudaMemcpyDeviceToHost, s));
-  FB2_CUDA(cudaStreamSynchronize(s));
-  return OK;
-}
-
-// step 4: the schedule itself
-int asm5_plan_fill(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
-                   const int64_t* batch_ptr, unsigned char* batch_i, uint32_t* ent, uint16_t* row_code, const void* slots,
-                   int slot_bytes, void* ws, cudaStream_t s) {
-  if (ntile <= 0) return OK;
-  if (slot_bytes != 1) return fail(ERR_UNSUPPORTED, "asm5: rows longer than 255 values take the v4 kernel");
-  const int nwords = slot_stride(L, 1) / 4;
-  Carver c(ws);
-  int* err = c.take<int>(ntile + 1);
-  FB2_CUDA(cudaMemsetAsync(err, 0, 4, s));
-  FB2_TRY(asm5_sched_launch(true, ntile, tile_row, crow, adj_ptr, adj_pair, L, nullptr, nullptr, batch_ptr, batch_i, ent, row_code,
-                            static_cast<const uint32_t*>(slots), nwords, err, s));
-  int herr = 0;
-  FB2_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, s));
-  FB2_CUDA(cudaStreamSynchronize(s));
-  if (herr) return fail(ERR_UNSUPPORTED, "asm5: schedule does not fit its encoding (code %d)", herr);
-  return OK;
-}
-
-template <int TD, int L>
-static int launch_asm5(const Asm4Args& g, Asm5Args a, cudaStream_t s) {
-  using GEO = A4Geo<TD>;
-  static_assert(sizeof(A4Tables<L, GEO::NH>) + sizeof(Asm5Args) < 32000, "element tables exceed the kernel parameter block");
-  cell_geometry4_kernel<TD><<<(unsigned)ceil_div(g.NC, 256), 256, 0, s>>>(g.node, g.cell, g.NC, g.Ms_host ? g.scal_d : 0.0, g.coef_d,
-                                                                         g.Mm_host ? g.scal_m : 0.0, g.coef_m, g.Hbuf);
-  a.H = g.Hbuf;
-  A4Tables<L, GEO::NH> tb;
-  a4_reduced_table<TD, L>(g.Ms_host, g.Mm_host, tb);
-  constexpr int D = 1;
-  constexpr int ENT_BYTES = 4 * a5_ent_words(SlotRec<uint8_t, L>::WORDS);
-  const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
-  if (grid == 0) return OK;
-  const size_t per_warp = (size_t)(a.acc_stride + (D + 1) * 32 * GEO::HS) * 8 + (size_t)(2 * D + 1) * ENT_BYTES;
-  const size_t smem = per_warp * FB2_ASM4_WARPS;
-  if (smem > 227 * 1024) return fail(ERR_UNSUPPORTED, "assemble v5: tiles do not fit shared memory (acc_stride=%d)", a.acc_stride);
-  auto k = assemble_const_v5_kernel<TD, L, D>;
-  FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a, tb);
-  FB2_LAUNCH_CHECK();
-  return OK;
-}
-
-int assemble_v5(int TD, int p, const Asm4Args& g, const Asm5Args& a, int threads, cudaStream_t s) {
-  (void)threads;       // CTA shape is compile time (FB2_ASM4_WARPS warps, FB2_ASM4_MINBLOCKS CTAs per SM)
-  switch (TD * 10 + p) {
-    case 21: return launch_asm5<2, 3>(g, a, s);
-    case 22: return launch_asm5<2, 6>(g, a, s);
-    case 23: return launch_asm5<2, 10>(g, a, s);
-    case 31: return launch_asm5<3, 4>(g, a, s);
-    case 32: return launch_asm5<3, 10>(g, a, s);
-    case 33: return launch_asm5<3, 20>(g, a, s);
-    default: return fail(ERR_UNSUPPORTED, "assemble v5: unsupported element TD=%d p=%d", TD, p);
-  }
-}
-
-}  // namespace fb2

@@ -66,27 +66,6 @@ struct Asm4Args {
   const double* H;
   double* values;
 };
-struct Asm5Args {
-  int64_t NC;
-  const int64_t* crow;
-  const int32_t* tile_row;      // (ntile+1)
-  int ntile, acc_stride;        // acc_stride: doubles per warp accumulator (max padded tile, even)
-  const int64_t* batch_ptr;     // (ntile+1)
-  const unsigned char* batch_i; // (nbatch)
-  const uint32_t* ent;          // (nbatch, ENT_WORDS)
-  const uint16_t* row_code;     // (nrow) (group base / 16) << 4 | class
-  const double* H;              // (NC, HS) geometry records
-  double* values;
-};
-size_t asm5_workspace_bytes(int64_t nrow, int ntile_max);
-int asm5_tiles_count(int64_t nrow, const int64_t* crow, int cap, int64_t* ntile_host, void* ws, cudaStream_t s);
-int asm5_tiles_fill(int64_t nrow, const int64_t* crow, int cap, int64_t ntile, int32_t* tile_row, void* ws, cudaStream_t s);
-int asm5_plan_count(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
-                    int64_t* batch_ptr, int64_t* nbatch_host, int* max_pad_host, void* ws, cudaStream_t s);
-int asm5_plan_fill(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
-                   const int64_t* batch_ptr, unsigned char* batch_i, uint32_t* ent, uint16_t* row_code, const void* slots,
-                   int slot_bytes, void* ws, cudaStream_t s);
-int assemble_v5(int TD, int p, const Asm4Args& g, const Asm5Args& a, int threads, cudaStream_t s);
 size_t asm4_workspace_bytes(int ntile);
 int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
                     int64_t* batch_ptr, int64_t* nbatch_host, void* ws, cudaStream_t s);

@@ -194,40 +194,6 @@ int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, 
   a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.Hbuf = geom_ws; a.values = values;
   return assemble_v4(TD, p, a, slot_bytes, S(stream));
 }
-// ---- v5: conflict-free transposed tiles, bulk-copied entry blocks ---------------------------------------------
-size_t fb2_asm5_workspace_bytes(int64_t nrow, int ntile_max) { return asm5_workspace_bytes(nrow, ntile_max); }
-int fb2_asm5_entry_words(int ldof) { return 32 * (2 + slot_stride(ldof, 1) / 4); }
-int fb2_asm5_tiles_count(int64_t nrow, const int64_t* crow, int cap, int64_t* ntile_host, void* ws, void* stream) {
-  if (cap < 1024) return fail(ERR_INVALID, "asm5: tile capacity must be >= 1024 values");
-  return asm5_tiles_count(nrow, crow, cap, ntile_host, ws, S(stream));
-}
-int fb2_asm5_tiles_fill(int64_t nrow, const int64_t* crow, int cap, int64_t ntile, int32_t* tile_row, void* ws, void* stream) {
-  return asm5_tiles_fill(nrow, crow, cap, ntile, tile_row, ws, S(stream));
-}
-int fb2_asm5_plan_count(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
-                        int ldof, int64_t* batch_ptr, int64_t* nbatch_host, int32_t* max_pad_host, void* ws, void* stream) {
-  return asm5_plan_count(ntile, tile_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, nbatch_host, max_pad_host, ws, S(stream));
-}
-int fb2_asm5_plan_fill(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
-                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, uint32_t* ent, uint16_t* row_code, const void* slots,
-                       int slot_bytes, void* ws, void* stream) {
-  return asm5_plan_fill(ntile, tile_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, batch_i, ent, row_code, slots, slot_bytes, ws,
-                        S(stream));
-}
-int fb2_assemble_scalar_const_v5(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
-                                 const int32_t* tile_row, int ntile, int acc_stride, const int64_t* batch_ptr, const uint8_t* batch_i,
-                                 const uint32_t* ent, const uint16_t* row_code, const double* Ms_host, const double* Mm_host,
-                                 double scal_d, const double* coef_d, double scal_m, const double* coef_m, double* geom_ws,
-                                 double* values, int threads, void* stream) {
-  if (!Ms_host && !Mm_host) return fail(ERR_INVALID, "assemble_scalar_const_v5: need a diffusion and/or a mass table");
-  Asm4Args g{};
-  g.node = node; g.cell = cell; g.NC = NC; g.Ms_host = Ms_host; g.Mm_host = Mm_host;
-  g.scal_d = scal_d; g.scal_m = scal_m; g.coef_d = coef_d; g.coef_m = coef_m; g.Hbuf = geom_ws;
-  Asm5Args a{};
-  a.NC = NC; a.crow = crow; a.tile_row = tile_row; a.ntile = ntile; a.acc_stride = acc_stride; a.batch_ptr = batch_ptr;
-  a.batch_i = batch_i; a.ent = ent; a.row_code = row_code; a.values = values;
-  return assemble_v5(TD, p, g, a, threads, S(stream));
-}
 int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,
                        int64_t* crow_out, int32_t* col_out, void* stream) {
   return expand_pattern(gdof_scalar, ncomp, dof_priority, crow_scalar, col_scalar, crow_out, col_out, S(stream));
@@ -303,6 +269,44 @@ int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const dou
                      void* partial_ws, int fuse_finalize, const int64_t own[4], void* stream) {
   return cg_update_xr(n, x, r, p, Ap, minv_diag, static_cast<CgScalars*>(scalars), partial_ws, fuse_finalize, S(stream), make_own(own));
 }
+// ---- multi-GPU CG over NVLink peer memory (csrc/peer.cu) -----------------------------------------------------------
+int fb2_peer_ctrl_bytes(void) { return (int)align_up(sizeof(PeerCtrl), 4096); }
+int fb2_cg_spmv_dot_ranges(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
+                           double* Ap, const int32_t* blk_lo, const int32_t* blk_hi, int nblk, int tile, int32_t max_row,
+                           double* dot_out_dev, void* scalars, void* partial_ws, const int64_t own[4], void* stream) {
+  if (nblk <= 0) {                                  // no rows in these ranges on this rank: the partial dot is 0
+    FB2_CUDA(cudaMemsetAsync(dot_out_dev, 0, sizeof(double), S(stream)));
+    return OK;
+  }
+  SpmvPlan pl{};
+  pl.blk_row = blk_lo; pl.blk_end = blk_hi; pl.nblk = nblk; pl.tile = tile; pl.max_row = max_row;
+  return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, dot_out_dev, partial_ws, S(stream), &pl, make_own(own),
+              static_cast<CgScalars*>(scalars));
+}
+int fb2_peer_allreduce(void* ctrl_mine, const uint64_t* peer_base_dev, int world, int rank, int kind, const double* src0,
+                       const double* src1, double* dst, void* scalars, int finalize, const uint64_t* epoch_dev, void* stream) {
+  return peer_allreduce(static_cast<PeerCtrl*>(ctrl_mine), reinterpret_cast<const unsigned long long*>(peer_base_dev), world, rank, kind,
+                        src0, src1, dst, static_cast<CgScalars*>(scalars), finalize,
+                        reinterpret_cast<const unsigned long long*>(epoch_dev), S(stream));
+}
+int fb2_peer_wait_halo(void* ctrl_mine, int nnb, const int32_t* nb_rank_host, const void* scalars, const uint64_t* epoch_dev,
+                       void* stream) {
+  return peer_wait_halo(static_cast<PeerCtrl*>(ctrl_mine), nnb, nb_rank_host, static_cast<const CgScalars*>(scalars),
+                        reinterpret_cast<const unsigned long long*>(epoch_dev), S(stream));
+}
+int fb2_cg_update_p_push(const int64_t own[4], double* p, const double* r, const double* minv_diag, const void* scalars, int nslice,
+                         const int64_t* lo, const int64_t* hi, const int64_t* peer_lo, void* const* peer_p, int nnb,
+                         void* const* nb_ctrl, int rank, uint32_t* counter_dev, const uint64_t* epoch_dev, void* stream) {
+  if (nslice < 0 || nslice > 4 || nnb < 0 || nnb > 2) return fail(ERR_INVALID, "cg_update_p_push: nslice=%d nnb=%d", nslice, nnb);
+  PeerPush push{};
+  push.nslice = nslice; push.nnb = nnb; push.rank = rank;
+  for (int k = 0; k < nslice; ++k) push.slice[k] = PeerSlice{lo[k], hi[k], peer_lo[k], static_cast<double*>(peer_p[k])};
+  for (int k = 0; k < nnb; ++k) push.nb_ctrl[k] = static_cast<PeerCtrl*>(nb_ctrl[k]);
+  push.counter = counter_dev;
+  push.epoch = reinterpret_cast<const unsigned long long*>(epoch_dev);
+  return cg_update_p_push(make_own(own), p, r, minv_diag, static_cast<const CgScalars*>(scalars), push, S(stream));
+}
+
 int64_t fb2_box_edges_before(int nx, int ny, int nz, int i, int j, int k) { return box_edges_before_host(nx, ny, nz, i, j, k); }
 int fb2_tet_box_slab(const double box[6], int nx, int ny, int nz, int cube_layer_lo, int cube_layer_hi, int p, double* node,
                      int32_t* cell, int32_t* cell2dof, void* stream) {

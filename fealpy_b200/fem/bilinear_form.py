@@ -155,69 +155,6 @@ def asm4_plan(space):
     return sym["asm4"]
 
 
-ASM5_CAP = int(_os.environ.get("FB2_ASM5_CAP", "0"))            # values per WARP tile of the v5 kernel (0 = largest that fits)
-ASM5_THREADS = 128                                                 # 4 warps per CTA, 2 CTAs per SM (compile time in csrc/assemble.cu)
-ASM5_SMEM = 227 * 1024
-
-
-def _asm5_try(sym, cap, ring_bytes):
-    """tiles + batch counts for one tile capacity; None when the padded tiles do not fit 8 warps per SM"""
-    lib = _lib.load()
-    dev = sym["crow"].device
-    gdof, L = sym["gdof"], sym["L"]
-    ws = _lib.workspace(lib.fb2_asm5_workspace_bytes(gdof, 0), dev)
-    nt = C.c_int64(0)
-    _lib.call("fb2_asm5_tiles_count", gdof, _lib.ptr(sym["crow"]), cap, C.byref(nt), _lib.ptr(ws), _lib.stream())
-    ntile = nt.value
-    tile_row = torch.empty(ntile + 1, dtype=torch.int32, device=dev)
-    _lib.call("fb2_asm5_tiles_fill", gdof, _lib.ptr(sym["crow"]), cap, ntile, _lib.ptr(tile_row), _lib.ptr(ws), _lib.stream())
-    ws = _lib.workspace(lib.fb2_asm5_workspace_bytes(gdof, ntile), dev)
-    batch_ptr = torch.empty(ntile + 1, dtype=torch.int64, device=dev)
-    nb, max_pad = C.c_int64(0), C.c_int32(0)
-    _lib.call("fb2_asm5_plan_count", ntile, _lib.ptr(tile_row), _lib.ptr(sym["crow"]), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
-              L, _lib.ptr(batch_ptr), C.byref(nb), C.byref(max_pad), _lib.ptr(ws), _lib.stream())
-    acc_stride = (max_pad.value + 15) // 16 * 16
-    if max_pad.value >= (1 << 30) or (acc_stride * 8 + ring_bytes) * 8 > ASM5_SMEM:
-        return None
-    return dict(tile_row=tile_row, ntile=ntile, cap=cap, batch_ptr=batch_ptr, nbatch=nb.value, acc_stride=acc_stride, ws=ws)
-
-
-def asm5_plan(space):
-    """tiles + conflict-free batch schedule of the v5 numeric kernel (cached per space; csrc/assemble.cu asm5_*).
-    Returns None when the pattern does not fit the v5 encoding (rows longer than 255 values, ldof > 20): the caller
-    then takes the v4 / v2 kernels.  The tile capacity is the largest of a short ladder whose padded (transposed)
-    tiles still leave room for 8 warps per SM."""
-    sym = symbolic_pattern(space)
-    if "asm5" in sym:
-        return sym["asm5"]
-    sym["asm5"] = None
-    if sym["slot_bytes"] != 1 or sym["L"] > 20 or sym["max_row"] > 255 or sym["gdof"] == 0:
-        return None
-    lib = _lib.load()
-    dev = sym["crow"].device
-    gdof, L = sym["gdof"], sym["L"]
-    ew = lib.fb2_asm5_entry_words(L)
-    HS = 8 if space.mesh.TD == 3 else 4
-    ring_bytes = 2 * 32 * HS * 8 + 3 * 4 * ew                       # geometry stages + entry slots per warp (depth 1)
-    pl = None
-    for cap in ([ASM5_CAP] if ASM5_CAP else [2560, 2432, 2304, 2176, 2048, 1792, 1536]):
-        pl = _asm5_try(sym, cap, ring_bytes)
-        if pl is not None:
-            break
-    if pl is None:
-        return None
-    nb, ntile = pl["nbatch"], pl["ntile"]
-    batch_i = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
-    ent = torch.empty(max(nb, 1) * ew, dtype=torch.int32, device=dev)
-    row_code = torch.empty(gdof, dtype=torch.int16, device=dev)
-    _lib.call("fb2_asm5_plan_fill", ntile, _lib.ptr(pl["tile_row"]), _lib.ptr(sym["crow"]), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
-              L, _lib.ptr(pl["batch_ptr"]), _lib.ptr(batch_i), _lib.ptr(ent), _lib.ptr(row_code), _lib.ptr(sym["slots"]), sym["slot_bytes"],
-              _lib.ptr(pl.pop("ws")), _lib.stream())
-    pl.update(batch_i=batch_i, ent=ent, row_code=row_code, entry_words=ew)
-    sym["asm5"] = pl
-    return pl
-
-
 def tensor_pattern(space):
     """pattern of a TensorFunctionSpace = scalar pattern (x) dense ncomp x ncomp blocks"""
     cache = getattr(space, "_b200_pattern", None)
@@ -368,23 +305,13 @@ class BilinearForm:
                 return None
             h = host_tables(mesh.TD, space.p, m["q"])[key]
             return h.ctypes.data_as(C.c_void_p)
-        kernel = _os.environ.get("FB2_ASM_KERNEL", "v5")
-        if kernel == "v5" and asm5_plan(space) is None:
-            kernel = "v4"          # rows longer than 255 values: the v5 slot / row-code encoding does not cover them
+        kernel = _os.environ.get("FB2_ASM_KERNEL", "auto")
+        if kernel == "auto":
+            kernel = "v4"
         if kernel == "v4" and (ASM4_TILE + sym["max_row"] >= 4096 or sym["max_row"] > 1024 or sym["L"] > 20):
             kernel = "v2"          # very long rows (high-valence meshes): tile offsets / first-touch bitmap of v4 do not cover them
         NH = mesh.TD * (mesh.TD + 1) // 2 + 1          # reduced geometry record (csrc/assemble.cu A4Geo)
         self.last_kernel = kernel
-        if kernel == "v5":
-            pl = asm5_plan(space)
-            geom = getattr(self, "_asm4_geom", None)      # per-cell geometry scratch, kept with the form (no allocator churn per assembly)
-            if geom is None or geom.shape[0] != sym["NC"] or geom.device != mesh.device:
-                geom = self._asm4_geom = torch.empty((sym["NC"], (NH + 1) // 2 * 2), dtype=torch.float64, device=mesh.device)
-            _lib.call("fb2_assemble_scalar_const_v5", mesh.TD, space.p, sym["NC"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
-                      _lib.ptr(sym["crow"]), _lib.ptr(pl["tile_row"]), pl["ntile"], pl["acc_stride"], _lib.ptr(pl["batch_ptr"]),
-                      _lib.ptr(pl["batch_i"]), _lib.ptr(pl["ent"]), _lib.ptr(pl["row_code"]), hostp(dm, "Ms"), hostp(mm, "Mm"),
-                      sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(geom), _lib.ptr(values), ASM5_THREADS, _lib.stream())
-            return sym["crow"], sym["col"], values
         if kernel == "v4":
             pl = asm4_plan(space)
             geom = getattr(self, "_asm4_geom", None)      # per-cell geometry scratch, kept with the form (no allocator churn per assembly)

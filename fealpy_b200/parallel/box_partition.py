@@ -95,6 +95,23 @@ class BoxSlab:
     def _edge_plane(self, plane):
         return (self._e(plane), self._e(plane + 1))
 
+    def row_split(self):
+        """(interior, boundary): window-local (lo, hi) ranges of the OWNED rows.  Boundary rows are the dofs of the first / last
+        owned node plane next to a neighbour (their cells reach into the halo plane); interior rows touch owned columns only,
+        so their part of the SpMV needs no halo value and overlaps the exchange."""
+        P0, P1 = self.own_planes
+        a = min(P0 + (1 if self.rank > 0 else 0), P1)
+        b = max(P1 - (1 if self.rank < self.world - 1 else 0), a)
+
+        def ranges(x0, x1):
+            out = []
+            if x1 > x0:
+                out.append((self._node_plane(x0)[0], self._node_plane(x1 - 1)[1]))
+                if self.p == 2:
+                    out.append((self._e(x0), self._e(x1)))
+            return out
+        return ranges(a, b), ranges(P0, a) + ranges(b, P1)
+
     @property
     def own_ranges(self):
         """(lo0, hi0, lo1, hi1) of the owned rows in window-local ids"""

@@ -163,27 +163,6 @@ int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, 
                                  int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d,
                                  const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* geom_ws, double* values,
                                  void* stream);
-/* v5 of the fused numeric phase (default for scalar forms with rows <= 255 values).  Same scheduled batches as v4, but the
- * warp's accumulator tile is stored transposed and XOR-swizzled so that the shared-memory accumulation is bank-conflict
- * free, and every batch's entry block arrives with one bulk asynchronous copy.  Plan (once per space):
- *   fb2_asm5_tiles_count/fill : tile_row (ntile+1) -- runs of rows holding <= cap values, row counts multiples of 16
- *   fb2_asm5_plan_count       : batch_ptr (ntile+1), number of batches, largest padded tile (doubles)
- *   fb2_asm5_plan_fill        : batch_i (nbatch), ent (nbatch x fb2_asm5_entry_words(ldof) uint32), row_code (nrow uint16)
- * ws >= fb2_asm5_workspace_bytes(nrow, ntile).  geom_ws: (NC, 8 [tet] / 4 [tri]) doubles of scratch. */
-size_t fb2_asm5_workspace_bytes(int64_t nrow, int ntile_max);
-int fb2_asm5_entry_words(int ldof);
-int fb2_asm5_tiles_count(int64_t nrow, const int64_t* crow, int cap, int64_t* ntile_host, void* ws, void* stream);
-int fb2_asm5_tiles_fill(int64_t nrow, const int64_t* crow, int cap, int64_t ntile, int32_t* tile_row, void* ws, void* stream);
-int fb2_asm5_plan_count(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
-                        int ldof, int64_t* batch_ptr, int64_t* nbatch_host, int32_t* max_pad_host, void* ws, void* stream);
-int fb2_asm5_plan_fill(int ntile, const int32_t* tile_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
-                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, uint32_t* ent, uint16_t* row_code, const void* slots,
-                       int slot_bytes, void* ws, void* stream);
-int fb2_assemble_scalar_const_v5(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
-                                 const int32_t* tile_row, int ntile, int acc_stride, const int64_t* batch_ptr, const uint8_t* batch_i,
-                                 const uint32_t* ent, const uint16_t* row_code, const double* Ms_host, const double* Mm_host,
-                                 double scal_d, const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* geom_ws,
-                                 double* values, int threads, void* stream);
 /* expands the scalar pattern to the tensor-space pattern */
 int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const int64_t* crow_scalar, const int32_t* col_scalar,
                        int64_t* crow_out, int32_t* col_out, void* stream);
@@ -225,6 +204,29 @@ int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const dou
                      void* partial_ws, int fuse_finalize, const int64_t own[4], void* stream);
 int fb2_cg_finalize(void* scalars, void* stream);
 int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_diag, void* scalars, void* stream);
+
+/* ---- multi-GPU CG over NVLink peer memory ----------------------------------------------------
+ * The halo exchange and the two scalar all-reduces of a CG iteration, done by the iteration's own kernels with stores
+ * into the neighbours' peer-mapped (symmetric) memory + sequence flags: no NCCL call inside the iteration.  Every rank owns a
+ * control block of fb2_peer_ctrl_bytes() bytes at the start of its symmetric buffer, followed by its vector p; peer_base_dev
+ * is a device array of the `world` base addresses.  *epoch_dev (device) is the base of the solve's sequence numbers (the host
+ * raises it by 2^32 per solve).  See csrc/peer.cu for the protocol and its ordering argument.
+ *   fb2_cg_spmv_dot_ranges : Ap = A p on the rows of a multi-range tile plan (blk_lo / blk_hi per tile), fused partial p.Ap
+ *   fb2_peer_wait_halo     : (1 warp) wait until the <= 2 neighbours' halo pushes of the previous iteration have landed
+ *   fb2_peer_allreduce     : (1 warp) *dst = sum over ranks (in rank order, bit-identical everywhere) of *src0 (+ *src1);
+ *                            finalize != 0 applies the stopping rules of solver/cg.py:97-121 to the reduced r.z
+ *   fb2_cg_update_p_push   : p = z + beta p on the owned rows, owned boundary slices stored into the neighbours' p, flags raised */
+int fb2_peer_ctrl_bytes(void);
+int fb2_cg_spmv_dot_ranges(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
+                           double* Ap, const int32_t* blk_lo, const int32_t* blk_hi, int nblk, int tile, int32_t max_row,
+                           double* dot_out_dev, void* scalars, void* partial_ws, const int64_t own[4], void* stream);
+int fb2_peer_allreduce(void* ctrl_mine, const uint64_t* peer_base_dev, int world, int rank, int kind, const double* src0,
+                       const double* src1, double* dst, void* scalars, int finalize, const uint64_t* epoch_dev, void* stream);
+int fb2_peer_wait_halo(void* ctrl_mine, int nnb, const int32_t* nb_rank_host, const void* scalars, const uint64_t* epoch_dev,
+                       void* stream);
+int fb2_cg_update_p_push(const int64_t own[4], double* p, const double* r, const double* minv_diag, const void* scalars, int nslice,
+                         const int64_t* lo, const int64_t* hi, const int64_t* peer_lo, void* const* peer_p, int nnb,
+                         void* const* nb_ctrl, int rank, uint32_t* counter_dev, const uint64_t* epoch_dev, void* stream);
 
 /* batched right-hand sides, b of shape (n, nb) row-major (solver/cg.py:88-121): per-column dots,
  * x/r update with alpha_k = rTr[k]/pAp[k], p update with beta_k = rTr_new[k]/rTr[k]; the host drives

@@ -943,90 +943,3 @@ def test_elasticity_dirichlet_jacobi_cg(case, U):
     x, info = cg(A2, F2, M=CSRTensor(d.crow, d.col, 1.0 / d.values, A2.shape), returninfo=True, atol=1e-14, rtol=1e-11)
     assert np.linalg.norm(x.cpu().numpy() - gold["x"]) / np.linalg.norm(gold["x"]) <= 1e-10
     assert abs(info["niter"] - gold["info"]["niter"]) <= 2
-
-
-@pytest.mark.parametrize("kind,dims,p,cap", [("tet", (6, 5, 4), 2, 2432), ("tet", (4, 4, 3), 3, 2304), ("tri", (31, 17), 1, 1024),
-                                             ("tri", (9, 8), 3, 2048), ("tet", (7, 6, 5), 1, 1024), ("tet", (9, 9, 9), 2, 0)])
-def test_asm5_schedule_invariants(kind, dims, p, cap, U, monkeypatch):
-    """the conflict-free batch schedule of the v5 numeric kernel (csrc/assemble.cu asm5_*), checked entry by entry: tiles
-    partition the rows (<= cap values, row counts multiples of 16 inside a chunk); every (cell, local index) pair exactly
-    once; a batch holds ONE local index, 32 different rows, and lane l carries a row of class l mod 16 (the 16 lanes of a
-    half-warp hit 16 different banks whatever their slots); rows meet their cells in (i, cell) order; the transposed
-    tile layout gives every value of the tile its own address; first-touch masks mark the first write of every value"""
-    from fealpy_b200.mesh import TetrahedronMesh, TriangleMesh
-    from fealpy_b200.functionspace import LagrangeFESpace
-    from fealpy_b200.fem import bilinear_form as bfm
-    monkeypatch.setattr(bfm, "ASM5_CAP", cap)
-    mesh = (TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], *dims) if kind == "tet" else TriangleMesh.from_box([0, 1, 0, 1], *dims))
-    space = LagrangeFESpace(mesh, p)
-    sym = bfm.symbolic_pattern(space)
-    pl = bfm.asm5_plan(space)
-    if kind == "tet" and p == 3 and pl is None:
-        return                                 # tet P3 tiles may not fit the v5 encoding / shared memory: the v4 kernel takes the form
-    assert pl is not None
-    cap = pl["cap"]
-    c2d = space.cell_to_dof().cpu().numpy()
-    NC, L = c2d.shape
-    gdof = sym["gdof"]
-    crow = sym["crow"].cpu().numpy()
-    tile_row = pl["tile_row"].cpu().numpy()
-    ntile = pl["ntile"]
-    assert tile_row[0] == 0 and tile_row[ntile] == gdof and np.all(np.diff(tile_row) > 0)
-    batch_ptr = pl["batch_ptr"].cpu().numpy()
-    batch_i = pl["batch_i"].cpu().numpy()
-    ew = pl["entry_words"]
-    ent = pl["ent"].cpu().numpy().view(np.uint32).reshape(-1, ew)[:pl["nbatch"]]
-    row_code = pl["row_code"].cpu().numpy().view(np.uint16).astype(np.int64)
-    assert batch_ptr[0] == 0 and batch_ptr[-1] == pl["nbatch"]
-    cells_all = ent[:, :32].view(np.int32)
-    code_all = ent[:, 32:64]
-    nw = (ew - 64) // 32
-    slot_bytes = ent[:, 64:].reshape(-1, nw, 32).transpose(0, 2, 1).copy().view(np.uint8).reshape(-1, 32, 4 * nw)[:, :, :L].astype(np.int64)
-    seen = np.zeros((NC, L), dtype=int)
-    lanes = np.arange(32)
-    for t in range(ntile):
-        r0, r1 = int(tile_row[t]), int(tile_row[t + 1])
-        nr = r1 - r0
-        assert crow[r1] - crow[r0] <= cap or nr == 1
-        if nr >= 16 and (r1 % 4096) != 0 and r1 != gdof:
-            assert nr % 16 == 0, "row count of a tile is a multiple of 16"
-        rc = row_code[r0:r1]
-        cls, gb = rc & 15, (rc >> 4) * 16
-        lens = np.diff(crow[r0:r1 + 1])
-        # layout: address of value s of row rho; all distinct, all inside the accumulator
-        addr = np.concatenate([gb[k] + 16 * np.arange(lens[k]) + ((cls[k] ^ np.arange(lens[k])) & 15) for k in range(nr)])
-        assert np.unique(addr).size == addr.size, "two values of a tile share an accumulator address"
-        assert addr.max() < pl["acc_stride"]
-        vstart = np.concatenate([[0], np.cumsum(lens)])
-        touched = np.zeros(int(vstart[-1]), dtype=bool)
-        code_to_row = {int(rc[k]): r0 + k for k in range(nr)}
-        assert len(code_to_row) == nr, "two rows of a tile share a (group, class) position"
-        last, per_i = {}, {}
-        for b in range(batch_ptr[t], batch_ptr[t + 1]):
-            i = int(batch_i[b])
-            live = cells_all[b] >= 0
-            assert live.any(), "empty batch"
-            cells = cells_all[b][live]
-            codes = code_all[b][live]
-            rcs, first = (codes & 0xfff).astype(np.int64), codes >> 12
-            rows = np.array([code_to_row[int(x)] for x in rcs])
-            assert len(set(rows.tolist())) == rows.size, "a row twice in one batch"
-            assert np.array_equal(c2d[cells, i], rows), "entry does not belong to its row / local index"
-            assert np.array_equal(rcs & 15, lanes[live] & 15), "lane l must carry a row of class l mod 16"
-            seen[cells, i] += 1
-            pos = (vstart[rows - r0])[:, None] + slot_bytes[b][live]
-            fm = ((first[:, None] >> np.arange(L)) & 1).astype(bool)
-            assert np.array_equal(fm, ~touched[pos]), "first-touch mask != (value not yet written in execution order)"
-            assert np.unique(pos).size == pos.size
-            touched[pos] = True
-            for r, c in zip(rows.tolist(), cells.tolist()):
-                assert last.get((r, i), -1) < c, "cells of a row out of order"
-                last[(r, i)] = c
-            per_i.setdefault(i, []).append(b)
-        assert touched.all(), "a value of the tile is never written (the kernel does not zero-fill)"
-        for i, lst in per_i.items():
-            assert lst == list(range(lst[0], lst[0] + len(lst))), "batches of one local index are contiguous"
-        assert sorted(per_i) == [int(batch_i[b]) for b in sorted(x[0] for x in per_i.values())], "local indices ascend"
-    assert np.all(seen == 1), "every (cell, local index) pair exactly once"
-    fill = NC * L / (32.0 * max(pl["nbatch"], 1))
-    assert fill > 0.35, fill

