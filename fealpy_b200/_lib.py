@@ -77,8 +77,9 @@ SIGNATURES = {
     "fb2_tet_box_slab": (_i32, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "fb2_cg_finalize": (_i32, [_p, _p]),
     "fb2_cg_update_p": (_i32, [_i64, _p, _p, _p, _p, _p]),
+    "fb2_gather_f64": (_i32, [_i64, _p, _p, _p, _p]),
     "fb2_peer_ctrl_bytes": (_i32, []),
-    "fb2_cg_spmv_dot_ranges": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p]),
+    "fb2_cg_spmv_dot_ranges": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "fb2_peer_allreduce": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p]),
     "fb2_peer_wait_halo": (_i32, [_p, _i32, _p, _p, _p, _p]),
     "fb2_cg_update_p_push": (_i32, [_p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p]),

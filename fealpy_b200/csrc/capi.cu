@@ -270,16 +270,25 @@ int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const dou
   return cg_update_xr(n, x, r, p, Ap, minv_diag, static_cast<CgScalars*>(scalars), partial_ws, fuse_finalize, S(stream), make_own(own));
 }
 // ---- multi-GPU CG over NVLink peer memory (csrc/peer.cu) -----------------------------------------------------------
+int fb2_gather_f64(int64_t n, const int64_t* idx, const double* v, double* out, void* stream) { return gather_f64(n, idx, v, out, S(stream)); }
 int fb2_peer_ctrl_bytes(void) { return (int)align_up(sizeof(PeerCtrl), 4096); }
 int fb2_cg_spmv_dot_ranges(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                           double* Ap, const int32_t* blk_lo, const int32_t* blk_hi, int nblk, int tile, int32_t max_row,
-                           double* dot_out_dev, void* scalars, void* partial_ws, const int64_t own[4], void* stream) {
-  if (nblk <= 0) {                                  // no rows in these ranges on this rank: the partial dot is 0
+                           double* Ap, const int32_t* blk_lo, const int32_t* blk_hi, int nblk, int first_halo_tile, int tile,
+                           int32_t max_row, double* dot_out_dev, void* scalars, void* partial_ws, const int64_t own[4],
+                           const void* ctrl_mine, int nnb, const int32_t* nb_rank_host, const uint64_t* epoch_dev, void* stream) {
+  if (nblk <= 0) {                                  // no rows on this rank: the partial dot is 0
     FB2_CUDA(cudaMemsetAsync(dot_out_dev, 0, sizeof(double), S(stream)));
     return OK;
   }
+  if (nnb < 0 || nnb > 2) return fail(ERR_INVALID, "cg_spmv_dot_ranges: at most two halo neighbours");
   SpmvPlan pl{};
   pl.blk_row = blk_lo; pl.blk_end = blk_hi; pl.nblk = nblk; pl.tile = tile; pl.max_row = max_row;
+  if (nnb > 0) {
+    pl.halo.flags = static_cast<const PeerCtrl*>(ctrl_mine)->hflag;     // (address arithmetic only: ctrl_mine is a device pointer)
+    pl.halo.epoch = reinterpret_cast<const unsigned long long*>(epoch_dev);
+    pl.halo.nnb = nnb; pl.halo.nb0 = nb_rank_host[0]; pl.halo.nb1 = nnb > 1 ? nb_rank_host[1] : 0;
+    pl.halo.first_tile = first_halo_tile;
+  }
   return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, dot_out_dev, partial_ws, S(stream), &pl, make_own(own),
               static_cast<CgScalars*>(scalars));
 }

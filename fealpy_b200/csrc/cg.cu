@@ -130,14 +130,29 @@ __global__ void __launch_bounds__(ST_THREADS) spmv_stream_kernel(int64_t n, cons
                                                                  const double* __restrict__ b, int mode,
                                                                  const int32_t* __restrict__ blk_row, int nblk, double* dot_out,
                                                                  double* partials, unsigned int* counter, const CgScalars* sc,
-                                                                 OwnRange own, const int32_t* __restrict__ blk_end) {
+                                                                 OwnRange own, const int32_t* __restrict__ blk_end, HaloWait hw) {
   if (sc && sc->done) return;
   extern __shared__ __align__(16) double prod[];
   const int tid = threadIdx.x;
   const int g = tid % G, grp = tid / G;
   constexpr int NGRP = ST_THREADS / G;
   double dsum = 0.0;
+  bool waited = hw.nnb == 0;
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    if (!waited && blk >= hw.first_tile) {
+      // tiles from hw.first_tile on hold boundary rows: they read halo entries of x that the neighbours push over NVLink
+      // (csrc/peer.cu).  The grid is persistent and fully resident, the flags are raised by OTHER GPUs: spinning is safe.
+      if (tid == 0) {
+        const unsigned long long seq = *hw.epoch + (unsigned long long)sc->niter;
+        for (int k = 0; k < hw.nnb; ++k) {
+          const volatile unsigned long long* f = hw.flags + (k == 0 ? hw.nb0 : hw.nb1);
+          while (*f < seq) { }
+        }
+        __threadfence_system();
+      }
+      __syncthreads();
+      waited = true;
+    }
     const int r0 = blk_row[blk], r1 = blk_end ? blk_end[blk] : blk_row[blk + 1];
     if (r0 == r1) continue;
     const int64_t v0 = crow[r0];
@@ -332,7 +347,7 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
   do {                                                                                                         \
     auto kern = spmv_stream_kernel<GV>;                                                                        \
     if (smem > 48 * 1024) FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, ST_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own, plan.blk_end); \
+    kern<<<grid, ST_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own, plan.blk_end, plan.halo); \
   } while (0)
   // lanes per row in the reduce phase: ONE (a thread sums its row sequentially out of shared memory) measured
   // best by a wide margin -- 1.60 ms/iteration against 1.92 with 8 lanes + shuffles (profiles/r01_tune_spmv.txt)

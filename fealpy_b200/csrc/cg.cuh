@@ -19,12 +19,21 @@ struct OwnRange {
   __host__ __device__ bool has(int64_t r) const { return (r >= lo0 && r < hi0) || (r >= lo1 && r < hi1); }
 };
 
+// multi-GPU: tiles >= first_tile read halo entries that the (<= 2) neighbours push over NVLink; the CTA that reaches such a
+// tile first waits until flags[nb] >= *epoch + sc->niter (csrc/peer.cu).  nnb == 0: no waiting (single GPU).
+struct HaloWait {
+  const unsigned long long* flags = nullptr;   // hflag array of this rank's PeerCtrl
+  const unsigned long long* epoch = nullptr;
+  int nnb = 0, nb0 = 0, nb1 = 0, first_tile = 0;
+};
+
 // row-aligned nnz tiling of a CSR matrix (built once per matrix, see spmv_plan_build)
 struct SpmvPlan {
   const int32_t* blk_row = nullptr;   // (nblk+1) first row of every tile
   const int64_t* blk_v0 = nullptr;    // (nblk+1) first value index of every tile (pipelined kernel) or null
   int nblk = 0, tile = 0, max_row = 0;
   const int32_t* blk_end = nullptr;   // optional (nblk): one-past-last row of every tile -- tiles of SEVERAL row ranges in one plan
+  HaloWait halo;
 };   // max blocks contributing partial sums per reduction
 
 size_t cg_workspace_bytes(int64_t n, int64_t nnz);
@@ -74,6 +83,7 @@ struct PeerPush {
 int peer_allreduce(PeerCtrl* mine, const unsigned long long* peer_base, int world, int rank, int kind, const double* src0,
                    const double* src1, double* dst, CgScalars* sc, int finalize, const unsigned long long* epoch, cudaStream_t s);
 int peer_wait_halo(PeerCtrl* mine, int nnb, const int* nb_rank, const CgScalars* sc, const unsigned long long* epoch, cudaStream_t s);
+int gather_f64(int64_t n, const int64_t* idx, const double* v, double* out, cudaStream_t s);
 int cg_update_p_push(OwnRange own, double* p, const double* r, const double* minv, const CgScalars* sc, const PeerPush& push,
                      cudaStream_t s);
 

@@ -118,6 +118,20 @@ __global__ void __launch_bounds__(256) cg_update_p_push_kernel(OwnRange own, dou
   }
 }
 
+// pack kernel of the general (Morton) partition: out[k] = v[idx[k]] -- the owned values one neighbour needs, contiguous
+__global__ void __launch_bounds__(256) gather_f64_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ v,
+                                                         double* __restrict__ out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) out[k] = v[idx[k]];
+}
+int gather_f64(int64_t n, const int64_t* idx, const double* v, double* out, cudaStream_t s) {
+  if (n <= 0) return OK;
+  int64_t b = ceil_div(n, 256);
+  const int64_t cap = kNumSM * 16;
+  gather_f64_kernel<<<(unsigned)(b > cap ? cap : b), 256, 0, s>>>(n, idx, v, out);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
 int peer_allreduce(PeerCtrl* mine, const unsigned long long* peer_base, int world, int rank, int kind, const double* src0,
                    const double* src1, double* dst, CgScalars* sc, int finalize, const unsigned long long* epoch, cudaStream_t s) {
   if (world < 1 || world > PEER_MAXW || rank < 0 || rank >= world || kind < 0 || kind > 1)

@@ -23,16 +23,37 @@ SC_RTR, SC_PAP, SC_RTR_NEW, SC_BNORM, SC_RNORM, SC_ALPHA, SC_BETA, SC_TMP = rang
 SC_NITER_I32, SC_DONE_I32 = 16, 17          # int32 view
 
 
+def _pack(v, idx):
+    """contiguous copy of v[idx] (the owned values a neighbour needs): the library's gather kernel on CUDA tensors"""
+    if v.is_cuda:
+        out = torch.empty(idx.shape[0], dtype=v.dtype, device=v.device)
+        _lib.call("fb2_gather_f64", idx.shape[0], _lib.ptr(idx), _lib.ptr(v), _lib.ptr(out), _lib.stream())
+        return out
+    return v[idx]
+
+
 def halo_exchange(v, exchanges, group=None):
-    """send owned boundary slices, receive halo slices (contiguous slices of `v`)"""
+    """send owned boundary values, receive halo values.  Slab partitions (box_partition.Exchange) send contiguous slices
+    of `v`; general partitions (mesh_partition.PackedExchange) send a packed gather v[send_idx]; every receive lands
+    directly in the peer's contiguous halo range."""
     if not exchanges:
         return
-    ops = []
+    ops, keep = [], []
     for ex in exchanges:
-        for lo, hi in ex.send:
-            ops.append(dist.P2POp(dist.isend, v[lo:hi], ex.peer, group))
+        idx = getattr(ex, "send_idx", None)
+        if idx is not None:
+            if idx.numel():
+                buf = _pack(v, idx)
+                keep.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, ex.peer, group))
+        else:
+            for lo, hi in ex.send:
+                ops.append(dist.P2POp(dist.isend, v[lo:hi], ex.peer, group))
         for lo, hi in ex.recv:
-            ops.append(dist.P2POp(dist.irecv, v[lo:hi], ex.peer, group))
+            if hi > lo:
+                ops.append(dist.P2POp(dist.irecv, v[lo:hi], ex.peer, group))
+    if not ops:
+        return
     for w in dist.batch_isend_irecv(ops):
         w.wait()
 

@@ -92,8 +92,15 @@ class PeerCG:
         self.own = (C.c_int64 * 4)(*[int(v) for v in part.own_ranges])
         interior, boundary = part.row_split()
         tile = A.SPMV_TILE
-        self.plan_int = _range_plan(A, interior, tile)
-        self.plan_bnd = _range_plan(A, boundary, tile)
+        # ONE plan: interior tiles first, boundary tiles (which wait for the neighbours' halo pushes inside the kernel) last
+        ilo, ihi, ni, mri = _range_plan(A, interior, tile)
+        blo_, bhi_, nbd, mrb = _range_plan(A, boundary, tile)
+        if ni and nbd:
+            self.plan = (torch.cat([ilo, blo_]).contiguous(), torch.cat([ihi, bhi_]).contiguous(), ni + nbd, ni, max(mri, mrb))
+        elif nbd:
+            self.plan = (blo_, bhi_, nbd, 0, mrb)
+        else:
+            self.plan = (ilo, ihi, ni, ni, mri)
         self.tile = tile
         self.sc = torch.zeros(32, dtype=torch.float64, device=dev)
         self.sc_i32 = self.sc.view(torch.int32)
@@ -122,17 +129,13 @@ class PeerCG:
         A, st = self.A, _lib.stream()
         sc, pws = _lib.ptr(self.sc), _lib.ptr(self.pws)
         pAp = C.c_void_p(self.sc.data_ptr() + 8 * SC_PAP)
-        tmp = C.c_void_p(self.sc.data_ptr() + 8 * SC_TMP)
         rtn = C.c_void_p(self.sc.data_ptr() + 8 * SC_RTR_NEW)
         ep = _lib.ptr(self.epoch)
-        blo, bhi, nb, mr = self.plan_int
+        blo, bhi, nb, first_bnd, mr = self.plan
         _lib.call("fb2_cg_spmv_dot_ranges", self.n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(self.p),
-                  _lib.ptr(self.Ap), _lib.ptr(blo), _lib.ptr(bhi), nb, self.tile, mr, pAp, sc, pws, self.own, st)
-        _lib.call("fb2_peer_wait_halo", _lib.ptr(self.ctrl), self.push["nnb"], self.push["nbr"], sc, ep, st)
-        blo, bhi, nb, mr = self.plan_bnd
-        _lib.call("fb2_cg_spmv_dot_ranges", self.n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(self.p),
-                  _lib.ptr(self.Ap), _lib.ptr(blo), _lib.ptr(bhi), nb, self.tile, mr, tmp, sc, pws, self.own, st)
-        _lib.call("fb2_peer_allreduce", _lib.ptr(self.ctrl), _lib.ptr(self.peer_base), self.world, self.rank, 0, pAp, tmp, pAp, sc, 0, ep, st)
+                  _lib.ptr(self.Ap), _lib.ptr(blo), _lib.ptr(bhi), nb, first_bnd, self.tile, mr, pAp, sc, pws, self.own,
+                  _lib.ptr(self.ctrl), self.push["nnb"], self.push["nbr"], ep, st)
+        _lib.call("fb2_peer_allreduce", _lib.ptr(self.ctrl), _lib.ptr(self.peer_base), self.world, self.rank, 0, pAp, None, pAp, sc, 0, ep, st)
         _lib.call("fb2_cg_update_xr", self.n, _lib.ptr(self.x), _lib.ptr(self.r), _lib.ptr(self.p), _lib.ptr(self.Ap), _lib.ptr(self.minv),
                   sc, pws, 0, self.own, st)
         _lib.call("fb2_peer_allreduce", _lib.ptr(self.ctrl), _lib.ptr(self.peer_base), self.world, self.rank, 1, rtn, None, rtn, sc, 1, ep, st)

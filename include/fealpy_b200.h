@@ -211,15 +211,20 @@ int fb2_cg_update_p(int64_t n, double* p, const double* r, const double* minv_di
  * control block of fb2_peer_ctrl_bytes() bytes at the start of its symmetric buffer, followed by its vector p; peer_base_dev
  * is a device array of the `world` base addresses.  *epoch_dev (device) is the base of the solve's sequence numbers (the host
  * raises it by 2^32 per solve).  See csrc/peer.cu for the protocol and its ordering argument.
- *   fb2_cg_spmv_dot_ranges : Ap = A p on the rows of a multi-range tile plan (blk_lo / blk_hi per tile), fused partial p.Ap
- *   fb2_peer_wait_halo     : (1 warp) wait until the <= 2 neighbours' halo pushes of the previous iteration have landed
+ *   fb2_cg_spmv_dot_ranges : Ap = A p on the rows of a multi-range tile plan (blk_lo / blk_hi per tile), fused partial p.Ap;
+ *                            tiles >= first_halo_tile (the boundary rows, placed last) wait inside the kernel until the
+ *                            neighbours' halo pushes of the previous iteration have landed -- the interior tiles overlap them
+ *   fb2_peer_wait_halo     : (1 warp) the same wait as a stand-alone kernel
  *   fb2_peer_allreduce     : (1 warp) *dst = sum over ranks (in rank order, bit-identical everywhere) of *src0 (+ *src1);
  *                            finalize != 0 applies the stopping rules of solver/cg.py:97-121 to the reduced r.z
  *   fb2_cg_update_p_push   : p = z + beta p on the owned rows, owned boundary slices stored into the neighbours' p, flags raised */
+/* pack kernel of the general-mesh partition (parallel/mesh_partition.py): out[k] = v[idx[k]], idx int64 local ids */
+int fb2_gather_f64(int64_t n, const int64_t* idx, const double* v, double* out, void* stream);
 int fb2_peer_ctrl_bytes(void);
 int fb2_cg_spmv_dot_ranges(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                           double* Ap, const int32_t* blk_lo, const int32_t* blk_hi, int nblk, int tile, int32_t max_row,
-                           double* dot_out_dev, void* scalars, void* partial_ws, const int64_t own[4], void* stream);
+                           double* Ap, const int32_t* blk_lo, const int32_t* blk_hi, int nblk, int first_halo_tile, int tile,
+                           int32_t max_row, double* dot_out_dev, void* scalars, void* partial_ws, const int64_t own[4],
+                           const void* ctrl_mine, int nnb, const int32_t* nb_rank_host, const uint64_t* epoch_dev, void* stream);
 int fb2_peer_allreduce(void* ctrl_mine, const uint64_t* peer_base_dev, int world, int rank, int kind, const double* src0,
                        const double* src1, double* dst, void* scalars, int finalize, const uint64_t* epoch_dev, void* stream);
 int fb2_peer_wait_halo(void* ctrl_mine, int nnb, const int32_t* nb_rank_host, const void* scalars, const uint64_t* epoch_dev,
