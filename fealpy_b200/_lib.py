@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfealpy_b200.so")
+LIB_PATH = os.environ.get("FB2_LIB_PATH") or os.path.join(_HERE, "libfealpy_b200.so")   # override: tuning builds (tools/build_variants.sh)
 
 FB2_ERRORS = {1: ValueError, 2: RuntimeError, 3: NotImplementedError, 4: RuntimeError}
 
@@ -56,18 +56,22 @@ SIGNATURES = {
     "fb2_assemble_from_ke": (_i32, [_i64, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _i32, _i32, _p, _p]),
     "fb2_asm4_workspace_bytes": (_sz, [_i32]),
     "fb2_asm4_plan_count": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p]),
-    "fb2_asm4_plan_fill": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _i32, _p]),
-    "fb2_assemble_scalar_const_v4": (_i32, [_i32, _i32, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _p,
+    "fb2_asm4_plan_fill": (_i32, [_i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p]),
+    "fb2_assemble_scalar_const_v4": (_i32, [_i32, _i32, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p,
                                             _f64, _p, _f64, _p, _p, _p, _p]),
     "fb2_expand_pattern": (_i32, [_i64, _i32, _i32, _p, _p, _p, _p, _p]),
     "fb2_partial_workspace_bytes": (_sz, []),
     "fb2_spmv_plan_blocks": (_i32, [_i64, _i32]),
-    "fb2_spmv_plan_build": (_i32, [_i64, _p, _i32, _p, _p, _i64, _p, _p]),
+    "fb2_spmv_plan_build": (_i32, [_i64, _p, _i32, _p, _i64, _p, _p]),
+    "fb2_spmv_colz_workspace_bytes": (_sz, [_i32]),
+    "fb2_spmv_colz_bytes": (_sz, [_i32, _i64, _i64]),
+    "fb2_spmv_colz_count": (_i32, [_i64, _p, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    "fb2_spmv_colz_fill": (_i32, [_i64, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "fb2_csr_spmv": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
     "fb2_csr_spmm": (_i32, [_i64, _p, _p, _p, _p, _p, _i32, _p]),
     "fb2_dot": (_i32, [_i64, _p, _p, _p, _p, _p]),
     "fb2_cg_workspace_bytes": (_sz, [_i64, _i64]),
-    "fb2_cg": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _i32, _p, _p, _p, _p]),
+    "fb2_cg": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _i32, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "fb2_cg_init": (_i32, [_p, _f64, _f64, _i32, _f64, _f64, _p]),
     "fb2_cg_residual": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
     "fb2_cg_start": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p]),

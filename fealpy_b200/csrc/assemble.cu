@@ -11,6 +11,8 @@
 //       recomputes the element-matrix row in registers and accumulates into its private
 //       segment of a shared-memory tile, which the CTA then streams out contiguously.
 // Deterministic by construction: no floating-point atomics, fixed summation order.
+#include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "sort_scan.cuh"
 #include "assemble.cuh"
@@ -853,14 +855,17 @@ namespace fb2 {
 constexpr int A4_MAXL = 32;
 constexpr int A4_BASE_BITS = 12;     // entry word = tile offset of the row (12 bits) | first-touch mask (ldof <= 20 bits)
 constexpr int A4_MAXROW = 1024;      // longest row the first-touch bitmap covers (SYM_CAP bounds a row anyway)
+__host__ __device__ constexpr int a4_block_words(int slot_nwords) { return 64 + 32 * slot_nwords + 4; }   // + a 16-byte header
 
 template <bool FILL>
 __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int32_t* __restrict__ blk_row, const int64_t* __restrict__ crow,
                                                             const int64_t* __restrict__ adj_ptr, const int* __restrict__ adj_pair, int L,
                                                             int* __restrict__ nbatch_of_tile, const int64_t* __restrict__ batch_ptr,
-                                                            unsigned char* __restrict__ batch_i, int* __restrict__ ent_cell,
-                                                            uint32_t* __restrict__ ent_base, uint32_t* __restrict__ ent_slots,
+                                                            unsigned char* __restrict__ batch_i, uint32_t* __restrict__ blocks,
                                                             const uint32_t* __restrict__ slot_words, int slot_nwords, int slot_bytes) {
+  // packed schedule: one contiguous block of BW 32-bit words per batch (a single bulk copy in the numeric kernel):
+  //   [0,32) cell id or -1 | [32,64) row offset in the tile | first-touch mask << 12 | [64,64+32W) slot records | header: local index i
+  const int64_t BW = a4_block_words(slot_nwords);
   constexpr unsigned FULL = 0xffffffffu;
   const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
@@ -894,8 +899,8 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
     const int Bi = __shfl_sync(FULL, B, i), offi = __shfl_sync(FULL, off, i), ci = __shfl_sync(FULL, cnt, i);
     for (int j = 0; j < Bi; ++j) {
       const int have = (ci - j + Bi - 1) / Bi;                 // entries k = j, j+B, j+2B, ... < cnt
-      if (lane == 0) batch_i[b0 + offi + j] = (unsigned char)i;
-      if (lane >= have) ent_cell[(b0 + offi + j) * 32 + lane] = -1;
+      if (lane == 0) { batch_i[b0 + offi + j] = (unsigned char)i; blocks[(b0 + offi + j) * BW + 64 + 32 * slot_nwords] = (uint32_t)i; }
+      if (lane >= have) blocks[(b0 + offi + j) * BW + lane] = 0xffffffffu;
     }
   }
   int dealt = 0;                                               // lane i: entries of local index i dealt so far
@@ -927,16 +932,17 @@ __global__ void __launch_bounds__(128) asm4_schedule_kernel(int ntile, const int
         const int wrap = max(0, k0 % Bi + m - Bi);
         for (int u = 0; u < m; ++u) {
           const int k = u < wrap ? k0 + (m - wrap) + u : k0 + (u - wrap);
-          const int64_t e = (b0 + offi + k % Bi) * 32 + k / Bi;
-          ent_cell[e] = fd.wide(adj_pair[q + u]);
+          uint32_t* blk = blocks + (b0 + offi + k % Bi) * BW;
+          const int pos = k / Bi;
+          blk[pos] = (uint32_t)fd.wide(adj_pair[q + u]);
           uint32_t first = 0;
-          for (int w = 0; w < slot_nwords; ++w) ent_slots[e * slot_nwords + w] = slot_words[(q + u) * slot_nwords + w];
+          for (int w = 0; w < slot_nwords; ++w) blk[64 + pos * slot_nwords + w] = slot_words[(q + u) * slot_nwords + w];
           for (int j = 0; j < L; ++j) {
             const uint32_t wd = slot_words[(q + u) * slot_nwords + (slot_bytes == 1 ? (j >> 2) : (j >> 1))];
             const int sl = slot_bytes == 1 ? (wd >> ((j & 3) * 8)) & 0xffu : (wd >> ((j & 1) * 16)) & 0xffffu;
             if (!((touched[sl >> 5] >> (sl & 31)) & 1u)) { first |= 1u << j; touched[sl >> 5] |= 1u << (sl & 31); }
           }
-          ent_base[e] = base | (first << A4_BASE_BITS);
+          blk[32 + pos] = base | (first << A4_BASE_BITS);
         }
       }
       q += m;
@@ -980,199 +986,164 @@ static void a4_reduced_table(const double* Ms, const double* Mm, A4Tables<L, A4G
     }
 }
 
+#ifndef FB2_ASM4_WARPS
+#define FB2_ASM4_WARPS 3       // 3 CTAs x 3 warps per SM (3.65 ms; 4 x 2: 3.72; 2 x 4: 3.68 -- profiles/r02_tune_asm_v6.txt)
+#endif
+#ifndef FB2_ASM4_MINBLOCKS
+#define FB2_ASM4_MINBLOCKS 3
+#endif
+
+// ---- v6 numeric kernel: the same schedule, operands through the bulk-copy engine and registers ----------------------
+// Its predecessor (git history, "v4") staged both operand streams of a batch through cp.async rings in shared memory; ncu
+// (profiles/r02_ncu_asm_experiments.txt): 393 warp instructions per batch, of which ~150 were operand plumbing (six LDGSTS
+// per lane, each with its address arithmetic and three hazard NOPs, plus the read-back of both rings) and 10 % of all
+// stall samples waited for the batch's local index.  Here
+//   * the batch block (656 bytes on tet P2, header word = local index) arrives with ONE cp.async.bulk issued by lane 0
+//     into a 4-deep ring, completion through an mbarrier per ring slot (SASS: UBLKCP + SYNCS);
+//   * the geometry record of the lane's cell is loaded straight into registers one batch ahead (the cell id of batch
+//     b+1 is already in shared memory when batch b starts): no staging ring, no read-back wavefronts;
+//   * the old value of a slot seeds the FMA chain (first-touch columns start from 0), so the accumulate is
+//     LDS -> 7 DFMA -> STS with no separate add.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ldg_nc_f64x4(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];\n" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+#ifndef FB2_ASM6_JC
+#define FB2_ASM6_JC 10     // all columns of a row in flight: 3.72 ms against 3.99 with 5 (tet P2 128^3; profiles/r02_tune_asm_v6.txt)
+#endif
 template <int TD, int L, typename SlotT, int I, typename TabT>
-__device__ __forceinline__ void a4_row(const TabT& tb, const double (&h)[A4Geo<TD>::NH],
+__device__ __forceinline__ void a6_row(const TabT& tb, const double (&h)[A4Geo<TD>::HS],
                                        const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], uint32_t first, double* __restrict__ my) {
   constexpr int NH = A4Geo<TD>::NH;
   using SR = SlotRec<SlotT, L>;
-  // columns in chunks of JC independent FMA chains.  (Tried and measured, profiles/r01_tune_asm_v4*.txt: chunks
-  // of 2, 5 or 10 make no difference; chunks separated by warp barriers to cap registers at 128 are slower;
-  // a PAIR of warps per tile, each on half of the columns (commit 16a3237: 16 warps/SM, 128 registers),
-  // runs in the same time -- the LSU data pipe goes from 58 % to 73 % busy because both warps read the
-  // entry and geometry records.  The kernel is bound by shared-memory wavefronts, not by latency.)
-#ifdef FB2_ASM4_JC
-  constexpr int JC = (L % FB2_ASM4_JC == 0) ? FB2_ASM4_JC : ((L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3));
-#else
-  constexpr int JC = (L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3);
-#endif
+  constexpr int JC = (L % FB2_ASM6_JC == 0) ? FB2_ASM6_JC : ((L % 5 == 0) ? 5 : ((L % 4 == 0) ? 4 : 3));
 #pragma unroll
   for (int j0 = 0; j0 < L; j0 += JC) {
-    double val[JC];
+    double s[JC];
 #pragma unroll
-    for (int jj = 0; jj < JC; ++jj) {
-      double s0 = 0.0, s1 = 0.0;
+    for (int jj = 0; jj < JC; ++jj) s[jj] = ((first >> (j0 + jj)) & 1u) ? 0.0 : my[SR::get(sw, j0 + jj)];
 #pragma unroll
-      for (int t = 0; t < NH; t += 2) {
-        s0 += tb.T[I][j0 + jj][t] * h[t];
-        if (t + 1 < NH) s1 += tb.T[I][j0 + jj][t + 1] * h[t + 1];
-      }
-      val[jj] = s0 + s1;
-    }
-    double old[JC];
+    for (int t = 0; t < NH; ++t)
 #pragma unroll
-    for (int jj = 0; jj < JC; ++jj) old[jj] = ((first >> (j0 + jj)) & 1u) ? 0.0 : my[SR::get(sw, j0 + jj)];
+      for (int jj = 0; jj < JC; ++jj) s[jj] = fma(tb.T[I][j0 + jj][t], h[t], s[jj]);
 #pragma unroll
-    for (int jj = 0; jj < JC; ++jj) my[SR::get(sw, j0 + jj)] = old[jj] + val[jj];
+    for (int jj = 0; jj < JC; ++jj) my[SR::get(sw, j0 + jj)] = s[jj];
   }
 }
-
 template <int TD, int L, typename SlotT, int I, typename TabT>
-__device__ __forceinline__ void a4_dispatch(int i, const TabT& tb, const double (&h)[A4Geo<TD>::NH],
+__device__ __forceinline__ void a6_dispatch(int i, const TabT& tb, const double (&h)[A4Geo<TD>::HS],
                                             const uint32_t (&sw)[SlotRec<SlotT, L>::WORDS], uint32_t first, double* __restrict__ my) {
-  if (i == I) a4_row<TD, L, SlotT, I, TabT>(tb, h, sw, first, my);
-  else if constexpr (I + 1 < L) a4_dispatch<TD, L, SlotT, I + 1, TabT>(i, tb, h, sw, first, my);
+  if (i == I) a6_row<TD, L, SlotT, I, TabT>(tb, h, sw, first, my);
+  else if constexpr (I + 1 < L) a6_dispatch<TD, L, SlotT, I + 1, TabT>(i, tb, h, sw, first, my);
 }
 
-#ifndef FB2_ASM4_WARPS
-#define FB2_ASM4_WARPS 4
+#ifndef FB2_ASM6_RING
+#define FB2_ASM6_RING 4
 #endif
-#ifndef FB2_ASM4_MINBLOCKS
-#define FB2_ASM4_MINBLOCKS 2
-#endif
+constexpr int A6_RING = FB2_ASM6_RING;        // batch blocks in flight per warp
 
-// ---- v4 numeric kernel: asynchronous-copy pipeline ------------------------------------
-// How a batch's operands reach the warp.  A first version prefetched ONE batch ahead through
-// registers: ncu showed 8 resident warps per SM, each stalled ~85 % of the time on the DEPENDENT pair
-// of global round trips (entry -> cell id -> geometry record).  Here both streams are cp.async rings
-// in the warp's private shared memory -- no registers held by data in flight, so the look-ahead is a
-// template parameter: entries run 2*D batches ahead, geometry records D batches ahead
-// (group G_b = {entries(b+2D), H(b+D)}; at the top of iteration b `wait_group D-1` retires G_{b-D},
-// which delivered H(b) and the cell ids needed to issue H(b+D)).  7.0 -> 5.0 ms on tet P2 128^3.
-//
-// Geometry stage layout.  A record is QP 16-byte units (4 on tetrahedra, 2 on triangles).  The 32
-// records of a batch are copied COOPERATIVELY -- consecutive lanes copy consecutive units, so one
-// cp.async instruction touches 8 / 16 records (few L1 tag look-ups) -- and then read back one record
-// per lane with LDS.128.  Records are packed (no padding) and unit p of record r sits at
-//     r*QP + ((p + (r*QP/8)) mod QP)
-// which makes BOTH sides conflict-free: a quarter-warp of the copy writes 8 consecutive units (a
-// rotation inside a record keeps them distinct), a quarter-warp of the read-back hits 8 distinct
-// 16-byte bank groups.  (With padded records the copy side cost 11 wavefronts per instruction
-// instead of 4 and was 43 % of the kernel's shared-memory traffic.)
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <int QP>
-__device__ __forceinline__ int a4_unit(int rec, int part) {      // swizzled 16-byte unit of (record, part)
-  static_assert(QP == 2 || QP == 4 || QP == 8, "record size must divide the 128-byte bank row");
-  return rec * QP + ((part + (rec * QP) / 8) & (QP - 1));
-}
-
-template <int TD, int L, typename SlotT, int D>
+template <int TD, int L, typename SlotT>
 __global__ void __launch_bounds__(FB2_ASM4_WARPS * 32, FB2_ASM4_MINBLOCKS)
-assemble_const_v4_kernel(const __grid_constant__ Asm4Args a, const __grid_constant__ A4Tables<L, A4Geo<TD>::NH> tb) {
+assemble_const_v6_kernel(const __grid_constant__ Asm4Args a, const __grid_constant__ A4Tables<L, A4Geo<TD>::NH> tb) {
   using GEO = A4Geo<TD>;
-  constexpr int NH = GEO::NH, HS = GEO::HS, QP = GEO::QP;
+  constexpr int HS = GEO::HS;
   using SR = SlotRec<SlotT, L>;
-  // ring depths: geometry stages, entry slots.  Geometry runs D batches ahead, entries 2D + 1: the entry block of a batch
-  // is streamed from DRAM exactly once, and with only 2D batches of look-ahead inside the SAME cp.async group as the geometry
-  // ncu's source view put 10 % of all warp samples on the instruction after `DEPBAR` (cp.async.wait_group), profiles/
-  // r02_ncu_asm_experiments.txt.  Now every iteration commits two groups, {geometry(b+D)} then {entries(b+2D+1)}, and waits
-  // with wait_group<1>: the newest entry block may stay in flight for another iteration.
-  constexpr int NHST = D + 1, NEST = 2 * D + 2;
-  constexpr int ENT_BYTES = 256 + 128 * SR::WORDS;              // 32 x (cell int32 | base+first-touch uint32 | slot words)
-  constexpr int ENT_CHUNKS = ENT_BYTES / 16;
+  constexpr int W = SR::WORDS, BW = a4_block_words(W), BLK_BYTES = BW * 4, NE = A6_RING;
+  static_assert(BLK_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
   extern __shared__ __align__(16) double sm4[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int tile = blockIdx.x * FB2_ASM4_WARPS + wid;
   if (tile >= a.ntile) return;
-  const size_t per_warp = (size_t)a.acc_stride + NHST * 32 * HS + NEST * (ENT_BYTES / 8);
-  double* acc = sm4 + (size_t)wid * per_warp;                   // this warp's private tile ...
-  double* hring = acc + a.acc_stride;                           // ... its geometry stages ...
-  unsigned char* ering = reinterpret_cast<unsigned char*>(hring + NHST * 32 * HS);   // ... and its entry slots
+  const size_t per_warp = (size_t)a.acc_stride + (NE * BLK_BYTES + ((NE * 8 + 15) & ~15)) / 8;     // keeps every warp's ring 16-byte aligned
+  double* acc = sm4 + (size_t)wid * per_warp;                                   // this warp's private tile ...
+  const uint32_t* ering = reinterpret_cast<const uint32_t*>(acc + a.acc_stride);  // ... its ring of batch blocks ...
+  const uint32_t ering_s = smem_u32(ering);
+  const uint32_t bar_s = ering_s + NE * BLK_BYTES;                              // ... and one mbarrier per ring slot
   const int64_t r0 = a.blk_row[tile], r1 = a.blk_row[tile + 1];
   const int64_t v0 = a.crow[r0];
   const int nval = (int)(a.crow[r1] - v0);
-  const int64_t b0 = a.batch_ptr[tile], b1 = a.batch_ptr[tile + 1];
+  const int64_t b0 = a.batch_ptr[tile];
+  const int nb = (int)(a.batch_ptr[tile + 1] - b0);
+  const unsigned char* gblk = reinterpret_cast<const unsigned char*>(a.blocks) + b0 * BLK_BYTES;
 
-  auto issue_entries = [&](int64_t b, int slot) {               // 36 x 16 B for tet P2: two cp.async per lane
-    unsigned char* dst = ering + slot * ENT_BYTES;
+  if (lane == 0) {
 #pragma unroll
-    for (int q0 = 0; q0 < ENT_CHUNKS; q0 += 32) {
-      const int q = q0 + lane;
-      if (q < ENT_CHUNKS) {
-        const unsigned char* src;
-        if (q < 8) src = reinterpret_cast<const unsigned char*>(a.ent_cell + b * 32) + q * 16;
-        else if (q < 16) src = reinterpret_cast<const unsigned char*>(a.ent_base + b * 32) + (q - 8) * 16;
-        else src = reinterpret_cast<const unsigned char*>(a.ent_slots + b * 32 * SR::WORDS) + (q - 16) * 16;
-        cp_async16(dst + q * 16, src);
+    for (int k = 0; k < NE; ++k) mbar_init(bar_s + 8 * k, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < NE; ++k)
+      if (k < nb) {
+        mbar_expect_tx(bar_s + 8 * k, BLK_BYTES);
+        bulk_g2s(ering_s + k * BLK_BYTES, gblk + (size_t)k * BLK_BYTES, BLK_BYTES, bar_s + 8 * k);
       }
-    }
-  };
-  auto issue_geometry = [&](int eslot, int hslot) {
-    const int* cells = reinterpret_cast<const int*>(ering + eslot * ENT_BYTES);
-    double* dst = hring + hslot * 32 * HS;
-#pragma unroll
-    for (int r = 0; r < QP; ++r) {
-      const int idx = r * 32 + lane, rec = idx / QP, part = idx % QP;
-      const int c = cells[rec];
-      if (c >= 0) cp_async16(dst + 2 * a4_unit<QP>(rec, part), a.H + (int64_t)c * HS + 2 * part);
-    }
-  };
-
-  // prologue: entries of the first 2D batches, then the geometry of the first D, then (own group) the entries of batch 2D
-  for (int k = 0; k < 2 * D; ++k)
-    if (b0 + k < b1) issue_entries(b0 + k, k);
-  cp_async_commit();                                            // (no zero fill of the tile: first-touch entries store)
-  int iq[D];                                                    // local index i of batches b .. b+D-1
-#pragma unroll
-  for (int k = 0; k < D; ++k) iq[k] = (b0 + k < b1) ? a.batch_i[b0 + k] : 0;
-  cp_async_wait<0>();
+  }
   __syncwarp();
+
+  // 256-bit loads (LDG.E.256, new on sm_100): a scattered load costs the L1 data pipe one wavefront per lane and
+  // instruction whatever its width -- ncu of the 128-bit version: 108 global wavefronts per batch, the pipe 82 % busy
+  auto load_h = [&](int cell, double (&h)[HS]) {
+    const double* src = a.H + (int64_t)cell * HS;
+    static_assert(HS % 4 == 0, "geometry records are multiples of 32 bytes");
 #pragma unroll
-  for (int k = 0; k < D; ++k) {
-    if (b0 + k < b1) issue_geometry(k, k);
-    cp_async_commit();
+    for (int t = 0; t < HS / 4; ++t) ldg_nc_f64x4(src + 4 * t, h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+  };
+
+  int celln = -1;
+  double hn[HS];
+#pragma unroll
+  for (int t = 0; t < HS; ++t) hn[t] = 0.0;
+  if (nb > 0) {
+    while (!mbar_try_wait(bar_s, 0)) { }
+    celln = (int)ering[lane];
+    if (celln >= 0) load_h(celln, hn);
   }
-  if (b0 + 2 * D < b1) issue_entries(b0 + 2 * D, 2 * D);
-  cp_async_commit();
-  int hs = 0, es = 0;                                           // ring positions of batch b
-  for (int64_t b = b0; b < b1; ++b) {
-    cp_async_wait<D>();                                         // all but the newest group ({entries(b+2D)}): geometry(b), entries(b+D) are in
-    __syncwarp();                                               // ... visible to all lanes; everyone is done with batch b-1
-    {
-      int hn = hs + D; if (hn >= NHST) hn -= NHST;              // == stage of batch b-1: free
-      int en = es + D; if (en >= NEST) en -= NEST;
-      int e3 = es + 2 * D + 1; if (e3 >= NEST) e3 -= NEST;      // == slot of batch b-1: free
-      if (b + D < b1) issue_geometry(en, hn);
-      cp_async_commit();
-      if (b + 2 * D + 1 < b1) issue_entries(b + 2 * D + 1, e3);
-      cp_async_commit();
+  int slot = 0;
+  uint32_t parity = 0;
+  for (int k = 0; k < nb; ++k) {
+    const uint32_t* ent = ering + slot * BW;
+    const int cell = celln;
+    double h[HS];
+#pragma unroll
+    for (int t = 0; t < HS; ++t) h[t] = hn[t];
+    const uint32_t bw = ent[32 + lane];
+    uint32_t sw[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) sw[w] = ent[64 + lane * W + w];
+    const int i = (int)ent[64 + 32 * W];
+    int nslot = slot + 1;
+    uint32_t nparity = parity;
+    if (nslot == NE) { nslot = 0; nparity ^= 1u; }
+    if (k + 1 < nb) {                                           // next batch: its block is (almost always) already here
+      while (!mbar_try_wait(bar_s + 8 * nslot, nparity)) { }
+      celln = (int)ering[nslot * BW + lane];
+      if (celln >= 0) load_h(celln, hn);
     }
-    const int i = iq[0];
-#pragma unroll
-    for (int k = 0; k + 1 < D; ++k) iq[k] = iq[k + 1];
-    iq[D - 1] = (b + D < b1) ? a.batch_i[b + D] : 0;
-    const unsigned char* ent = ering + es * ENT_BYTES;
-    const int cell = reinterpret_cast<const int*>(ent)[lane];
-    if (cell >= 0) {
-      const uint32_t bw = reinterpret_cast<const uint32_t*>(ent + 128)[lane];
-      const int base = (int)(bw & ((1u << A4_BASE_BITS) - 1u));
-      uint32_t sw[SR::WORDS];
-#pragma unroll
-      for (int w = 0; w < SR::WORDS; ++w) sw[w] = reinterpret_cast<const uint32_t*>(ent + 256)[lane * SR::WORDS + w];
-      double h[NH];
-      {
-        const double* hst = hring + hs * 32 * HS;
-        double hh[HS];
-#pragma unroll
-        for (int t = 0; t < QP; ++t) {
-          const double2 v = *reinterpret_cast<const double2*>(hst + 2 * a4_unit<QP>(lane, t));
-          hh[2 * t] = v.x; hh[2 * t + 1] = v.y;
-        }
-#pragma unroll
-        for (int t = 0; t < NH; ++t) h[t] = hh[t];
-      }
-      a4_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, bw >> A4_BASE_BITS, acc + base);
+    if (cell >= 0) a6_dispatch<TD, L, SlotT, 0>(i, tb, h, sw, bw >> A4_BASE_BITS, acc + (bw & ((1u << A4_BASE_BITS) - 1u)));
+    __syncwarp();                                               // every lane is done with the block in `slot` ...
+    if (lane == 0 && k + NE < nb) {                             // ... which is refilled with batch k + NE
+      mbar_expect_tx(bar_s + 8 * slot, BLK_BYTES);
+      bulk_g2s(ering_s + slot * BLK_BYTES, gblk + (size_t)(k + NE) * BLK_BYTES, BLK_BYTES, bar_s + 8 * slot);
     }
-    if (++hs == NHST) hs = 0;
-    if (++es == NEST) es = 0;
+    slot = nslot; parity = nparity;
   }
-  cp_async_wait<0>();
   __syncwarp();
   double* out = a.values + v0;
   for (int t = lane; t < nval; t += 32) out[t] = acc[t];
@@ -1220,7 +1191,7 @@ int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, cons
   void* scan_ws = c.take<char>(scan_workspace_bytes(ntile + 1));
   if (ntile > 0)
     asm4_schedule_kernel<false><<<(unsigned)ceil_div((int64_t)ntile * 32, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, cnt, nullptr,
-                                                                               nullptr, nullptr, nullptr, nullptr, nullptr, 0, 1);
+                                                                               nullptr, nullptr, nullptr, 0, 1);
   FB2_LAUNCH_CHECK();
   FB2_TRY(exclusive_scan_i32(cnt, batch_ptr, ntile, true, scan_ws, s));
   FB2_CUDA(cudaMemcpyAsync(nbatch_host, batch_ptr + ntile, 8, cudaMemcpyDeviceToHost, s));
@@ -1229,12 +1200,12 @@ int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, cons
 }
 
 int asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
-                   const int64_t* batch_ptr, unsigned char* batch_i, int* ent_cell, uint32_t* ent_base, uint32_t* ent_slots,
-                   const void* slots, int slot_bytes, cudaStream_t s) {
+                   const int64_t* batch_ptr, unsigned char* batch_i, uint32_t* blocks, const void* slots, int slot_bytes,
+                   cudaStream_t s) {
   if (ntile <= 0) return OK;
   const int nwords = slot_stride(L, slot_bytes) * slot_bytes / 4;
   asm4_schedule_kernel<true><<<(unsigned)ceil_div((int64_t)ntile * 32, 128), 128, 0, s>>>(ntile, blk_row, crow, adj_ptr, adj_pair, L, nullptr, batch_ptr,
-                                                                            batch_i, ent_cell, ent_base, ent_slots,
+                                                                            batch_i, blocks,
                                                                             static_cast<const uint32_t*>(slots), nwords, slot_bytes);
   FB2_LAUNCH_CHECK();
   return OK;
@@ -1251,14 +1222,13 @@ static int launch_asm4(Asm4Args a, int slot_bytes, cudaStream_t s) {
   a.acc_stride = (a.tile + a.max_row + 1) & ~1;
   A4Tables<L, GEO::NH> tb;
   a4_reduced_table<TD, L>(a.Ms_host, a.Mm_host, tb);
-  static const int depth = [] { const char* e = getenv("FB2_ASM4_DEPTH"); const int d = e ? atoi(e) : 1; return d == 2 ? 2 : 1; }();
   if (a.tile + a.max_row >= (1 << A4_BASE_BITS) || a.max_row > A4_MAXROW)
     return fail(ERR_UNSUPPORTED, "assemble v4: tile offsets exceed %d bits (tile=%d max_row=%d)", A4_BASE_BITS, a.tile, a.max_row);
   const unsigned grid = (unsigned)ceil_div(a.ntile, FB2_ASM4_WARPS);
   if (grid == 0) return OK;
   const int words = slot_stride(L, slot_bytes) * slot_bytes / 4;
-  // per warp: accumulator tile + (D+1) geometry stages + (2D+2) entry slots
-  const size_t per_warp = (size_t)(a.acc_stride + (depth + 1) * 32 * GEO::HS) * 8 + (size_t)(2 * depth + 2) * (256 + 128 * words);
+  // per warp: accumulator tile + A6_RING batch blocks + their mbarriers
+  const size_t per_warp = (size_t)a.acc_stride * 8 + (size_t)A6_RING * a4_block_words(words) * 4 + ((A6_RING * 8 + 15) & ~15);
   const size_t smem = (size_t)FB2_ASM4_WARPS * per_warp;
   if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "assemble v4: tiles do not fit shared memory (tile=%d max_row=%d)", a.tile, a.max_row);
 #define FB2_A4_LAUNCH(KERN)                                                                          \
@@ -1267,13 +1237,8 @@ static int launch_asm4(Asm4Args a, int slot_bytes, cudaStream_t s) {
     FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     k<<<grid, FB2_ASM4_WARPS * 32, smem, s>>>(a, tb);                                                \
   } while (0)
-  if (slot_bytes == 1) {
-    if (depth == 1) FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint8_t, 1>));
-    else FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint8_t, 2>));
-  } else {
-    if (depth == 1) FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint16_t, 1>));
-    else FB2_A4_LAUNCH((assemble_const_v4_kernel<TD, L, uint16_t, 2>));
-  }
+  if (slot_bytes == 1) FB2_A4_LAUNCH((assemble_const_v6_kernel<TD, L, uint8_t>));
+  else FB2_A4_LAUNCH((assemble_const_v6_kernel<TD, L, uint16_t>));
 #undef FB2_A4_LAUNCH
   FB2_LAUNCH_CHECK();
   return OK;

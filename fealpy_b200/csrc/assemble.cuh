@@ -52,9 +52,8 @@ struct Asm4Args {
   int ntile, tile, max_row, acc_stride;
   const int64_t* batch_ptr;     // (ntile+1)
   const unsigned char* batch_i; // (nbatch) local index shared by the batch
-  const int* ent_cell;          // (nbatch*32) cell id or -1 (padding)
-  const uint32_t* ent_base;         // (nbatch*32) offset of the entry's row inside the tile (12 bits) | first-touch column mask
-  const uint32_t* ent_slots;    // (nbatch*32, words) packed slot record
+  const uint32_t* blocks;       // (nbatch, 64 + 32*words + 4) packed batch blocks: 32 cell ids (-1 = padding) | 32 x (row offset in the
+                                // tile (12 bits) | first-touch column mask) | 32 slot records | header word: local index i
   const double* Ms;             // device tables (null = term absent)
   const double* Mm;
   const double* Ms_host;        // host copies (go into the kernel parameter block)
@@ -70,8 +69,8 @@ size_t asm4_workspace_bytes(int ntile);
 int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
                     int64_t* batch_ptr, int64_t* nbatch_host, void* ws, cudaStream_t s);
 int asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
-                   const int64_t* batch_ptr, unsigned char* batch_i, int* ent_cell, uint32_t* ent_base, uint32_t* ent_slots,
-                   const void* slots, int slot_bytes, cudaStream_t s);
+                   const int64_t* batch_ptr, unsigned char* batch_i, uint32_t* blocks, const void* slots, int slot_bytes,
+                   cudaStream_t s);
 int assemble_v4(int TD, int p, const Asm4Args& a, int slot_bytes, cudaStream_t s);
 size_t sym_workspace_bytes(int64_t NC, int L, int64_t gdof);
 int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, int64_t* crow, int64_t* nnz_host,

@@ -175,21 +175,19 @@ int fb2_asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, 
   return asm4_plan_count(ntile, blk_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, nbatch_host, ws, S(stream));
 }
 int fb2_asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
-                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, int32_t* ent_cell, uint32_t* ent_base,
-                       uint32_t* ent_slots, const void* slots, int slot_bytes, void* stream) {
-  return asm4_plan_fill(ntile, blk_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, batch_i, ent_cell, ent_base, ent_slots, slots,
-                        slot_bytes, S(stream));
+                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, uint32_t* blocks, const void* slots, int slot_bytes,
+                       void* stream) {
+  return asm4_plan_fill(ntile, blk_row, crow, adj_ptr, adj_pair, ldof, batch_ptr, batch_i, blocks, slots, slot_bytes, S(stream));
 }
 int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
                                  const int32_t* blk_row, int ntile, int tile, int32_t max_row, const int64_t* batch_ptr,
-                                 const uint8_t* batch_i, const int32_t* ent_cell, const uint32_t* ent_base, const uint32_t* ent_slots,
-                                 int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d, const double* coef_d,
+                                 const uint8_t* batch_i, const uint32_t* blocks, int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d, const double* coef_d,
                                  double scal_m, const double* coef_m, double* geom_ws, double* values, void* stream) {
   const double *Ms = Ms_host, *Mm = Mm_host;      // only their presence matters on the device side
   if (!Ms && !Mm) return fail(ERR_INVALID, "assemble_scalar_const_v4: need a diffusion and/or a mass table");
   Asm4Args a{};
   a.node = node; a.cell = cell; a.NC = NC; a.crow = crow; a.blk_row = blk_row; a.ntile = ntile; a.tile = tile; a.max_row = max_row;
-  a.batch_ptr = batch_ptr; a.batch_i = batch_i; a.ent_cell = ent_cell; a.ent_base = ent_base; a.ent_slots = ent_slots;
+  a.batch_ptr = batch_ptr; a.batch_i = batch_i; a.blocks = blocks;
   a.Ms = Ms; a.Mm = Mm; a.Ms_host = Ms_host; a.Mm_host = Mm_host;
   a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.Hbuf = geom_ws; a.values = values;
   return assemble_v4(TD, p, a, slot_bytes, S(stream));
@@ -202,24 +200,34 @@ int fb2_expand_pattern(int64_t gdof_scalar, int ncomp, int dof_priority, const i
 // ---- K3/K4 ----------------------------------------------------------------------------------
 size_t fb2_partial_workspace_bytes(void) { return partial_workspace_bytes(); }
 int fb2_spmv_plan_blocks(int64_t nnz, int tile) { return spmv_plan_blocks(nnz, tile); }
-int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t* blk_v0, int64_t nnz,
-                        int32_t* max_row_host, void* stream) {
+int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t nnz, int32_t* max_row_host, void* stream) {
   const int nblk = spmv_plan_blocks(nnz, tile);
   int* dmax = blk_row + nblk + 1;        // the caller allocates nblk + 2 entries; the last one is scratch
-  FB2_TRY(spmv_plan_build(n, crow, tile, nblk, blk_row, dmax, S(stream), blk_v0));
+  FB2_TRY(spmv_plan_build(n, crow, tile, nblk, blk_row, dmax, S(stream)));
   FB2_CUDA(cudaMemcpyAsync(max_row_host, dmax, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
   FB2_CUDA(cudaStreamSynchronize(S(stream)));
   return OK;
 }
-static SpmvPlan make_plan(const int32_t* blk_row, int64_t nnz, int tile, int max_row, const int64_t* blk_v0 = nullptr) {
+size_t fb2_spmv_colz_workspace_bytes(int nblk) { return spmv_colz_workspace_bytes(nblk); }
+size_t fb2_spmv_colz_bytes(int nblk, int64_t nnz, int64_t total_distinct) { return spmv_colz_bytes(nblk, nnz, total_distinct); }
+int fb2_spmv_colz_count(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
+                        int64_t* uoff, int64_t* total_distinct_host, void* ws, void* stream) {
+  return spmv_colz_count(nnz, crow, col, blk_row, blk_end, nblk, uoff, total_distinct_host, ws, S(stream));
+}
+int fb2_spmv_colz_fill(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
+                       const int64_t* uoff, void* colz, void* stream) {
+  return spmv_colz_fill(nnz, crow, col, blk_row, blk_end, nblk, uoff, colz, S(stream));
+}
+static SpmvPlan make_plan(const int32_t* blk_row, int64_t nnz, int tile, int max_row, const void* colz = nullptr) {
   SpmvPlan pl{};
-  pl.blk_row = blk_row; pl.blk_v0 = blk_v0; pl.tile = tile; pl.max_row = max_row;
+  pl.blk_row = blk_row; pl.tile = tile; pl.max_row = max_row;
   pl.nblk = blk_row ? spmv_plan_blocks(nnz, tile) : 0;
+  if (blk_row) spmv_colz_attach(pl, nnz, colz);
   return pl;
 }
 int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x, double* y,
-                 const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row, void* stream) {
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, blk_v0);
+                 const int32_t* blk_row, const void* colz, int tile, int32_t max_row, void* stream) {
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, colz);
   return spmv(n, nnz, crow, col, values, x, y, nullptr, 0, nullptr, nullptr, S(stream), blk_row ? &pl : nullptr);
 }
 int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
@@ -231,9 +239,11 @@ int fb2_dot(int64_t n, const double* a, const double* b, double* out_dev, void* 
 }
 size_t fb2_cg_workspace_bytes(int64_t n, int64_t nnz) { return cg_workspace_bytes(n, nnz); }
 int fb2_cg(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
-           const double* minv_diag, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_host,
-           double* residual_host, void* stream) {
-  return cg_solve(n, nnz, crow, col, values, b, x, minv_diag, atol, rtol, maxit, chunk, ws, niter_host, residual_host, S(stream));
+           const double* minv_diag, double atol, double rtol, int maxit, int chunk, const int32_t* blk_row, const void* colz,
+           int tile, int32_t max_row, void* ws, int* niter_host, double* residual_host, void* stream) {
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, colz);
+  return cg_solve(n, nnz, crow, col, values, b, x, minv_diag, atol, rtol, maxit, chunk, ws, niter_host, residual_host, S(stream),
+                  blk_row ? &pl : nullptr);
 }
 int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm, double rTr, void* stream) {
   CgScalars* sc = static_cast<CgScalars*>(scalars);
@@ -249,9 +259,9 @@ static OwnRange make_own(const int64_t* own) {
   return o;
 }
 int fb2_cg_residual(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                    const double* b, double* r, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row,
+                    const double* b, double* r, const int32_t* blk_row, const void* colz, int tile, int32_t max_row,
                     void* stream) {
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, blk_v0);
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, colz);
   return spmv(n, nnz, crow, col, values, x, r, b, 1, nullptr, nullptr, S(stream), blk_row ? &pl : nullptr);
 }
 int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p, void* scalars, void* partial_ws,
@@ -259,10 +269,10 @@ int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p,
   return cg_start(n, r, minv_diag, p, static_cast<CgScalars*>(scalars), partial_ws, make_own(own), S(stream));
 }
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row, void* scalars,
+                    double* Ap, const int32_t* blk_row, const void* colz, int tile, int32_t max_row, void* scalars,
                     void* partial_ws, const int64_t own[4], void* stream) {
   CgScalars* sc = static_cast<CgScalars*>(scalars);
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, blk_v0);
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, colz);
   return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, &sc->pAp, partial_ws, S(stream), blk_row ? &pl : nullptr, make_own(own), sc);
 }
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,

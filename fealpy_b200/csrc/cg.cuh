@@ -30,7 +30,11 @@ struct HaloWait {
 // row-aligned nnz tiling of a CSR matrix (built once per matrix, see spmv_plan_build)
 struct SpmvPlan {
   const int32_t* blk_row = nullptr;   // (nblk+1) first row of every tile
-  const int64_t* blk_v0 = nullptr;    // (nblk+1) first value index of every tile (pipelined kernel) or null
+  // optional staged-x column stream (spmv_colz_count / spmv_colz_fill): per tile the ascending list of its distinct columns
+  // (ucol[uoff[t] .. uoff[t+1]); empty = the tile gathers directly through the 32-bit `col`) and per value its position in it
+  const int64_t* uoff = nullptr;
+  const int32_t* ucol = nullptr;
+  const uint16_t* lidx = nullptr;
   int nblk = 0, tile = 0, max_row = 0;
   const int32_t* blk_end = nullptr;   // optional (nblk): one-past-last row of every tile -- tiles of SEVERAL row ranges in one plan
   HaloWait halo;
@@ -38,8 +42,14 @@ struct SpmvPlan {
 
 size_t cg_workspace_bytes(int64_t n, int64_t nnz);
 int spmv_plan_blocks(int64_t nnz, int tile);
-int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t* blk_row, int* max_row_dev, cudaStream_t s,
-                    int64_t* blk_v0 = nullptr);
+int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t* blk_row, int* max_row_dev, cudaStream_t s);
+size_t spmv_colz_workspace_bytes(int nblk);
+size_t spmv_colz_bytes(int nblk, int64_t nnz, int64_t total_distinct);
+int spmv_colz_count(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
+                    int64_t* uoff, int64_t* total_host, void* ws, cudaStream_t s);
+int spmv_colz_fill(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
+                   const int64_t* uoff, void* colz, cudaStream_t s);
+void spmv_colz_attach(SpmvPlan& plan, int64_t nnz, const void* colz);      // plan.nblk must be set
 
 // y = A x  (mode 0),  y = b - A x (mode 1); optional fused dot  sum_r x[r]*y[r] -> *dot_out (deterministic)
 size_t partial_workspace_bytes();
@@ -54,7 +64,7 @@ int dot(int64_t n, const double* a, const double* b, double* out, void* partial_
 // full solve: reference recurrence (solver/cg.py:76-123); x holds x0 on entry, the solution on exit
 int cg_solve(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* b, double* x,
              const double* minv_diag, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_out,
-             double* resid_out, cudaStream_t s);
+             double* resid_out, cudaStream_t s, const SpmvPlan* prebuilt = nullptr);
 
 // building blocks for the distributed (multi-GPU) driver
 int cg_init_scalars(CgScalars* sc, double atol, double rtol, int maxit, cudaStream_t s);

@@ -65,5 +65,10 @@ __device__ __forceinline__ int ld_stream(const int* p) {
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ unsigned ld_stream(const unsigned short* p) {
+  unsigned short v;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
 
 }  // namespace fb2

@@ -121,7 +121,7 @@ def row_tiling(crow, nrow, nnz, tile):
     nblk = lib.fb2_spmv_plan_blocks(nnz, tile)
     blk_row = torch.empty(nblk + 2, dtype=torch.int32, device=crow.device)
     mr = C.c_int32(0)
-    _lib.call("fb2_spmv_plan_build", nrow, _lib.ptr(crow), tile, _lib.ptr(blk_row), None, nnz, C.byref(mr), _lib.stream())
+    _lib.call("fb2_spmv_plan_build", nrow, _lib.ptr(crow), tile, _lib.ptr(blk_row), nnz, C.byref(mr), _lib.stream())
     return blk_row, nblk
 
 
@@ -144,14 +144,14 @@ def asm4_plan(space):
     nb = nb.value
     nwords = lib.fb2_slot_stride(sym["L"], sym["slot_bytes"]) * sym["slot_bytes"] // 4
     batch_i = torch.empty(nb, dtype=torch.uint8, device=dev)
-    ent_cell = torch.empty(nb * 32, dtype=torch.int32, device=dev)
-    ent_base = torch.zeros(nb * 32, dtype=torch.int32, device=dev)
-    ent_slots = torch.zeros(nb * 32 * nwords, dtype=torch.int32, device=dev)
+    # one packed block per batch (include/fealpy_b200.h): the numeric kernel fetches it with a single bulk copy
+    bw = 64 + 32 * nwords + 4
+    blocks = torch.zeros((nb, bw), dtype=torch.int32, device=dev)
     _lib.call("fb2_asm4_plan_fill", ntile, _lib.ptr(blk_row), _lib.ptr(sym["crow"]), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
-              sym["L"], _lib.ptr(batch_ptr), _lib.ptr(batch_i), _lib.ptr(ent_cell), _lib.ptr(ent_base), _lib.ptr(ent_slots),
-              _lib.ptr(sym["slots"]), sym["slot_bytes"], _lib.stream())
-    sym["asm4"] = dict(blk_row=blk_row, ntile=ntile, tile=ASM4_TILE, batch_ptr=batch_ptr, batch_i=batch_i, ent_cell=ent_cell,
-                       ent_base=ent_base, ent_slots=ent_slots, nbatch=nb)
+              sym["L"], _lib.ptr(batch_ptr), _lib.ptr(batch_i), _lib.ptr(blocks), _lib.ptr(sym["slots"]), sym["slot_bytes"], _lib.stream())
+    sym["asm4"] = dict(blk_row=blk_row, ntile=ntile, tile=ASM4_TILE, batch_ptr=batch_ptr, batch_i=batch_i, blocks=blocks,
+                       ent_cell=blocks[:, :32], ent_base=blocks[:, 32:64], ent_slots=blocks[:, 64:64 + 32 * nwords],
+                       header_i=blocks[:, 64 + 32 * nwords], nbatch=nb)
     return sym["asm4"]
 
 
@@ -319,8 +319,7 @@ class BilinearForm:
                 geom = self._asm4_geom = torch.empty((sym["NC"], (NH + 1) // 2 * 2), dtype=torch.float64, device=mesh.device)
             _lib.call("fb2_assemble_scalar_const_v4", mesh.TD, space.p, sym["NC"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
                       _lib.ptr(sym["crow"]), _lib.ptr(pl["blk_row"]), pl["ntile"], pl["tile"], sym["max_row"], _lib.ptr(pl["batch_ptr"]),
-                      _lib.ptr(pl["batch_i"]), _lib.ptr(pl["ent_cell"]), _lib.ptr(pl["ent_base"]), _lib.ptr(pl["ent_slots"]),
-                      sym["slot_bytes"], hostp(dm, "Ms"), hostp(mm, "Mm"),
+                      _lib.ptr(pl["batch_i"]), _lib.ptr(pl["blocks"]), sym["slot_bytes"], hostp(dm, "Ms"), hostp(mm, "Mm"),
                       sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(geom), _lib.ptr(values), _lib.stream())
             return sym["crow"], sym["col"], values
         _lib.call("fb2_assemble_scalar_const", mesh.TD, space.p, sym["NC"], sym["gdof"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),

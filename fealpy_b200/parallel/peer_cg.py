@@ -33,7 +33,7 @@ def _range_plan(A, ranges, tile):
         blk = torch.empty(nblk + 2, dtype=torch.int32, device=dev)
         mr = C.c_int32(0)
         sub = A.crow[lo:hi + 1]
-        _lib.call("fb2_spmv_plan_build", hi - lo, _lib.ptr(sub), tile, _lib.ptr(blk), None, nnz_r, C.byref(mr), _lib.stream())
+        _lib.call("fb2_spmv_plan_build", hi - lo, _lib.ptr(sub), tile, _lib.ptr(blk), nnz_r, C.byref(mr), _lib.stream())
         max_row = max(max_row, mr.value)
         lo_parts.append(blk[:nblk] + lo)
         hi_parts.append(blk[1:nblk + 1] + lo)

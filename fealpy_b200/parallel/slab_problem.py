@@ -19,20 +19,20 @@ class WindowSpace:
         self.mesh, self.p = mesh, p
         self._c2d, self._n = cell2dof, n_local
         self.itype, self.ftype, self.device = mesh.itype, mesh.ftype, mesh.device
-        self.TD = self.GD = 3
+        self.TD, self.GD = mesh.TD, mesh.node.shape[1]
         self.ctype = "C"
 
     def number_of_global_dofs(self):
         return self._n
 
     def number_of_local_dofs(self, doftype="cell"):
-        return number_of_local_dofs(3, self.p)
+        return number_of_local_dofs(self.TD, self.p)
 
     def cell_to_dof(self, index=None):
         return self._c2d if index is None else self._c2d[index]
 
-    def geo_dimension(self): return 3
-    def top_dimension(self): return 3
+    def geo_dimension(self): return self.GD
+    def top_dimension(self): return self.TD
 
 
 class SlabProblem:

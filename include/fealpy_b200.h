@@ -147,20 +147,25 @@ int fb2_assemble_elasticity_p1(int TD, int64_t NC, const double* node, const int
  * index (warp-uniform element-table row) and touch 32 different rows (conflict-free adds);
  * geom_ws = NC * 2*ceil((TD*(TD+1)/2+1)/2) doubles of scratch for the per-cell geometry (8 per
  * tetrahedron, 4 per triangle).  The element tables are HOST pointers here: they travel in the kernel
- * parameter block (constant bank), which costs no load/store-unit bandwidth.  Pad entries of a
- * batch carry ent_cell = -1.  ent_base[e] = offset of the entry's row inside its tile (low 12 bits:
- * tile + max_row < 4096) | mask of the columns whose value this entry is the FIRST to touch (bit j + 12):
- * those are stored, the others load-add-stored, so the accumulator tile needs no zero fill. */
+ * parameter block (constant bank), which costs no load/store-unit bandwidth.
+ * The schedule is ONE packed array `blocks`: per batch BW = 64 + 32*W + 4 uint32 words (W = words of a slot record =
+ * fb2_slot_stride(ldof, slot_bytes) * slot_bytes / 4), fetched by the numeric kernel with a single bulk copy:
+ *   words [0,32)        cell id of lane's entry, 0xffffffff = pad lane
+ *   words [32,64)       offset of the entry's row inside its tile (low 12 bits: tile + max_row < 4096) | mask of the columns
+ *                       whose value this entry is the FIRST to touch (bit j + 12): those are stored, the others
+ *                       load-add-stored, so the accumulator tile needs no zero fill
+ *   words [64,64+32W)   the 32 slot records (position of the cell's j-th dof inside the row)
+ *   word  64+32W        the batch's local index i (also in batch_i[b]); 3 pad words
+ * `blocks` must be zero-initialised by the caller before fb2_asm4_plan_fill. */
 size_t fb2_asm4_workspace_bytes(int ntile);
 int fb2_asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
                         int ldof, int64_t* batch_ptr, int64_t* nbatch_host, void* ws, void* stream);
 int fb2_asm4_plan_fill(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int32_t* adj_pair,
-                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, int32_t* ent_cell, uint32_t* ent_base,
-                       uint32_t* ent_slots, const void* slots, int slot_bytes, void* stream);
+                       int ldof, const int64_t* batch_ptr, uint8_t* batch_i, uint32_t* blocks, const void* slots, int slot_bytes,
+                       void* stream);
 int fb2_assemble_scalar_const_v4(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const int64_t* crow,
                                  const int32_t* blk_row, int ntile, int tile, int32_t max_row, const int64_t* batch_ptr,
-                                 const uint8_t* batch_i, const int32_t* ent_cell, const uint32_t* ent_base, const uint32_t* ent_slots,
-                                 int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d,
+                                 const uint8_t* batch_i, const uint32_t* blocks, int slot_bytes, const double* Ms_host, const double* Mm_host, double scal_d,
                                  const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* geom_ws, double* values,
                                  void* stream);
 /* expands the scalar pattern to the tensor-space pattern */
@@ -174,31 +179,48 @@ size_t fb2_partial_workspace_bytes(void);           /* zero-initialise once */
 /* SpMV plan (built once per matrix): row-aligned tiles of `tile` stored values.
  * blk_row has fb2_spmv_plan_blocks(nnz, tile) + 1 int32 entries; *max_row_host = longest row. */
 int fb2_spmv_plan_blocks(int64_t nnz, int tile);
-int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t* blk_v0, int64_t nnz,
-                        int32_t* max_row_host, void* stream);      /* blk_v0 (blocks+1 int64, may be NULL): first value index per tile */
-/* y = A x.  blk_row may be NULL (row-per-lane-group kernel); with a plan the streaming kernel runs. */
+int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t nnz, int32_t* max_row_host, void* stream);
+/* Optional staged-x column stream of a plan (`colz`, built once per pattern).  The SpMV is bound by the L1 data pipe, not by
+ * DRAM: a warp's gather x[col] touches ~12 cache lines.  The rows of one tile share most columns, so the plan stores per tile
+ * the ascending list of its DISTINCT columns and per stored value a 16-bit position in that list; the kernel stages x[list] in
+ * shared memory once per tile and the products read from there.  Stream per nonzero: 8 + 2 bytes (+ 4 per distinct column)
+ * instead of 12.  Tiles with more than 1536 distinct columns or more than 4096 values keep gathering through the 32-bit `col`.
+ * Results are bit-identical with and without it (same products, same summation order).
+ *   nblk    = fb2_spmv_plan_blocks(nnz, tile) (or the tile count of a multi-range plan: blk_end != NULL gives every tile's
+ *             one-past-last row, NULL means blk_row[t+1])
+ *   count   : uoff (nblk+1 int64, device) = exclusive scan of the tiles' distinct-column counts; *total_distinct_host = uoff[nblk]
+ *   fill    : writes colz (fb2_spmv_colz_bytes(nblk, nnz, total_distinct) bytes) = [uoff | 16-bit positions | distinct columns] */
+size_t fb2_spmv_colz_workspace_bytes(int nblk);
+size_t fb2_spmv_colz_bytes(int nblk, int64_t nnz, int64_t total_distinct);
+int fb2_spmv_colz_count(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
+                        int64_t* uoff, int64_t* total_distinct_host, void* ws, void* stream);
+int fb2_spmv_colz_fill(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
+                       const int64_t* uoff, void* colz, void* stream);
+/* y = A x.  blk_row may be NULL (row-per-lane-group kernel); with a plan the streaming kernel runs; colz may be NULL. */
 int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                 double* y, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row, void* stream);
+                 double* y, const int32_t* blk_row, const void* colz, int tile, int32_t max_row, void* stream);
 int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
                  void* stream);
 int fb2_dot(int64_t n, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream);
 size_t fb2_cg_workspace_bytes(int64_t n, int64_t nnz);
 /* x: x0 on entry, solution on exit.  minv_diag: NULL or the diagonal of M (z = M r).
- * maxit < 0 means "no limit" (reference maxit=None).  chunk <= 0: automatic. */
+ * maxit < 0 means "no limit" (reference maxit=None).  chunk <= 0: automatic.
+ * blk_row / colz / tile / max_row: a prebuilt SpMV plan of the matrix (fb2_spmv_plan_build, fb2_spmv_colz_build); blk_row NULL:
+ * the solver builds an uncompressed plan in its workspace. */
 int fb2_cg(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
-           const double* minv_diag, double atol, double rtol, int maxit, int chunk, void* ws, int* niter_host,
-           double* residual_host, void* stream);
+           const double* minv_diag, double atol, double rtol, int maxit, int chunk, const int32_t* blk_row, const void* colz,
+           int tile, int32_t max_row, void* ws, int* niter_host, double* residual_host, void* stream);
 /* building blocks of the distributed driver (device-resident scalars in `scalars`, 256 bytes) */
 int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm, double rTr, void* stream);
 /* own[4] = {lo0, hi0, lo1, hi1}: rows (owned dofs of this rank) that contribute to the dot
  * products; NULL = all rows.  The caller all-reduces scalars[1] (p.Ap) / scalars[2] (r.z). */
 int fb2_cg_residual(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                    const double* b, double* r, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row,
+                    const double* b, double* r, const int32_t* blk_row, const void* colz, int tile, int32_t max_row,
                     void* stream);
 int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p, void* scalars, void* partial_ws,
                  const int64_t own[4], void* stream);
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, const int32_t* blk_row, const int64_t* blk_v0, int tile, int32_t max_row, void* scalars,
+                    double* Ap, const int32_t* blk_row, const void* colz, int tile, int32_t max_row, void* scalars,
                     void* partial_ws, const int64_t own[4], void* stream);
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,
                      void* partial_ws, int fuse_finalize, const int64_t own[4], void* stream);

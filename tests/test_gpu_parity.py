@@ -587,12 +587,14 @@ def test_asm4_schedule_invariants(kind, dims, p, tile, U, monkeypatch):
     blk_row = pl["blk_row"].cpu().numpy()[:pl["ntile"] + 1]
     batch_ptr = pl["batch_ptr"].cpu().numpy()
     batch_i = pl["batch_i"].cpu().numpy()
-    ent_cell = pl["ent_cell"].cpu().numpy().reshape(-1, 32)
-    ent_word = pl["ent_base"].cpu().numpy().astype(np.uint32).reshape(-1, 32)
+    # the schedule is one packed block per batch (include/fealpy_b200.h); ent_* are strided views of it
+    ent_cell = pl["ent_cell"].contiguous().cpu().numpy().reshape(-1, 32)
+    ent_word = pl["ent_base"].contiguous().cpu().numpy().astype(np.uint32).reshape(-1, 32)
+    assert np.array_equal(pl["header_i"].cpu().numpy(), batch_i), "the block header repeats the batch's local index"
     ent_base, ent_first = ent_word & 0xfff, ent_word >> 12
     assert batch_ptr[0] == 0 and batch_ptr[-1] == ent_cell.shape[0] == batch_i.shape[0]
     sb = sym["slot_bytes"]
-    raw = pl["ent_slots"].cpu().numpy().view(np.uint8 if sb == 1 else np.uint16)
+    raw = pl["ent_slots"].contiguous().cpu().numpy().view(np.uint8 if sb == 1 else np.uint16)
     ent_slot = raw.reshape(ent_cell.shape[0], 32, -1)[:, :, :L].astype(np.int64)     # (batch, lane, column) -> position in the row
     seen = np.zeros((NC, L), dtype=int)
     for t in range(pl["ntile"]):
@@ -943,3 +945,91 @@ def test_elasticity_dirichlet_jacobi_cg(case, U):
     x, info = cg(A2, F2, M=CSRTensor(d.crow, d.col, 1.0 / d.values, A2.shape), returninfo=True, atol=1e-14, rtol=1e-11)
     assert np.linalg.norm(x.cpu().numpy() - gold["x"]) / np.linalg.norm(gold["x"]) <= 1e-10
     assert abs(info["niter"] - gold["info"]["niter"]) <= 2
+
+
+def _colz_tables(A):
+    """(blk_row, uoff (nblk+1), lidx (nnz) uint16, ucol) views of a plan's staged-x column stream [uoff | lidx | ucol]"""
+    from fealpy_b200 import _lib
+    blk_row, colz, tile, _ = A.spmv_plan()
+    nblk = _lib.load().fb2_spmv_plan_blocks(A.nnz, tile)
+    al = lambda b: -(-b // 256) * 256
+    raw = colz.cpu().numpy()
+    uoff = raw[:8 * (nblk + 1)].view(np.int64)
+    o1 = al(8 * (nblk + 1))
+    lidx = raw[o1:o1 + 2 * A.nnz].view(np.uint16)
+    o2 = o1 + al(2 * A.nnz)
+    ucol = raw[o2:o2 + 4 * int(uoff[-1])].view(np.int32)
+    return blk_row.cpu().numpy()[:nblk + 1], uoff, lidx, ucol
+
+
+@pytest.mark.parametrize("kind,n,p", [("tet", 10, 2), ("tri", 70, 3), ("tet", 14, 1)])
+def test_staged_columns_decode_and_spmv_bit_identical(kind, n, p, U, monkeypatch):
+    """the staged-x column stream of the SpMV plan (csrc/cg.cu xl_count_kernel / xl_fill_kernel): per tile the ascending list
+    of its distinct columns and per value a 16-bit position in it.  It decodes to `col` on every staged tile, and y = A x is
+    BIT-identical with and without it (same products, same summation order)"""
+    from fealpy_b200.mesh import TetrahedronMesh, TriangleMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    from fealpy_b200.sparse import CSRTensor
+    mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], n, n, n) if kind == "tet" else TriangleMesh.from_box([0, 1, 0, 1], n, n)
+    bform = BilinearForm(LagrangeFESpace(mesh, p), share_pattern=False)
+    bform.add_integrator(ScalarDiffusionIntegrator(), ScalarMassIntegrator())
+    A = bform.assembly()
+    blk_row, uoff, lidx, ucol = _colz_tables(A)
+    crow, col = A.crow.cpu().numpy(), A.col.cpu().numpy()
+    nstaged = 0
+    for t in range(len(blk_row) - 1):
+        a, b = crow[blk_row[t]], crow[blk_row[t + 1]]
+        u = ucol[uoff[t]:uoff[t + 1]]
+        if len(u) == 0:
+            continue
+        nstaged += 1
+        assert np.array_equal(u, np.unique(col[a:b])), f"tile {t}: the list is not the sorted distinct columns"
+        assert np.array_equal(u[lidx[a:b]], col[a:b]), f"tile {t} does not decode"
+    assert nstaged >= 0.9 * (len(blk_row) - 1), "FEM tiles are staged"
+    x = U.t64(np.random.default_rng(3).standard_normal(A.shape[1]))
+    y_z = A @ x
+    monkeypatch.setattr(CSRTensor, "COMPRESS_COLS", False)
+    B = CSRTensor(A.crow.clone(), A.col.clone(), A.values, A.shape)
+    assert B.spmv_plan()[1] is None
+    assert torch.equal(y_z, B @ x)
+
+
+def test_staged_columns_fall_back_on_scattered_patterns(U):
+    """a tile of a random pattern has more distinct columns than the staging buffer holds (1536): it keeps the direct gather
+    through the 32-bit columns; banded rows in the same matrix are staged -- both kinds of tile in one SpMV"""
+    from fealpy_b200.sparse import CSRTensor
+    rng = np.random.default_rng(11)
+    n, m = 3000, 400000
+    rows = [np.sort(rng.choice(m, 40, replace=False)) if r < 2000 else np.arange(r, r + 40) for r in range(n)]
+    crow = np.concatenate([[0], np.cumsum([len(c) for c in rows])]).astype(np.int64)
+    col = np.concatenate(rows).astype(np.int32)
+    val = rng.standard_normal(col.size)
+    A = CSRTensor(torch.tensor(crow, device="cuda"), torch.tensor(col, device="cuda"), U.t64(val), (n, m))
+    _, uoff, _, _ = _colz_tables(A)
+    cnt = np.diff(uoff)
+    assert (cnt == 0).any() and (cnt > 0).any(), "both direct-gather and staged tiles"
+    x = rng.standard_normal(m)
+    y = (A @ U.t64(x)).cpu().numpy()
+    yref = np.zeros(n)
+    np.add.at(yref, np.repeat(np.arange(n), np.diff(crow)), val * x[col])
+    assert np.allclose(y, yref, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind,dims,p,world", [("tet", (6, 5, 4), 2, 3), ("tet", (5, 4, 4), 1, 2), ("tri", (14, 11), 3, 5), ("tet", (4, 3, 3), 3, 2)])
+def test_morton_partition_owned_rows_bit_identical_on_gpu(kind, dims, p, world, U):
+    """general-mesh partition (parallel/mesh_partition.py) on a relabelled / shuffled / jittered mesh: one GPU plays every
+    rank in turn; each rank's owned rows of ITS local assembly are bit-identical to the single-GPU matrix, every dof is owned
+    exactly once (the 2-GPU NCCL solve of the same partition is tests/test_multi_gpu.py)"""
+    from fealpy_b200.mesh import TriangleMesh, TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.parallel import verify_partition
+    node, cell = _relabelled_mesh(kind, dims, seed=41 + p)
+    mesh = (TriangleMesh if kind == "tri" else TetrahedronMesh)(U.t64(node), U.t64(cell))
+    space = LagrangeFESpace(mesh, p)
+    owned = 0
+    for r in range(world):
+        v = verify_partition(mesh, space, world, r, torch.device("cuda"), solve=False)
+        assert v["owned_rows_bit_identical"], v
+        owned += v["n_owned"]
+    assert owned == space.number_of_global_dofs()
