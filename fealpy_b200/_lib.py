@@ -63,19 +63,15 @@ SIGNATURES = {
     "fb2_partial_workspace_bytes": (_sz, []),
     "fb2_spmv_plan_blocks": (_i32, [_i64, _i32]),
     "fb2_spmv_plan_build": (_i32, [_i64, _p, _i32, _p, _i64, _p, _p]),
-    "fb2_spmv_colz_workspace_bytes": (_sz, [_i32]),
-    "fb2_spmv_colz_bytes": (_sz, [_i32, _i64, _i64]),
-    "fb2_spmv_colz_count": (_i32, [_i64, _p, _p, _p, _p, _i32, _p, _p, _p, _p]),
-    "fb2_spmv_colz_fill": (_i32, [_i64, _p, _p, _p, _p, _i32, _p, _p, _p]),
-    "fb2_csr_spmv": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
+    "fb2_csr_spmv": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
     "fb2_csr_spmm": (_i32, [_i64, _p, _p, _p, _p, _p, _i32, _p]),
     "fb2_dot": (_i32, [_i64, _p, _p, _p, _p, _p]),
     "fb2_cg_workspace_bytes": (_sz, [_i64, _i64]),
-    "fb2_cg": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _i32, _p, _p, _i32, _i32, _p, _p, _p, _p]),
+    "fb2_cg": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p]),
     "fb2_cg_init": (_i32, [_p, _f64, _f64, _i32, _f64, _f64, _p]),
-    "fb2_cg_residual": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
+    "fb2_cg_residual": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p]),
     "fb2_cg_start": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p]),
-    "fb2_cg_spmv_dot": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
+    "fb2_cg_spmv_dot": (_i32, [_i64, _i64, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "fb2_cg_update_xr": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "fb2_box_edges_before": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "fb2_tet_box_slab": (_i32, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),

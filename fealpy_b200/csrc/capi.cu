@@ -208,26 +208,15 @@ int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_r
   FB2_CUDA(cudaStreamSynchronize(S(stream)));
   return OK;
 }
-size_t fb2_spmv_colz_workspace_bytes(int nblk) { return spmv_colz_workspace_bytes(nblk); }
-size_t fb2_spmv_colz_bytes(int nblk, int64_t nnz, int64_t total_distinct) { return spmv_colz_bytes(nblk, nnz, total_distinct); }
-int fb2_spmv_colz_count(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
-                        int64_t* uoff, int64_t* total_distinct_host, void* ws, void* stream) {
-  return spmv_colz_count(nnz, crow, col, blk_row, blk_end, nblk, uoff, total_distinct_host, ws, S(stream));
-}
-int fb2_spmv_colz_fill(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
-                       const int64_t* uoff, void* colz, void* stream) {
-  return spmv_colz_fill(nnz, crow, col, blk_row, blk_end, nblk, uoff, colz, S(stream));
-}
-static SpmvPlan make_plan(const int32_t* blk_row, int64_t nnz, int tile, int max_row, const void* colz = nullptr) {
+static SpmvPlan make_plan(const int32_t* blk_row, int64_t nnz, int tile, int max_row) {
   SpmvPlan pl{};
   pl.blk_row = blk_row; pl.tile = tile; pl.max_row = max_row;
   pl.nblk = blk_row ? spmv_plan_blocks(nnz, tile) : 0;
-  if (blk_row) spmv_colz_attach(pl, nnz, colz);
   return pl;
 }
 int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x, double* y,
-                 const int32_t* blk_row, const void* colz, int tile, int32_t max_row, void* stream) {
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, colz);
+                 const int32_t* blk_row, int tile, int32_t max_row, void* stream) {
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
   return spmv(n, nnz, crow, col, values, x, y, nullptr, 0, nullptr, nullptr, S(stream), blk_row ? &pl : nullptr);
 }
 int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
@@ -239,9 +228,9 @@ int fb2_dot(int64_t n, const double* a, const double* b, double* out_dev, void* 
 }
 size_t fb2_cg_workspace_bytes(int64_t n, int64_t nnz) { return cg_workspace_bytes(n, nnz); }
 int fb2_cg(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
-           const double* minv_diag, double atol, double rtol, int maxit, int chunk, const int32_t* blk_row, const void* colz,
+           const double* minv_diag, double atol, double rtol, int maxit, int chunk, const int32_t* blk_row,
            int tile, int32_t max_row, void* ws, int* niter_host, double* residual_host, void* stream) {
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, colz);
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
   return cg_solve(n, nnz, crow, col, values, b, x, minv_diag, atol, rtol, maxit, chunk, ws, niter_host, residual_host, S(stream),
                   blk_row ? &pl : nullptr);
 }
@@ -259,9 +248,9 @@ static OwnRange make_own(const int64_t* own) {
   return o;
 }
 int fb2_cg_residual(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                    const double* b, double* r, const int32_t* blk_row, const void* colz, int tile, int32_t max_row,
+                    const double* b, double* r, const int32_t* blk_row, int tile, int32_t max_row,
                     void* stream) {
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, colz);
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
   return spmv(n, nnz, crow, col, values, x, r, b, 1, nullptr, nullptr, S(stream), blk_row ? &pl : nullptr);
 }
 int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p, void* scalars, void* partial_ws,
@@ -269,10 +258,10 @@ int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p,
   return cg_start(n, r, minv_diag, p, static_cast<CgScalars*>(scalars), partial_ws, make_own(own), S(stream));
 }
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, const int32_t* blk_row, const void* colz, int tile, int32_t max_row, void* scalars,
+                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars,
                     void* partial_ws, const int64_t own[4], void* stream) {
   CgScalars* sc = static_cast<CgScalars*>(scalars);
-  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row, colz);
+  const SpmvPlan pl = make_plan(blk_row, nnz, tile, max_row);
   return spmv(n, nnz, crow, col, values, p, Ap, nullptr, 0, &sc->pAp, partial_ws, S(stream), blk_row ? &pl : nullptr, make_own(own), sc);
 }
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,

@@ -7,7 +7,6 @@
 // returned, z = M r with M a diagonal (Jacobi) preconditioner or identity.
 // SpMV semantics: sparse/csr_tensor.py:411-452 -> backend csr_spmm (numpy_backend.py:180-199).
 #include "cg.cuh"
-#include "sort_scan.cuh"
 
 #include <climits>
 #include <cstdlib>
@@ -118,22 +117,26 @@ __global__ void __launch_bounds__(CG_THREADS) spmm_kernel(int64_t n, const int64
 // unrolled loads (memory-level parallelism independent of the row lengths), gathers x and
 // parks the products in shared memory; phase 2 reduces each row with G lanes.  Row sums and
 // the fused p.Ap partials are formed in a fixed order -> bitwise reproducible.
+// Round-2 experiments on this kernel, all measured SLOWER on tet P2 128^3 and removed again (profiles/r02_tune_spmv.txt;
+// the kernel is bound by the latency / L2 sector traffic of the x gather -- DRAM 58 % busy, issue slots 23 %):
+//   * 16-bit window-relative column stream (10 instead of 12 bytes per nonzero): 1.61 vs 1.66 ms per CG iteration (-3 %);
+//   * per-tile list of distinct columns, x staged in shared memory, 16-bit positions: 2.37 ms (a third dependent phase);
+//   * (val, col) tiles fetched by cp.async.bulk + mbarrier into a double buffer, products in place: 1.95 - 3.4 ms
+//     depending on threads / tile (fewer gathers in flight than 8 resident CTAs x 256 threads of this kernel).
 constexpr int ST_UNROLL = 4;
 #ifndef FB2_ST_THREADS
 #define FB2_ST_THREADS 256
 #endif
 constexpr int ST_THREADS = FB2_ST_THREADS;     // threads per CTA of the streaming SpMV kernel
 
-template <int G, bool Z>
+template <int G>
 __global__ void __launch_bounds__(ST_THREADS) spmv_stream_kernel(int64_t n, const int64_t* __restrict__ crow,
                                                                  const int32_t* __restrict__ col, const double* __restrict__ val,
                                                                  const double* __restrict__ x, double* __restrict__ y,
                                                                  const double* __restrict__ b, int mode,
                                                                  const int32_t* __restrict__ blk_row, int nblk, double* dot_out,
                                                                  double* partials, unsigned int* counter, const CgScalars* sc,
-                                                                 OwnRange own, const int32_t* __restrict__ blk_end, HaloWait hw,
-                                                                 const int64_t* __restrict__ uoff, const int32_t* __restrict__ ucol,
-                                                                 const uint16_t* __restrict__ lidx, int xs_off) {
+                                                                 OwnRange own, const int32_t* __restrict__ blk_end, HaloWait hw) {
   if (sc && sc->done) return;
   extern __shared__ __align__(16) double prod[];
   const int tid = threadIdx.x;
@@ -162,26 +165,7 @@ __global__ void __launch_bounds__(ST_THREADS) spmv_stream_kernel(int64_t n, cons
     const int nval = (int)(crow[r1] - v0);
     const double* __restrict__ vp = val + v0;
     const int32_t* __restrict__ cp = col + v0;
-    // staged x: the tile's distinct columns come first (ascending ids, coalesced-ish gather), products read them by 16-bit position
-    int U = 0;
-    if (Z) U = (int)(uoff[blk + 1] - uoff[blk]);
-    if (Z && U > 0) {
-      double* xs = prod + xs_off;
-      const int32_t* __restrict__ up = ucol + uoff[blk];
-      for (int k = tid; k < U; k += ST_THREADS) xs[k] = x[ld_stream(up + k)];
-      __syncthreads();
-      const uint16_t* __restrict__ zp = lidx + v0;
-      int k = tid;
-      for (; k + (ST_UNROLL - 1) * ST_THREADS < nval; k += ST_UNROLL * ST_THREADS) {
-        double vv[ST_UNROLL];
-        unsigned cz[ST_UNROLL];
-#pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) { vv[u] = ld_stream(vp + k + u * ST_THREADS); cz[u] = ld_stream(zp + k + u * ST_THREADS); }
-#pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * ST_THREADS] = vv[u] * xs[cz[u]];
-      }
-      for (; k < nval; k += ST_THREADS) prod[k] = ld_stream(vp + k) * xs[ld_stream(zp + k)];
-    } else {
+    {
       int k = tid;
       for (; k + (ST_UNROLL - 1) * ST_THREADS < nval; k += ST_UNROLL * ST_THREADS) {
         double vv[ST_UNROLL];
@@ -226,101 +210,6 @@ __global__ void __launch_bounds__(256) partition_rows_kernel(const int64_t* __re
     if (crow[mid] < target) lo = mid + 1; else hi = mid;
   }
   blk_row[b] = (int32_t)lo;
-}
-
-// ---- staged-x column stream ("colz") -----------------------------------------------------------------------------------
-// ncu of the streaming SpMV: the L1 data pipe, not DRAM, is what limits it -- a warp's gather x[col] touches ~12 different
-// 128-byte lines (one wavefront each), and halving the index bytes alone moved the time by 3 %.  FEM rows of one tile share
-// most of their columns (tet P2: 2560 values reference ~750 distinct columns), so the plan stores per tile the sorted list of
-// its distinct columns (`ucol`) and per value a 16-bit position in that list (`lidx`).  The kernel first stages x[ucol[.]]
-// in shared memory (ascending ids: few lines per warp), then every product reads its operand from there.  The stream per
-// nonzero is 8 + 2 bytes (+ 4 bytes per distinct column, ~1.2 per nonzero) instead of 12, and x is fetched from L2 once per
-// tile instead of ~3 times.  Tiles with more than XL_UCAP distinct columns (or more than XL_SORT values) keep the direct
-// gather from the 32-bit `col`.
-constexpr int XL_SORT = 4096;                 // values of a tile the build kernels sort in shared memory
-constexpr int XL_UCAP = 1536;                 // staged x entries per tile (12 KB of shared memory)
-
-__device__ __forceinline__ void xl_sort_tile(int* key, int nval) {       // ascending bitonic sort of key[0..XL_SORT), padded with INT_MAX
-  for (int k = threadIdx.x; k < XL_SORT; k += blockDim.x) if (k >= nval) key[k] = INT_MAX;
-  __syncthreads();
-  for (int size = 2; size <= XL_SORT; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < XL_SORT / 2; t += blockDim.x) {
-        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const int a = key[lo], b = key[hi];
-        if ((a > b) == up) { key[lo] = b; key[hi] = a; }
-      }
-      __syncthreads();
-    }
-}
-
-// pass 1: distinct columns per tile (0 = the tile is not staged)
-__global__ void __launch_bounds__(256) xl_count_kernel(const int64_t* __restrict__ crow, const int32_t* __restrict__ col,
-                                                       const int32_t* __restrict__ blk_row, const int32_t* __restrict__ blk_end,
-                                                       int32_t* __restrict__ ucount) {
-  __shared__ int key[XL_SORT];
-  __shared__ int total;
-  const int t = blockIdx.x;
-  const int r0 = blk_row[t], r1 = blk_end ? blk_end[t] : blk_row[t + 1];
-  const int64_t v0 = crow[r0];
-  const int64_t nv = crow[r1] - v0;
-  if (nv <= 0 || nv > XL_SORT) { if (threadIdx.x == 0) ucount[t] = 0; return; }
-  const int nval = (int)nv;
-  if (threadIdx.x == 0) total = 0;
-  for (int k = threadIdx.x; k < nval; k += blockDim.x) key[k] = col[v0 + k];
-  __syncthreads();
-  xl_sort_tile(key, nval);
-  int mine = 0;
-  for (int k = threadIdx.x; k < nval; k += blockDim.x) mine += (k == 0 || key[k] != key[k - 1]) ? 1 : 0;
-  mine = (int)__reduce_add_sync(0xffffffffu, mine);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&total, mine);
-  __syncthreads();
-  if (threadIdx.x == 0) ucount[t] = total <= XL_UCAP ? total : 0;
-}
-
-// pass 2: the distinct columns (ascending) and every value's position among them
-__global__ void __launch_bounds__(256) xl_fill_kernel(const int64_t* __restrict__ crow, const int32_t* __restrict__ col,
-                                                      const int32_t* __restrict__ blk_row, const int32_t* __restrict__ blk_end,
-                                                      const int64_t* __restrict__ uoff, int32_t* __restrict__ ucol,
-                                                      uint16_t* __restrict__ lidx) {
-  __shared__ int key[XL_SORT];
-  __shared__ int uniq[XL_UCAP];
-  __shared__ int wsum[8];
-  const int t = blockIdx.x;
-  const int U = (int)(uoff[t + 1] - uoff[t]);
-  if (U == 0) return;
-  const int r0 = blk_row[t], r1 = blk_end ? blk_end[t] : blk_row[t + 1];
-  const int64_t v0 = crow[r0];
-  const int nval = (int)(crow[r1] - v0);
-  for (int k = threadIdx.x; k < nval; k += blockDim.x) key[k] = col[v0 + k];
-  __syncthreads();
-  xl_sort_tile(key, nval);
-  // compact the run heads in order: chunks of 256 sorted keys, exclusive prefix of the head flags
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int base = 0;
-  for (int c0 = 0; c0 < nval; c0 += 256) {
-    const int k = c0 + threadIdx.x;
-    const int head = (k < nval && (k == 0 || key[k] != key[k - 1])) ? 1 : 0;
-    const unsigned m = __ballot_sync(0xffffffffu, head);
-    if (lane == 0) wsum[wid] = __popc(m);
-    __syncthreads();
-    int before = base;
-    for (int w = 0; w < wid; ++w) before += wsum[w];
-    if (head) uniq[before + __popc(m & ((1u << lane) - 1u))] = key[k];
-    int all = 0;
-    for (int w = 0; w < 8; ++w) all += wsum[w];
-    base += all;
-    __syncthreads();
-  }
-  int32_t* uc = ucol + uoff[t];
-  for (int k = threadIdx.x; k < U; k += blockDim.x) uc[k] = uniq[k];
-  for (int k = threadIdx.x; k < nval; k += blockDim.x) {
-    const int c = col[v0 + k];
-    int lo = 0, hi = U - 1;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (uniq[mid] < c) lo = mid + 1; else hi = mid; }
-    lidx[v0 + k] = (uint16_t)lo;
-  }
 }
 
 __global__ void __launch_bounds__(256) max_row_kernel(const int64_t* __restrict__ crow, int64_t n, int* out) {
@@ -450,54 +339,10 @@ int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t*
   return OK;
 }
 
-// colz buffer layout: [uoff (nblk+1) int64 | lidx (nnz) uint16 | ucol (total distinct) int32]
-static size_t colz_off_lidx(int nblk) { return align_up((size_t)(nblk + 1) * sizeof(int64_t)); }
-static size_t colz_off_ucol(int nblk, int64_t nnz) { return colz_off_lidx(nblk) + align_up((size_t)(nnz > 0 ? nnz : 1) * sizeof(uint16_t)); }
-size_t spmv_colz_workspace_bytes(int nblk) { return align_up((size_t)(nblk + 1) * sizeof(int32_t)) + scan_workspace_bytes(nblk + 1) + 256; }
-size_t spmv_colz_bytes(int nblk, int64_t nnz, int64_t total_distinct) {
-  return colz_off_ucol(nblk, nnz) + align_up((size_t)(total_distinct > 0 ? total_distinct : 1) * sizeof(int32_t));
-}
-int spmv_colz_count(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
-                    int64_t* uoff, int64_t* total_host, void* ws, cudaStream_t s) {
-  *total_host = 0;
-  if (nnz <= 0 || nblk <= 0) return OK;
-  Carver c(ws);
-  int32_t* ucount = c.take<int32_t>(nblk + 1);
-  void* scan_ws = c.take<char>(scan_workspace_bytes(nblk + 1));
-  xl_count_kernel<<<(unsigned)nblk, 256, 0, s>>>(crow, col, blk_row, blk_end, ucount);
-  FB2_LAUNCH_CHECK();
-  FB2_TRY(exclusive_scan_i32(ucount, uoff, nblk, true, scan_ws, s));
-  FB2_CUDA(cudaMemcpyAsync(total_host, uoff + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  FB2_CUDA(cudaStreamSynchronize(s));
-  return OK;
-}
-int spmv_colz_fill(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
-                   const int64_t* uoff, void* colz, cudaStream_t s) {
-  if (nnz <= 0 || nblk <= 0) return OK;
-  char* base = static_cast<char*>(colz);
-  FB2_CUDA(cudaMemcpyAsync(base, uoff, (size_t)(nblk + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-  xl_fill_kernel<<<(unsigned)nblk, 256, 0, s>>>(crow, col, blk_row, blk_end, reinterpret_cast<const int64_t*>(base),
-                                               reinterpret_cast<int32_t*>(base + colz_off_ucol(nblk, nnz)),
-                                               reinterpret_cast<uint16_t*>(base + colz_off_lidx(nblk)));
-  FB2_LAUNCH_CHECK();
-  return OK;
-}
-void spmv_colz_attach(SpmvPlan& plan, int64_t nnz, const void* colz) {
-  plan.uoff = nullptr; plan.ucol = nullptr; plan.lidx = nullptr;
-  if (!colz || nnz <= 0 || plan.nblk <= 0) return;
-  const char* base = static_cast<const char*>(colz);
-  plan.uoff = reinterpret_cast<const int64_t*>(base);
-  plan.lidx = reinterpret_cast<const uint16_t*>(base + colz_off_lidx(plan.nblk));
-  plan.ucol = reinterpret_cast<const int32_t*>(base + colz_off_ucol(plan.nblk, nnz));
-}
-
 static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* val, const double* x,
                               double* y, const double* b, int mode, const SpmvPlan& plan, double* dot_out, double* partials,
                               unsigned int* counter, const CgScalars* sc, cudaStream_t s, OwnRange own) {
-  size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
-  const bool z = plan.uoff != nullptr && plan.ucol != nullptr && plan.lidx != nullptr;
-  const int xs_off = (plan.tile + plan.max_row + 1) & ~1;            // staged x entries follow the product tile
-  if (z) smem = (size_t)(xs_off + XL_UCAP) * sizeof(double);
+  const size_t smem = (size_t)(plan.tile + plan.max_row) * sizeof(double);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
   static const int per_sm_cap = [] { const char* e = getenv("FB2_SPMV_PERSM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2048 / ST_THREADS; }();
   const int per_sm = (int)std::min<size_t>(per_sm_cap, (200 * 1024) / (smem + 1024));
@@ -506,9 +351,9 @@ static int spmv_stream_launch(int64_t n, int64_t nnz, const int64_t* crow, const
   if (grid < 1) grid = 1;
 #define FB2_ST(GV)                                                                                             \
   do {                                                                                                         \
-    auto kern = z ? spmv_stream_kernel<GV, true> : spmv_stream_kernel<GV, false>;                              \
+    auto kern = spmv_stream_kernel<GV>;                                                                        \
     if (smem > 48 * 1024) FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, ST_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own, plan.blk_end, plan.halo, plan.uoff, plan.ucol, plan.lidx, xs_off); \
+    kern<<<grid, ST_THREADS, smem, s>>>(n, crow, col, val, x, y, b, mode, plan.blk_row, plan.nblk, dot_out, partials, counter, sc, own, plan.blk_end, plan.halo); \
   } while (0)
   // lanes per row in the reduce phase: ONE (a thread sums its row sequentially out of shared memory) measured
   // best by a wide margin -- 1.60 ms/iteration against 1.92 with 8 lanes + shuffles (profiles/r01_tune_spmv.txt)

@@ -30,11 +30,6 @@ struct HaloWait {
 // row-aligned nnz tiling of a CSR matrix (built once per matrix, see spmv_plan_build)
 struct SpmvPlan {
   const int32_t* blk_row = nullptr;   // (nblk+1) first row of every tile
-  // optional staged-x column stream (spmv_colz_count / spmv_colz_fill): per tile the ascending list of its distinct columns
-  // (ucol[uoff[t] .. uoff[t+1]); empty = the tile gathers directly through the 32-bit `col`) and per value its position in it
-  const int64_t* uoff = nullptr;
-  const int32_t* ucol = nullptr;
-  const uint16_t* lidx = nullptr;
   int nblk = 0, tile = 0, max_row = 0;
   const int32_t* blk_end = nullptr;   // optional (nblk): one-past-last row of every tile -- tiles of SEVERAL row ranges in one plan
   HaloWait halo;
@@ -43,13 +38,6 @@ struct SpmvPlan {
 size_t cg_workspace_bytes(int64_t n, int64_t nnz);
 int spmv_plan_blocks(int64_t nnz, int tile);
 int spmv_plan_build(int64_t n, const int64_t* crow, int tile, int nblk, int32_t* blk_row, int* max_row_dev, cudaStream_t s);
-size_t spmv_colz_workspace_bytes(int nblk);
-size_t spmv_colz_bytes(int nblk, int64_t nnz, int64_t total_distinct);
-int spmv_colz_count(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
-                    int64_t* uoff, int64_t* total_host, void* ws, cudaStream_t s);
-int spmv_colz_fill(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
-                   const int64_t* uoff, void* colz, cudaStream_t s);
-void spmv_colz_attach(SpmvPlan& plan, int64_t nnz, const void* colz);      // plan.nblk must be set
 
 // y = A x  (mode 0),  y = b - A x (mode 1); optional fused dot  sum_r x[r]*y[r] -> *dot_out (deterministic)
 size_t partial_workspace_bytes();

@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) tet_slab_kernel(double x0, double x1, dou
   const int64_t nyz = (int64_t)(d.ny + 1) * (d.nz + 1);
   const int nplanes = cl1 - cl0 + 1;
   const int64_t NNw = (int64_t)nplanes * nyz, NB = (int64_t)(cl1 - cl0) * d.ny * d.nz;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < NNw; t += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; node != nullptr && t < NNw; t += (int64_t)gridDim.x * blockDim.x) {
     const int il = (int)(t / nyz);
     const int rem = (int)(t - (int64_t)il * nyz);
     const int j = rem / (d.nz + 1), k = rem % (d.nz + 1);
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256) tet_slab_kernel(double x0, double x1, dou
       const int cidx = K[q][v];
       vi[v] = il + CO[cidx][0]; vj[v] = j + CO[cidx][1]; vk[v] = k + CO[cidx][2];
       vloc[v] = (int64_t)vi[v] * nyz + (int64_t)vj[v] * (d.nz + 1) + vk[v];      // window-local node id
-      cell[4 * t + v] = (int)vloc[v];
+      if (cell) cell[4 * t + v] = (int)vloc[v];
     }
     if (p == 1) {
 #pragma unroll

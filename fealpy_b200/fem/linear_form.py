@@ -166,11 +166,11 @@ class DirichletBC:
             uh = torch.zeros_like(f)
         uh, _ = self.space.boundary_interpolate(gd=gd, uh=uh, threshold=self.threshold, method=self.method)
         uh = uh.contiguous()
-        blk, bv0, tile, mr = A.spmv_plan()
+        blk, tile, mr = A.spmv_plan()
         out = torch.empty_like(f)
         n = A.shape[0]
         _lib.call("fb2_cg_residual", n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(uh),
-                  _lib.ptr(f.contiguous()), _lib.ptr(out), _lib.ptr(blk), _lib.ptr(bv0), tile, mr, _lib.stream())      # out = f - A uh
+                  _lib.ptr(f.contiguous()), _lib.ptr(out), _lib.ptr(blk), tile, mr, _lib.stream())      # out = f - A uh
         _lib.call("fb2_bc_vector", n, _lib.ptr(self._mask), _lib.ptr(uh), _lib.ptr(out), _lib.stream())
         return out
 

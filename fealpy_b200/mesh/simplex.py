@@ -9,6 +9,7 @@ library (csrc/topo.cu); torch tensors are only containers.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -52,7 +53,16 @@ class SimplexMesh:
     def geo_dimension(self): return self.node.shape[1]
     def number_of_nodes(self): return self.node.shape[0]
     def number_of_cells(self): return self.cell.shape[0]
-    def number_of_edges(self): return self.edge.shape[0]
+    def number_of_edges(self):
+        if self._edge is None and self._closed_form_box():
+            nx, ny, nz = self._box_dims
+            return int(_lib.load().fb2_box_edges_before(nx, ny, nz, nx, ny, nz))
+        return self.edge.shape[0]
+
+    def _closed_form_box(self):
+        """True for an untouched TetrahedronMesh.from_box mesh (FB2_BOX_CLOSED_FORM=0 forces the generic sort path)"""
+        return (self.TD == 3 and getattr(self, "_box_dims", None) is not None
+                and os.environ.get("FB2_BOX_CLOSED_FORM", "1") != "0")
     def number_of_faces(self): return self.face.shape[0]
 
     def entity(self, etype):
@@ -134,6 +144,15 @@ class SimplexMesh:
         if p not in self._c2ip:
             if p == 1:
                 self._c2ip[p] = self.cell
+            elif p == 2 and self._closed_form_box():
+                # from_box tetrahedra: edge id = number of edges leaving smaller nodes (csrc/topo.cu) -- the same ids the
+                # sorted-unique construction gives (tests: test_from_box_closed_form_numbering), without sorting 75 M keys
+                nx, ny, nz = self._box_dims
+                out = torch.empty((self.number_of_cells(), 10), dtype=torch.int32, device=self.device)
+                b = (C.c_double * 6)(*[float(v) for v in self.box])
+                with torch.cuda.device(self.device):
+                    _lib.call("fb2_tet_box_slab", b, nx, ny, nz, 0, nx, 2, None, None, _lib.ptr(out), _lib.stream())
+                self._c2ip[p] = out
             else:
                 if p > 3:
                     raise NotImplementedError("fealpy_b200 supports Lagrange degree p = 1..3")
@@ -304,4 +323,5 @@ class TetrahedronMesh(SimplexMesh):
             _lib.call("fb2_tet_from_box", b, nx, ny, nz, _lib.ptr(node), _lib.ptr(cell), _lib.stream())
         m = cls(node, cell)
         m.box = list(box)
+        m._box_dims = (int(nx), int(ny), int(nz))      # closed-form edge count / P2 numbering (no edge sort on the assembly path)
         return m

@@ -89,18 +89,18 @@ class CudaCgOps:
                   0.0, _lib.stream())
 
     def residual(self, x, b):
-        A, (blk, bv0, tile, mr) = self.A, self.plan
+        A, (blk, tile, mr) = self.A, self.plan
         _lib.call("fb2_cg_residual", self.n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(x), _lib.ptr(b),
-                  _lib.ptr(self.r), _lib.ptr(blk), _lib.ptr(bv0), tile, mr, _lib.stream())
+                  _lib.ptr(self.r), _lib.ptr(blk), tile, mr, _lib.stream())
 
     def start(self):
         _lib.call("fb2_cg_start", self.n, _lib.ptr(self.r), _lib.ptr(self.minv), _lib.ptr(self.p), _lib.ptr(self.sc),
                   _lib.ptr(self.pws), self.own, _lib.stream())
 
     def spmv_dot(self):
-        A, (blk, bv0, tile, mr) = self.A, self.plan
+        A, (blk, tile, mr) = self.A, self.plan
         _lib.call("fb2_cg_spmv_dot", self.n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(self.p),
-                  _lib.ptr(self.Ap), _lib.ptr(blk), _lib.ptr(bv0), tile, mr, _lib.ptr(self.sc), _lib.ptr(self.pws), self.own, _lib.stream())
+                  _lib.ptr(self.Ap), _lib.ptr(blk), tile, mr, _lib.ptr(self.sc), _lib.ptr(self.pws), self.own, _lib.stream())
 
     def update_xr(self, x):
         _lib.call("fb2_cg_update_xr", self.n, _lib.ptr(x), _lib.ptr(self.r), _lib.ptr(self.p), _lib.ptr(self.Ap), _lib.ptr(self.minv),

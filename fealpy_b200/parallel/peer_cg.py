@@ -155,9 +155,9 @@ class PeerCG:
         halo_exchange(x, self.part.exchanges, grp)
         _lib.call("fb2_cg_init", _lib.ptr(self.sc), float(atol), float(rtol), -1 if maxit is None else int(maxit), float(bnorm), 0.0,
                   _lib.stream())
-        blk, bv0, tile, mr = self.full_plan
+        blk, tile, mr = self.full_plan
         _lib.call("fb2_cg_residual", self.n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(x), _lib.ptr(b),
-                  _lib.ptr(self.r), _lib.ptr(blk), _lib.ptr(bv0), tile, mr, _lib.stream())
+                  _lib.ptr(self.r), _lib.ptr(blk), tile, mr, _lib.stream())
         _lib.call("fb2_cg_start", self.n, _lib.ptr(self.r), _lib.ptr(self.minv), _lib.ptr(self.p), _lib.ptr(self.sc), _lib.ptr(self.pws),
                   self.own, _lib.stream())
         dist.all_reduce(self.sc[SC_RTR:SC_RTR + 1], op=dist.ReduceOp.SUM, group=grp)

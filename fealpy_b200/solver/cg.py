@@ -114,9 +114,9 @@ def cg(A, b, x0=None, M=None, *, batch_first=False, atol=1e-12, rtol=1e-8, maxit
     bb = b.contiguous()
     ws = _lib.workspace(lib.fb2_cg_workspace_bytes(n, A.nnz), b.device)
     niter, resid = C.c_int(0), C.c_double(0.0)
-    blk_row, colz, tile, max_row = A.spmv_plan()        # cached per pattern (row tiling + compressed column stream)
+    blk_row, tile, max_row = A.spmv_plan()        # cached per pattern
     _lib.call("fb2_cg", n, A.nnz, _lib.ptr(A.crow), _lib.ptr(A.col), _lib.ptr(A.values), _lib.ptr(bb), _lib.ptr(x), _lib.ptr(minv),
-              float(atol), float(rtol), -1 if maxit is None else int(maxit), 0, _lib.ptr(blk_row), _lib.ptr(colz), tile, max_row,
+              float(atol), float(rtol), -1 if maxit is None else int(maxit), 0, _lib.ptr(blk_row), tile, max_row,
               _lib.ptr(ws), C.byref(niter), C.byref(resid), _lib.stream())
     info = {"residual": resid.value, "niter": niter.value}
     return (x, info) if returninfo else x

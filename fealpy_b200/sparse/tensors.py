@@ -22,21 +22,6 @@ def _bits(n: int) -> int:
     return b
 
 
-def build_colz(nnz, crow, col, blk_row, blk_end, nblk):
-    """staged-x column stream of an SpMV tile plan (include/fealpy_b200.h, fb2_spmv_colz_*): one uint8 buffer"""
-    lib = _lib.load()
-    dev = crow.device
-    uoff = torch.empty(nblk + 1, dtype=torch.int64, device=dev)
-    ws = torch.empty(lib.fb2_spmv_colz_workspace_bytes(nblk), dtype=torch.uint8, device=dev)
-    total = C.c_int64(0)
-    _lib.call("fb2_spmv_colz_count", nnz, _lib.ptr(crow), _lib.ptr(col), _lib.ptr(blk_row), _lib.ptr(blk_end), nblk, _lib.ptr(uoff),
-              C.byref(total), _lib.ptr(ws), _lib.stream())
-    colz = torch.empty(lib.fb2_spmv_colz_bytes(nblk, nnz, total.value), dtype=torch.uint8, device=dev)
-    _lib.call("fb2_spmv_colz_fill", nnz, _lib.ptr(crow), _lib.ptr(col), _lib.ptr(blk_row), _lib.ptr(blk_end), nblk, _lib.ptr(uoff),
-              _lib.ptr(colz), _lib.stream())
-    return colz
-
-
 class CSRTensor:
     def __init__(self, crow: torch.Tensor, col: torch.Tensor, values, spshape=None):
         if not isinstance(crow, torch.Tensor) or not isinstance(col, torch.Tensor):
@@ -87,9 +72,9 @@ class CSRTensor:
             x = other.contiguous()
             if x.ndim == 1:
                 y = torch.empty(n, dtype=torch.float64, device=x.device)
-                blk_row, colz, tile, max_row = self.spmv_plan()
+                blk_row, tile, max_row = self.spmv_plan()
                 _lib.call("fb2_csr_spmv", n, self.nnz, _lib.ptr(self._crow), _lib.ptr(self._col), _lib.ptr(self._values),
-                          _lib.ptr(x), _lib.ptr(y), _lib.ptr(blk_row), _lib.ptr(colz), tile, max_row, _lib.stream())
+                          _lib.ptr(x), _lib.ptr(y), _lib.ptr(blk_row), tile, max_row, _lib.stream())
                 return y
             if x.ndim == 2:
                 y = torch.empty((n, x.shape[1]), dtype=torch.float64, device=x.device)
@@ -103,16 +88,14 @@ class CSRTensor:
 
     SPMV_TILE = int(__import__('os').environ.get('FB2_SPMV_TILE', '2560'))
 
-    COMPRESS_COLS = __import__('os').environ.get('FB2_SPMV_COLZ', '1') != '0'
-
     def spmv_plan(self):
-        """(blk_row, colz, tile, max_row): row-aligned nnz tiling of the streaming SpMV kernel and the compressed column
-        stream (include/fealpy_b200.h, fb2_spmv_colz_build).  It depends on the pattern only, so it is cached ON the `crow`
-        tensor: every matrix assembled on one space (shared crow / col, see BilinearForm.share_pattern) reuses it."""
+        """(blk_row, tile, max_row): row-aligned nnz tiling of the streaming SpMV kernels.  It depends on the pattern only, so
+        it is cached ON the `crow` tensor: every matrix assembled on one space (shared crow / col, see
+        BilinearForm.share_pattern) reuses it."""
         if getattr(self, "_plan", None) is None:
             cached = getattr(self._crow, "_fb2_spmv_plan", None)
-            if cached is not None and cached[0] is self._col and cached[1][2] == self.SPMV_TILE:
-                self._plan = cached[1]
+            if cached is not None and cached[1] == self.SPMV_TILE:
+                self._plan = cached
                 return self._plan
             lib = _lib.load()
             n = self._spshape[0]
@@ -120,12 +103,9 @@ class CSRTensor:
             blk_row = torch.empty(nblk + 2, dtype=torch.int32, device=self.device)
             mr = C.c_int32(0)
             _lib.call("fb2_spmv_plan_build", n, _lib.ptr(self._crow), self.SPMV_TILE, _lib.ptr(blk_row), self.nnz, C.byref(mr), _lib.stream())
-            colz = None
-            if self.COMPRESS_COLS and self.nnz > 0 and self._col.dtype == torch.int32:
-                colz = build_colz(self.nnz, self._crow, self._col, blk_row, None, nblk)
-            self._plan = (blk_row, colz, self.SPMV_TILE, mr.value)
+            self._plan = (blk_row, self.SPMV_TILE, mr.value)
             try:
-                self._crow._fb2_spmv_plan = (self._col, self._plan)
+                self._crow._fb2_spmv_plan = self._plan
             except AttributeError:
                 pass
         return self._plan

@@ -49,7 +49,8 @@ int fb2_tensor_cell_to_dof(const int32_t* cell2dof, int64_t NC, int ldof, int GD
  * [cube_layer_lo, cube_layer_hi), node planes [lo, hi]; node coordinates and cell2dof follow the
  * GLOBAL from_box numbering in closed form (no sort), expressed in the slab's window:
  * nodes -> [0, NNw), edges whose smaller node lies in the window -> NNw + (global edge id -
- * fb2_box_edges_before(nx,ny,nz,lo,0,0)).  p = 1 or 2. */
+ * fb2_box_edges_before(nx,ny,nz,lo,0,0)).  p = 1 or 2.  node / cell may be NULL (only cell2dof is wanted: the whole box,
+ * layers [0, nx), gives the global P2 numbering of a from_box mesh without building its edges). */
 int64_t fb2_box_edges_before(int nx, int ny, int nz, int i, int j, int k);
 int fb2_tet_box_slab(const double box[6], int nx, int ny, int nz, int cube_layer_lo, int cube_layer_hi, int p, double* node,
                      int32_t* cell, int32_t* cell2dof, void* stream);
@@ -180,47 +181,31 @@ size_t fb2_partial_workspace_bytes(void);           /* zero-initialise once */
  * blk_row has fb2_spmv_plan_blocks(nnz, tile) + 1 int32 entries; *max_row_host = longest row. */
 int fb2_spmv_plan_blocks(int64_t nnz, int tile);
 int fb2_spmv_plan_build(int64_t n, const int64_t* crow, int tile, int32_t* blk_row, int64_t nnz, int32_t* max_row_host, void* stream);
-/* Optional staged-x column stream of a plan (`colz`, built once per pattern).  The SpMV is bound by the L1 data pipe, not by
- * DRAM: a warp's gather x[col] touches ~12 cache lines.  The rows of one tile share most columns, so the plan stores per tile
- * the ascending list of its DISTINCT columns and per stored value a 16-bit position in that list; the kernel stages x[list] in
- * shared memory once per tile and the products read from there.  Stream per nonzero: 8 + 2 bytes (+ 4 per distinct column)
- * instead of 12.  Tiles with more than 1536 distinct columns or more than 4096 values keep gathering through the 32-bit `col`.
- * Results are bit-identical with and without it (same products, same summation order).
- *   nblk    = fb2_spmv_plan_blocks(nnz, tile) (or the tile count of a multi-range plan: blk_end != NULL gives every tile's
- *             one-past-last row, NULL means blk_row[t+1])
- *   count   : uoff (nblk+1 int64, device) = exclusive scan of the tiles' distinct-column counts; *total_distinct_host = uoff[nblk]
- *   fill    : writes colz (fb2_spmv_colz_bytes(nblk, nnz, total_distinct) bytes) = [uoff | 16-bit positions | distinct columns] */
-size_t fb2_spmv_colz_workspace_bytes(int nblk);
-size_t fb2_spmv_colz_bytes(int nblk, int64_t nnz, int64_t total_distinct);
-int fb2_spmv_colz_count(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
-                        int64_t* uoff, int64_t* total_distinct_host, void* ws, void* stream);
-int fb2_spmv_colz_fill(int64_t nnz, const int64_t* crow, const int32_t* col, const int32_t* blk_row, const int32_t* blk_end, int nblk,
-                       const int64_t* uoff, void* colz, void* stream);
-/* y = A x.  blk_row may be NULL (row-per-lane-group kernel); with a plan the streaming kernel runs; colz may be NULL. */
+/* y = A x.  blk_row may be NULL (row-per-lane-group kernel); with a plan the streaming kernel runs. */
 int fb2_csr_spmv(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                 double* y, const int32_t* blk_row, const void* colz, int tile, int32_t max_row, void* stream);
+                 double* y, const int32_t* blk_row, int tile, int32_t max_row, void* stream);
 int fb2_csr_spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* values, const double* X, double* Y, int nb,
                  void* stream);
 int fb2_dot(int64_t n, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream);
 size_t fb2_cg_workspace_bytes(int64_t n, int64_t nnz);
 /* x: x0 on entry, solution on exit.  minv_diag: NULL or the diagonal of M (z = M r).
  * maxit < 0 means "no limit" (reference maxit=None).  chunk <= 0: automatic.
- * blk_row / colz / tile / max_row: a prebuilt SpMV plan of the matrix (fb2_spmv_plan_build, fb2_spmv_colz_build); blk_row NULL:
- * the solver builds an uncompressed plan in its workspace. */
+ * blk_row / tile / max_row: a prebuilt SpMV plan of the matrix (fb2_spmv_plan_build); blk_row NULL: the solver builds one in its
+ * workspace. */
 int fb2_cg(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* b, double* x,
-           const double* minv_diag, double atol, double rtol, int maxit, int chunk, const int32_t* blk_row, const void* colz,
+           const double* minv_diag, double atol, double rtol, int maxit, int chunk, const int32_t* blk_row,
            int tile, int32_t max_row, void* ws, int* niter_host, double* residual_host, void* stream);
 /* building blocks of the distributed driver (device-resident scalars in `scalars`, 256 bytes) */
 int fb2_cg_init(void* scalars, double atol, double rtol, int maxit, double bnorm, double rTr, void* stream);
 /* own[4] = {lo0, hi0, lo1, hi1}: rows (owned dofs of this rank) that contribute to the dot
  * products; NULL = all rows.  The caller all-reduces scalars[1] (p.Ap) / scalars[2] (r.z). */
 int fb2_cg_residual(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* x,
-                    const double* b, double* r, const int32_t* blk_row, const void* colz, int tile, int32_t max_row,
+                    const double* b, double* r, const int32_t* blk_row, int tile, int32_t max_row,
                     void* stream);
 int fb2_cg_start(int64_t n, const double* r, const double* minv_diag, double* p, void* scalars, void* partial_ws,
                  const int64_t own[4], void* stream);
 int fb2_cg_spmv_dot(int64_t n, int64_t nnz, const int64_t* crow, const int32_t* col, const double* values, const double* p,
-                    double* Ap, const int32_t* blk_row, const void* colz, int tile, int32_t max_row, void* scalars,
+                    double* Ap, const int32_t* blk_row, int tile, int32_t max_row, void* scalars,
                     void* partial_ws, const int64_t own[4], void* stream);
 int fb2_cg_update_xr(int64_t n, double* x, double* r, const double* p, const double* Ap, const double* minv_diag, void* scalars,
                      void* partial_ws, int fuse_finalize, const int64_t own[4], void* stream);

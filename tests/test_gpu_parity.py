@@ -947,75 +947,6 @@ def test_elasticity_dirichlet_jacobi_cg(case, U):
     assert abs(info["niter"] - gold["info"]["niter"]) <= 2
 
 
-def _colz_tables(A):
-    """(blk_row, uoff (nblk+1), lidx (nnz) uint16, ucol) views of a plan's staged-x column stream [uoff | lidx | ucol]"""
-    from fealpy_b200 import _lib
-    blk_row, colz, tile, _ = A.spmv_plan()
-    nblk = _lib.load().fb2_spmv_plan_blocks(A.nnz, tile)
-    al = lambda b: -(-b // 256) * 256
-    raw = colz.cpu().numpy()
-    uoff = raw[:8 * (nblk + 1)].view(np.int64)
-    o1 = al(8 * (nblk + 1))
-    lidx = raw[o1:o1 + 2 * A.nnz].view(np.uint16)
-    o2 = o1 + al(2 * A.nnz)
-    ucol = raw[o2:o2 + 4 * int(uoff[-1])].view(np.int32)
-    return blk_row.cpu().numpy()[:nblk + 1], uoff, lidx, ucol
-
-
-@pytest.mark.parametrize("kind,n,p", [("tet", 10, 2), ("tri", 70, 3), ("tet", 14, 1)])
-def test_staged_columns_decode_and_spmv_bit_identical(kind, n, p, U, monkeypatch):
-    """the staged-x column stream of the SpMV plan (csrc/cg.cu xl_count_kernel / xl_fill_kernel): per tile the ascending list
-    of its distinct columns and per value a 16-bit position in it.  It decodes to `col` on every staged tile, and y = A x is
-    BIT-identical with and without it (same products, same summation order)"""
-    from fealpy_b200.mesh import TetrahedronMesh, TriangleMesh
-    from fealpy_b200.functionspace import LagrangeFESpace
-    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
-    from fealpy_b200.sparse import CSRTensor
-    mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], n, n, n) if kind == "tet" else TriangleMesh.from_box([0, 1, 0, 1], n, n)
-    bform = BilinearForm(LagrangeFESpace(mesh, p), share_pattern=False)
-    bform.add_integrator(ScalarDiffusionIntegrator(), ScalarMassIntegrator())
-    A = bform.assembly()
-    blk_row, uoff, lidx, ucol = _colz_tables(A)
-    crow, col = A.crow.cpu().numpy(), A.col.cpu().numpy()
-    nstaged = 0
-    for t in range(len(blk_row) - 1):
-        a, b = crow[blk_row[t]], crow[blk_row[t + 1]]
-        u = ucol[uoff[t]:uoff[t + 1]]
-        if len(u) == 0:
-            continue
-        nstaged += 1
-        assert np.array_equal(u, np.unique(col[a:b])), f"tile {t}: the list is not the sorted distinct columns"
-        assert np.array_equal(u[lidx[a:b]], col[a:b]), f"tile {t} does not decode"
-    assert nstaged >= 0.9 * (len(blk_row) - 1), "FEM tiles are staged"
-    x = U.t64(np.random.default_rng(3).standard_normal(A.shape[1]))
-    y_z = A @ x
-    monkeypatch.setattr(CSRTensor, "COMPRESS_COLS", False)
-    B = CSRTensor(A.crow.clone(), A.col.clone(), A.values, A.shape)
-    assert B.spmv_plan()[1] is None
-    assert torch.equal(y_z, B @ x)
-
-
-def test_staged_columns_fall_back_on_scattered_patterns(U):
-    """a tile of a random pattern has more distinct columns than the staging buffer holds (1536): it keeps the direct gather
-    through the 32-bit columns; banded rows in the same matrix are staged -- both kinds of tile in one SpMV"""
-    from fealpy_b200.sparse import CSRTensor
-    rng = np.random.default_rng(11)
-    n, m = 3000, 400000
-    rows = [np.sort(rng.choice(m, 40, replace=False)) if r < 2000 else np.arange(r, r + 40) for r in range(n)]
-    crow = np.concatenate([[0], np.cumsum([len(c) for c in rows])]).astype(np.int64)
-    col = np.concatenate(rows).astype(np.int32)
-    val = rng.standard_normal(col.size)
-    A = CSRTensor(torch.tensor(crow, device="cuda"), torch.tensor(col, device="cuda"), U.t64(val), (n, m))
-    _, uoff, _, _ = _colz_tables(A)
-    cnt = np.diff(uoff)
-    assert (cnt == 0).any() and (cnt > 0).any(), "both direct-gather and staged tiles"
-    x = rng.standard_normal(m)
-    y = (A @ U.t64(x)).cpu().numpy()
-    yref = np.zeros(n)
-    np.add.at(yref, np.repeat(np.arange(n), np.diff(crow)), val * x[col])
-    assert np.allclose(y, yref, rtol=0, atol=1e-12)
-
-
 @pytest.mark.parametrize("kind,dims,p,world", [("tet", (6, 5, 4), 2, 3), ("tet", (5, 4, 4), 1, 2), ("tri", (14, 11), 3, 5), ("tet", (4, 3, 3), 3, 2)])
 def test_morton_partition_owned_rows_bit_identical_on_gpu(kind, dims, p, world, U):
     """general-mesh partition (parallel/mesh_partition.py) on a relabelled / shuffled / jittered mesh: one GPU plays every
@@ -1033,3 +964,18 @@ def test_morton_partition_owned_rows_bit_identical_on_gpu(kind, dims, p, world, 
         assert v["owned_rows_bit_identical"], v
         owned += v["n_owned"]
     assert owned == space.number_of_global_dofs()
+
+
+@pytest.mark.parametrize("dims", [(5, 4, 3), (3, 7, 2), (1, 1, 1), (6, 6, 6)])
+def test_from_box_closed_form_numbering(dims, U, monkeypatch):
+    """P2 numbering of a from_box tetrahedral mesh in closed form (fb2_tet_box_slab over the whole box: no edge sort on the
+    assembly path) == the generic sorted-unique construction, which is pinned bit-exact against the reference's golden files"""
+    from fealpy_b200.mesh import TetrahedronMesh
+    m1 = TetrahedronMesh.from_box([0, 1, 0, 2, -1, 1], *dims)
+    c_closed = m1.cell_to_ipoint(2)
+    assert m1._edge is None, "no edge construction on the closed-form path"
+    n_closed = m1.number_of_global_ipoints(2)
+    monkeypatch.setenv("FB2_BOX_CLOSED_FORM", "0")
+    m2 = TetrahedronMesh.from_box([0, 1, 0, 2, -1, 1], *dims)
+    assert torch.equal(c_closed, m2.cell_to_ipoint(2)) and m2._edge is not None
+    assert n_closed == m2.number_of_global_ipoints(2) and m1.number_of_edges() == m2.edge.shape[0]

@@ -26,13 +26,7 @@ for k in range(6):
     torch.cuda.synchronize()
     ts.append(s0.elapsed_time(s1) / max(info["niter"], 1))
 ts = ts[1:]
-plan = A_sys.spmv_plan()
-ncomp = "-"
-if plan[1] is not None:
-    nblk = (A_sys.nnz + plan[2] - 1) // plan[2]
-    uoff = plan[1][:8 * (nblk + 1)].view(torch.int64)
-    ncomp = f"{float(((uoff[1:] - uoff[:-1]) > 0).float().mean()):.4f} distinct/nnz {float(uoff[-1]) / A_sys.nnz:.3f}"
 gdof = A_sys.shape[0]
 bytes_it = 12 * A_sys.nnz + 8 * (gdof + 1) + 104 * gdof
-print(f"cfg {cfg} n {n} colz {os.environ.get('FB2_SPMV_COLZ', '1')} tiles staged {ncomp}: {min(ts):.4f} ms/it (med {statistics.median(ts):.4f}), "
+print(f"cfg {cfg} n {n} kernel {os.environ.get('FB2_SPMV_KERNEL', 'tma')}: {min(ts):.4f} ms/it (med {statistics.median(ts):.4f}), "
       f"{1e3 / min(ts):.1f} it/s, algorithmic {bytes_it / min(ts) / 1e6:.0f} GB/s, x checksum {float(x.sum()):.12e}", flush=True)
