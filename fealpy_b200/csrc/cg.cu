@@ -122,15 +122,17 @@ __global__ void __launch_bounds__(CG_THREADS) spmm_kernel(int64_t n, const int64
 //   * 16-bit window-relative column stream (10 instead of 12 bytes per nonzero): 1.61 vs 1.66 ms per CG iteration (-3 %);
 //   * per-tile list of distinct columns, x staged in shared memory, 16-bit positions: 2.37 ms (a third dependent phase);
 //   * (val, col) tiles fetched by cp.async.bulk + mbarrier into a double buffer, products in place: 1.95 - 3.4 ms
-//     depending on threads / tile (fewer gathers in flight than 8 resident CTAs x 256 threads of this kernel).
+//     depending on threads / tile (fewer gathers in flight than 8 resident CTAs x 256 threads of this kernel);
+//   * SM-chunked tile map (co-resident CTAs sweep adjacent tiles, for L1 reuse of x): 1.73 vs 1.67 ms.
 constexpr int ST_UNROLL = 4;
 #ifndef FB2_ST_THREADS
 #define FB2_ST_THREADS 256
 #endif
 constexpr int ST_THREADS = FB2_ST_THREADS;     // threads per CTA of the streaming SpMV kernel
 
+// (2048 / ST_THREADS resident CTAs: the kernel lives on occupancy -- at 40 registers (6 CTAs) it ran 2.17 instead of 1.65 ms)
 template <int G>
-__global__ void __launch_bounds__(ST_THREADS) spmv_stream_kernel(int64_t n, const int64_t* __restrict__ crow,
+__global__ void __launch_bounds__(ST_THREADS, 2048 / ST_THREADS) spmv_stream_kernel(int64_t n, const int64_t* __restrict__ crow,
                                                                  const int32_t* __restrict__ col, const double* __restrict__ val,
                                                                  const double* __restrict__ x, double* __restrict__ y,
                                                                  const double* __restrict__ b, int mode,

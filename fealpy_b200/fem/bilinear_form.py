@@ -91,8 +91,13 @@ def symbolic_pattern(space):
     crow = torch.empty(gdof + 1, dtype=torch.int64, device=dev)
     ws = _lib.workspace(lib.fb2_sym_workspace_bytes(NC, L, gdof), dev)
     nnz, max_row = C.c_int64(0), C.c_int32(0)
-    try:        # scratch for the candidates' ranks (2 bytes per (cell, i, j)): the fill pass then need not rank them again
-        stash = None if _os.environ.get("FB2_SYM_NO_STASH") else torch.empty(NC * L * L, dtype=torch.int16, device=dev)
+    try:        # scratch for the candidates' ranks (2 bytes per (cell, i, j)): the fill pass then need not rank them again.
+        # Sized so that asm4_plan() can take it over as its schedule buffer (~21 bytes per (cell, i)): a multi-GB cudaMalloc
+        # costs ~1.6 ms per GB on a fresh process, which is most of what a cold assembly pays on top of its kernels
+        nwords = lib.fb2_slot_stride(L, 1) // 4
+        est_blocks = int(NC * L / 32 / 0.80 + 1024) * (64 + 32 * nwords + 4) * 4
+        stash_bytes = max(2 * NC * L * L, est_blocks if L <= 20 else 0)
+        stash = None if _os.environ.get("FB2_SYM_NO_STASH") else torch.empty(stash_bytes, dtype=torch.uint8, device=dev)
     except torch.cuda.OutOfMemoryError:
         stash = None
     _lib.call("fb2_sym_count", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow),
@@ -103,10 +108,10 @@ def symbolic_pattern(space):
     slots = torch.zeros(NC * L * stride, dtype=torch.uint8 if slot_bytes == 1 else torch.int16, device=dev)
     _lib.call("fb2_sym_fill", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow), _lib.ptr(col),
               _lib.ptr(slots), slot_bytes, _lib.ptr(stash), _lib.stream())
-    del stash
     blk_row, nblk = row_tiling(crow, gdof, nnz.value, ASM_TILE)
     cache = dict(adj_ptr=adj_ptr, adj_pair=adj_pair, crow=crow, col=col, slots=slots, slot_bytes=slot_bytes,
-                 max_row=max_row.value, nnz=nnz.value, NC=NC, L=L, gdof=gdof, blk_row=blk_row, nblk=nblk, tile=ASM_TILE)
+                 max_row=max_row.value, nnz=nnz.value, NC=NC, L=L, gdof=gdof, blk_row=blk_row, nblk=nblk, tile=ASM_TILE,
+                 scratch=stash)          # handed to asm4_plan(), dropped by the first kernel that does not want it
     space._b200_symbolic = cache
     return cache
 
@@ -146,7 +151,12 @@ def asm4_plan(space):
     batch_i = torch.empty(nb, dtype=torch.uint8, device=dev)
     # one packed block per batch (include/fealpy_b200.h): the numeric kernel fetches it with a single bulk copy
     bw = 64 + 32 * nwords + 4
-    blocks = torch.zeros((nb, bw), dtype=torch.int32, device=dev)
+    scratch = sym.pop("scratch", None)
+    if scratch is not None and scratch.numel() >= nb * bw * 4:
+        blocks = scratch[:nb * bw * 4].view(torch.int32).view(nb, bw).zero_()      # the symbolic phase's rank scratch, recycled
+    else:
+        blocks = torch.zeros((nb, bw), dtype=torch.int32, device=dev)
+    del scratch
     _lib.call("fb2_asm4_plan_fill", ntile, _lib.ptr(blk_row), _lib.ptr(sym["crow"]), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
               sym["L"], _lib.ptr(batch_ptr), _lib.ptr(batch_i), _lib.ptr(blocks), _lib.ptr(sym["slots"]), sym["slot_bytes"], _lib.stream())
     sym["asm4"] = dict(blk_row=blk_row, ntile=ntile, tile=ASM4_TILE, batch_ptr=batch_ptr, batch_i=batch_i, blocks=blocks,
@@ -453,6 +463,9 @@ class BilinearForm:
         else:
             crow, col, values = self._assemble_gather(out)
             self.last_path = "gather"
+        if self.last_path != "coo":          # the symbolic phase's rank scratch: only the v4 schedule recycles it
+            sp = self.space.scalar_space if self._is_tensor_space() else self.space
+            getattr(sp, "_b200_symbolic", {}).pop("scratch", None)
         if not self.share_pattern and self.last_path != "coo":
             crow, col = crow.clone(), col.clone()
         M = CSRTensor(crow, col, values, self.shape)
