@@ -329,19 +329,11 @@ int sym_count(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr,
               int* max_row_host, uint16_t* stash, void* ws, cudaStream_t s) {
   const int64_t npair = NC * L;
   if (npair >= ((int64_t)1 << 31)) return fail(ERR_UNSUPPORTED, "sym_count: NC*ldof=%lld exceeds int32 pair ids", (long long)npair);
-  Carver c(ws);
+  FB2_TRY(build_adjacency(c2d, NC, L, gdof, adj_ptr, adj_pair, ws, s));
+  Carver c(ws);                         // same carving as build_adjacency
   int* deg = c.take<int>(gdof);         // reused as rowlen
   int* cursor = c.take<int>(gdof);      // cursor[0..1] reused as flags at the end
   void* scan_ws = c.take<char>(scan_workspace_bytes(gdof + 1));
-  FB2_CUDA(cudaMemsetAsync(deg, 0, (size_t)gdof * 4, s));
-  FB2_CUDA(cudaMemsetAsync(cursor, 0, (size_t)gdof * 4, s));
-  if (npair > 0) deg_kernel<<<grid_for(npair), 256, 0, s>>>(c2d, npair, deg);
-  FB2_TRY(exclusive_scan_i32(deg, adj_ptr, gdof, true, scan_ws, s));
-  if (npair > 0) {
-    adj_fill_kernel<<<grid_for(npair), 256, 0, s>>>(c2d, npair, adj_ptr, cursor, adj_pair);
-    adj_sort_kernel<<<grid_for(gdof), 256, 0, s>>>(gdof, L, adj_ptr, adj_pair);
-  }
-  FB2_LAUNCH_CHECK();
   FB2_CUDA(cudaMemsetAsync(cursor, 0, 8, s));
   int* rowlen = deg;
   const unsigned nb = (unsigned)std::min<int64_t>(ceil_div(gdof, SYM_WARPS), (int64_t)kNumSM * 16);
@@ -1163,6 +1155,108 @@ __global__ void __launch_bounds__(256) cell_geometry4_kernel(const double* __res
   const int64_t ncell = (NC - c0) < 256 ? (NC - c0) : 256;
   double* dst = H + c0 * HS;
   for (int64_t t = threadIdx.x; t < ncell * HS; t += 256) dst[t] = stage[t];       // contiguous, fully coalesced
+}
+
+// ---- matrix-free product of the same forms: v = A u without A and without K_e (fem/bilinear_form.py:126-158) ----------
+// The reference forms gv = einsum('cij,cj->ci', K_e, u[cell2dof]) and index_adds it into v.  Here one thread owns one
+// cell: geometry -> reduced record h (registers), u gathered through cell2dof, and
+//     w_i = sum_t h_t * (sum_j T[i][j][t] u_j)
+// with the folded table T in the kernel parameter block (warp-uniform operands, L*L*NH + L*NH DFMAs per cell, no
+// element matrix anywhere).  The (NC, L) block w goes to HBM once (8*L bytes per cell instead of 8*L*L for K_e) and the
+// row-owner gather of gather_vector() sums it per dof in the fixed (i, cell) order: no atomics, bit-reproducible.
+template <int TD, int L>
+__global__ void __launch_bounds__(128) matfree_cell_kernel(const double* __restrict__ node, const int* __restrict__ cell,
+                                                           const int* __restrict__ c2d, int64_t NC, double scal_d,
+                                                           const double* __restrict__ coef_d, double scal_m,
+                                                           const double* __restrict__ coef_m, const double* __restrict__ u,
+                                                           double* __restrict__ w,
+                                                           const __grid_constant__ A4Tables<L, A4Geo<TD>::NH> tb) {
+  using GEO = A4Geo<TD>;
+  constexpr int NV = TD + 1, NG = GEO::NG, NR = GEO::NR, NH = GEO::NH;
+  __shared__ double stage[128 * L];
+  const int64_t c0 = (int64_t)blockIdx.x * 128;
+  const int64_t c = c0 + threadIdx.x;
+  if (c < NC) {
+    int v[NV];
+    double x[NV][TD], cm, G[NG], h[NH], ul[L];
+    load_verts<TD>(cell, c, v);
+    const int* dofs = c2d + c * L;
+#pragma unroll
+    for (int j = 0; j < L; ++j) ul[j] = u[dofs[j]];
+    load_coords<TD>(node, v, x);
+    geo_from_coords(x, cm, G);
+    const double kd = scal_d * (coef_d ? coef_d[c] : 1.0);
+    int t = 0;
+#pragma unroll
+    for (int m = 1; m <= TD; ++m)
+#pragma unroll
+      for (int n = m; n <= TD; ++n) h[t++] = kd * G[GEO::full(m, n)];
+    h[NR] = scal_m * (coef_m ? coef_m[c] : 1.0) * cm;
+    double* out = stage + threadIdx.x * L;
+#pragma unroll(L <= 10 ? L : 1)
+    for (int i = 0; i < L; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int tt = 0; tt < NH; ++tt) {
+        double z = 0.0;
+#pragma unroll
+        for (int j = 0; j < L; ++j) z = fma(tb.T[i][j][tt], ul[j], z);
+        acc = fma(h[tt], z, acc);
+      }
+      out[i] = acc;
+    }
+  }
+  __syncthreads();
+  const int64_t ncell = (NC - c0) < 128 ? (NC - c0) : 128;
+  double* dst = w + c0 * L;
+  for (int64_t t = threadIdx.x; t < ncell * L; t += 128) dst[t] = stage[t];       // contiguous, fully coalesced
+}
+
+template <int TD, int L>
+static int launch_matfree(const MatfreeArgs& a, cudaStream_t s) {
+  using GEO = A4Geo<TD>;
+  A4Tables<L, GEO::NH> tb;
+  a4_reduced_table<TD, L>(a.Ms_host, a.Mm_host, tb);
+  matfree_cell_kernel<TD, L><<<(unsigned)ceil_div(a.NC, 128), 128, 0, s>>>(a.node, a.cell, a.c2d, a.NC, a.Ms_host ? a.scal_d : 0.0, a.coef_d,
+                                                                           a.Mm_host ? a.scal_m : 0.0, a.coef_m, a.u, a.w, tb);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int matfree_scalar_const(int TD, int p, const MatfreeArgs& a, cudaStream_t s) {
+  if (a.NC <= 0) return OK;
+  switch (TD * 10 + p) {
+    case 21: return launch_matfree<2, 3>(a, s);
+    case 22: return launch_matfree<2, 6>(a, s);
+    case 23: return launch_matfree<2, 10>(a, s);
+    case 31: return launch_matfree<3, 4>(a, s);
+    case 32: return launch_matfree<3, 10>(a, s);
+    case 33: return launch_matfree<3, 20>(a, s);
+    default: return fail(ERR_UNSUPPORTED, "matfree: unsupported element TD=%d p=%d", TD, p);
+  }
+}
+
+// dof -> (cell, local index) adjacency alone (the first half of sym_count): what a matrix-free product or a load
+// vector needs of the symbolic phase
+size_t adjacency_workspace_bytes(int64_t gdof) { return align_up((size_t)gdof * 4) * 2 + scan_workspace_bytes(gdof + 1) + 1024; }
+
+int build_adjacency(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, void* ws, cudaStream_t s) {
+  const int64_t npair = NC * L;
+  if (npair >= ((int64_t)1 << 31)) return fail(ERR_UNSUPPORTED, "adjacency: NC*ldof=%lld exceeds int32 pair ids", (long long)npair);
+  Carver c(ws);
+  int* deg = c.take<int>(gdof);
+  int* cursor = c.take<int>(gdof);
+  void* scan_ws = c.take<char>(scan_workspace_bytes(gdof + 1));
+  FB2_CUDA(cudaMemsetAsync(deg, 0, (size_t)gdof * 4, s));
+  FB2_CUDA(cudaMemsetAsync(cursor, 0, (size_t)gdof * 4, s));
+  if (npair > 0) deg_kernel<<<grid_for(npair), 256, 0, s>>>(c2d, npair, deg);
+  FB2_TRY(exclusive_scan_i32(deg, adj_ptr, gdof, true, scan_ws, s));
+  if (npair > 0) {
+    adj_fill_kernel<<<grid_for(npair), 256, 0, s>>>(c2d, npair, adj_ptr, cursor, adj_pair);
+    adj_sort_kernel<<<grid_for(gdof), 256, 0, s>>>(gdof, L, adj_ptr, adj_pair);
+  }
+  FB2_LAUNCH_CHECK();
+  return OK;
 }
 
 size_t asm4_workspace_bytes(int ntile) { return align_up((size_t)(ntile + 1) * 4) + scan_workspace_bytes(ntile + 1) + 1024; }

@@ -65,6 +65,22 @@ struct Asm4Args {
   const double* H;
   double* values;
 };
+struct MatfreeArgs {
+  const double* node;
+  const int* cell;
+  const int* c2d;
+  int64_t NC;
+  const double* Ms_host;        // host tables (null = term absent); folded into the kernel parameter block
+  const double* Mm_host;
+  double scal_d, scal_m;
+  const double* coef_d;         // per-cell or null
+  const double* coef_m;
+  const double* u;              // (gdof)
+  double* w;                    // (NC, L) per-cell products K_e u_e
+};
+int matfree_scalar_const(int TD, int p, const MatfreeArgs& a, cudaStream_t s);
+size_t adjacency_workspace_bytes(int64_t gdof);
+int build_adjacency(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, void* ws, cudaStream_t s);
 size_t asm4_workspace_bytes(int ntile);
 int asm4_plan_count(int ntile, const int32_t* blk_row, const int64_t* crow, const int64_t* adj_ptr, const int* adj_pair, int L,
                     int64_t* batch_ptr, int64_t* nbatch_host, void* ws, cudaStream_t s);

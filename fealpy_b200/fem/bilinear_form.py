@@ -116,6 +116,27 @@ def symbolic_pattern(space):
     return cache
 
 
+def adjacency(space):
+    """dof -> (cell, local index) adjacency of a scalar space (cached): the part of the symbolic phase a matrix-free
+    product needs; the full pattern's copy is used when it already exists"""
+    sym = getattr(space, "_b200_symbolic", None)
+    if sym is not None:
+        return sym
+    adj = getattr(space, "_b200_adjacency", None)
+    if adj is not None:
+        return adj
+    lib = _lib.load()
+    c2d = space.cell_to_dof().contiguous()
+    NC, L = c2d.shape
+    gdof = space.number_of_global_dofs()
+    adj_ptr = torch.empty(gdof + 1, dtype=torch.int64, device=c2d.device)
+    adj_pair = torch.empty(NC * L, dtype=torch.int32, device=c2d.device)
+    ws = _lib.workspace(lib.fb2_adjacency_workspace_bytes(gdof), c2d.device)
+    _lib.call("fb2_adjacency", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(ws), _lib.stream())
+    adj = space._b200_adjacency = dict(adj_ptr=adj_ptr, adj_pair=adj_pair, NC=NC, L=L, gdof=gdof)
+    return adj
+
+
 import os as _os
 ASM_TILE = int(_os.environ.get("FB2_ASM_TILE", "4096"))      # CSR values per CTA of the numeric assembly kernels
 
@@ -288,6 +309,19 @@ class BilinearForm:
                 m["scal"] = 0.0
         return merged
 
+    @staticmethod
+    def _plan_parts(m):
+        """(scalar factor, per-cell coefficient or None) of one merged term of _plan_fused()"""
+        if m is None:
+            return 0.0, None
+        return (1.0, m["arr"].contiguous()) if m["arr"] is not None else (m["scal"], None)
+
+    def _host_table(self, m, key):
+        if m is None:
+            return None
+        h = host_tables(self.space.mesh.TD, self.space.p, m["q"])[key]
+        return h.ctypes.data_as(C.c_void_p)
+
     def _values_buffer(self, nnz, device, out):
         if out is None:
             return torch.empty(nnz, dtype=torch.float64, device=device)
@@ -301,20 +335,9 @@ class BilinearForm:
         sym = symbolic_pattern(space)
         values = self._values_buffer(sym["nnz"], mesh.device, out)
         dm, mm = plan.get("diffusion"), plan.get("mass")
-
-        def parts(m):
-            if m is None:
-                return 0.0, None
-            return (1.0, m["arr"].contiguous()) if m["arr"] is not None else (m["scal"], None)
-        sd, ad = parts(dm)
-        sm_, am = parts(mm)
-        NV = mesh.TD + 1
-
-        def hostp(m, key):
-            if m is None:
-                return None
-            h = host_tables(mesh.TD, space.p, m["q"])[key]
-            return h.ctypes.data_as(C.c_void_p)
+        sd, ad = self._plan_parts(dm)
+        sm_, am = self._plan_parts(mm)
+        hostp = self._host_table
         kernel = _os.environ.get("FB2_ASM_KERNEL", "auto")
         if kernel == "auto":
             kernel = "v4"
@@ -482,11 +505,28 @@ class BilinearForm:
             raise NotImplementedError("matrix-free products on tensor spaces are not on the accelerated path; call assembly()")
         if not isinstance(u, torch.Tensor) or u.ndim != 1 or u.dtype != torch.float64:
             raise NotImplementedError("matrix-free products take a 1-D float64 CUDA tensor")
-        sym = symbolic_pattern(self.space)
+        sym = adjacency(self.space)
         if u.shape[0] != sym["gdof"]:
             raise ValueError("shape mismatch")
-        ke = self._summed_ke()
         v = torch.empty_like(u)
+        plan = self._plan_fused() if self.assembly_path in ("auto", "fused") else None
+        if plan is not None:
+            # constant / per-cell coefficients: neither A nor K_e is formed (csrc/assemble.cu matfree_cell_kernel)
+            space, mesh = self.space, self.space.mesh
+            dm, mm = plan.get("diffusion"), plan.get("mass")
+            sd, ad = self._plan_parts(dm)
+            sm_, am = self._plan_parts(mm)
+            ws = getattr(self, "_matfree_ws", None)       # (NC, l) per-cell products, kept with the form
+            if ws is None or ws.shape != (sym["NC"], sym["L"]) or ws.device != u.device:
+                ws = self._matfree_ws = torch.empty((sym["NC"], sym["L"]), dtype=torch.float64, device=u.device)
+            _lib.call("fb2_matfree_scalar_const", mesh.TD, space.p, sym["NC"], sym["gdof"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
+                      _lib.ptr(space.cell_to_dof().contiguous()), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
+                      self._host_table(dm, "Ms"), self._host_table(mm, "Mm"), sd, _lib.ptr(ad), sm_, _lib.ptr(am),
+                      _lib.ptr(u.contiguous()), _lib.ptr(ws), _lib.ptr(v), _lib.stream())
+            self.last_matfree = "fused"
+            return v
+        ke = self._summed_ke()
+        self.last_matfree = "ke"
         _lib.call("fb2_matfree_apply", sym["gdof"], sym["L"], _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
                   _lib.ptr(self.space.cell_to_dof().contiguous()), _lib.ptr(ke), _lib.ptr(u.contiguous()), _lib.ptr(v), _lib.stream())
         return v

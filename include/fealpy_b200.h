@@ -265,6 +265,20 @@ int fb2_gather_vector(int64_t gdof, const int64_t* adj_ptr, const int32_t* adj_p
  * fem/bilinear_form.py:126-158): row-owner gather over the adjacency of fb2_sym_count, no atomics */
 int fb2_matfree_apply(int64_t gdof, int ldof, const int64_t* adj_ptr, const int32_t* adj_pair, const int32_t* cell2dof,
                       const double* Ke, const double* u, double* v, void* stream);
+/* dof -> (cell, local index) adjacency alone (first half of fb2_sym_count): all a matrix-free product or a load vector
+ * needs of the symbolic phase.  ws: fb2_adjacency_workspace_bytes(gdof) */
+size_t fb2_adjacency_workspace_bytes(int64_t gdof);
+int fb2_adjacency(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, int64_t* adj_ptr, int32_t* adj_pair, void* ws,
+                  void* stream);
+/* fused matrix-free v = A u for scalar diffusion + mass forms with constant / per-cell coefficients (the forms
+ * fb2_assemble_scalar_const_v4 assembles): neither A nor K_e is formed.  One thread per cell recomputes the geometry,
+ * gathers u through cell2dof and writes w_c = K_c u_c (NC, ldof) to `cell_ws`; the row-owner gather over the adjacency
+ * sums it per dof in fixed order (no atomics).  Replaces einsum('cij,cj->ci') + index_add of fem/bilinear_form.py:126-158.
+ * Ms_host / Mm_host: host tables as for fb2_assemble_scalar_const_v4 (null = term absent). */
+int fb2_matfree_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,
+                             const int32_t* cell2dof, const int64_t* adj_ptr, const int32_t* adj_pair, const double* Ms_host,
+                             const double* Mm_host, double scal_d, const double* coef_d_cell, double scal_m,
+                             const double* coef_m_cell, const double* u, double* cell_ws, double* v, void* stream);
 size_t fb2_bc_workspace_bytes(int64_t n);
 /* canonical CSR of the constrained matrix: boundary rows/columns removed, unit diagonal on boundary rows */
 int fb2_bc_matrix_count(int64_t n, const int64_t* crow, const int32_t* col, const uint8_t* isbd, int64_t* crow_new,

@@ -471,6 +471,16 @@ def assemble(groups, gdof):
     return tocsr(r, c, v, gdof)
 
 
+def matfree_apply(groups, gdof, u):
+    """BilinearForm.__matmul__ before assembly (fem/bilinear_form.py:126-158): per group
+    gv = einsum('cij,cj->ci', K_e, u[cell2dof]) index_added into v (np.add.at = (cell, i) order)."""
+    v = np.zeros(gdof)
+    for ke, c2d in groups:
+        gv = np.einsum("cij,cj->ci", ke, u[c2d])
+        np.add.at(v, c2d.reshape(-1), gv.reshape(-1))
+    return v
+
+
 # --------------------------------------------------------------------------------------
 # SpMV + CG  (backend/numpy_backend.py:180-199 -> scipy csr_matvec; solver/cg.py:14-123)
 # --------------------------------------------------------------------------------------

@@ -194,6 +194,85 @@ def test_reference_bilinear_form_matmul(k, p, U):
     assert float(((bform @ x) - z).norm()) == 0.0
 
 
+@pytest.mark.parametrize("mesh_kind,p,n", [("tri", 1, 9), ("tri", 2, 7), ("tri", 3, 6), ("tet", 1, 5), ("tet", 2, 4), ("tet", 3, 3)])
+def test_fused_matfree_matches_oracle(mesh_kind, p, n, U):
+    """row f4 without K_e: `form @ u` before assembly on constant / per-cell coefficient forms runs the fused
+    cell kernel + row-owner gather (csrc/assemble.cu matfree_cell_kernel); compared with the oracle's restatement of
+    fem/bilinear_form.py:126-158 (einsum + index_add on the oracle's element matrices), with the K_e-based product and
+    with the assembled product.  Jittered geometry, per-cell diffusion coefficient, scalar mass coefficient."""
+    from oracle import fem_oracle as O
+    from fealpy_b200.mesh import TriangleMesh, TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    rng = np.random.default_rng(1234 + 10 * p + n)
+    if mesh_kind == "tri":
+        node, cell = O.tri_from_box([0, 1, 0, 2], n, n + 1)
+    else:
+        node, cell = O.tet_from_box([0, 1, 0, 2, -1, 0], n, n + 1, n)
+    node = node + rng.uniform(-0.2, 0.2, node.shape) / (n + 1)
+    om = O.Mesh(node, cell)
+    NC = cell.shape[0]
+    kappa = rng.uniform(0.5, 2.0, NC)
+    c2d = om.cell_to_ipoint(p)
+    gdof = int(c2d.max()) + 1
+    groups = [(O.diffusion_element(om, p, coef=kappa), c2d), (O.mass_element(om, p, coef=2.5), c2d)]
+    u = rng.standard_normal(gdof)
+    v_ref = O.matfree_apply(groups, gdof, u)
+
+    cls = TriangleMesh if mesh_kind == "tri" else TetrahedronMesh
+    mesh = cls(U.t64(node), U.t64(cell.astype(np.int32)))
+    space = LagrangeFESpace(mesh, p)
+    assert np.array_equal(space.cell_to_dof().cpu().numpy(), c2d)
+
+    def form(path):
+        bf = BilinearForm(space, assembly_path=path)
+        bf.add_integrator(ScalarDiffusionIntegrator(coef=U.t64(kappa)))
+        bf.add_integrator(ScalarMassIntegrator(coef=2.5))
+        return bf
+    ud = U.t64(u)
+    f1 = form("auto")
+    v1 = f1 @ ud
+    assert f1.last_matfree == "fused" and f1._M is None and not hasattr(space, "_b200_symbolic")
+    f2 = form("gather")
+    v2 = f2 @ ud
+    assert f2.last_matfree == "ke"
+    v3 = form("auto").assembly() @ ud
+    scale = np.abs(v_ref).max()
+    for v in (v1, v2, v3):
+        assert np.abs(v.cpu().numpy() - v_ref).max() <= 1e-12 * scale
+    assert torch.equal(v1, f1 @ ud), "bit-reproducible (fixed summation order, no atomics)"
+    # only a mass term / only a diffusion term
+    for ints, grp in (([ScalarMassIntegrator(coef=U.t64(kappa))], [(O.mass_element(om, p, coef=kappa), c2d)]),
+                      ([ScalarDiffusionIntegrator(coef=3.0)], [(O.diffusion_element(om, p, coef=3.0), c2d)])):
+        bf = BilinearForm(space)
+        bf.add_integrator(*ints)
+        w = (bf @ ud).cpu().numpy()
+        w_ref = O.matfree_apply(grp, gdof, u)
+        assert bf.last_matfree == "fused" and np.abs(w - w_ref).max() <= 1e-12 * np.abs(w_ref).max()
+
+
+def test_fused_matfree_at_size_and_in_cg(U):
+    """tet P2 40^3: the fused matrix-free product equals the assembled SpMV to rounding, and cg() on the unassembled form
+    (operator-valued A, solver/cg.py:10-14) reaches the assembled solve's solution"""
+    from fealpy_b200.mesh import TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator
+    from fealpy_b200.solver import cg
+    mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], 40, 40, 40)
+    space = LagrangeFESpace(mesh, 2)
+    form = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).add_integrator(ScalarMassIntegrator())
+    g = torch.Generator(device="cuda").manual_seed(7)
+    u = torch.rand(space.number_of_global_dofs(), dtype=torch.float64, device="cuda", generator=g)
+    w = form @ u
+    assert form.last_matfree == "fused" and form._M is None
+    xs = cg(form, w, atol=1e-14, rtol=1e-12, maxit=2000)        # matrix-free solve: A x = A u
+    form2 = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).add_integrator(ScalarMassIntegrator())
+    A = form2.assembly()
+    z = A @ u
+    assert float((w - z).abs().max()) <= 1e-13 * float(z.abs().max())
+    assert float((xs - u).norm() / u.norm()) <= 1e-9
+
+
 @pytest.mark.parametrize("mesh_kind,p,n", [("tri", 1, 96), ("tri", 3, 40), ("tet", 1, 20), ("tet", 2, 14), ("tet", 3, 6)])
 def test_paths_agree_and_properties_at_size(mesh_kind, p, n, U):
     """sizes beyond the golden ladder: the three device paths must give the same pattern

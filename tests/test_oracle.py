@@ -110,8 +110,7 @@ def test_ref_bilinear_form_matmul(k, p):
     c2d = m.cell_to_ipoint(p)
     gdof = m.number_of_global_ipoints(p)
     x = np.random.default_rng(p).random(gdof)
-    y = np.zeros(gdof)
-    np.add.at(y, c2d.ravel(), np.einsum("cij,cj->ci", Ke, x[c2d]).ravel())
+    y = O.matfree_apply([(Ke, c2d)], gdof, x)
     crow, col, val = O.assemble([(Ke, c2d)], gdof)
     assert np.linalg.norm(y - O.csr_matvec(crow, col, val, x)) < 1e-12
 
