@@ -123,7 +123,16 @@ __global__ void __launch_bounds__(CG_THREADS) spmm_kernel(int64_t n, const int64
 //   * per-tile list of distinct columns, x staged in shared memory, 16-bit positions: 2.37 ms (a third dependent phase);
 //   * (val, col) tiles fetched by cp.async.bulk + mbarrier into a double buffer, products in place: 1.95 - 3.4 ms
 //     depending on threads / tile (fewer gathers in flight than 8 resident CTAs x 256 threads of this kernel);
-//   * SM-chunked tile map (co-resident CTAs sweep adjacent tiles, for L1 reuse of x): 1.73 vs 1.67 ms.
+//   * SM-chunked tile map (co-resident CTAs sweep adjacent tiles, for L1 reuse of x): 1.73 vs 1.67 ms;
+//   * the per-tile chain of dependent loads (blk_row -> crow[r0] -> stream -> gather -> barrier -> crow[r] -> x[r]) cut to
+//     stream -> gather by issuing the other loads one phase early: with plain loads 1.616 vs 1.612 ms (no change: eight
+//     resident CTAs already hide the chain), with 4/8-byte cp.async into shared memory 2.56 ms (small LDGSTS that miss to
+//     DRAM park in the LSU queue: mio_throttle 15.8 per issue);
+//   * bound experiment (tools/gpu_spmv_bound.py, SpMV alone): real columns 1.356 ms, a row's columns consecutive 1.249 ms,
+//     every column = 0 (free gather) 1.163 ms, dofs renumbered along a Morton curve 1.380 / 1.432 ms -- the gather costs
+//     14 % of the kernel, no DOF reordering can recover more than that, and the Z-curve is worse than the lexicographic
+//     numbering of from_box.  The remaining gap to a plain copy (0.92 ms for the same bytes) is the stream -> shared memory
+//     -> row-sum structure itself.
 constexpr int ST_UNROLL = 4;
 #ifndef FB2_ST_THREADS
 #define FB2_ST_THREADS 256

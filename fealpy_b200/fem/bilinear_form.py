@@ -465,6 +465,18 @@ class BilinearForm:
             raise ValueError(f"Unsupported format {format}.")
         if not self.integrators:
             raise ValueError("no integrators added")
+        flat = self._flat_integrators()
+        for it in flat:                      # classification (incl. the evaluation of callable coefficients) happens once
+            if hasattr(it, "describe"):      # per assembly(), whichever path ends up using it
+                it._describe_memo = (None, None)
+        try:
+            return self._assembly_impl(format, out)
+        finally:
+            for it in flat:
+                if hasattr(it, "describe"):
+                    it._describe_memo = None
+
+    def _assembly_impl(self, format, out):
         path = self.assembly_path
         plan = None
         if path in ("auto", "fused"):

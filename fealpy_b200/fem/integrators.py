@@ -104,6 +104,15 @@ class _ScalarCellIntegrator(Integrator):
 
     def describe(self, space):
         """classification used by BilinearForm's fused path"""
+        memo = getattr(self, "_describe_memo", None)      # set by BilinearForm.assembly() for the duration of one call:
+        if memo is not None and memo[0] is space:         # a callable coefficient is evaluated once per assembly
+            return memo[1]
+        d = self._describe(space)
+        if memo is not None:
+            self._describe_memo = (space, d)
+        return d
+
+    def _describe(self, space):
         mesh = _check_space(space)
         q = self._q(space)
         tabs = device_tables(mesh.TD, space.p, q, mesh.device)
