@@ -667,14 +667,15 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         tot = torch.tensor([nnz, NC, part.n_owned], dtype=torch.int64, device=dev)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        nnz_glob, NC_glob, gdof_glob = (int(v) for v in tot)
+        nnz_glob, NC_ghosted, gdof_glob = (int(v) for v in tot)      # every rank also assembles one ghost layer of cells
+        NC_glob = 6 * (n * world if cfg_id == 2 else n) * n * n       # cells of the one box the ranks share
         if e2e is not None:
             ev_ = torch.tensor([nnz * 1.0 / e2e["value"], 1.0 / e2e["cg_iters_per_s"]], dtype=torch.float64, device=dev)
             dist.all_reduce(ev_, op=dist.ReduceOp.MAX)
             e2e["value"] = nnz_glob / float(ev_[0])
             e2e["cg_iters_per_s"] = 1.0 / float(ev_[1])
     else:
-        nnz_glob, NC_glob, gdof_glob = nnz, NC, gdof
+        nnz_glob, NC_glob, gdof_glob, NC_ghosted = nnz, NC, gdof, NC
     t_asm, t_cg, t_wall = (float(v) for v in times)
 
     if rank == 0:
@@ -698,7 +699,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * (t_asm + t_cg) / args.steps, "higher_is_better": True,
             "scaling": "weak" if cfg_id != 5 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(cfg_id, n, args.cg_iters, world),
-            "problem": {"NC": NC_glob, "gdof": gdof_glob, "nnz": nnz_glob, "assembly_path": path,
+            "problem": {"NC": NC_glob, "NC_assembled_incl_ghost_layers": NC_ghosted, "gdof": gdof_glob, "nnz": nnz_glob, "assembly_path": path,
                         "pattern": "warm (symbolic pattern cached per space, shared by the returned matrices: share_pattern=True)"},
             "cg": {"iters_per_s": iters / t_cg, "iters_per_step": args.cg_iters, "ms_per_iter": 1e3 * t_cg / iters,
                    "preconditioner": "jacobi" if M is not None else None, "converged_solve": conv,
