@@ -35,6 +35,8 @@ SIGNATURES = {
     "fb2_tensor_cell_to_dof": (_i32, [_p, _i64, _i32, _i32, _i64, _i32, _p, _p]),
     "fb2_elem_scalar_const": (_i32, [_i32, _i32, _i64, _p, _p, _p, _p, _f64, _p, _f64, _p, _p, _p]),
     "fb2_elem_scalar_quad": (_i32, [_i32, _i32, _i64, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _p]),
+    "fb2_elem_scalar_const_acc": (_i32, [_i32, _i32, _i64, _p, _p, _p, _p, _f64, _p, _f64, _p, _p, _i32, _p]),
+    "fb2_elem_scalar_quad_fused": (_i32, [_i32, _i32, _i64, _p, _p, _i32, _i32, _p, _p, _i32, _p, _p, _p, _f64, _p, _f64, _p, _p, _i32, _p]),
     "fb2_elem_elasticity": (_i32, [_i32, _i32, _i64, _p, _p, _p, _f64, _f64, _f64, _i32, _p, _p]),
     "fb2_cell_gradients": (_i32, [_i32, _i64, _p, _p, _p, _p]),
     "fb2_grad_basis": (_i32, [_i32, _i64, _i32, _i32, _p, _p, _p, _p]),

@@ -72,14 +72,33 @@ int fb2_elem_scalar_const(int TD, int p, int64_t NC, const double* node, const i
   a.Ms = Ms; a.Mm = Mm; a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.out = out;
   return elem_const(TD, p, a, S(stream));
 }
-int fb2_elem_scalar_quad(int TD, int p, int64_t NC, const double* node, const int32_t* cell, int is_mass, int NQ, const double* ws,
-                         const double* table, int coef_kind, const double* coef, double* out, void* stream) {
+int fb2_elem_scalar_const_acc(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const double* Ms, const double* Mm,
+                              double scal_d, const double* coef_d, double scal_m, const double* coef_m, double* out, int accumulate,
+                              void* stream) {
+  if (!Ms && !Mm) return fail(ERR_INVALID, "elem_scalar_const: need a diffusion and/or a mass table");
+  ElemConstArgs a{};
+  a.node = node; a.cell = cell; a.NC = NC;
+  a.has_diff = Ms != nullptr; a.has_mass = Mm != nullptr;
+  a.Ms = Ms; a.Mm = Mm; a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.out = out;
+  a.accumulate = accumulate ? 1 : 0;
+  return elem_const(TD, p, a, S(stream));
+}
+int fb2_elem_scalar_quad_fused(int TD, int p, int64_t NC, const double* node, const int32_t* cell, int is_mass, int NQ,
+                               const double* ws, const double* table, int coef_kind, const double* coef, const double* Ms_const,
+                               const double* Mm_const, double scal_d, const double* coef_d_cell, double scal_m,
+                               const double* coef_m_cell, double* out, int accumulate, void* stream) {
   if (coef_kind != 2 && coef_kind != 3) return fail(ERR_INVALID, "elem_scalar_quad: coef_kind must be 2 (NC,NQ) or 3 (NC,NQ,GD,GD)");
   if (is_mass && coef_kind == 3) return fail(ERR_INVALID, "elem_scalar_quad: matrix coefficients apply to diffusion only");
   ElemQuadArgs a{};
   a.node = node; a.cell = cell; a.NC = NC; a.is_mass = is_mass; a.NQ = NQ; a.ws = ws; a.tab = table;
-  a.coef_kind = coef_kind; a.coef = coef; a.out = out;
+  a.coef_kind = coef_kind; a.coef = coef; a.out = out; a.accumulate = accumulate ? 1 : 0;
+  a.xMs = Ms_const; a.xMm = Mm_const; a.x_scal_d = scal_d; a.x_scal_m = scal_m; a.x_coef_d = coef_d_cell; a.x_coef_m = coef_m_cell;
   return elem_quad(TD, p, a, S(stream));
+}
+int fb2_elem_scalar_quad(int TD, int p, int64_t NC, const double* node, const int32_t* cell, int is_mass, int NQ, const double* ws,
+                         const double* table, int coef_kind, const double* coef, double* out, void* stream) {
+  return fb2_elem_scalar_quad_fused(TD, p, NC, node, cell, is_mass, NQ, ws, table, coef_kind, coef, nullptr, nullptr, 0.0, nullptr, 0.0,
+                                    nullptr, out, 0, stream);
 }
 int fb2_elem_elasticity(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const double* M4, double d_diag,
                         double d_lam, double d_shear, int dof_priority, double* out, void* stream) {

@@ -86,12 +86,19 @@ struct WarpStage {
 };
 
 template <int LL>
-__device__ __forceinline__ void warp_flush(const double* stage, double* __restrict__ out, int64_t c0, int64_t NC) {
+__device__ __forceinline__ void warp_flush(const double* stage, double* __restrict__ out, int64_t c0, int64_t NC, int accumulate = 0) {
   constexpr int S = WarpStage<LL>::S;
   const int lane = threadIdx.x & 31;
   const int64_t ncell = (NC - c0) < 32 ? (NC - c0) : 32;
   const int64_t tot = ncell * LL;
   double* dst = out + c0 * LL;
+  if (accumulate) {
+    for (int64_t idx = lane; idx < tot; idx += 32) {
+      const int cl = (int)(idx / LL), e = (int)(idx - (int64_t)cl * LL);
+      dst[idx] += stage[cl * S + e];
+    }
+    return;
+  }
   for (int64_t idx = lane; idx < tot; idx += 32) {
     const int cl = (int)(idx / LL), e = (int)(idx - (int64_t)cl * LL);
     dst[idx] = stage[cl * S + e];
@@ -153,13 +160,14 @@ __global__ void __launch_bounds__(128) elem_const_kernel(ElemConstArgs a) {
         }
         if (a.has_mass) v += km * sMm[i * L + j];
         if (STAGED) stage[lane * WarpStage<LL>::S + i * L + j] = v;
+        else if (a.accumulate) a.out[c * LL + i * L + j] += v;
         else a.out[c * LL + i * L + j] = v;
       }
     }
   }
   if (STAGED) {
     __syncwarp();
-    warp_flush<LL>(stage, a.out, c0, a.NC);
+    warp_flush<LL>(stage, a.out, c0, a.NC, a.accumulate);
   }
 }
 
@@ -170,11 +178,26 @@ __global__ void __launch_bounds__(128) elem_const_kernel(ElemConstArgs a) {
 //   mass:      K[i][j] = cm * sum_q w_q kappa[c,q] phi_i phi_j
 // rows are processed in passes of RB rows so that the accumulators stay in registers.
 // -------------------------------------------------------------------------------------
-template <int TD, int L, int RB, int R0, bool STAGED>
+// constant-coefficient terms folded into the quadrature kernel's final write (see ElemQuadArgs)
+template <int TD>
+struct QuadExtra {
+  static constexpr int NG = (TD + 1) * (TD + 2) / 2;
+  const double* sMs;     // shared-memory copies (null = absent)
+  const double* sMm;
+  double kd, km;         // km already carries |K|
+};
+
+// SYM (scalar coefficient fields and mass terms): K_e is symmetric -- products commute and (i, j), (j, i) are summed over
+// (q, d) in the same order -- so only j >= i is accumulated (55 instead of 100 FMA chains per quadrature point on 10 local
+// dofs, gradients formed only for the columns a pass still needs) and the block is mirrored on the way out.  ncu of the
+// full version on config 3 (profiles/r02_ncu_asm_v6.txt): FP64 pipe 63.5 % busy, 252 registers -- the kernel is bound by
+// its DFMA count, which is what this halves.  (DMMA cannot help on B200: its FP64 tensor peak equals the DFMA peak.)
+template <int TD, int L, int RB, int R0, bool STAGED, bool SYM>
 __device__ __forceinline__ void quad_pass(const ElemQuadArgs& a, const Geo<TD>& g, const double* sW, const double* sT,
-                                          const double* coefc, double* stage, int64_t c) {
+                                          const double* coefc, double* stage, int64_t c, const QuadExtra<TD>& xt) {
   constexpr int NV = TD + 1, LL = L * L;
   constexpr int NR = (R0 + RB <= L) ? RB : (L - R0);     // rows in this pass
+  constexpr int J0 = SYM ? R0 : 0;                       // first column this pass touches
   const int NQ = a.NQ, lane = threadIdx.x & 31;
   double acc[NR][L];
 #pragma unroll
@@ -191,13 +214,14 @@ __device__ __forceinline__ void quad_pass(const ElemQuadArgs& a, const Geo<TD>& 
       for (int i = 0; i < NR; ++i) {
         const double pi = wk * ph[R0 + i];
 #pragma unroll
-        for (int j = 0; j < L; ++j) acc[i][j] += pi * ph[j];
+        for (int j = 0; j < L; ++j)
+          if (!SYM || j >= R0 + i) acc[i][j] = fma(pi, ph[j], acc[i][j]);
       }
     } else {
-      double gp[L][TD];                       // physical gradients of all basis functions at q
+      double gp[L][TD];                       // physical gradients of the basis functions at q (columns >= J0)
       const double* R = sT + q * L * NV;
 #pragma unroll
-      for (int j = 0; j < L; ++j)
+      for (int j = J0; j < L; ++j)
 #pragma unroll
         for (int m = 0; m < TD; ++m) {
           double s = 0.0;
@@ -205,7 +229,7 @@ __device__ __forceinline__ void quad_pass(const ElemQuadArgs& a, const Geo<TD>& 
           for (int b = 0; b < NV; ++b) s += R[j * NV + b] * g.D[b][m];
           gp[j][m] = s;
         }
-      if (a.coef_kind == 3) {                 // full matrix coefficient: gphi_i^T C gphi_j
+      if constexpr (!SYM) {                   // full matrix coefficient: gphi_i^T C gphi_j (C need not be symmetric)
         double C[TD][TD];
 #pragma unroll
         for (int d = 0; d < TD; ++d)
@@ -222,12 +246,9 @@ __device__ __forceinline__ void quad_pass(const ElemQuadArgs& a, const Geo<TD>& 
             tv[n] = s;
           }
 #pragma unroll
-          for (int j = 0; j < L; ++j) {
-            double s = 0.0;
+          for (int j = 0; j < L; ++j)
 #pragma unroll
-            for (int n = 0; n < TD; ++n) s += tv[n] * gp[j][n];
-            acc[i][j] += s;
-          }
+            for (int n = 0; n < TD; ++n) acc[i][j] = fma(tv[n], gp[j][n], acc[i][j]);
         }
       } else {
         const double wk = w * coefc[q];
@@ -237,28 +258,56 @@ __device__ __forceinline__ void quad_pass(const ElemQuadArgs& a, const Geo<TD>& 
 #pragma unroll
           for (int n = 0; n < TD; ++n) tv[n] = wk * gp[R0 + i][n];
 #pragma unroll
-          for (int j = 0; j < L; ++j) {
-            double s = 0.0;
+          for (int j = R0 + i; j < L; ++j)
 #pragma unroll
-            for (int n = 0; n < TD; ++n) s += tv[n] * gp[j][n];
-            acc[i][j] += s;
-          }
+            for (int n = 0; n < TD; ++n) acc[i][j] = fma(tv[n], gp[j][n], acc[i][j]);
         }
       }
     }
+  }
+  double G[QuadExtra<TD>::NG];          // kd |K| grad(lambda_k).grad(lambda_l), upper triangle: formed here, after the
+  if (xt.sMs) {                         // quadrature loop, so that it holds no registers while the accumulators are hot
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int l = k; l < NV; ++l) {
+        double d = 0.0;
+#pragma unroll
+        for (int m = 0; m < TD; ++m) d += g.D[k][m] * g.D[l][m];
+        G[t++] = d * g.cm * xt.kd;
+      }
   }
 #pragma unroll
   for (int i = 0; i < NR; ++i)
 #pragma unroll
     for (int j = 0; j < L; ++j) {
-      const double v = acc[i][j] * g.cm;
-      if (STAGED) stage[lane * WarpStage<LL>::S + (R0 + i) * L + j] = v;
-      else a.out[c * LL + (R0 + i) * L + j] = v;
+      if (SYM && j < R0 + i) continue;
+      double v = acc[i][j] * g.cm;
+      if (xt.sMs) {
+        const double* m = xt.sMs + ((R0 + i) * L + j) * QuadExtra<TD>::NG;
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t < QuadExtra<TD>::NG; ++t) s += m[t] * G[t];
+        v += s;
+      }
+      if (xt.sMm) v += xt.km * xt.sMm[(R0 + i) * L + j];
+      const int e0 = (R0 + i) * L + j, e1 = j * L + (R0 + i);       // (i, j) and its mirror image
+      if (STAGED) {
+        stage[lane * WarpStage<LL>::S + e0] = v;
+        if (SYM && e1 != e0) stage[lane * WarpStage<LL>::S + e1] = v;
+      } else if (a.accumulate) {
+        a.out[c * LL + e0] += v;
+        if (SYM && e1 != e0) a.out[c * LL + e1] += v;
+      } else {
+        a.out[c * LL + e0] = v;
+        if (SYM && e1 != e0) a.out[c * LL + e1] = v;
+      }
     }
-  if constexpr (R0 + RB < L) quad_pass<TD, L, RB, R0 + RB, STAGED>(a, g, sW, sT, coefc, stage, c);
+  if constexpr (R0 + RB < L) quad_pass<TD, L, RB, R0 + RB, STAGED, SYM>(a, g, sW, sT, coefc, stage, c, xt);
 }
 
-template <int TD, int L, int RB, bool STAGED>
+template <int TD, int L, int RB, bool STAGED, bool SYM>
 __global__ void __launch_bounds__(128) elem_quad_kernel(ElemQuadArgs a) {
   constexpr int NV = TD + 1, LL = L * L;
   extern __shared__ __align__(16) double sm[];
@@ -266,9 +315,14 @@ __global__ void __launch_bounds__(128) elem_quad_kernel(ElemQuadArgs a) {
   double* sW = sm;                                     // [NQ]
   double* sT = sW + NQ;                                // diffusion: R[NQ][L][NV]; mass: phi[NQ][L]
   const int tab = a.is_mass ? NQ * L : NQ * L * NV;
-  double* sStage = sT + tab;
+  constexpr int NG = QuadExtra<TD>::NG;
+  double* sXs = sT + tab;                              // folded constant terms: Ms [LL][NG], Mm [LL]
+  double* sXm = sXs + (a.xMs ? LL * NG : 0);
+  double* sStage = sXm + (a.xMm ? LL : 0);
   for (int i = threadIdx.x; i < NQ; i += blockDim.x) sW[i] = a.ws[i];
   for (int i = threadIdx.x; i < tab; i += blockDim.x) sT[i] = a.tab[i];
+  if (a.xMs) for (int i = threadIdx.x; i < LL * NG; i += blockDim.x) sXs[i] = a.xMs[i];
+  if (a.xMm) for (int i = threadIdx.x; i < LL; i += blockDim.x) sXm[i] = a.xMm[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -280,11 +334,16 @@ __global__ void __launch_bounds__(128) elem_quad_kernel(ElemQuadArgs a) {
     Geo<TD> g;
     load_geo(a.node, a.cell, c, g);
     const double* coefc = a.coef + c * (int64_t)NQ * (a.coef_kind == 3 ? TD * TD : 1);
-    quad_pass<TD, L, RB, 0, STAGED>(a, g, sW, sT, coefc, stage, c);
+    QuadExtra<TD> xt;
+    xt.sMs = a.xMs ? sXs : nullptr;
+    xt.sMm = a.xMm ? sXm : nullptr;
+    xt.kd = a.x_scal_d * (a.x_coef_d ? a.x_coef_d[c] : 1.0);
+    xt.km = a.x_scal_m * (a.x_coef_m ? a.x_coef_m[c] : 1.0) * g.cm;
+    quad_pass<TD, L, RB, 0, STAGED, SYM>(a, g, sW, sT, coefc, stage, c, xt);
   }
   if (STAGED) {
     __syncwarp();
-    warp_flush<LL>(stage, a.out, c0, a.NC);
+    warp_flush<LL>(stage, a.out, c0, a.NC, a.accumulate);
   }
 }
 
@@ -458,12 +517,13 @@ template <int TD, int L>
 static int launch_quad(const ElemQuadArgs& a, cudaStream_t s) {
   constexpr int NV = TD + 1, LL = L * L;
   constexpr int RB = L <= 6 ? L : (L <= 10 ? 5 : 2);
-  size_t tab = ((size_t)a.NQ + (size_t)a.NQ * L * (a.is_mass ? 1 : NV)) * sizeof(double);
+  constexpr int NG = NV * (NV + 1) / 2;
+  size_t tab = ((size_t)a.NQ + (size_t)a.NQ * L * (a.is_mass ? 1 : NV) + (a.xMs ? LL * NG : 0) + (a.xMm ? LL : 0)) * sizeof(double);
   constexpr bool STAGED = WarpStage<LL>::bytes_per_warp <= 26 * 1024;
   const int warps = 4;
   size_t smem = tab + (STAGED ? warps * WarpStage<LL>::bytes_per_warp : 0);
   if (smem > 220 * 1024) return fail(ERR_UNSUPPORTED, "elem_quad: quadrature table too large for shared memory (NQ=%d)", a.NQ);
-  auto kern = elem_quad_kernel<TD, L, RB, STAGED>;
+  auto kern = a.coef_kind == 3 ? elem_quad_kernel<TD, L, RB, STAGED, false> : elem_quad_kernel<TD, L, RB, STAGED, true>;
   FB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t nb = ceil_div(a.NC, 32 * warps);
   kern<<<(unsigned)nb, 32 * warps, smem, s>>>(a);

@@ -15,6 +15,7 @@ struct ElemConstArgs {
   const double* coef_d;  // optional per-cell factor (NC,) or null
   const double* coef_m;
   double* out;           // (NC, L, L)
+  int accumulate;        // 1: out += K (a later term of the same group / form), 0: out = K
 };
 
 struct ElemQuadArgs {
@@ -28,6 +29,14 @@ struct ElemQuadArgs {
   int coef_kind;         // 2: (NC,NQ) scalar field, 3: (NC,NQ,GD,GD) matrix field (diffusion only)
   const double* coef;
   double* out;
+  int accumulate;        // 1: out += K, 0: out = K
+  // optional constant / per-cell coefficient terms folded into the same pass (the K of elem_const_kernel):
+  // K += x_kd * (xMs : G) + x_km * |K| * xMm -- a variable-coefficient diffusion plus a constant mass term writes K_e once
+  const double* xMs;     // [L][L][NG] or null
+  const double* xMm;     // [L][L] or null
+  double x_scal_d, x_scal_m;
+  const double* x_coef_d;
+  const double* x_coef_m;
 };
 
 struct ElemElasticityArgs {

@@ -362,8 +362,62 @@ class BilinearForm:
                   sd, _lib.ptr(ad), sm_, _lib.ptr(am), _lib.ptr(values), _lib.stream())
         return sym["crow"], sym["col"], values
 
+    def _summed_ke_scalar(self):
+        """sum of several scalar diffusion / mass integrators written ONCE into one (NC, l, l) block: constant and per-cell
+        terms are merged per (kind, q) and folded into the first quadrature-loop kernel's final write, every further kernel
+        accumulates in place (csrc/elem.cu) -- no per-integrator block, no torch add.  None: not applicable."""
+        if self._is_tensor_space():
+            return None
+        its = self._flat_integrators()
+        if len(its) < 2 or not all(hasattr(it, "describe") and hasattr(it, "KIND") for it in its):
+            return None
+        space, mesh = self.space, self.space.mesh
+        descs = [it.describe(space) for it in its]
+        const, quad = {"diffusion": {}, "mass": {}}, []
+        for d in descs:
+            if d["coef_kind"] in ("scalar", "cell"):
+                m = const[d["kind"]].setdefault(d["q"], dict(tabs=d["tabs"], scal=0.0, arr=None))
+                if d["coef_kind"] == "scalar":
+                    if m["arr"] is None:
+                        m["scal"] += d["coef"]
+                    else:
+                        m["arr"] = m["arr"] + d["coef"]
+                else:
+                    m["arr"] = d["coef"] + (m["scal"] if m["arr"] is None else m["arr"])
+                    m["scal"] = 0.0
+            else:
+                quad.append(d)
+        dts, mts = list(const["diffusion"].values()), list(const["mass"].values())
+        bundles = [(dts[k] if k < len(dts) else None, mts[k] if k < len(mts) else None) for k in range(max(len(dts), len(mts)))]
+        TD, p, NC = mesh.TD, space.p, mesh.number_of_cells()
+        L = space.number_of_local_dofs()
+        out = torch.empty((NC, L, L), dtype=torch.float64, device=mesh.device)
+
+        def cargs(b):
+            dm, mm = b if b is not None else (None, None)
+            sd, ad = self._plan_parts(dm)
+            sm_, am = self._plan_parts(mm)
+            return (_lib.ptr(dm["tabs"]["Ms"]) if dm else None, _lib.ptr(mm["tabs"]["Mm"]) if mm else None, sd, _lib.ptr(ad), sm_, _lib.ptr(am))
+        first = True
+        for d in quad:
+            is_mass = d["kind"] == "mass"
+            tabs = d["tabs"]
+            fold = bundles.pop(0) if (first and bundles) else None
+            _lib.call("fb2_elem_scalar_quad_fused", TD, p, NC, _lib.ptr(mesh.node), _lib.ptr(mesh.cell), int(is_mass), tabs["ws"].shape[0],
+                      _lib.ptr(tabs["ws"]), _lib.ptr(tabs["phi"] if is_mass else tabs["R"]), 2 if d["coef_kind"] == "quad" else 3,
+                      _lib.ptr(d["coef"]), *cargs(fold), _lib.ptr(out), 0 if first else 1, _lib.stream())
+            first = False
+        for b in bundles:
+            ms, mm, sd, ad, sm_, am = cargs(b)
+            _lib.call("fb2_elem_scalar_const_acc", TD, p, NC, _lib.ptr(mesh.node), _lib.ptr(mesh.cell), ms, mm, sd, ad, sm_, am,
+                      _lib.ptr(out), 0 if first else 1, _lib.stream())
+            first = False
+        return out
+
     def _summed_ke(self):
-        ke = None
+        ke = self._summed_ke_scalar()
+        if ke is not None:
+            return ke
         for it in self.integrators.values():
             k = it.assembly(self.space)
             if not isinstance(k, torch.Tensor) or k.ndim != 3:

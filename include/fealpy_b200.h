@@ -70,6 +70,17 @@ int fb2_elem_scalar_const(int TD, int p, int64_t NC, const double* node, const i
  * coef_kind 2 -> coef (NC,NQ), 3 -> coef (NC,NQ,GD,GD) (diffusion only). */
 int fb2_elem_scalar_quad(int TD, int p, int64_t NC, const double* node, const int32_t* cell, int is_mass, int NQ, const double* ws,
                          const double* table, int coef_kind, const double* coef, double* out, void* stream);
+/* The same kernels for a SUM of integrators written into one block (GroupIntegrator / several groups on the K_e gather path):
+ * `accumulate` != 0 adds to `out` instead of overwriting it, and the quadrature kernel can fold constant / per-cell coefficient
+ * terms (the K of fb2_elem_scalar_const: Ms_const / Mm_const device tables or NULL) into its own final write -- a variable
+ * diffusion plus a constant mass term then writes K_e once. */
+int fb2_elem_scalar_const_acc(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const double* Ms, const double* Mm,
+                              double scal_d, const double* coef_d_cell, double scal_m, const double* coef_m_cell, double* out,
+                              int accumulate, void* stream);
+int fb2_elem_scalar_quad_fused(int TD, int p, int64_t NC, const double* node, const int32_t* cell, int is_mass, int NQ,
+                               const double* ws, const double* table, int coef_kind, const double* coef, const double* Ms_const,
+                               const double* Mm_const, double scal_d, const double* coef_d_cell, double scal_m,
+                               const double* coef_m_cell, double* out, int accumulate, void* stream);
 /* isotropic linear elasticity; M4 (l,l,TD+1,TD+1) device table; out (NC, GD*l, GD*l). */
 int fb2_elem_elasticity(int TD, int p, int64_t NC, const double* node, const int32_t* cell, const double* M4, double d_diag,
                         double d_lam, double d_shear, int dof_priority, double* out, void* stream);
