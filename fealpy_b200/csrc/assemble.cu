@@ -599,7 +599,7 @@ __device__ __forceinline__ double pick(const double (&d)[N], int k) {
   return v;
 }
 
-template <typename SlotT, int ETD, int NC>
+template <typename SlotT, int ETD, int NC, int U>
 __global__ void __launch_bounds__(128) assemble_from_ke_kernel(AsmKeArgs a) {
   extern __shared__ __align__(16) double acc[];
   const int L = ETD > 0 ? ETD + 1 : a.L;                   // lanes per group: one per local (scalar) column dof j
@@ -654,7 +654,8 @@ __global__ void __launch_bounds__(128) assemble_from_ke_kernel(AsmKeArgs a) {
       };
       // pairs in chunks of U: the element-matrix rows of a chunk are independent loads (memory-level
       // parallelism), the adds then run in pair order; the next chunk's pair ids are fetched meanwhile
-      constexpr int U = NC == 1 ? 8 : 4;
+      // (U = 8 for scalar forms on meshes of high valence, 4 for tensor spaces; 2 where a dof meets few cells -- tri P3 has
+      // 2.2 pairs per row, most of an 8-wide chunk would be predicated-off instructions: 2.71 -> see profiles/r02_tune_gather.txt)
       int pr[U], prn[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) pr[u] = q0 + u < q1 ? a.adj_pair[q0 + u] : 0;
@@ -766,19 +767,28 @@ int assemble_const(int TD, int p, const AsmConstArgs& a, int slot_bytes, int max
   }
 }
 
-template <int ETD, int NC>
-static int launch_gather(const AsmKeArgs& a, int slot_bytes, size_t smem, cudaStream_t s) {
-  if (slot_bytes == 1) {
-    auto k = assemble_from_ke_kernel<uint8_t, ETD, NC>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)a.nblk, 128, smem, s>>>(a);
-  } else {
-    auto k = assemble_from_ke_kernel<uint16_t, ETD, NC>;
-    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)a.nblk, 128, smem, s>>>(a);
-  }
+template <typename SlotT, int ETD, int NC, int U>
+static int launch_gather_u(const AsmKeArgs& a, size_t smem, cudaStream_t s) {
+  auto k = assemble_from_ke_kernel<SlotT, ETD, NC, U>;
+  FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)a.nblk, 128, smem, s>>>(a);
   FB2_LAUNCH_CHECK();
   return OK;
+}
+
+template <int ETD, int NC>
+static int launch_gather(const AsmKeArgs& a, int slot_bytes, size_t smem, cudaStream_t s) {
+  // (cell, i) pairs per row: chunk of independent element-row loads in flight per lane group
+  static const int forced = [] { const char* e = getenv("FB2_GATHER_U"); return e ? atoi(e) : 0; }();
+  const double valence = a.gdof > 0 ? (double)a.ncell * a.L / (double)a.gdof : 8.0;
+  if constexpr (NC == 1) {
+    const int u = forced ? forced : (valence < 4.0 ? 2 : 8);
+    if (u <= 2) return slot_bytes == 1 ? launch_gather_u<uint8_t, ETD, NC, 2>(a, smem, s) : launch_gather_u<uint16_t, ETD, NC, 2>(a, smem, s);
+    if (u <= 4) return slot_bytes == 1 ? launch_gather_u<uint8_t, ETD, NC, 4>(a, smem, s) : launch_gather_u<uint16_t, ETD, NC, 4>(a, smem, s);
+    return slot_bytes == 1 ? launch_gather_u<uint8_t, ETD, NC, 8>(a, smem, s) : launch_gather_u<uint16_t, ETD, NC, 8>(a, smem, s);
+  } else {
+    return slot_bytes == 1 ? launch_gather_u<uint8_t, ETD, NC, 4>(a, smem, s) : launch_gather_u<uint16_t, ETD, NC, 4>(a, smem, s);
+  }
 }
 
 int assemble_from_ke(AsmKeArgs a, int slot_bytes, int max_row, cudaStream_t s) {

@@ -25,6 +25,7 @@ struct AsmConstArgs {
 
 struct AsmKeArgs {
   int64_t gdof;               // scalar dofs
+  int64_t ncell;              // cells (the average number of (cell, i) pairs per row picks the gather's chunk size)
   int64_t nnz_out;
   int L, ncomp, dof_priority;
   const double* Ke;           // (NC, L*ncomp, L*ncomp)

@@ -169,7 +169,7 @@ int fb2_assemble_from_ke(int64_t NC, int ldof, int ncomp, int dof_priority, int6
                          const int64_t* crow_scalar, int32_t max_row, const int64_t* crow_out, const int32_t* blk_row, int nblk,
                          int tile, double* values, void* stream) {
   AsmKeArgs a{};
-  a.gdof = gdof_scalar; a.L = ldof; a.ncomp = ncomp; a.dof_priority = dof_priority; a.Ke = Ke;
+  a.gdof = gdof_scalar; a.ncell = NC; a.L = ldof; a.ncomp = ncomp; a.dof_priority = dof_priority; a.Ke = Ke;
   a.adj_ptr = adj_ptr; a.adj_pair = adj_pair; a.slots = slots; a.crow_s = crow_scalar;
   a.crow_out = crow_out ? crow_out : crow_scalar; a.values = values;
   a.nnz_out = 0;
@@ -183,7 +183,7 @@ int fb2_assemble_elasticity_p1(int TD, int64_t NC, const double* node, const int
                                void* stream) {
   FB2_TRY(cell_gradients(TD, NC, node, cell, geo_ws, S(stream)));
   AsmKeArgs a{};
-  a.gdof = gdof_scalar; a.dof_priority = dof_priority; a.adj_ptr = adj_ptr; a.adj_pair = adj_pair; a.slots = slots;
+  a.gdof = gdof_scalar; a.ncell = NC; a.dof_priority = dof_priority; a.adj_ptr = adj_ptr; a.adj_pair = adj_pair; a.slots = slots;
   a.crow_s = crow_scalar; a.crow_out = crow_out; a.values = values; a.blk_row = blk_row; a.nblk = nblk; a.tile = tile;
   a.geo = geo_ws; a.d_diag = d_diag; a.d_lam = d_lam; a.d_shear = d_shear; a.wsum = wsum;
   return assemble_elasticity_p1(TD, a, slot_bytes, max_row, S(stream));

@@ -14,6 +14,8 @@ dev = torch.device("cuda", 0)
 st = torch.cuda.Stream()
 with torch.cuda.stream(st):
     prob = bench.Problem(cfg, n, dev, 1, 0)
+    if os.environ.get("FB2_ASM_PATH"):                 # force 'gather' / 'coo' on a form the fused kernel would take
+        prob.bform.assembly_path = os.environ["FB2_ASM_PATH"]
     A = prob.assemble()
     torch.cuda.synchronize()
     ev = lambda: torch.cuda.Event(enable_timing=True)
