@@ -86,8 +86,9 @@ SIGNATURES = {
     "fb2_peer_wait_halo": (_i32, [_p, _i32, _p, _p, _p, _p]),
     "fb2_cg_update_p_push": (_i32, [_p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _i32, _p, _p, _p]),
     "fb2_bcg_dots": (_i32, [_i64, _i32, _p, _p, _p, _p, _p]),
-    "fb2_bcg_update_xr": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
-    "fb2_bcg_update_p": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p]),
+    "fb2_bcg_update_xr": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fb2_bcg_update_p": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "fb2_bcg_check": (_i32, [_i32, _p, _f64, _f64, _i32, _p, _p]),
     "fb2_elem_source": (_i32, [_i32, _i64, _i32, _i32, _p, _p, _p, _i32, _f64, _p, _p, _p]),
     "fb2_gather_vector": (_i32, [_i64, _p, _p, _p, _p, _p]),
     "fb2_matfree_apply": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),

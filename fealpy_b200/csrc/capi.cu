@@ -348,12 +348,16 @@ int fb2_bcg_dots(int64_t n, int nb, const double* a, const double* b, double* ou
   return bcg_dots(n, nb, a, b, out_dev, partial_ws, S(stream));
 }
 int fb2_bcg_update_xr(int64_t n, int nb, double* x, double* r, const double* p, const double* Ap, const double* rTr, const double* pAp,
-                      void* stream) {
-  return bcg_update_xr(n, nb, x, r, p, Ap, rTr, pAp, S(stream));
+                      const double* state, void* stream) {
+  return bcg_update_xr(n, nb, x, r, p, Ap, rTr, pAp, state, S(stream));
 }
 int fb2_bcg_update_p(int64_t n, int nb, double* p, const double* r, const double* minv_diag, const double* rTr_new, const double* rTr,
-                     void* stream) {
-  return bcg_update_p(n, nb, p, r, minv_diag, rTr_new, rTr, S(stream));
+                     const double* state, void* stream) {
+  return bcg_update_p(n, nb, p, r, minv_diag, rTr_new, rTr, state, S(stream));
+}
+int fb2_bcg_check(int nb, const double* rTr_new, double atol, double rtol_bnorm, int maxit, double* state, void* stream) {
+  if (!state) return fail(ERR_INVALID, "bcg_check: state is required");
+  return bcg_check(nb, rTr_new, atol, rtol_bnorm, maxit, state, S(stream));
 }
 
 // ---- next rows: source vector, Dirichlet -----------------------------------------------------

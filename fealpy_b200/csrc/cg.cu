@@ -434,7 +434,10 @@ int spmm(int64_t n, const int64_t* crow, const int32_t* col, const double* val, 
   if (n <= 0 || nb <= 0) return OK;
   int64_t nbk = ceil_div(n, CG_THREADS / 8);
   if (nbk > (int64_t)kNumSM * 64) nbk = (int64_t)kNumSM * 64;
-  for (int b0 = 0; b0 < nb; b0 += 4) spmm_kernel<8, 4><<<(unsigned)nbk, CG_THREADS, 0, s>>>(n, crow, col, val, X, Y, nb, b0);
+  // A is streamed once per group of right-hand sides: 8 columns per pass (one 64-byte run of X per nonzero), 4 when nb <= 4
+  if (nb <= 4) spmm_kernel<8, 4><<<(unsigned)nbk, CG_THREADS, 0, s>>>(n, crow, col, val, X, Y, nb, 0);
+  else
+    for (int b0 = 0; b0 < nb; b0 += 8) spmm_kernel<8, 8><<<(unsigned)nbk, CG_THREADS, 0, s>>>(n, crow, col, val, X, Y, nb, b0);
   FB2_LAUNCH_CHECK();
   return OK;
 }
@@ -628,9 +631,14 @@ __global__ void __launch_bounds__(CG_THREADS) bcg_dots_kernel(int64_t n, int B, 
 }
 
 // x += alpha_k p ; r -= alpha_k Ap   with alpha_k = rTr[k] / pAp[k]
+// `state` (device, 4 doubles: done flag, iteration count, residual norm, pad; may be null): once the joint stopping test
+// (bcg_check_kernel) has fired, the update kernels do nothing -- the host can run several iterations per poll and x stays
+// the iterate of the stopping iteration, as in the reference (solver/cg.py:97-121)
 __global__ void __launch_bounds__(CG_THREADS) bcg_update_xr_kernel(int64_t n, int B, double* __restrict__ x, double* __restrict__ r,
                                                                    const double* __restrict__ p, const double* __restrict__ Ap,
-                                                                   const double* __restrict__ rTr, const double* __restrict__ pAp) {
+                                                                   const double* __restrict__ rTr, const double* __restrict__ pAp,
+                                                                   const double* __restrict__ state) {
+  if (state && state[0] != 0.0) return;
   const int64_t tot = n * B;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(t % B);
@@ -643,13 +651,32 @@ __global__ void __launch_bounds__(CG_THREADS) bcg_update_xr_kernel(int64_t n, in
 // p = z + beta_k p  with beta_k = rTr_new[k] / rTr[k],  z = minv .* r (or r)
 __global__ void __launch_bounds__(CG_THREADS) bcg_update_p_kernel(int64_t n, int B, double* __restrict__ p, const double* __restrict__ r,
                                                                   const double* __restrict__ minv, const double* __restrict__ rTr_new,
-                                                                  const double* __restrict__ rTr) {
+                                                                  const double* __restrict__ rTr, const double* __restrict__ state) {
+  if (state && state[0] != 0.0) return;
   const int64_t tot = n * B;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(t % B);
     const double z = minv ? minv[t / B] * r[t] : r[t];
     p[t] = z + (rTr_new[k] / rTr[k]) * p[t];
   }
+}
+
+// joint stopping test of the batched solve on the device: r_norm = sqrt(sum_k rTr_new[k]); atol, then rtol * |b|, then maxit
+__global__ void bcg_check_kernel(int B, const double* __restrict__ rTr_new, double atol, double rtol_bnorm, int maxit, double* state) {
+  if (state[0] != 0.0) return;
+  double t = 0.0;
+  for (int k = 0; k < B; ++k) t += rTr_new[k];
+  const double rn = sqrt(t);
+  const double it = state[1] + 1.0;
+  state[1] = it;
+  state[2] = rn;
+  if (rn < atol || rn < rtol_bnorm || (maxit >= 0 && it >= (double)maxit)) state[0] = 1.0;
+}
+
+int bcg_check(int B, const double* rTr_new, double atol, double rtol_bnorm, int maxit, double* state, cudaStream_t s) {
+  bcg_check_kernel<<<1, 1, 0, s>>>(B, rTr_new, atol, rtol_bnorm, maxit, state);
+  FB2_LAUNCH_CHECK();
+  return OK;
 }
 
 int bcg_dots(int64_t n, int B, const double* a, const double* b, double* out, void* partial_ws, cudaStream_t s) {
@@ -662,14 +689,14 @@ int bcg_dots(int64_t n, int B, const double* a, const double* b, double* out, vo
   return OK;
 }
 int bcg_update_xr(int64_t n, int B, double* x, double* r, const double* p, const double* Ap, const double* rTr, const double* pAp,
-                  cudaStream_t s) {
-  bcg_update_xr_kernel<<<vec_grid(n * B), CG_THREADS, 0, s>>>(n, B, x, r, p, Ap, rTr, pAp);
+                  const double* state, cudaStream_t s) {
+  bcg_update_xr_kernel<<<vec_grid(n * B), CG_THREADS, 0, s>>>(n, B, x, r, p, Ap, rTr, pAp, state);
   FB2_LAUNCH_CHECK();
   return OK;
 }
 int bcg_update_p(int64_t n, int B, double* p, const double* r, const double* minv, const double* rTr_new, const double* rTr,
-                 cudaStream_t s) {
-  bcg_update_p_kernel<<<vec_grid(n * B), CG_THREADS, 0, s>>>(n, B, p, r, minv, rTr_new, rTr);
+                 const double* state, cudaStream_t s) {
+  bcg_update_p_kernel<<<vec_grid(n * B), CG_THREADS, 0, s>>>(n, B, p, r, minv, rTr_new, rTr, state);
   FB2_LAUNCH_CHECK();
   return OK;
 }

@@ -88,7 +88,8 @@ int cg_update_p_push(OwnRange own, double* p, const double* r, const double* min
 // batched right-hand sides (row-major (n, B))
 int bcg_dots(int64_t n, int B, const double* a, const double* b, double* out, void* partial_ws, cudaStream_t s);
 int bcg_update_xr(int64_t n, int B, double* x, double* r, const double* p, const double* Ap, const double* rTr, const double* pAp,
-                  cudaStream_t s);
+                  const double* state, cudaStream_t s);
 int bcg_update_p(int64_t n, int B, double* p, const double* r, const double* minv, const double* rTr_new, const double* rTr,
-                 cudaStream_t s);
+                 const double* state, cudaStream_t s);
+int bcg_check(int B, const double* rTr_new, double atol, double rtol_bnorm, int maxit, double* state, cudaStream_t s);
 }  // namespace fb2

@@ -108,9 +108,13 @@ def symbolic_pattern(space):
     slots = torch.zeros(NC * L * stride, dtype=torch.uint8 if slot_bytes == 1 else torch.int16, device=dev)
     _lib.call("fb2_sym_fill", _lib.ptr(c2d), NC, L, gdof, _lib.ptr(adj_ptr), _lib.ptr(adj_pair), _lib.ptr(crow), _lib.ptr(col),
               _lib.ptr(slots), slot_bytes, _lib.ptr(stash), _lib.stream())
-    blk_row, nblk = row_tiling(crow, gdof, nnz.value, ASM_TILE)
+    # CTA tile of the gather kernels: where a dof meets few cells (tri P3: 2.2 (cell, i) pairs per row) the gather is bound by
+    # latency and wants more resident CTAs -- 2048-value tiles: 4.03 against 4.76 ms on config 3; the high-valence tensor
+    # gather of config 4 wants the large tile (5.36 against 6.13 ms).  profiles/r02_tune_gather.txt
+    tile = ASM_TILE if ("FB2_ASM_TILE" in _os.environ or NC * L >= 4 * gdof) else 2048
+    blk_row, nblk = row_tiling(crow, gdof, nnz.value, tile)
     cache = dict(adj_ptr=adj_ptr, adj_pair=adj_pair, crow=crow, col=col, slots=slots, slot_bytes=slot_bytes,
-                 max_row=max_row.value, nnz=nnz.value, NC=NC, L=L, gdof=gdof, blk_row=blk_row, nblk=nblk, tile=ASM_TILE,
+                 max_row=max_row.value, nnz=nnz.value, NC=NC, L=L, gdof=gdof, blk_row=blk_row, nblk=nblk, tile=tile,
                  scratch=stash)          # handed to asm4_plan(), dropped by the first kernel that does not want it
     space._b200_symbolic = cache
     return cache

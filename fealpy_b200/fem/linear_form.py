@@ -14,7 +14,7 @@ import torch
 from .. import _lib
 from ..basis import device_tables, host_tables, number_of_local_dofs
 from ..sparse import CSRTensor
-from .bilinear_form import symbolic_pattern
+from .bilinear_form import adjacency
 from .integrators import Integrator, _Variant, _check_space, process_coef
 
 
@@ -51,6 +51,57 @@ class ScalarSourceIntegrator(Integrator):
         return out
 
 
+class VectorSourceIntegrator(Integrator):
+    """(f, v) for a vector field f on a TensorFunctionSpace; element vectors (NC, ldof * GD) in the space's dof layout
+    (fem/vector_source_integrator.py:12-58 with functional.linear_integral:57-59: F[c, I] = |K| sum_q w_q phi_I(q) . f(c, q)).
+    `source`: a callable (cartesian or barycentric) or a tensor giving (NC, NQ, GD) values."""
+
+    def __init__(self, source=None, q=None, *, index=slice(None), batched=False):
+        super().__init__()
+        if index != slice(None):
+            raise NotImplementedError("index= sub-selection is not on the accelerated path")
+        if batched:
+            raise NotImplementedError("batched sources are not on the accelerated path")
+        self.source, self.q, self.index, self.batched = source, q, index, batched
+
+    def assembly(self, space, indices=None):
+        if indices is not None:
+            raise NotImplementedError("chunked (indices=...) assembly is not needed on the GPU path")
+        sspace = getattr(space, "scalar_space", None)
+        if sspace is None:
+            raise RuntimeError("VectorSourceIntegrator needs a TensorFunctionSpace")
+        mesh = _check_space(sspace)
+        TD, p, NC, GD = mesh.TD, sspace.p, mesh.number_of_cells(), space.dof_numel
+        q = p + 3 if self.q is None else self.q
+        tabs = device_tables(TD, p, q, mesh.device)
+        L = number_of_local_dofs(TD, p)
+        NQ = tabs["ws"].shape[0]
+        if "phiw" not in tabs:
+            tabs["phiw"] = (tabs["ws"][:, None] * tabs["phi"]).contiguous()
+        f = self.source
+        if f is None:
+            raise ValueError("VectorSourceIntegrator needs a source")
+        if callable(f):
+            bcs = host_tables(TD, p, q)["bcs"]
+            if getattr(f, "coordtype", "barycentric") == "barycentric":
+                f = f(torch.as_tensor(bcs, dtype=torch.float64, device=mesh.device), index=slice(None))
+            else:
+                f = f(mesh.bc_to_point(bcs))
+        if not isinstance(f, torch.Tensor) or f.ndim != 3 or f.shape[-1] != GD:
+            raise NotImplementedError("VectorSourceIntegrator on the accelerated path takes a vector field of shape (NC, NQ, GD)")
+        f = f.to(device=mesh.device, dtype=torch.float64).expand(NC, NQ, GD)
+        parts = []
+        for a in range(GD):
+            fa = f[..., a].contiguous()
+            out = torch.empty((NC, L), dtype=torch.float64, device=mesh.device)
+            _lib.call("fb2_elem_source", TD, NC, L, NQ, _lib.ptr(mesh.node), _lib.ptr(mesh.cell), _lib.ptr(tabs["phiw"]), 2, 1.0,
+                      _lib.ptr(fa), _lib.ptr(out), _lib.stream())
+            parts.append(out)
+        if space.dof_priority:                       # local index a * ldof + i
+            return torch.cat(parts, dim=1).contiguous()
+        return torch.stack(parts, dim=2).reshape(NC, L * GD).contiguous()      # local index i * GD + a
+
+
 class LinearForm:
     def __init__(self, space, batch_size: int = 0):
         if isinstance(space, (tuple, list)):
@@ -59,8 +110,6 @@ class LinearForm:
             space = space[0]
         if batch_size:
             raise NotImplementedError("batched forms are not on the accelerated path")
-        if hasattr(space, "scalar_space"):
-            raise NotImplementedError("vector-valued linear forms are not on the accelerated path yet")
         self.space, self.integrators, self._cursor, self._V = space, {}, 0, None
 
     @property
@@ -83,7 +132,7 @@ class LinearForm:
         if format != "dense":
             raise ValueError(f"Unsupported format {format}.") if format != "coo" else NotImplementedError("format='coo'")
         space = self.space
-        sym = symbolic_pattern(space)
+        sym = adjacency(space)          # a load vector needs the dof -> (cell, i) lists only, not the CSR pattern
         fe = None
         for it in self.integrators.values():
             v = it.assembly(space)

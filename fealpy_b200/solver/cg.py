@@ -30,7 +30,7 @@ def _minv_diag(M, n, device):
 def _cg_operator(A, b, x0, M, atol, rtol, maxit, returninfo):
     """The reference recurrence (solver/cg.py:76-123) for operator-valued A (and M): the products are Python-level
     `A @ p` calls, the vector updates and inner products are the library's kernels (fb2_dot, fb2_bcg_update_xr/p with a
-    batch of one); the stopping test reads one scalar per iteration, as the reference does."""
+    batch of one); the stopping test runs on the device and is polled every few iterations."""
     if b.device.type != "cuda" or b.dtype != torch.float64:
         raise RuntimeError("fealpy_b200.solver.cg needs float64 CUDA tensors; there is no CPU fallback")
     n, dev = b.shape[0], b.device
@@ -60,22 +60,27 @@ def _cg_operator(A, b, x0, M, atol, rtol, maxit, returninfo):
     z = precond(r)
     p = z.clone()
     dot(r, z, rTr)
-    it = 0
-    while True:
-        Ap = (A @ p).contiguous()
-        dot(p, Ap, pAp)
-        _lib.call("fb2_bcg_update_xr", n, 1, _lib.ptr(x), _lib.ptr(r), _lib.ptr(p), _lib.ptr(Ap), _lib.ptr(rTr), _lib.ptr(pAp),
-                  _lib.stream())
-        z = precond(r)
-        dot(r, z, rTr_new)
-        r_norm = float(rTr_new.item()) ** 0.5
-        it += 1
-        info["residual"], info["niter"] = r_norm, it
-        if r_norm < atol or r_norm < rtol * b_norm or (maxit is not None and it >= maxit):
-            break
-        # p = z + beta p ; fb2_bcg_update_p forms z = minv .* r itself, so a general z goes in as "r" with minv = NULL
-        _lib.call("fb2_bcg_update_p", n, 1, _lib.ptr(p), _lib.ptr(z), None, _lib.ptr(rTr_new), _lib.ptr(rTr), _lib.stream())
-        rTr.copy_(rTr_new)
+    # stopping test on the device (fb2_bcg_check); after it fires the update kernels do nothing, so x stays the iterate of
+    # the stopping iteration while the host polls the state block only every _BCG_CHECK_EVERY iterations
+    state = torch.zeros(4, dtype=torch.float64, device=dev)
+    mit = -1 if maxit is None else int(maxit)
+    done = False
+    while not done:
+        for _ in range(_BCG_CHECK_EVERY):
+            Ap = (A @ p).contiguous()
+            dot(p, Ap, pAp)
+            _lib.call("fb2_bcg_update_xr", n, 1, _lib.ptr(x), _lib.ptr(r), _lib.ptr(p), _lib.ptr(Ap), _lib.ptr(rTr), _lib.ptr(pAp),
+                      _lib.ptr(state), _lib.stream())
+            z = precond(r)
+            dot(r, z, rTr_new)
+            _lib.call("fb2_bcg_check", 1, _lib.ptr(rTr_new), float(atol), float(rtol) * b_norm, mit, _lib.ptr(state), _lib.stream())
+            # p = z + beta p ; fb2_bcg_update_p forms z = minv .* r itself, so a general z goes in as "r" with minv = NULL
+            _lib.call("fb2_bcg_update_p", n, 1, _lib.ptr(p), _lib.ptr(z), None, _lib.ptr(rTr_new), _lib.ptr(rTr), _lib.ptr(state),
+                      _lib.stream())
+            rTr, rTr_new = rTr_new, rTr
+        st = state.tolist()
+        done = st[0] != 0.0
+        info["residual"], info["niter"] = st[2], int(st[1])
     return (x, info) if returninfo else x
 
 
@@ -122,6 +127,9 @@ def cg(A, b, x0=None, M=None, *, batch_first=False, atol=1e-12, rtol=1e-8, maxit
     return (x, info) if returninfo else x
 
 
+_BCG_CHECK_EVERY = 8
+
+
 def _cg_batched(A, b, x0, M, batch_first, atol, rtol, maxit, returninfo):
     """b of shape (dof, batch) (or (batch, dof) with batch_first): per-column alpha/beta, joint stopping
     test on sqrt(sum_k r_k.z_k) -- solver/cg.py:58-121.  Host-driven loop over fb2_csr_spmm + fb2_bcg_*."""
@@ -150,21 +158,29 @@ def _cg_batched(A, b, x0, M, batch_first, atol, rtol, maxit, returninfo):
         pAp = torch.empty_like(rTr)
         _lib.call("fb2_bcg_dots", n, B, _lib.ptr(r), _lib.ptr(z), _lib.ptr(rTr), _lib.ptr(pws), _lib.stream())
         b_norm = float(torch.linalg.norm(bb))
-        it = 0
-        while True:
-            Ap = A @ p
-            _lib.call("fb2_bcg_dots", n, B, _lib.ptr(p), _lib.ptr(Ap), _lib.ptr(pAp), _lib.ptr(pws), _lib.stream())
-            _lib.call("fb2_bcg_update_xr", n, B, _lib.ptr(x), _lib.ptr(r), _lib.ptr(p), _lib.ptr(Ap), _lib.ptr(rTr), _lib.ptr(pAp),
-                      _lib.stream())
-            z = r if minv is None else minv[:, None] * r
-            _lib.call("fb2_bcg_dots", n, B, _lib.ptr(r), _lib.ptr(z), _lib.ptr(rTr_new), _lib.ptr(pws), _lib.stream())
-            r_norm = float(rTr_new.sum().sqrt())
-            it += 1
-            info["residual"], info["niter"] = r_norm, it
-            if r_norm < atol or r_norm < rtol * b_norm or (maxit is not None and it >= maxit):
-                break
-            _lib.call("fb2_bcg_update_p", n, B, _lib.ptr(p), _lib.ptr(r), _lib.ptr(minv), _lib.ptr(rTr_new), _lib.ptr(rTr), _lib.stream())
-            rTr, rTr_new = rTr_new, rTr
+        # the stopping test runs on the device (fb2_bcg_check); once it fires the update kernels do nothing, so the host
+        # polls the 4-double state block only every CHECK_EVERY iterations instead of synchronising in each one
+        state = torch.zeros(4, dtype=torch.float64, device=dev)
+        Ap = torch.empty_like(bb)
+        z = r if minv is None else torch.empty_like(r)
+        mit = -1 if maxit is None else int(maxit)
+        done = False
+        while not done:
+            for _ in range(_BCG_CHECK_EVERY):
+                A.matmul(p, out=Ap)
+                _lib.call("fb2_bcg_dots", n, B, _lib.ptr(p), _lib.ptr(Ap), _lib.ptr(pAp), _lib.ptr(pws), _lib.stream())
+                _lib.call("fb2_bcg_update_xr", n, B, _lib.ptr(x), _lib.ptr(r), _lib.ptr(p), _lib.ptr(Ap), _lib.ptr(rTr), _lib.ptr(pAp),
+                          _lib.ptr(state), _lib.stream())
+                if minv is not None:
+                    torch.mul(minv[:, None], r, out=z)
+                _lib.call("fb2_bcg_dots", n, B, _lib.ptr(r), _lib.ptr(z), _lib.ptr(rTr_new), _lib.ptr(pws), _lib.stream())
+                _lib.call("fb2_bcg_check", B, _lib.ptr(rTr_new), float(atol), float(rtol) * b_norm, mit, _lib.ptr(state), _lib.stream())
+                _lib.call("fb2_bcg_update_p", n, B, _lib.ptr(p), _lib.ptr(r), _lib.ptr(minv), _lib.ptr(rTr_new), _lib.ptr(rTr),
+                          _lib.ptr(state), _lib.stream())
+                rTr, rTr_new = rTr_new, rTr
+            st = state.tolist()                       # one device->host read per CHECK_EVERY iterations
+            done = st[0] != 0.0
+            info["residual"], info["niter"] = st[2], int(st[1])
     if batch_first:
         x = x.swapaxes(0, 1)
     return (x, info) if returninfo else x

@@ -58,7 +58,9 @@ class CSRTensor:
         return f"CSRTensor(shape={self.shape}, nnz={self.nnz}, device={self.device})"
 
     # --- products (sparse/csr_tensor.py:411-452 -> csr_spmm) --------------------------------
-    def matmul(self, other):
+    def matmul(self, other, out=None):
+        """A @ other; `out` (optional, beyond the reference signature): a contiguous float64 result buffer of the right shape,
+        so that solver loops allocate nothing per product"""
         if isinstance(other, torch.Tensor):
             if self._values is None:
                 raise ValueError("Cannot multiply a CSRTensor without values")
@@ -70,14 +72,17 @@ class CSRTensor:
             if other.dtype != torch.float64 or self._col.dtype != torch.int32:
                 raise TypeError("fealpy_b200 SpMV needs float64 values/vectors and int32 column indices")
             x = other.contiguous()
+            if out is not None and not (out.dtype == torch.float64 and out.is_contiguous() and out.device == x.device
+                                        and tuple(out.shape) == (n,) + tuple(x.shape[1:])):
+                raise ValueError("out must be a contiguous float64 tensor of the result's shape on the operand's device")
             if x.ndim == 1:
-                y = torch.empty(n, dtype=torch.float64, device=x.device)
+                y = torch.empty(n, dtype=torch.float64, device=x.device) if out is None else out
                 blk_row, tile, max_row = self.spmv_plan()
                 _lib.call("fb2_csr_spmv", n, self.nnz, _lib.ptr(self._crow), _lib.ptr(self._col), _lib.ptr(self._values),
                           _lib.ptr(x), _lib.ptr(y), _lib.ptr(blk_row), tile, max_row, _lib.stream())
                 return y
             if x.ndim == 2:
-                y = torch.empty((n, x.shape[1]), dtype=torch.float64, device=x.device)
+                y = torch.empty((n, x.shape[1]), dtype=torch.float64, device=x.device) if out is None else out
                 _lib.call("fb2_csr_spmm", n, _lib.ptr(self._crow), _lib.ptr(self._col), _lib.ptr(self._values), _lib.ptr(x),
                           _lib.ptr(y), x.shape[1], _lib.stream())
                 return y

@@ -256,9 +256,14 @@ int fb2_cg_update_p_push(const int64_t own[4], double* p, const double* r, const
  * the loop with fb2_csr_spmm.  All scalar arrays live on the device. */
 int fb2_bcg_dots(int64_t n, int nb, const double* a, const double* b, double* out_dev, void* partial_ws, void* stream);
 int fb2_bcg_update_xr(int64_t n, int nb, double* x, double* r, const double* p, const double* Ap, const double* rTr, const double* pAp,
-                      void* stream);
+                      const double* state, void* stream);
 int fb2_bcg_update_p(int64_t n, int nb, double* p, const double* r, const double* minv_diag, const double* rTr_new, const double* rTr,
-                     void* stream);
+                     const double* state, void* stream);
+/* the joint stopping test on the device (solver/cg.py:97-121: r_norm = sqrt(sum_k rTr_new[k]) against atol, then rtol*|b|, then
+ * maxit; maxit < 0 = none).  `state`: 4 device doubles, zero-initialised by the caller = (done flag, iterations, r_norm, pad);
+ * once done is raised the update kernels that receive `state` do nothing, so the host may launch several iterations per poll
+ * and x remains the iterate of the stopping iteration. */
+int fb2_bcg_check(int nb, const double* rTr_new, double atol, double rtol_bnorm, int maxit, double* state, void* stream);
 
 /* ---- next rows: right-hand side and Dirichlet step ------------------------
  * replaces ScalarSourceIntegrator.assembly + LinearForm.assembly (fem/scalar_source_integrator.py:13-57,

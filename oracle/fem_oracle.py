@@ -552,6 +552,27 @@ def source_vector(mesh: Mesh, p: int, f, q=None):
     return F
 
 
+def vector_source_vector(mesh: Mesh, p: int, f, ncomp: int, dof_priority: bool, q=None):
+    """LinearForm + VectorSourceIntegrator on a TensorFunctionSpace (fem/vector_source_integrator.py:44-58,
+    functional.py:57-59): F_e[c, I] = |K| sum_q w_q phi_I(q) . f(c, q) with the tensor basis phi_(i,a) = phi_i e_a
+    (functionspace/utils.py generate_tensor_basis), local index i*ncomp + a (dof_priority False) or a*ldof + i (True);
+    index_added through the tensor cell2dof."""
+    q = p + 3 if q is None else q
+    bcs, ws = quadrature(mesh.TD, q)
+    cm = mesh.cell_measure()
+    phi = shape_function(bcs, p)                      # (NQ, ldof)
+    val = eval_coef(mesh, f, bcs)                     # (NC, NQ, ncomp)
+    fe = np.einsum("c,q,qi,cqa->cia", cm, ws, phi, val)
+    NC, L = fe.shape[0], fe.shape[1]
+    fe = fe.transpose(0, 2, 1).reshape(NC, ncomp * L) if dof_priority else fe.reshape(NC, L * ncomp)
+    c2d = mesh.cell_to_ipoint(p)
+    sg = mesh.number_of_global_ipoints(p)
+    c2d_t = tensor_cell_to_dof(c2d, sg, ncomp, dof_priority)
+    F = np.zeros(sg * ncomp)
+    np.add.at(F, c2d_t.reshape(-1), fe.reshape(-1))
+    return F
+
+
 def boundary_dof_flag(mesh: Mesh, p: int, threshold=None, method=None):
     """functionspace/dofs.py:23-55.  method None / 'centroid': a callable threshold selects boundary FACES by their
     barycentres and every dof of a kept face is flagged; 'interp': it selects boundary dofs by their interpolation points."""

@@ -111,6 +111,9 @@ def gd_vector(p):
     return np.stack([0.1 * p[..., 1], -0.2 * p[..., 0] * p[..., -1], 0.05 + 0.0 * p[..., 0]], axis=-1)[..., :p.shape[-1]]
 
 
+gd_vector.coordtype = "cartesian"
+
+
 THRESHOLDS = {"thr_partial": thr_partial}
 
 # Poisson problems with Dirichlet BC + source (rows f1/f2): -div(grad u) = f, u = g on the boundary

@@ -647,6 +647,20 @@ def test_batched_rhs_cg_matches_oracle(batch_first, U):
     y = (A @ U.t64(Bm)).cpu().numpy()                                     # SpMM against the oracle SpMV
     ref = np.stack([O.csr_matvec(crow, col, val, Bm[:, k]) for k in range(3)], axis=1)
     assert np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
+    # wider batches (8 columns per pass of A, then the remainder) and a solve cut by maxit between two host polls: the
+    # device-side stopping test must freeze x at the stopping iteration (the host reads the state every 8 iterations)
+    for nb, maxit in ((8, 5), (11, 13), (1, 3)):
+        Bw = rng.standard_normal((n, nb))
+        mv = lambda v: np.stack([O.csr_matvec(crow, col, val, v[:, k]) for k in range(v.shape[1])], axis=1)
+        yw = (A @ U.t64(Bw)).cpu().numpy()
+        assert np.max(np.abs(yw - mv(Bw))) <= 1e-12 * np.max(np.abs(yw))
+        xo, oinfo = O.cg(mv, Bw, atol=0.0, rtol=0.0, maxit=maxit)
+        bt = U.t64(Bw.T.copy() if batch_first else Bw)
+        x, info = cg(A, bt, batch_first=batch_first, returninfo=True, atol=0.0, rtol=0.0, maxit=maxit)
+        xg = x.cpu().numpy().T if batch_first else x.cpu().numpy()
+        assert info["niter"] == oinfo["niter"] == maxit
+        assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) <= 1e-10
+        assert abs(info["residual"] - oinfo["residual"]) <= 1e-9 * abs(oinfo["residual"])
 
 
 def _relabelled_mesh(kind, dims, seed):
@@ -1080,6 +1094,15 @@ def test_elasticity_dirichlet_jacobi_cg(case, U):
     x, info = cg(A2, F2, M=CSRTensor(d.crow, d.col, 1.0 / d.values, A2.shape), returninfo=True, atol=1e-14, rtol=1e-11)
     assert np.linalg.norm(x.cpu().numpy() - gold["x"]) / np.linalg.norm(gold["x"]) <= 1e-10
     assert abs(info["niter"] - gold["info"]["niter"]) <= 2
+    # vector load: LinearForm + VectorSourceIntegrator on the tensor space against the reference run
+    from fealpy_b200.fem import LinearForm, VectorSourceIntegrator
+    from fealpy_b200.basis import host_tables
+    Fv = LinearForm(space).add_integrator(VectorSourceIntegrator(source=U.torch_coef_func(C.gd_vector), q=case["q"])).assembly()
+    assert np.max(np.abs(Fv.cpu().numpy() - gold["F_vsrc"])) <= 1e-13 * np.max(np.abs(gold["F_vsrc"]))
+    bcs = host_tables(mesh.TD, case["p"], case["p"] + 3 if case["q"] is None else case["q"])["bcs"]
+    vals = U.t64(C.gd_vector(mesh.bc_to_point(bcs).cpu().numpy()))            # the same field as an (NC, NQ, GD) tensor
+    Fv2 = LinearForm(space).add_integrator(VectorSourceIntegrator(source=vals, q=case["q"])).assembly()
+    assert torch.equal(Fv, Fv2), "tensor-valued and callable sources give the same load"
 
 
 @pytest.mark.parametrize("kind,dims,p,world", [("tet", (6, 5, 4), 2, 3), ("tet", (5, 4, 4), 1, 2), ("tri", (14, 11), 3, 5), ("tet", (4, 3, 3), 3, 2)])

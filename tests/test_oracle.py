@@ -239,3 +239,6 @@ def test_oracle_tensor_bc_matches_reference_run(case):
     x, info = O.cg(lambda w: A @ w, F2, Minv=lambda r: r / diag, atol=1e-14, rtol=1e-11)
     assert abs(info["niter"] - gold["info"]["niter"]) <= 2
     assert np.linalg.norm(x - gold["x"]) / np.linalg.norm(gold["x"]) < 1e-10
+    # vector load of the reference's LinearForm + VectorSourceIntegrator on the tensor space
+    Fv = O.vector_source_vector(m, p, C.gd_vector, GD, prio, q=case["q"])
+    assert G.rel_err(Fv, gold["F_vsrc"]) < 1e-13

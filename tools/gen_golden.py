@@ -20,7 +20,7 @@ from fealpy.backend import backend_manager as bm  # noqa: E402
 from fealpy.mesh import TriangleMesh, TetrahedronMesh  # noqa: E402
 from fealpy.functionspace import LagrangeFESpace, TensorFunctionSpace  # noqa: E402
 from fealpy.fem import (BilinearForm, LinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator,  # noqa: E402
-                        LinearElasticityIntegrator, ScalarSourceIntegrator, DirichletBC)
+                        LinearElasticityIntegrator, ScalarSourceIntegrator, VectorSourceIntegrator, DirichletBC)
 from fealpy.material.elastic_material import LinearElasticMaterial  # noqa: E402
 from fealpy.solver import cg  # noqa: E402
 from fealpy.decorator import cartesian  # noqa: E402
@@ -273,8 +273,13 @@ def run_tensor_bc_case(case):
     dd = (A2s - Ao)
     assert (abs(dd).max() if dd.nnz else 0.0) < 1e-13, f"{name}: tensor BC matrix differs"
     A2s.eliminate_zeros()
+    # vector load: reference LinearForm + VectorSourceIntegrator on the tensor space (fem/vector_source_integrator.py)
+    fsrc = cartesian(lambda pts: C.gd_vector(pts))
+    Fv = np.asarray(LinearForm(space).add_integrator(VectorSourceIntegrator(source=fsrc, q=case["q"])).assembly())
+    Fvo = O.vector_source_vector(mesh_o, p, C.gd_vector, GD, prio, q=case["q"])
+    assert rel_err(Fvo, Fv) < 1e-13, f"{name}: oracle vector source differs"
     out = dict(node=np.asarray(mesh.node), cell=np.asarray(mesh.cell), crow=np.asarray(A.crow), col=np.asarray(A.col),
-               values=np.asarray(A.values), F=np.asarray(F), isbd=isbd, F_bc=np.asarray(F2), uh=uh,
+               values=np.asarray(A.values), F=np.asarray(F), isbd=isbd, F_bc=np.asarray(F2), uh=uh, F_vsrc=Fv,
                Abc_indptr=A2s.indptr.astype(np.int64), Abc_indices=A2s.indices.astype(np.int32), Abc_data=A2s.data,
                x=np.asarray(x),
                info=np.array(json.dumps(dict(gdof=int(gdof), niter=int(cinfo["niter"]), residual=float(cinfo["residual"])))))
