@@ -187,6 +187,8 @@ class SimplexMesh:
 
     def interpolation_points(self, p):
         """(gdof, GD) coordinates of the global interpolation points."""
+        if p == 1:                          # the nodes themselves (a 12.6 M-cell gather + scatter took 212 ms for nothing)
+            return self.node.clone()
         gdof = self.number_of_global_ipoints(p)
         mi = torch.as_tensor(self.multi_index_matrix(p) / p, dtype=torch.float64, device=self.device)
         pts = torch.einsum("cjk,ij->cik", self.node[self.cell.long()], mi)

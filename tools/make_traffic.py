@@ -37,11 +37,18 @@ out = {}
 for arg in sys.argv[1:]:
     cfg, path = arg.split("=")
     seq = parse(path)
-    last = {}
+    # a representative launch per kernel: the median (by duration) of its full-length launches -- the CG graph replays
+    # a chunk of iterations and the launches after the stopping iteration exit at once, those must not be picked
+    groups = {}
     for d in seq:
-        last[base(d["name"])] = d
+        groups.setdefault(base(d["name"]), []).append(d)
+    last = {}
+    for k, lst in groups.items():
+        tmax = max(x["gpu__time_duration.sum"] for x in lst)
+        full = sorted((x for x in lst if x["gpu__time_duration.sum"] >= 0.5 * tmax), key=lambda x: x["gpu__time_duration.sum"])
+        last[k] = full[len(full) // 2]
     ent = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none "
-                     "python tools/gpu_traffic_probe.py %s (per launch; last occurrence of each kernel)" % cfg,
+                     "python tools/gpu_traffic_probe.py %s (per launch; median full-length launch of each kernel)" % cfg,
            "assembly_kernels": {}, "cg_kernels": {}}
     for k in ASM:
         if k in last:
