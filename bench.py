@@ -691,7 +691,7 @@ def run_ours(args):
         asm_gbs = b_warm * args.steps / t_asm / 1e9          # per GPU (rank 0's share of the bytes, max-over-ranks time)
         cg_gbs = b_it * iters / t_cg / 1e9
         path = bform.last_path
-        asm_kernel = {"fused": "cell_geometry4_kernel + assemble_const_v4/v5_kernel", "gather": "elem_* (K1) + assemble_from_ke_kernel",
+        asm_kernel = {"fused": "cell_geometry4_kernel + assemble_const_v6_kernel", "gather": "elem_* (K1) + assemble_from_ke_kernel",
                       "fused-elasticity-p1": "cell_gradients_kernel + assemble_from_ke_kernel<ETD=3>"}.get(path, path)
         asm_launches = {"fused": 2, "fused-elasticity-p1": 2}.get(path, 6)
         line = {
