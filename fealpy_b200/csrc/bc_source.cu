@@ -95,15 +95,25 @@ int gather_vector(int64_t gdof, const int64_t* adj_ptr, const int* adj_pair, con
 // ---- Dirichlet ---------------------------------------------------------------------------
 // matrix: rows/columns of boundary dofs removed, unit diagonal on boundary rows (canonical
 // sorted CSR; the reference reaches the same matrix through _mul + spdiags, dirichlet_bc.py:133-229)
+// Eight lanes own a row and stride over its entries (coalesced 32-/64-byte runs of col / val instead of one thread
+// walking a whole row: DirichletBC.apply 60.9 -> 4.5 ms on the 286 M-nonzero elasticity matrix, profiles/r02_cold_breakdown.txt); kept entries
+// keep their order -- the output position of an entry is the number of kept entries before it, from a ballot.
+constexpr int BC_G = 8;
+
 __global__ void __launch_bounds__(256) bc_count_kernel(int64_t n, const int64_t* __restrict__ crow, const int* __restrict__ col,
                                                        const uint8_t* __restrict__ isbd, int* __restrict__ cnt) {
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-    int c = 1;
-    if (!isbd[r]) {
-      c = 0;
-      for (int64_t k = crow[r]; k < crow[r + 1]; ++k) c += isbd[col[k]] ? 0 : 1;
-    }
-    cnt[r] = c;
+  const int g = threadIdx.x % BC_G;
+  const int64_t ngroup = (int64_t)gridDim.x * (blockDim.x / BC_G);
+  const int64_t nrow_pad = (n + 31) / 32 * 32;           // whole warps stay in the loop together (shuffles below)
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / BC_G; r < nrow_pad; r += ngroup) {
+    int c = 0;
+    const bool live = r < n;
+    const bool bd = live && isbd[r];
+    if (live && !bd)
+      for (int64_t k = crow[r] + g; k < crow[r + 1]; k += BC_G) c += isbd[col[k]] ? 0 : 1;
+#pragma unroll
+    for (int o = BC_G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (live && g == 0) cnt[r] = bd ? 1 : c;
   }
 }
 
@@ -111,16 +121,32 @@ __global__ void __launch_bounds__(256) bc_fill_kernel(int64_t n, const int64_t* 
                                                       const double* __restrict__ val, const uint8_t* __restrict__ isbd,
                                                       const int64_t* __restrict__ crow_new, int* __restrict__ col_new,
                                                       double* __restrict__ val_new) {
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-    int64_t o = crow_new[r];
-    if (isbd[r]) {
-      col_new[o] = (int)r;
-      val_new[o] = 1.0;
-    } else {
-      for (int64_t k = crow[r]; k < crow[r + 1]; ++k) {
-        const int c = col[k];
-        if (!isbd[c]) { col_new[o] = c; val_new[o] = val[k]; ++o; }
+  const int lane = threadIdx.x & 31, g = lane % BC_G, gsh = lane / BC_G * BC_G;
+  const unsigned below = (1u << g) - 1u;
+  const int64_t ngroup = (int64_t)gridDim.x * (blockDim.x / BC_G);
+  const int64_t nrow_pad = (n + 31) / 32 * 32;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / BC_G; r < nrow_pad; r += ngroup) {
+    const bool live = r < n;
+    const bool bd = live && isbd[r];
+    int64_t o = live ? crow_new[r] : 0;
+    const int64_t k0 = live ? crow[r] : 0, k1 = (live && !bd) ? crow[r + 1] : k0;
+    if (bd && g == 0) { col_new[o] = (int)r; val_new[o] = 1.0; }
+    // rows of one warp have different lengths: every lane runs as many rounds as the warp's longest row needs
+    int rounds = (int)((k1 - k0 + BC_G - 1) / BC_G);
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, of));
+    for (int t = 0; t < rounds; ++t) {
+      const int64_t k = k0 + (int64_t)t * BC_G + g;
+      int c = 0;
+      bool keep = false;
+      if (k < k1) { c = col[k]; keep = !isbd[c]; }
+      const unsigned kept = (__ballot_sync(0xffffffffu, keep) >> gsh) & ((1u << BC_G) - 1u);
+      if (keep) {
+        const int64_t dst = o + __popc(kept & below);
+        col_new[dst] = c;
+        val_new[dst] = val[k];
       }
+      o += __popc(kept);
     }
   }
 }
@@ -139,7 +165,7 @@ int bc_matrix_count(int64_t n, const int64_t* crow, const int* col, const uint8_
   Carver c(ws);
   int* cnt = c.take<int>(n);
   void* scan_ws = c.take<char>(scan_workspace_bytes(n));
-  if (n > 0) bc_count_kernel<<<grid_for(n), 256, 0, s>>>(n, crow, col, isbd, cnt);
+  if (n > 0) bc_count_kernel<<<grid_for(n * BC_G), 256, 0, s>>>(n, crow, col, isbd, cnt);
   FB2_LAUNCH_CHECK();
   FB2_TRY(exclusive_scan_i32(cnt, crow_new, n, true, scan_ws, s));
   FB2_CUDA(cudaMemcpyAsync(nnz_host, crow_new + n, 8, cudaMemcpyDeviceToHost, s));
@@ -150,7 +176,7 @@ int bc_matrix_count(int64_t n, const int64_t* crow, const int* col, const uint8_
 int bc_matrix_fill(int64_t n, const int64_t* crow, const int* col, const double* val, const uint8_t* isbd, const int64_t* crow_new,
                    int* col_new, double* val_new, cudaStream_t s) {
   if (n <= 0) return OK;
-  bc_fill_kernel<<<grid_for(n), 256, 0, s>>>(n, crow, col, val, isbd, crow_new, col_new, val_new);
+  bc_fill_kernel<<<grid_for(n * BC_G), 256, 0, s>>>(n, crow, col, val, isbd, crow_new, col_new, val_new);
   FB2_LAUNCH_CHECK();
   return OK;
 }
