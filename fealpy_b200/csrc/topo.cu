@@ -8,6 +8,7 @@
 //             cell_to_ipoint      mesh/triangle_mesh.py:218-270, tetrahedron_mesh.py:388-441,
 //                                 edge_to_ipoint mesh/mesh_base.py:188-210
 // Here: sorted-tuple keys -> stable radix sort (payload = position) -> head flags -> scan.
+#include <cstdlib>
 #include "common.cuh"
 #include "sort_scan.cuh"
 #include "topo.cuh"
@@ -117,6 +118,54 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t* __restrict__
     head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
+// ---- faces of meshes with more than 2^21 nodes: the sorted vertex triple does not fit one 64-bit key --------------------
+// (tet from_box 128^3 has 2 146 689 nodes: 3 x 22 bits.)  The stable LSD sort runs in two legs instead: by (b, d) with the
+// original position as payload, then by a through that payload -- the order of the single wide key, first occurrences first.
+__device__ __forceinline__ void sorted_triple(const int* __restrict__ cell, int NV, const LocalEnt& le, int64_t t, uint64_t& a,
+                                              uint64_t& b, uint64_t& d) {
+  const int64_t c = t / le.n;
+  const int e = (int)(t - c * le.n);
+  a = (uint32_t)cell[c * NV + le.v[e][0]];
+  b = (uint32_t)cell[c * NV + le.v[e][1]];
+  d = (uint32_t)cell[c * NV + le.v[e][2]];
+  if (a > b) { uint64_t q = a; a = b; b = q; }
+  if (b > d) { uint64_t q = b; b = d; d = q; }
+  if (a > b) { uint64_t q = a; a = b; b = q; }
+}
+
+__global__ void __launch_bounds__(256) entity_keys_lo_kernel(const int* __restrict__ cell, int64_t NC, int NV, LocalEnt le, int vbits,
+                                                             uint64_t* __restrict__ keys) {
+  const int64_t n = NC * le.n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t a, b, d;
+    sorted_triple(cell, NV, le, t, a, b, d);
+    keys[t] = (b << vbits) | d;
+  }
+}
+
+__global__ void __launch_bounds__(256) entity_keys_hi_kernel(const int* __restrict__ cell, int NV, LocalEnt le,
+                                                             const uint32_t* __restrict__ perm, int64_t n, uint64_t* __restrict__ keys) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t a, b, d;
+    sorted_triple(cell, NV, le, perm[i], a, b, d);
+    keys[i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) heads_wide_kernel(const int* __restrict__ cell, int NV, LocalEnt le,
+                                                         const uint32_t* __restrict__ perm, int64_t n, uint8_t* __restrict__ head) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t h = 1;
+    if (i > 0) {
+      uint64_t a, b, d, a0, b0, d0;
+      sorted_triple(cell, NV, le, perm[i], a, b, d);
+      sorted_triple(cell, NV, le, perm[i - 1], a0, b0, d0);
+      h = (a != a0 || b != b0 || d != d0) ? 1 : 0;
+    }
+    head[i] = h;
+  }
+}
+
 // cell2ent[perm[i]] = id(i);  ent[id] = vertices of the first occurrence (original orientation)
 __global__ void __launch_bounds__(256) entity_fill_kernel(const int* __restrict__ cell, int NV, LocalEnt le,
                                                           const uint32_t* __restrict__ perm, const uint8_t* __restrict__ head,
@@ -169,7 +218,11 @@ int build_entities(const int* cell, int64_t NC, int TD, int kind, int64_t NN, in
   const int64_t n = NC * le.n;
   if (n <= 0) { *count_host = 0; return OK; }
   const int vbits = bits_for(NN);
-  if (vbits * le.nve > 63) return fail(ERR_UNSUPPORTED, "build_entities: %d-vertex keys need %d bits (NN=%lld too large)", le.nve, vbits * le.nve, (long long)NN);
+  // faces of meshes with more than 2^21 nodes: two-leg sort (FB2_TOPO_FORCE_WIDE=1 takes that path on any mesh: tests)
+  const char* fw = getenv("FB2_TOPO_FORCE_WIDE");
+  const bool wide = vbits * le.nve > 63 || (le.nve == 3 && fw && fw[0] == '1');
+  if (wide && (le.nve != 3 || 2 * vbits > 63))
+    return fail(ERR_UNSUPPORTED, "build_entities: %d-vertex keys need %d bits (NN=%lld too large)", le.nve, vbits * le.nve, (long long)NN);
   Carver c(ws);
   uint64_t* keys = c.take<uint64_t>(n);
   uint32_t* perm = c.take<uint32_t>(n);
@@ -177,13 +230,26 @@ int build_entities(const int* cell, int64_t NC, int TD, int kind, int64_t NN, in
   uint8_t* head = c.take<uint8_t>(n);
   int64_t* S = c.take<int64_t>(n + 1);
   void* scan_ws = c.take<char>(scan_workspace_bytes(n));
-  entity_keys_kernel<<<grid_for(n), 256, 0, s>>>(cell, NC, NV, le, vbits, keys);
-  FB2_LAUNCH_CHECK();
   uint64_t* ks = nullptr;
   uint32_t* ps = nullptr;
-  FB2_TRY(radix_sort_pairs(keys, perm, n, vbits * le.nve, sort_ws, s, &ks, &ps));
-  if (ps != perm) FB2_CUDA(cudaMemcpyAsync(perm, ps, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
-  heads_kernel<<<grid_for(n), 256, 0, s>>>(ks, n, head);
+  if (!wide) {
+    entity_keys_kernel<<<grid_for(n), 256, 0, s>>>(cell, NC, NV, le, vbits, keys);
+    FB2_LAUNCH_CHECK();
+    FB2_TRY(radix_sort_pairs(keys, perm, n, vbits * le.nve, sort_ws, s, &ks, &ps));
+    if (ps != perm) FB2_CUDA(cudaMemcpyAsync(perm, ps, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    heads_kernel<<<grid_for(n), 256, 0, s>>>(ks, n, head);
+  } else {
+    entity_keys_lo_kernel<<<grid_for(n), 256, 0, s>>>(cell, NC, NV, le, vbits, keys);
+    FB2_LAUNCH_CHECK();
+    FB2_TRY(radix_sort_pairs(keys, perm, n, 2 * vbits, sort_ws, s, &ks, &ps));      // leg 1: by (b, d), payload = position
+    if (ps != perm) FB2_CUDA(cudaMemcpyAsync(perm, ps, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    entity_keys_hi_kernel<<<grid_for(n), 256, 0, s>>>(cell, NV, le, perm, n, keys);
+    FB2_LAUNCH_CHECK();
+    ps = perm;                                                                      // leg 2: by a, payload carried (stable)
+    FB2_TRY(radix_sort_pairs(keys, perm, n, vbits, sort_ws, s, &ks, &ps));
+    if (ps != perm) FB2_CUDA(cudaMemcpyAsync(perm, ps, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    heads_wide_kernel<<<grid_for(n), 256, 0, s>>>(cell, NV, le, perm, n, head);
+  }
   FB2_LAUNCH_CHECK();
   FB2_TRY(exclusive_scan_u8(head, S, n, true, scan_ws, s));
   entity_fill_kernel<<<grid_for(n), 256, 0, s>>>(cell, NV, le, perm, head, S, n, cell2ent, nullptr);

@@ -40,8 +40,8 @@ class LagrangeFESpace:
     def cell_to_dof(self, index=None):
         return self.mesh.cell_to_ipoint(self.p, index=index)
 
-    def interpolation_points(self):
-        return self.mesh.interpolation_points(self.p)
+    def interpolation_points(self, index=None):
+        return self.mesh.interpolation_points(self.p, index=index)
 
     def geo_dimension(self): return self.GD
     def top_dimension(self): return self.TD
@@ -98,7 +98,7 @@ class LagrangeFESpace:
             flag = self._boundary_face_dofs()
             if callable(threshold):
                 idx = flag.nonzero().reshape(-1)
-                sel = torch.as_tensor(threshold(self.interpolation_points()[idx]), device=self.device).to(torch.bool)
+                sel = torch.as_tensor(threshold(self.interpolation_points(index=flag)[idx]), device=self.device).to(torch.bool)
                 flag = torch.zeros_like(flag)
                 flag[idx[sel]] = True
             return flag
@@ -112,7 +112,7 @@ class LagrangeFESpace:
                 uh = torch.zeros_like(gd)
             uh[..., isD] = gd[isD]
         elif callable(gd):
-            val = gd(self.interpolation_points()[isD])
+            val = gd(self.interpolation_points(index=isD)[isD])
             if uh is None:
                 uh = torch.zeros(self.number_of_global_dofs(), dtype=self.ftype, device=self.device)
             uh[..., isD] = val
@@ -182,8 +182,8 @@ class TensorFunctionSpace:
             self._c2d = out
         return self._c2d if index is None else self._c2d[index]
 
-    def interpolation_points(self):
-        return self.scalar_space.interpolation_points()
+    def interpolation_points(self, index=None):
+        return self.scalar_space.interpolation_points(index=index)
 
     def is_boundary_dof(self, threshold=None, method="interp"):
         """functionspace/tensor_space.py:159-188: the scalar flag repeated over the components (or one threshold per
@@ -219,7 +219,7 @@ class TensorFunctionSpace:
             if isinstance(threshold, (tuple, torch.Tensor)):
                 raise NotImplementedError("callable gd with per-component / tensor thresholds is not on the accelerated path")
             sflag = s.is_boundary_dof(threshold, method=method)
-            val = gd(s.interpolation_points()[sflag])                 # (nbd, ncomp)
+            val = gd(s.interpolation_points(index=sflag)[sflag])     # (nbd, ncomp)
             sg = s.number_of_global_dofs()
             view = uh.view(n, sg) if self.dof_priority else uh.view(sg, n)
             if self.dof_priority:

@@ -714,6 +714,64 @@ def test_relabelled_mesh_matches_oracle(kind, dims, p, U):
     assert np.array_equal(space.is_boundary_dof().cpu().numpy(), O.boundary_dof_flag(om, p))
 
 
+def test_dirichlet_problem_at_config2_size(U):
+    """row f1 at BASELINE config 2's size (tet P2 128^3: 2 146 689 nodes -- face keys need the two-leg sort; 17 M dofs): the
+    boundary dof count is the closed form (2n+1)^3 - (2n-1)^3, boundary rows of the constrained matrix are unit rows, the
+    right-hand side carries g on the boundary, interior rows keep their interior entries, and CG reduces the residual"""
+    from fealpy_b200.mesh import TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.fem import BilinearForm, ScalarDiffusionIntegrator, DirichletBC, LinearForm, ScalarSourceIntegrator
+    from fealpy_b200.solver import cg
+    n = 128
+    mesh = TetrahedronMesh.from_box([0, 1, 0, 1, 0, 1], n, n, n)
+    space = LagrangeFESpace(mesh, 2)
+    A = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator()).assembly()
+
+    def g(p):
+        return torch.sin(p[..., 0]) * torch.cos(p[..., 1]) + p[..., 2]
+    g.coordtype = "cartesian"
+    F = LinearForm(space).add_integrator(ScalarSourceIntegrator(1.0)).assembly()
+    assert abs(float(F.sum()) - 1.0) <= 1e-12                      # integral of 1 over the unit cube
+    bc = DirichletBC(space, gd=g)
+    bd = bc.is_boundary_dof
+    assert int(bd.sum()) == (2 * n + 1) ** 3 - (2 * n - 1) ** 3
+    ip = space.interpolation_points(index=bd)
+    on_boundary = ((ip[bd] == 0.0) | (ip[bd] == 1.0)).any(dim=1)
+    assert bool(on_boundary.all())
+    A2, F2 = bc.apply(A, F)
+    assert torch.equal(F2[bd], g(ip[bd]))
+    rows = bd.nonzero().reshape(-1)
+    assert bool(((A2.crow[rows + 1] - A2.crow[rows]) == 1).all())
+    assert torch.equal(A2.col[A2.crow[rows]].long(), rows) and bool((A2.values[A2.crow[rows]] == 1.0).all())
+    assert not bool(bd[A2.col.long()][~bd.repeat_interleave(A2.crow[1:] - A2.crow[:-1])].any()), "no boundary column in an interior row"
+    x, info = cg(A2, F2, maxit=60, returninfo=True)
+    r0 = float((F2 - A2 @ torch.zeros_like(F2)).norm())
+    assert float((F2 - A2 @ x).norm()) < 0.05 * r0 and torch.equal(x[bd], F2[bd])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,p", [((5, 4, 3), 3), ((6, 5, 4), 2)])
+def test_wide_face_keys_match_oracle(dims, p, U, monkeypatch):
+    """tetrahedral meshes with more than 2^21 nodes (from_box 128^3) cannot pack a sorted vertex triple into one 64-bit
+    key: faces are then sorted in two stable legs (csrc/topo.cu).  FB2_TOPO_FORCE_WIDE=1 takes that path on a relabelled
+    small mesh: face table, cell2face, boundary flags and the P3 numbering (which uses the faces) against the oracle, and
+    bit-identical to the single-key path."""
+    from oracle import fem_oracle as O
+    from fealpy_b200.mesh import TetrahedronMesh
+    from fealpy_b200.functionspace import LagrangeFESpace
+    node, cell = _relabelled_mesh("tet", dims, seed=91 + p)
+    om = O.Mesh(node, cell)
+    ref = TetrahedronMesh(U.t64(node), U.t64(cell))
+    f0, c2f0 = ref.face.clone(), ref.cell2face.clone()
+    monkeypatch.setenv("FB2_TOPO_FORCE_WIDE", "1")
+    mesh = TetrahedronMesh(U.t64(node), U.t64(cell))
+    assert torch.equal(mesh.face, f0) and torch.equal(mesh.cell2face, c2f0)
+    assert np.array_equal(mesh.face.cpu().numpy(), om.face) and np.array_equal(mesh.cell2face.cpu().numpy(), om.cell2face)
+    space = LagrangeFESpace(mesh, p)
+    assert np.array_equal(space.cell_to_dof().cpu().numpy(), om.cell_to_ipoint(p))
+    assert np.array_equal(space.is_boundary_dof().cpu().numpy(), O.boundary_dof_flag(om, p))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,dims,p,tile", [("tet", (6, 5, 4), 2, 2560), ("tet", (5, 4, 3), 3, 2560), ("tri", (31, 17), 1, 512),
                                               ("tri", (9, 8), 3, 640), ("tet", (7, 6, 5), 1, 256)])
