@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
           if (head) col[cbase + rank] = (int)(key >> SYM_KBITS);
           const int pl = fd.small(kk);
           slots[(a0 + pl) * slot_stride + (kk - pl * L)] = (SlotT)rank;
-        } else if (stash) {                        // rank and representative flag per candidate for sym_replay_kernel
+        } else if (stash) {                        // rank and representative flag per candidate for sym_replay_flat_kernel
           stash[a0 * L + kk] = (uint16_t)((rank << 1) | (head ? 1 : 0));
         }
       }
@@ -315,26 +315,27 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) sym_rows_kernel(const int* __r
   }
 }
 
-// fill pass from the stash of the count pass: per candidate (rank << 1 | representative) -- no sort, one
-// warp per row, coalesced reads; the column of a representative is re-gathered from cell2dof
+// fill pass from the stash of the count pass: per candidate (rank << 1 | representative) -- no ranking again; the column
+// of a representative is re-gathered from cell2dof.  Flat over the adjacency positions: position q = (row r, pair) knows
+// its row without a search (r = cell2dof[pair]), so one THREAD replays the ldof candidates of one position -- contiguous
+// 2*ldof-byte stash reads and ldof-byte slot writes per thread (a warp-per-row version measured 0.8 ms slower)
 template <typename SlotT>
-__global__ void __launch_bounds__(256) sym_replay_kernel(const int* __restrict__ c2d, int L, int64_t gdof, const int64_t* __restrict__ adj_ptr,
-                                                         const int* __restrict__ adj_pair, const int64_t* __restrict__ crow,
-                                                         const uint16_t* __restrict__ stash, int* __restrict__ col,
-                                                         SlotT* __restrict__ slots, int slot_stride) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+__global__ void __launch_bounds__(256) sym_replay_flat_kernel(const int* __restrict__ c2d, int L, int64_t npos,
+                                                              const int* __restrict__ adj_pair, const int64_t* __restrict__ crow,
+                                                              const uint16_t* __restrict__ stash, int* __restrict__ col,
+                                                              SlotT* __restrict__ slots, int slot_stride) {
   const FastDiv fd(L);
-  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < gdof; r += nwarp) {
-    const int64_t a0 = adj_ptr[r];
-    const int ncand = (int)(adj_ptr[r + 1] - a0) * L;
-    const int64_t cbase = crow[r];
-    const uint16_t* st = stash + a0 * L;
-    for (int k = lane; k < ncand; k += 32) {
-      const int e = st[k], rank = e >> 1;
-      const int pl = fd.small(k), j = k - pl * L;
-      slots[(a0 + pl) * slot_stride + j] = (SlotT)rank;
-      if (e & 1) col[cbase + rank] = c2d[(int64_t)fd.wide(adj_pair[a0 + pl]) * L + j];
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < npos; q += (int64_t)gridDim.x * blockDim.x) {
+    const int pair = adj_pair[q];
+    const int64_t cell = fd.wide(pair);
+    const int64_t cbase = crow[c2d[pair]];
+    const uint16_t* __restrict__ st = stash + q * L;
+    SlotT* __restrict__ sl = slots + q * slot_stride;
+    const int* __restrict__ dofs = c2d + cell * L;
+    for (int j = 0; j < L; ++j) {
+      const int e = st[j], rank = e >> 1;
+      sl[j] = (SlotT)rank;
+      if (e & 1) col[cbase + rank] = dofs[j];
     }
   }
 }
@@ -390,9 +391,10 @@ int sym_fill(const int* c2d, int64_t NC, int L, int64_t gdof, const int64_t* adj
   if (stash) {
     if (slot_bytes != 1 && slot_bytes != 2) return fail(ERR_INVALID, "sym_fill: slot_bytes must be 1 or 2");
     const int st = slot_stride(L, slot_bytes);
-    const unsigned g = (unsigned)std::min<int64_t>(ceil_div(gdof, 8), (int64_t)kNumSM * 8);
-    if (slot_bytes == 1) sym_replay_kernel<uint8_t><<<g, 256, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, stash, col, (uint8_t*)slots, st);
-    else sym_replay_kernel<uint16_t><<<g, 256, 0, s>>>(c2d, L, gdof, adj_ptr, adj_pair, crow, stash, col, (uint16_t*)slots, st);
+    const int64_t npos = NC * L;
+    const unsigned g = grid_for(npos);
+    if (slot_bytes == 1) sym_replay_flat_kernel<uint8_t><<<g, 256, 0, s>>>(c2d, L, npos, adj_pair, crow, stash, col, (uint8_t*)slots, st);
+    else sym_replay_flat_kernel<uint16_t><<<g, 256, 0, s>>>(c2d, L, npos, adj_pair, crow, stash, col, (uint16_t*)slots, st);
     FB2_LAUNCH_CHECK();
     return OK;
   }
