@@ -155,6 +155,21 @@ __global__ void __launch_bounds__(ST_THREADS, 2048 / ST_THREADS) spmv_stream_ker
   constexpr int NGRP = ST_THREADS / G;
   double dsum = 0.0;
   bool waited = hw.nnb == 0;
+  // L2 policies (profiles/r02_tune_spmv.txt, call h24): gathering x with evict_last keeps it in L2 while 5.8 GB of matrix
+  // stream past (config 4: 0.861 -> 0.837 ms per CG iteration, config 2: 1.604 -> 1.591, config 3 unchanged); marking the
+  // (val, col) stream evict_first on top of that, or alone, measured no better (knob kept for tuning builds)
+#ifdef FB2_STREAM_L2_EVICT_FIRST
+  const uint64_t pol_s = l2_policy_evict_first();
+#define FB2_LDS(p) ld_stream((p), pol_s)
+#else
+#define FB2_LDS(p) ld_stream(p)
+#endif
+#ifndef FB2_GATHER_L2_DEFAULT
+  const uint64_t pol_x = l2_policy_evict_last();
+#define FB2_LDX(p) ld_hint((p), pol_x)
+#else
+#define FB2_LDX(p) (*(p))
+#endif
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
     if (!waited && blk >= hw.first_tile) {
       // tiles from hw.first_tile on hold boundary rows: they read halo entries of x that the neighbours push over NVLink
@@ -182,11 +197,11 @@ __global__ void __launch_bounds__(ST_THREADS, 2048 / ST_THREADS) spmv_stream_ker
         double vv[ST_UNROLL];
         int cc[ST_UNROLL];
 #pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) { vv[u] = ld_stream(vp + k + u * ST_THREADS); cc[u] = ld_stream(cp + k + u * ST_THREADS); }
+        for (int u = 0; u < ST_UNROLL; ++u) { vv[u] = FB2_LDS(vp + k + u * ST_THREADS); cc[u] = FB2_LDS(cp + k + u * ST_THREADS); }
 #pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * ST_THREADS] = vv[u] * x[cc[u]];
+        for (int u = 0; u < ST_UNROLL; ++u) prod[k + u * ST_THREADS] = vv[u] * FB2_LDX(x + cc[u]);
       }
-      for (; k < nval; k += ST_THREADS) prod[k] = ld_stream(vp + k) * x[ld_stream(cp + k)];
+      for (; k < nval; k += ST_THREADS) prod[k] = FB2_LDS(vp + k) * FB2_LDX(x + FB2_LDS(cp + k));
     }
     __syncthreads();
     for (int base = r0; base < r1; base += NGRP) {
