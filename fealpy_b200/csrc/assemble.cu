@@ -1044,6 +1044,10 @@ __device__ __forceinline__ void ldg_nc_f64x4(const double* p, double& a, double&
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];\n" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
+__device__ __forceinline__ void ldg_nc_f64x4(const double* p, double& a, double& b, double& c, double& d, uint64_t pol) {
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;\n" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
+}
+
 #ifndef FB2_ASM6_JC
 #define FB2_ASM6_JC 10     // all columns of a row in flight: 3.72 ms against 3.99 with 5 (tet P2 128^3; profiles/r02_tune_asm_v6.txt)
 #endif
@@ -1102,6 +1106,24 @@ assemble_const_v6_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
   const int nb = (int)(a.batch_ptr[tile + 1] - b0);
   const unsigned char* gblk = reinterpret_cast<const unsigned char*>(a.blocks) + b0 * BLK_BYTES;
 
+  // L2 policies (profiles/r02_tune_asm_v6.txt, call h25): the geometry records are re-read ~10 times through L2 and
+  // stay (evict_last), the schedule blocks are read once (evict_first) and the values are written once (st.global.cs):
+  // 3.647 -> 3.567 ms on config 2 with all three (records alone: no change; + streaming stores 3.60).  -DFB2_A6_NO_L2_POLICY
+  // restores the default policies.
+#ifndef FB2_A6_NO_L2_POLICY
+#define FB2_A6_H_KEEP
+#define FB2_A6_BLK_FIRST
+#define FB2_A6_ST_CS
+#endif
+#ifdef FB2_A6_H_KEEP
+  const uint64_t pol_h = l2_policy_evict_last();
+#endif
+#ifdef FB2_A6_BLK_FIRST
+  const uint64_t pol_b = l2_policy_evict_first();
+#define A6_BULK(dst, src, bytes, bar) bulk_g2s((dst), (src), (bytes), (bar), pol_b)
+#else
+#define A6_BULK(dst, src, bytes, bar) bulk_g2s((dst), (src), (bytes), (bar))
+#endif
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < NE; ++k) mbar_init(bar_s + 8 * k, 1);
@@ -1111,7 +1133,7 @@ assemble_const_v6_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
     for (int k = 0; k < NE; ++k)
       if (k < nb) {
         mbar_expect_tx(bar_s + 8 * k, BLK_BYTES);
-        bulk_g2s(ering_s + k * BLK_BYTES, gblk + (size_t)k * BLK_BYTES, BLK_BYTES, bar_s + 8 * k);
+        A6_BULK(ering_s + k * BLK_BYTES, gblk + (size_t)k * BLK_BYTES, BLK_BYTES, bar_s + 8 * k);
       }
   }
   __syncwarp();
@@ -1122,7 +1144,12 @@ assemble_const_v6_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
     const double* src = a.H + (int64_t)cell * HS;
     static_assert(HS % 4 == 0, "geometry records are multiples of 32 bytes");
 #pragma unroll
-    for (int t = 0; t < HS / 4; ++t) ldg_nc_f64x4(src + 4 * t, h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+    for (int t = 0; t < HS / 4; ++t)
+#ifdef FB2_A6_H_KEEP
+      ldg_nc_f64x4(src + 4 * t, h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3], pol_h);
+#else
+      ldg_nc_f64x4(src + 4 * t, h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+#endif
   };
 
   int celln = -1;
@@ -1159,13 +1186,18 @@ assemble_const_v6_kernel(const __grid_constant__ Asm4Args a, const __grid_consta
     __syncwarp();                                               // every lane is done with the block in `slot` ...
     if (lane == 0 && k + NE < nb) {                             // ... which is refilled with batch k + NE
       mbar_expect_tx(bar_s + 8 * slot, BLK_BYTES);
-      bulk_g2s(ering_s + slot * BLK_BYTES, gblk + (size_t)(k + NE) * BLK_BYTES, BLK_BYTES, bar_s + 8 * slot);
+      A6_BULK(ering_s + slot * BLK_BYTES, gblk + (size_t)(k + NE) * BLK_BYTES, BLK_BYTES, bar_s + 8 * slot);
     }
     slot = nslot; parity = nparity;
   }
   __syncwarp();
   double* out = a.values + v0;
+#ifdef FB2_A6_ST_CS
+  for (int t = lane; t < nval; t += 32) __stcs(out + t, acc[t]);
+#else
   for (int t = lane; t < nval; t += 32) out[t] = acc[t];
+#endif
+#undef A6_BULK
 }
 
 // per-cell record H = (kd * g_mn for 1 <= m <= n <= TD, km * |K|), padded to a multiple of 2 doubles
