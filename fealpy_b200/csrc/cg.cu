@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(CG_THREADS) spmm_kernel(int64_t n, const int64
 //     14 % of the kernel, no DOF reordering can recover more than that, and the Z-curve is worse than the lexicographic
 //     numbering of from_box.  The remaining gap to a plain copy (0.92 ms for the same bytes) is the stream -> shared memory
 //     -> row-sum structure itself.
-constexpr int ST_UNROLL = 4;
+#ifndef FB2_ST_UNROLL
+#define FB2_ST_UNROLL 4
+#endif
+constexpr int ST_UNROLL = FB2_ST_UNROLL;
 #ifndef FB2_ST_THREADS
 #define FB2_ST_THREADS 256
 #endif
