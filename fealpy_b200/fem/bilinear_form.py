@@ -25,7 +25,7 @@ import torch
 
 from .. import _lib
 from ..basis import host_tables
-from ..sparse import COOTensor, CSRTensor
+from ..sparse import CSRTensor
 from .integrators import Integrator
 
 

@@ -10,7 +10,6 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from ..basis import number_of_local_dofs
 
 
 class LagrangeFESpace:

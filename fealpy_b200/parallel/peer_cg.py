@@ -15,7 +15,7 @@ import torch
 import torch.distributed as dist
 
 from .. import _lib
-from .dist_cg import SC_RTR, SC_PAP, SC_RTR_NEW, SC_BNORM, SC_RNORM, SC_TMP, SC_NITER_I32, SC_DONE_I32, halo_exchange
+from .dist_cg import SC_RTR, SC_PAP, SC_RTR_NEW, SC_RNORM, SC_NITER_I32, SC_DONE_I32, halo_exchange
 
 
 def _range_plan(A, ranges, tile):
