@@ -791,6 +791,22 @@ def existing_gpu_leg(cfg_id, dev):
         t1 = time.perf_counter()
         out = {"kind": "reference pytorch backend, device=cuda", "n": n, "nnz": int(A.nnz), "value": A.nnz / (t1 - t0), "unit": UNIT,
                "assembly_s": t1 - t0}
+        # a second, larger size (BASELINE.md section 4 asks for 32^3 / 64^3): assembly only
+        n2 = {2: 64, 4: 64}.get(cfg_id)
+        if n2:
+            try:
+                prob2 = RefProblem(cfg_id, n2, backend="pytorch", device=str(dev))
+                A2_ = prob2.assemble()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                A2_ = prob2.assemble()
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+                out["larger"] = {"n": n2, "nnz": int(A2_.nnz), "value": A2_.nnz / dt, "unit": UNIT, "assembly_s": dt}
+                del prob2, A2_
+                torch.cuda.empty_cache()
+            except Exception as e:
+                out["larger"] = {"n": n2, "error": f"{type(e).__name__}: {str(e)[:200]}"}
         _emit(json.dumps(dict(out, cg_error="the reference's torch-cuda cg did not return (CUDA fault)")))     # survives a fault below
         try:
             A2, b, M = prob.rhs_and_system(A)
