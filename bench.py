@@ -104,7 +104,7 @@ def measured_traffic(cfg_id):
 
 
 class ClockSampler:
-    """SM clocks / throttle reasons sampled DURING the timed region.  In-process NVML (a 100 ms thread) when
+    """SM clocks / throttle reasons sampled DURING the timed region.  In-process NVML (a 30 ms thread) when
     nvidia_ml_py is importable -- an external `nvidia-smi -lms` loop was seen to stall this process's CUDA calls by
     ~30 ms per step on some boxes -- else nvidia-smi."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -125,7 +125,7 @@ class ClockSampler:
                 self.samples.append((float(sm), float(mx), {k for k, v in R.items() if bits & v}))
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.03)      # 30 ms: short configs (config 1: 8 ms per step) still get samples
 
     def start(self):
         try:
