@@ -125,7 +125,7 @@ class ClockSampler:
                 self.samples.append((float(sm), float(mx), {k for k, v in R.items() if bits & v}))
             except Exception:
                 pass
-            self.stop_flag.wait(0.03)      # 30 ms: short configs (config 1: 8 ms per step) still get samples
+            self.stop_flag.wait(float(os.environ.get("FB2_BENCH_SAMPLER_S", "0.03")))      # 30 ms: short configs (config 1: 8 ms per step) still get samples
 
     def start(self):
         try:
