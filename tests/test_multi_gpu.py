@@ -81,3 +81,34 @@ def test_two_gpu_morton_partition_matches_single_gpu(kind, dims, p):
         v = out[r]
         assert v["owned_rows_bit_identical"], v
         assert v["niter_ok"] and v["x_rel"] <= 1e-10, v
+
+
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
+def test_four_gpu_slab_matches_single_gpu(mode):
+    """four x-slabs: the interior ranks have two neighbours (both halo directions live)"""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(4, _free_port(), 2, mode, out), nprocs=4, join=True)
+    for r in range(4):
+        v = out[r]
+        assert v["owned_rows_bit_identical"], v
+        assert v["niter_ok"] and v["x_rel"] <= 1e-10, v
+        assert v["mode"] == mode
+
+
+@pytest.mark.parametrize("kind,dims,p", [("tet", (8, 7, 6), 2), ("tri", (30, 23), 3)])
+def test_four_gpu_morton_partition_matches_single_gpu(kind, dims, p):
+    """Morton partition over 4 GPUs: ranks with up to three neighbours, packed sends to each (NCCL)"""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_morton, args=(4, _free_port(), kind, dims, p, out), nprocs=4, join=True)
+    for r in range(4):
+        v = out[r]
+        assert v["owned_rows_bit_identical"], v
+        assert v["niter_ok"] and v["x_rel"] <= 1e-10, v
