@@ -571,15 +571,13 @@ class BilinearForm:
         """assembled product if assembly() was called, else matrix-free (fem/bilinear_form.py:126-158)"""
         if self._M is not None:
             return self._M @ u
-        if self._is_tensor_space():
-            raise NotImplementedError("matrix-free products on tensor spaces are not on the accelerated path; call assembly()")
         if not isinstance(u, torch.Tensor) or u.ndim != 1 or u.dtype != torch.float64:
             raise NotImplementedError("matrix-free products take a 1-D float64 CUDA tensor")
         sym = adjacency(self.space)
         if u.shape[0] != sym["gdof"]:
             raise ValueError("shape mismatch")
         v = torch.empty_like(u)
-        plan = self._plan_fused() if self.assembly_path in ("auto", "fused") else None
+        plan = self._plan_fused() if (self.assembly_path in ("auto", "fused") and not self._is_tensor_space()) else None
         if plan is not None:
             # constant / per-cell coefficients: neither A nor K_e is formed (csrc/assemble.cu matfree_cell_kernel)
             space, mesh = self.space, self.space.mesh

@@ -65,6 +65,22 @@ def test_assembly_csr(case, path, U):
     assert torch.equal(A.values, B.values) and torch.equal(A.col, B.col) and torch.equal(A.crow, B.crow)
 
 
+@pytest.mark.parametrize("path", ["auto", "gather"])
+@pytest.mark.parametrize("case", [c for c in C.CASES if not c.get("values_only_checksum")], ids=lambda c: c["name"])
+def test_matrix_free_product_matches_reference_run(case, path, U):
+    """row f4 pinned to the reference: `bform @ u` on the UNASSEMBLED form (fem/bilinear_form.py:126-158) as the real FEALPy
+    computed it (tests/golden, tools/gen_golden.py) -- scalar forms through the fused kernel where it applies ('auto') and
+    through the K_e product ('gather'), tensor-space (elasticity) forms through the K_e product"""
+    gold = G.load(case["name"])
+    mesh, space, bform, _ = U.make_form(case, gold, path=path)
+    w = bform @ U.t64(gold["matfree_u"])
+    assert bform._M is None
+    ref = gold["matfree_w"]
+    assert np.max(np.abs(w.cpu().numpy() - ref)) <= 1e-12 * np.max(np.abs(ref))
+    if path == "gather":
+        assert bform.last_matfree == "ke"
+
+
 @pytest.mark.parametrize("case", [c for c in C.CASES if c.get("cg")], ids=lambda c: c["name"])
 def test_spmv_and_cg(case, U):
     from fealpy_b200.solver import cg

@@ -150,6 +150,15 @@ def build_oracle_case(case, gold):
     return m, c2d, c2d_use, gdof, groups, Kes
 
 
+@pytest.mark.parametrize("case", [c for c in C.CASES if not c.get("values_only_checksum")], ids=lambda c: c["name"])
+def test_oracle_matrix_free_matches_reference_run(case):
+    """BilinearForm.__matmul__ before assembly as the real reference computed it (fem/bilinear_form.py:126-158)"""
+    gold = G.load(case["name"])
+    m, c2d, c2d_use, gdof, groups, Kes = build_oracle_case(case, gold)
+    w = O.matfree_apply(groups, gdof, gold["matfree_u"])
+    assert G.rel_err(w, gold["matfree_w"]) < 1e-13
+
+
 @pytest.mark.parametrize("case", C.CASES, ids=[c["name"] for c in C.CASES])
 def test_oracle_matches_reference_run(case):
     gold = G.load(case["name"])

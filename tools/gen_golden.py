@@ -7,6 +7,7 @@ against it.  Build-container only (needs /root/reference); the fixtures are comm
 import json
 import os
 import sys
+import zlib
 
 import numpy as np
 
@@ -64,7 +65,7 @@ def resolve_coef(spec, mesh_o, q, p):
     TD = mesh_o.TD
     qq = p + 3 if q is None else q
     NQ = len(O.quadrature(TD, qq)[1])
-    arr = C.coef_array(coef, mesh_o.NC, NQ, mesh_o.GD, seed=hash(coef) % 1000 + mesh_o.NC)
+    arr = C.coef_array(coef, mesh_o.NC, NQ, mesh_o.GD, seed=zlib.crc32(coef.encode()) % 1000 + mesh_o.NC)      # (str hash() is salted per process: not reproducible)
     return arr, arr, arr
 
 
@@ -138,6 +139,14 @@ def run_case(case):
         bform.add_integrator(*ints)
         groups_o.append((Ke_o_sum, c2d_use))
 
+    # matrix-free product of the UNASSEMBLED form (BilinearForm.__matmul__, fem/bilinear_form.py:126-158): row f4's pin
+    if not case.get("values_only_checksum"):
+        um = np.random.default_rng(1000 + gdof).standard_normal(gdof)
+        assert bform._M is None
+        wm = np.asarray(bform @ um)
+        wo = O.matfree_apply(groups_o, gdof, um)
+        assert rel_err(wo, wm) < 1e-13, f"{name}: oracle matrix-free product differs"
+        out.update(matfree_u=um, matfree_w=wm)
     A = bform.assembly()
     crow, col, val = np.asarray(A.crow), np.asarray(A.col), np.asarray(A.values)
     ocrow, ocol, oval = O.assemble(groups_o, gdof)
