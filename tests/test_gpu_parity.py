@@ -515,6 +515,37 @@ def test_distributed_driver_single_rank_matches_cg(U):
 
 
 @pytest.mark.parametrize("case", C.BC_CASES, ids=lambda c: c["name"])
+def test_dirichlet_operator_matches_reference_run(case, U):
+    """DirichletBCOperator on the UNASSEMBLED form (fem/dirichlet_bc_operator.py:13-67) against the reference's own
+    operator outputs (golden): Dirichlet set, init_solution(), apply(F, uh) and `op @ u` through the fused matrix-free
+    product; then cg(op, ...) reproduces the golden solution of the constrained system (whole-boundary cases)"""
+    from fealpy_b200.fem import (BilinearForm, LinearForm, ScalarDiffusionIntegrator, ScalarMassIntegrator, ScalarSourceIntegrator,
+                                 DirichletBCOperator)
+    from fealpy_b200.functionspace import LagrangeFESpace
+    from fealpy_b200.solver import cg
+    gold = G.load(case["name"])
+    mesh = U.make_mesh(case, gold)
+    space = LagrangeFESpace(mesh, case["p"])
+    form = BilinearForm(space).add_integrator(ScalarDiffusionIntegrator())
+    if case.get("reaction"):
+        form.add_integrator(ScalarMassIntegrator())
+    thr = U.torch_coef_func(C.THRESHOLDS[case["threshold"]]) if case.get("threshold") else None
+    op = DirichletBCOperator(form, gd=U.torch_coef_func(C.kappa_cart), threshold=thr)
+    assert np.array_equal(op.is_boundary_dof.cpu().numpy(), gold["op_isbd"])
+    uh = op.init_solution()
+    np.testing.assert_allclose(uh.cpu().numpy(), gold["op_uh"], atol=1e-15)
+    F = LinearForm(space).add_integrator(ScalarSourceIntegrator(U.torch_coef_func(C.source_cart))).assembly()
+    Fop = op.apply(F, uh)
+    assert np.max(np.abs(Fop.cpu().numpy() - gold["op_F"])) <= 1e-12 * np.max(np.abs(gold["op_F"]))
+    w = op @ U.t64(gold["op_u"])
+    assert form._M is None and form.last_matfree == "fused"
+    assert np.max(np.abs(w.cpu().numpy() - gold["op_w"])) <= 1e-12 * np.max(np.abs(gold["op_w"]))
+    if not case.get("threshold"):      # whole boundary: the same constrained system as the golden DirichletBC solve of this case
+        x = cg(op, Fop, atol=1e-14, rtol=1e-11)
+        assert np.linalg.norm(x.cpu().numpy() - gold["x"]) / np.linalg.norm(gold["x"]) <= 1e-9
+
+
+@pytest.mark.parametrize("case", C.BC_CASES, ids=lambda c: c["name"])
 def test_poisson_source_dirichlet_cg(case, U):
     """rows f1/f2: LinearForm + ScalarSourceIntegrator, DirichletBC.apply, then cg -- against the
     reference run (golden) of the same Poisson problem"""

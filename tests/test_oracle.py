@@ -217,6 +217,38 @@ def test_oracle_bc_matches_reference_run(case):
     assert np.linalg.norm(x - gold["x"]) / np.linalg.norm(gold["x"]) < 1e-10
 
 
+@pytest.mark.parametrize("case", C.BC_CASES, ids=[c["name"] for c in C.BC_CASES])
+def test_oracle_dirichlet_operator_matches_reference_run(case):
+    """the matrix-free constrained operator (fem/dirichlet_bc_operator.py:13-67) restated on the oracle's matrix-free
+    product, against the reference's own DirichletBCOperator outputs on the unassembled form"""
+    gold = G.load(case["name"])
+    m = O.Mesh(gold["node"], gold["cell"])
+    p = case["p"]
+    c2d = m.cell_to_ipoint(p)
+    gdof = m.number_of_global_ipoints(p)
+    ke = O.diffusion_element(m, p)
+    if case.get("reaction"):
+        ke = ke + O.mass_element(m, p)
+    groups = [(ke, c2d)]
+    thr = C.THRESHOLDS[case["threshold"]] if case.get("threshold") else None
+    bd = O.boundary_dof_flag(m, p, thr, None)                 # the operator's constructor has no `method`
+    assert np.array_equal(bd, gold["op_isbd"])
+    ip = m.interpolation_points(p)
+    uh = np.zeros(gdof)
+    uh[bd] = C.kappa_cart(ip[bd])                              # init_solution(): boundary_interpolate with the flag as threshold
+    np.testing.assert_allclose(uh, gold["op_uh"], atol=1e-15)
+    F = O.source_vector(m, p, C.source_cart)
+    Fop = F - O.matfree_apply(groups, gdof, uh)
+    Fop[bd] = uh[bd]
+    assert G.rel_err(Fop, gold["op_F"]) < 1e-13
+    v = gold["op_u"].copy()
+    val = v[bd].copy()
+    v[bd] = 0.0
+    w = O.matfree_apply(groups, gdof, v)
+    w[bd] = val
+    assert G.rel_err(w, gold["op_w"]) < 1e-13
+
+
 @pytest.mark.parametrize("case", C.TENSOR_BC_CASES, ids=[c["name"] for c in C.TENSOR_BC_CASES])
 def test_oracle_tensor_bc_matches_reference_run(case):
     """elasticity + TensorFunctionSpace Dirichlet data + Jacobi CG against the reference run"""

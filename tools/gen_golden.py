@@ -223,8 +223,24 @@ def run_bc_case(case):
     d = (A2s - Ao)
     assert (abs(d).max() if d.nnz else 0.0) < 1e-13, f"{name}: BC matrix differs"
     A2s.eliminate_zeros()
+    # the matrix-free constrained operator on the UNASSEMBLED form (fem/dirichlet_bc_operator.py:13-67); its constructor has
+    # no `method`: the Dirichlet set is is_boundary_dof(threshold) with the default (face-centroid) selection
+    from fealpy.fem.dirichlet_bc_operator import DirichletBCOperator
+    bform_free = BilinearForm(space)
+    bform_free.add_integrator(ScalarDiffusionIntegrator())
+    if case.get("reaction"):
+        bform_free.add_integrator(ScalarMassIntegrator())
+    op = DirichletBCOperator(bform_free, gd=g, threshold=thr)
+    op_isbd = np.asarray(op.is_boundary_dof)
+    assert np.array_equal(op_isbd, O.boundary_dof_flag(mesh_o, p, thr, None)), f"{name}: operator flags differ"
+    op_uh = np.asarray(op.init_solution())
+    op_F = np.asarray(op.apply(F, op_uh))
+    op_u = np.random.default_rng(2000 + gdof).standard_normal(gdof)
+    op_w = np.asarray(op @ op_u)
+    assert bform_free._M is None
     out = dict(node=np.asarray(mesh.node), cell=np.asarray(mesh.cell), cell2dof=np.asarray(space.cell_to_dof()),
                crow=np.asarray(A.crow), col=np.asarray(A.col), values=np.asarray(A.values),
+               op_isbd=op_isbd, op_uh=op_uh, op_F=op_F, op_u=op_u, op_w=op_w,
                F=F, isbd=isbd, isbd_val=isbd_val, ipoints=ip, F_bc=np.asarray(F2),
                Abc_indptr=A2s.indptr.astype(np.int64), Abc_indices=A2s.indices.astype(np.int32), Abc_data=A2s.data,
                x=np.asarray(x),
