@@ -672,6 +672,21 @@ def test_config4_tet_p1_elasticity_full_size(U):
 
 
 @pytest.mark.parametrize("batch_first", [False, True])
+@pytest.mark.parametrize("case", [c for c in C.CASES if c.get("cg") and "bcg_B" in G.load(c["name"])], ids=lambda c: c["name"])
+def test_batched_rhs_cg_matches_reference_run(case, batch_first, U):
+    """cg with three right-hand sides at once against the real reference's batched solve (golden bcg_B / bcg_x / bcg_niter)"""
+    from fealpy_b200.solver import cg
+    gold = G.load(case["name"])
+    mesh, space, bform, _ = U.make_form(case, gold)
+    A = bform.assembly()
+    Bm = gold["bcg_B"]
+    x, info = cg(A, U.t64(Bm.T.copy() if batch_first else Bm), batch_first=batch_first, returninfo=True, atol=1e-14, rtol=1e-12)
+    xg = x.cpu().numpy().T if batch_first else x.cpu().numpy()
+    assert abs(info["niter"] - gold["info"]["bcg_niter"]) <= 1
+    assert np.linalg.norm(xg - gold["bcg_x"]) / np.linalg.norm(gold["bcg_x"]) <= 1e-10
+
+
+@pytest.mark.parametrize("batch_first", [False, True])
 def test_batched_rhs_cg_matches_oracle(batch_first, U):
     """b of shape (dof, batch): per-column alpha/beta, joint stopping test (solver/cg.py:58-121)"""
     from oracle import fem_oracle as O

@@ -217,6 +217,20 @@ def test_oracle_bc_matches_reference_run(case):
     assert np.linalg.norm(x - gold["x"]) / np.linalg.norm(gold["x"]) < 1e-10
 
 
+BCG_CASES = [c for c in C.CASES if c.get("cg") and "bcg_B" in G.load(c["name"])]
+
+
+@pytest.mark.parametrize("case", BCG_CASES, ids=lambda c: c["name"])
+def test_oracle_batched_cg_matches_reference_run(case):
+    """cg with a (dof, batch) right-hand side as the real reference solved it (solver/cg.py:58-121)"""
+    gold = G.load(case["name"])
+    crow, col, val = gold["crow"], gold["col"], gold["values"]
+    mv = lambda v: np.stack([O.csr_matvec(crow, col, val, v[:, k]) for k in range(v.shape[1])], axis=1)
+    x, info = O.cg(mv, gold["bcg_B"], atol=1e-14, rtol=1e-12)
+    assert abs(info["niter"] - gold["info"]["bcg_niter"]) <= 1
+    assert np.linalg.norm(x - gold["bcg_x"]) / np.linalg.norm(gold["bcg_x"]) < 1e-10
+
+
 @pytest.mark.parametrize("case", C.BC_CASES, ids=[c["name"] for c in C.BC_CASES])
 def test_oracle_dirichlet_operator_matches_reference_run(case):
     """the matrix-free constrained operator (fem/dirichlet_bc_operator.py:13-67) restated on the oracle's matrix-free

@@ -172,6 +172,15 @@ def run_case(case):
         assert ex < 1e-10, f"{name}: oracle CG solution differs {ex}"
         out.update(b=b, x=np.asarray(x))
         info.update(niter=int(cinfo["niter"]), residual=float(cinfo["residual"]))
+        if gdof <= 1000:
+            # batched right-hand sides (solver/cg.py:58-121: per-column alpha / beta, joint stopping test) through the reference
+            Bm = np.random.default_rng(3000 + gdof).standard_normal((gdof, 3))
+            xb, binfo = cg(A, Bm, returninfo=True, atol=1e-14, rtol=1e-12)
+            xbo, boinfo = O.cg(lambda v: np.stack([O.csr_matvec(ocrow, ocol, oval, v[:, k]) for k in range(v.shape[1])], axis=1), Bm,
+                               atol=1e-14, rtol=1e-12)
+            assert abs(boinfo["niter"] - binfo["niter"]) <= 1 and np.linalg.norm(xbo - xb) / np.linalg.norm(xb) < 1e-10, name
+            out.update(bcg_B=Bm, bcg_x=np.asarray(xb))
+            info.update(bcg_niter=int(binfo["niter"]), bcg_residual=float(binfo["residual"]))
     out["info"] = np.array(json.dumps(info))
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
     print(f"{name:36s} gdof {gdof:7d} nnz {A.nnz:8d} " + (f"cg {info.get('niter')}" if case.get('cg') else ""))
