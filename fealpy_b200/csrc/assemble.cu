@@ -1242,8 +1242,11 @@ __global__ void __launch_bounds__(256) cell_geometry4_kernel(const double* __res
 // with the folded table T in the kernel parameter block (warp-uniform operands, L*L*NH + L*NH DFMAs per cell, no
 // element matrix anywhere).  The (NC, L) block w goes to HBM once (8*L bytes per cell instead of 8*L*L for K_e) and the
 // row-owner gather of gather_vector() sums it per dof in the fixed (i, cell) order: no atomics, bit-reproducible.
+#ifndef FB2_MF_MINBLOCKS
+#define FB2_MF_MINBLOCKS 1
+#endif
 template <int TD, int L>
-__global__ void __launch_bounds__(128) matfree_cell_kernel(const double* __restrict__ node, const int* __restrict__ cell,
+__global__ void __launch_bounds__(128, FB2_MF_MINBLOCKS) matfree_cell_kernel(const double* __restrict__ node, const int* __restrict__ cell,
                                                            const int* __restrict__ c2d, int64_t NC, double scal_d,
                                                            const double* __restrict__ coef_d, double scal_m,
                                                            const double* __restrict__ coef_m, const double* __restrict__ u,
@@ -1271,7 +1274,12 @@ __global__ void __launch_bounds__(128) matfree_cell_kernel(const double* __restr
       for (int n = m; n <= TD; ++n) h[t++] = kd * G[GEO::full(m, n)];
     h[NR] = scal_m * (coef_m ? coef_m[c] : 1.0) * cm;
     double* out = stage + threadIdx.x * L;
-#pragma unroll(L <= 10 ? L : 1)
+#ifdef FB2_MF_IUNROLL
+    constexpr int IU = FB2_MF_IUNROLL;
+#else
+    constexpr int IU = L <= 6 ? L : 1;      // 10 rows unrolled: 156-198 registers, 2.11 ms; rolled: 74 registers, 1.80 ms (tet P2 128^3)
+#endif
+#pragma unroll(IU)
     for (int i = 0; i < L; ++i) {
       double acc = 0.0;
 #pragma unroll
