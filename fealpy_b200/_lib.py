@@ -94,7 +94,8 @@ SIGNATURES = {
     "fb2_matfree_apply": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "fb2_adjacency_workspace_bytes": (_sz, [_i64]),
     "fb2_adjacency": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _p]),
-    "fb2_matfree_scalar_const": (_i32, [_i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _f64, _p, _f64, _p, _p, _p, _p, _p]),
+    "fb2_matfree_scalar_const": (_i32, [_i32, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _p, _f64, _p, _p, _p, _p, _p]),
+    "fb2_pair_positions": (_i32, [_i64, _p, _p, _p]),
     "fb2_bc_workspace_bytes": (_sz, [_i64]),
     "fb2_bc_matrix_count": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     "fb2_bc_matrix_fill": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -1250,7 +1250,7 @@ __global__ void __launch_bounds__(128, FB2_MF_MINBLOCKS) matfree_cell_kernel(con
                                                            const int* __restrict__ c2d, int64_t NC, double scal_d,
                                                            const double* __restrict__ coef_d, double scal_m,
                                                            const double* __restrict__ coef_m, const double* __restrict__ u,
-                                                           double* __restrict__ w,
+                                                           double* __restrict__ w, const int* __restrict__ pair_pos,
                                                            const __grid_constant__ A4Tables<L, A4Geo<TD>::NH> tb) {
   using GEO = A4Geo<TD>;
   constexpr int NV = TD + 1, NG = GEO::NG, NR = GEO::NR, NH = GEO::NH;
@@ -1294,8 +1294,46 @@ __global__ void __launch_bounds__(128, FB2_MF_MINBLOCKS) matfree_cell_kernel(con
   }
   __syncthreads();
   const int64_t ncell = (NC - c0) < 128 ? (NC - c0) : 128;
+  if (pair_pos) {
+    // adjacency order: entry (c, i) goes to the position of pair c*L+i in its dof's list, so that the per-dof sum reads ONE
+    // contiguous run (the pair-ordered block was read back at sector granularity: 4.8 GB for 1.0 GB of payload); the
+    // scattered 8-byte stores of one dof's run come from cells that are neighbours in memory and merge in L2
+    const int* __restrict__ pos = pair_pos + c0 * L;
+    for (int64_t t = threadIdx.x; t < ncell * L; t += 128) w[pos[t]] = stage[t];
+    return;
+  }
   double* dst = w + c0 * L;
   for (int64_t t = threadIdx.x; t < ncell * L; t += 128) dst[t] = stage[t];       // contiguous, fully coalesced
+}
+
+// pair_pos[pair] = position of (cell, i) pair in the adjacency lists (inverse of adj_pair)
+__global__ void __launch_bounds__(256) pair_position_kernel(int64_t npos, const int* __restrict__ adj_pair, int* __restrict__ pair_pos) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < npos; q += (int64_t)gridDim.x * blockDim.x)
+    pair_pos[adj_pair[q]] = (int)q;
+}
+
+// F[d] = sum of the contiguous run w[adj_ptr[d] .. adj_ptr[d+1]) in order (the order of gather_vector_kernel)
+__global__ void __launch_bounds__(256) segment_sum_kernel(int64_t gdof, const int64_t* __restrict__ adj_ptr, const double* __restrict__ w,
+                                                          double* __restrict__ F) {
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < gdof; d += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int64_t q = adj_ptr[d]; q < adj_ptr[d + 1]; ++q) s += w[q];
+    F[d] = s;
+  }
+}
+
+int pair_positions(int64_t npos, const int* adj_pair, int* pair_pos, cudaStream_t s) {
+  if (npos <= 0) return OK;
+  pair_position_kernel<<<grid_for(npos), 256, 0, s>>>(npos, adj_pair, pair_pos);
+  FB2_LAUNCH_CHECK();
+  return OK;
+}
+
+int segment_sum(int64_t gdof, const int64_t* adj_ptr, const double* w, double* F, cudaStream_t s) {
+  if (gdof <= 0) return OK;
+  segment_sum_kernel<<<grid_for(gdof), 256, 0, s>>>(gdof, adj_ptr, w, F);
+  FB2_LAUNCH_CHECK();
+  return OK;
 }
 
 template <int TD, int L>
@@ -1304,7 +1342,7 @@ static int launch_matfree(const MatfreeArgs& a, cudaStream_t s) {
   A4Tables<L, GEO::NH> tb;
   a4_reduced_table<TD, L>(a.Ms_host, a.Mm_host, tb);
   matfree_cell_kernel<TD, L><<<(unsigned)ceil_div(a.NC, 128), 128, 0, s>>>(a.node, a.cell, a.c2d, a.NC, a.Ms_host ? a.scal_d : 0.0, a.coef_d,
-                                                                           a.Mm_host ? a.scal_m : 0.0, a.coef_m, a.u, a.w, tb);
+                                                                           a.Mm_host ? a.scal_m : 0.0, a.coef_m, a.u, a.w, a.pair_pos, tb);
   FB2_LAUNCH_CHECK();
   return OK;
 }

@@ -77,9 +77,12 @@ struct MatfreeArgs {
   const double* coef_d;         // per-cell or null
   const double* coef_m;
   const double* u;              // (gdof)
-  double* w;                    // (NC, L) per-cell products K_e u_e
+  double* w;                    // (NC, L) per-cell products K_e u_e: pair order, or adjacency order when pair_pos is given
+  const int* pair_pos;          // (NC*L) position of every (cell, i) pair in the adjacency lists, or null
 };
 int matfree_scalar_const(int TD, int p, const MatfreeArgs& a, cudaStream_t s);
+int pair_positions(int64_t npos, const int* adj_pair, int* pair_pos, cudaStream_t s);
+int segment_sum(int64_t gdof, const int64_t* adj_ptr, const double* w, double* F, cudaStream_t s);
 size_t adjacency_workspace_bytes(int64_t gdof);
 int build_adjacency(const int* c2d, int64_t NC, int L, int64_t gdof, int64_t* adj_ptr, int* adj_pair, void* ws, cudaStream_t s);
 size_t asm4_workspace_bytes(int ntile);

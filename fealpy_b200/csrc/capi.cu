@@ -380,15 +380,19 @@ size_t fb2_adjacency_workspace_bytes(int64_t gdof) { return adjacency_workspace_
 int fb2_adjacency(const int32_t* c2d, int64_t NC, int ldof, int64_t gdof, int64_t* adj_ptr, int32_t* adj_pair, void* ws, void* stream) {
   return build_adjacency(c2d, NC, ldof, gdof, adj_ptr, adj_pair, ws, S(stream));
 }
+int fb2_pair_positions(int64_t npos, const int32_t* adj_pair, int32_t* pair_pos, void* stream) {
+  return pair_positions(npos, adj_pair, pair_pos, S(stream));
+}
 int fb2_matfree_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell, const int32_t* cell2dof,
-                             const int64_t* adj_ptr, const int32_t* adj_pair, const double* Ms_host, const double* Mm_host,
-                             double scal_d, const double* coef_d, double scal_m, const double* coef_m, const double* u,
-                             double* cell_ws, double* v, void* stream) {
+                             const int64_t* adj_ptr, const int32_t* adj_pair, const int32_t* pair_pos, const double* Ms_host,
+                             const double* Mm_host, double scal_d, const double* coef_d, double scal_m, const double* coef_m,
+                             const double* u, double* cell_ws, double* v, void* stream) {
   if (!Ms_host && !Mm_host) return fail(ERR_INVALID, "matfree_scalar_const: need a diffusion and/or a mass table");
   MatfreeArgs a{};
   a.node = node; a.cell = cell; a.c2d = cell2dof; a.NC = NC; a.Ms_host = Ms_host; a.Mm_host = Mm_host;
-  a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.u = u; a.w = cell_ws;
+  a.scal_d = scal_d; a.scal_m = scal_m; a.coef_d = coef_d; a.coef_m = coef_m; a.u = u; a.w = cell_ws; a.pair_pos = pair_pos;
   FB2_TRY(matfree_scalar_const(TD, p, a, S(stream)));
+  if (pair_pos) return segment_sum(gdof, adj_ptr, cell_ws, v, S(stream));
   return gather_vector(gdof, adj_ptr, adj_pair, cell_ws, v, S(stream));
 }
 size_t fb2_bc_workspace_bytes(int64_t n) { return bc_workspace_bytes(n); }

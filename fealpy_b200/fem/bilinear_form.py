@@ -587,8 +587,17 @@ class BilinearForm:
             ws = getattr(self, "_matfree_ws", None)       # (NC, l) per-cell products, kept with the form
             if ws is None or ws.shape != (sym["NC"], sym["L"]) or ws.device != u.device:
                 ws = self._matfree_ws = torch.empty((sym["NC"], sym["L"]), dtype=torch.float64, device=u.device)
+            # cell products in adjacency order (contiguous per-dof sum: 1.29 against 1.79 ms at tet P2 128^3, faster than the
+            # assembled SpMV's 1.35 ms) once the block outgrows L2; a block that stays in L2 is gathered in pair order
+            # (config 1: 0.111 against 0.122 ms).  pair_pos = inverse of adj_pair, built once per space.
+            order = _os.environ.get("FB2_MATFREE_ORDER", "adj" if sym["NC"] * sym["L"] * 8 > (64 << 20) else "pair")
+            pos = sym.get("pair_pos") if order == "adj" else None
+            if pos is None and order == "adj":
+                pos = torch.empty(sym["NC"] * sym["L"], dtype=torch.int32, device=u.device)
+                _lib.call("fb2_pair_positions", sym["NC"] * sym["L"], _lib.ptr(sym["adj_pair"]), _lib.ptr(pos), _lib.stream())
+                sym["pair_pos"] = pos
             _lib.call("fb2_matfree_scalar_const", mesh.TD, space.p, sym["NC"], sym["gdof"], _lib.ptr(mesh.node), _lib.ptr(mesh.cell),
-                      _lib.ptr(space.cell_to_dof().contiguous()), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]),
+                      _lib.ptr(space.cell_to_dof().contiguous()), _lib.ptr(sym["adj_ptr"]), _lib.ptr(sym["adj_pair"]), _lib.ptr(pos),
                       self._host_table(dm, "Ms"), self._host_table(mm, "Mm"), sd, _lib.ptr(ad), sm_, _lib.ptr(am),
                       _lib.ptr(u.contiguous()), _lib.ptr(ws), _lib.ptr(v), _lib.stream())
             self.last_matfree = "fused"

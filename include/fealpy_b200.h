@@ -292,9 +292,13 @@ int fb2_adjacency(const int32_t* cell2dof, int64_t NC, int ldof, int64_t gdof, i
  * sums it per dof in fixed order (no atomics).  Replaces einsum('cij,cj->ci') + index_add of fem/bilinear_form.py:126-158.
  * Ms_host / Mm_host: host tables as for fb2_assemble_scalar_const_v4 (null = term absent). */
 int fb2_matfree_scalar_const(int TD, int p, int64_t NC, int64_t gdof, const double* node, const int32_t* cell,
-                             const int32_t* cell2dof, const int64_t* adj_ptr, const int32_t* adj_pair, const double* Ms_host,
-                             const double* Mm_host, double scal_d, const double* coef_d_cell, double scal_m,
+                             const int32_t* cell2dof, const int64_t* adj_ptr, const int32_t* adj_pair, const int32_t* pair_pos,
+                             const double* Ms_host, const double* Mm_host, double scal_d, const double* coef_d_cell, double scal_m,
                              const double* coef_m_cell, const double* u, double* cell_ws, double* v, void* stream);
+/* pair_pos (NC*ldof int32, optional argument of fb2_matfree_scalar_const): the position of every (cell, i) pair in the
+ * adjacency lists.  With it the cell kernel writes its products in adjacency order and the per-dof sum reads one contiguous
+ * run (same summation order, bit-identical result; NULL = pair order + gather). */
+int fb2_pair_positions(int64_t npos, const int32_t* adj_pair, int32_t* pair_pos, void* stream);
 size_t fb2_bc_workspace_bytes(int64_t n);
 /* canonical CSR of the constrained matrix: boundary rows/columns removed, unit diagonal on boundary rows */
 int fb2_bc_matrix_count(int64_t n, const int64_t* crow, const int32_t* col, const uint8_t* isbd, int64_t* crow_new,
